@@ -1,0 +1,940 @@
+// libsonic_b200: context, weight store, pipeline orchestration and the extern "C" surface (include/sonic_b200.h).
+// Everything runs on the handle's own stream; the only host<->device traffic per call is the PCM upload, a few
+// hundred bytes of prompt metadata and the token ids coming back.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <string.h>
+#include <stdlib.h>
+#include <type_traits>
+#include <map>
+#include <mutex>
+#include <set>
+#include <string>
+#include <vector>
+
+#include "../../include/sonic_b200.h"
+#include "common.cuh"
+#include "kernels.h"
+#include "gemm_tc.h"
+
+using namespace sonic;
+
+namespace {
+
+constexpr int kMels = 128, kFrames = 3000, kWinSamples = 480000;
+constexpr int kEncH = 1280, kEncHeads = 20, kEncHd = 64, kEncInter = 5120, kEncT = 1500, kEncRot = 32;
+constexpr int kDecH = 2048, kDecHeads = 16, kDecKv = 4, kDecHd = 128, kDecInter = 6144, kVocab = 59264;
+constexpr int kQkvDec = (kDecHeads + 2 * kDecKv) * kDecHd;   // 3072
+constexpr int kAudioTok = 59260, kMerged = 375;
+constexpr float kLnEps = 1e-5f, kRmsEps = 1e-5f, kTheta = 10000.0f;
+constexpr int kMaxTaps = 12;
+
+thread_local std::string g_last_error;
+
+// ---- conversion kernels for the weight upload ----------------------------------------------------------------------------
+template <typename TS> __device__ __forceinline__ float src_f32(const TS* p, size_t i);
+template <> __device__ __forceinline__ float src_f32<float>(const float* p, size_t i) { return p[i]; }
+template <> __device__ __forceinline__ float src_f32<bf16>(const bf16* p, size_t i) { return __bfloat162float(p[i]); }
+
+// dst[(row0 + r*row_step) * cols + c] = src[r*cols + c]
+template <typename TS, typename TD>
+__global__ void convert_rows_kernel(const TS* __restrict__ src, TD* __restrict__ dst, long long rows, long long cols, long long row0,
+                                    long long row_step) {
+  const long long total = rows * cols;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / cols, c = i - r * cols;
+    dst[(row0 + r * row_step) * cols + c] = from_f32<TD>(src_f32<TS>(src, (size_t)i));
+  }
+}
+// conv weight [co][ci][3] -> [co][k*ci_n + ci]
+template <typename TS, typename TD>
+__global__ void convert_conv_kernel(const TS* __restrict__ src, TD* __restrict__ dst, long long co, long long ci) {
+  const long long total = co * ci * 3;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long o = i / (ci * 3), rem = i - o * ci * 3, c = rem / 3, k = rem - c * 3;
+    dst[o * ci * 3 + k * ci + c] = from_f32<TD>(src_f32<TS>(src, (size_t)i));
+  }
+}
+// fp32 vector, optionally rounded through bf16 (the reference holds every parameter in the model dtype)
+template <typename TS>
+__global__ void convert_vec_kernel(const TS* __restrict__ src, float* __restrict__ dst, long long n, int round_bf16) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float v = src_f32<TS>(src, (size_t)i);
+    if (round_bf16) v = __bfloat162float(__float2bfloat16_rn(v));
+    dst[i] = v;
+  }
+}
+template <typename TS, typename TD>
+__global__ void convert_flat_kernel(const TS* __restrict__ src, TD* __restrict__ dst, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    dst[i] = from_f32<TD>(to_f32(src[i]));
+}
+__global__ void set_int_kernel(int* p, int v, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+struct EncLayerW {
+  float *ln1_g, *ln1_b, *ln2_g, *ln2_b, *bqkv, *bo, *b1, *b2;
+  void *wqkv, *wo, *fc1, *fc2;
+};
+struct DecLayerW {
+  float *rms1, *rms2;
+  void *wqkv, *wo, *wgu, *wdown;
+};
+
+}  // namespace
+
+struct sonic_ctx {
+  sonic_config cfg;
+  cudaStream_t stream = nullptr;
+  std::mutex mu;
+  std::string err;
+  std::vector<void*> allocs;
+  int64_t bytes = 0;
+  int64_t launches = 0;
+  size_t esz = 2;                       // activation / weight element size
+  bool is_f32 = false;
+  bool force_simt = false;
+
+  // weights
+  void *conv1_w = nullptr, *conv2_w = nullptr, *proj1_w = nullptr, *proj2_w = nullptr, *embed = nullptr, *lm_head = nullptr;
+  float *conv1_b = nullptr, *conv2_b = nullptr, *enc_norm_g = nullptr, *enc_norm_b = nullptr, *proj1_b = nullptr, *proj2_b = nullptr,
+        *final_norm = nullptr;
+  std::vector<EncLayerW> enc;
+  std::vector<DecLayerW> dec;
+  std::set<std::string> loaded;
+  void* staging = nullptr;
+  size_t staging_bytes = 0;
+  bool finalized = false;
+
+  // tables
+  void* mel_tables = nullptr;
+  float *rope_enc_cos = nullptr, *rope_enc_sin = nullptr, *rope_dec_cos = nullptr, *rope_dec_sin = nullptr;
+  int max_ctx = 0;
+
+  // mel buffers
+  float* pcm_dev = nullptr;
+  long long* offs_dev = nullptr;
+  int* lens_dev = nullptr;
+  unsigned *peak_bits = nullptr, *gmax_bits = nullptr;
+  float *mel_raw = nullptr, *mel_feat = nullptr;
+  void* mel_tm = nullptr;
+  std::vector<int> last_lens;           // lengths of the segments currently held in mel_tm
+  int last_batch = 0;
+
+  // encoder buffers
+  void *h1 = nullptr, *ex = nullptr, *eu = nullptr, *eqkv = nullptr, *eattn = nullptr, *emlp = nullptr, *a1 = nullptr, *audio = nullptr;
+  // decoder buffers
+  void *dx = nullptr, *du = nullptr, *dqkv = nullptr, *dattn = nullptr, *dact = nullptr, *kcache = nullptr, *vcache = nullptr;
+  float* logits = nullptr;
+  int *d_ids = nullptr, *d_audio_src = nullptr, *d_row_seg = nullptr, *d_row_pos = nullptr, *d_tok_off = nullptr, *d_last_rows = nullptr;
+  GreedyState gs{};
+  int* h_pinned = nullptr;              // pinned scratch for metadata upload / flags
+  size_t h_pinned_ints = 0;
+  std::map<int, cudaGraphExec_t> decode_graphs;
+  std::map<int, int64_t> decode_graph_kernels;
+
+  // probes (debug)
+  std::map<std::string, std::pair<void*, size_t>> probes;   // name -> (device ptr in activation dtype, elems)
+  std::map<std::string, std::pair<float*, size_t>> probes_f32;
+
+  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev_user[2] = {nullptr, nullptr};
+  float stage_ms[4] = {0, 0, 0, 0};
+};
+
+namespace {
+
+int fail(sonic_ctx* h, const std::string& msg) {
+  if (h) h->err = msg;
+  g_last_error = msg;
+  return -1;
+}
+int fail_cuda(sonic_ctx* h, cudaError_t e, const char* what) {
+  return fail(h, std::string(what) + ": " + cudaGetErrorName(e) + " (" + cudaGetErrorString(e) + ")");
+}
+#define CK(expr)                                                   \
+  do {                                                             \
+    cudaError_t _e = (expr);                                       \
+    if (_e != cudaSuccess) return fail_cuda(h, _e, #expr);         \
+  } while (0)
+#define CKL(expr, nk)                                              \
+  do {                                                             \
+    cudaError_t _e = (expr);                                       \
+    if (_e != cudaSuccess) return fail_cuda(h, _e, #expr);         \
+    h->launches += (nk);                                           \
+  } while (0)
+
+template <typename P>
+int dalloc(sonic_ctx* h, P** p, size_t bytes, bool zero = false) {
+  void* q = nullptr;
+  if (bytes == 0) bytes = 16;
+  CK(cudaMalloc(&q, bytes));
+  if (zero) CK(cudaMemsetAsync(q, 0, bytes, h->stream));
+  h->allocs.push_back(q);
+  h->bytes += (int64_t)bytes;
+  *p = reinterpret_cast<P*>(q);
+  return 0;
+}
+#define DA(ptr, bytes)            \
+  if (dalloc(h, &(ptr), (bytes))) return -1
+#define DAZ(ptr, bytes)                 \
+  if (dalloc(h, &(ptr), (bytes), true)) return -1
+
+// ---- slaney mel filter bank (transformers/audio_utils.py:263-332,356-375,453-544), float64 then cast to fp32 ------------
+double hz_to_mel(double f) { return f >= 1000.0 ? 15.0 + log(f / 1000.0) * (27.0 / log(6.4)) : 3.0 * f / 200.0; }
+double mel_to_hz(double m) { return m >= 15.0 ? 1000.0 * exp((log(6.4) / 27.0) * (m - 15.0)) : 200.0 * m / 3.0; }
+void build_mel_taps(std::vector<int>& start, std::vector<int>& count, std::vector<float>& w) {
+  const int nb = 201;
+  std::vector<double> hz(kMels + 2);
+  const double m0 = hz_to_mel(0.0), m1 = hz_to_mel(8000.0);
+  for (int i = 0; i < kMels + 2; ++i) hz[i] = mel_to_hz(m0 + (m1 - m0) * i / (kMels + 1));
+  start.assign(kMels, 0); count.assign(kMels, 0); w.assign((size_t)kMels * kMaxTaps, 0.f);
+  for (int m = 0; m < kMels; ++m) {
+    const double enorm = 2.0 / (hz[m + 2] - hz[m]);
+    int lo = -1, hi = -1;
+    std::vector<float> col(nb);
+    for (int k = 0; k < nb; ++k) {
+      const double f = 8000.0 * k / (nb - 1);
+      const double down = (f - hz[m]) / (hz[m + 1] - hz[m]);
+      const double up = (hz[m + 2] - f) / (hz[m + 2] - hz[m + 1]);
+      double v = fmax(0.0, fmin(down, up)) * enorm;
+      col[k] = (float)v;
+      if (col[k] != 0.f) { if (lo < 0) lo = k; hi = k; }
+    }
+    if (lo < 0) { lo = 0; hi = 0; }
+    start[m] = lo;
+    count[m] = (hi - lo + 1 > kMaxTaps) ? kMaxTaps : hi - lo + 1;
+    for (int j = 0; j < count[m]; ++j) w[(size_t)m * kMaxTaps + j] = col[lo + j];
+  }
+}
+
+int n_valid_frames(long long n) {
+  if (n > kWinSamples) n = kWinSamples;
+  return (int)((n + 159) / 160);
+}
+int n_audio_tokens(long long n) {
+  const int f = n_valid_frames(n);
+  const int c = (f - 1) / 2 + 1;
+  return (c - 4) / 4 + 1;
+}
+
+// ---- typed pipeline -------------------------------------------------------------------------------------------------------
+template <typename T>
+struct Engine {
+  static int gemm(sonic_ctx* h, GemmArgs g, bool swap) {
+    if (std::is_same<T, float>::value) { CKL(launch_gemm_simt<float>(g, h->stream), 1); return 0; }
+    if (h->force_simt) { CKL(launch_gemm_simt<bf16>(g, h->stream), 1); return 0; }
+    CKL(launch_gemm_tc(g, swap, h->stream), 1);
+    return 0;
+  }
+  static GemmArgs lin(const void* A, long long lda, const void* W, int K, void* C, long long ldc, const float* bias, int M, int N,
+                      int act = ACT_NONE, const void* resid = nullptr, long long ldr = 0) {
+    GemmArgs g;
+    memset(&g, 0, sizeof(g));
+    g.A = A; g.lda = lda; g.a_bstride = 0; g.W = W; g.ldw = K; g.C = C; g.ldc = ldc; g.c_bstride = 0; g.c_row0 = 0;
+    g.bias = bias; g.resid = resid; g.ldr = ldr; g.r_bstride = 0; g.M = M; g.N = N; g.K = K; g.batch = 1; g.act = act; g.out_f32 = 0;
+    return g;
+  }
+  static int probe(sonic_ctx* h, const char* name, const void* src, size_t elems) {
+    if (!h->cfg.debug) return 0;
+    auto it = h->probes.find(name);
+    if (it == h->probes.end() || it->second.second < elems) {
+      void* p = nullptr;
+      if (dalloc(h, &p, elems * sizeof(T))) return -1;
+      h->probes[name] = {p, elems};
+      it = h->probes.find(name);
+    }
+    it->second.second = elems;
+    CK(cudaMemcpyAsync(it->second.first, src, elems * sizeof(T), cudaMemcpyDeviceToDevice, h->stream));
+    return 0;
+  }
+
+  static int mel(sonic_ctx* h, const float* pcm_dev, int batch, int max_len, int flags, float* feat_dev) {
+    CKL(launch_mel<T>(pcm_dev, h->offs_dev, h->lens_dev, batch, max_len, flags & 3, h->mel_tables, h->peak_bits, h->gmax_bits,
+                      h->mel_raw, feat_dev, reinterpret_cast<T*>(h->mel_tm), h->stream),
+        (flags & SONIC_FLAG_PEAK_NORM) ? 4 : 3);
+    return 0;
+  }
+
+  static int encode(sonic_ctx* h, int B) {
+    T* mel_tm = reinterpret_cast<T*>(h->mel_tm);
+    T *h1 = reinterpret_cast<T*>(h->h1), *x = reinterpret_cast<T*>(h->ex), *u = reinterpret_cast<T*>(h->eu);
+    T *qkv = reinterpret_cast<T*>(h->eqkv), *attn = reinterpret_cast<T*>(h->eattn), *mlp = reinterpret_cast<T*>(h->emlp);
+    const int rows = B * kEncT;
+    if (probe(h, "mel_tm", mel_tm, (size_t)B * (kFrames + 2) * kMels)) return -1;
+    {  // conv1 + GELU (modeling_glmasr.py:317)
+      GemmArgs g = lin(mel_tm, kMels, h->conv1_w, 3 * kMels, h1, kEncH, h->conv1_b, kFrames, kEncH, ACT_GELU);
+      g.batch = B; g.a_bstride = (long long)(kFrames + 2) * kMels; g.c_bstride = (long long)(kFrames + 2) * kEncH; g.c_row0 = 1;
+      g.conv_cin = kMels; g.conv_stride = 1; g.conv_rows_pad = kFrames + 2;
+      if (gemm(h, g, false)) return -1;
+    }
+    {  // conv2 (stride 2) + GELU (modeling_glmasr.py:318)
+      GemmArgs g = lin(h1, 2 * kEncH, h->conv2_w, 3 * kEncH, x, kEncH, h->conv2_b, kEncT, kEncH, ACT_GELU);
+      g.batch = B; g.a_bstride = (long long)(kFrames + 2) * kEncH; g.c_bstride = (long long)kEncT * kEncH;
+      g.conv_cin = kEncH; g.conv_stride = 2; g.conv_rows_pad = kFrames + 2;
+      if (gemm(h, g, false)) return -1;
+    }
+    if (probe(h, "conv_out", x, (size_t)rows * kEncH)) return -1;
+    for (int l = 0; l < h->cfg.enc_layers; ++l) {
+      const EncLayerW& w = h->enc[l];
+      CKL(launch_layernorm<T>(x, u, w.ln1_g, w.ln1_b, rows, kEncH, kLnEps, h->stream), 1);
+      if (gemm(h, lin(u, kEncH, w.wqkv, kEncH, qkv, 3 * kEncH, w.bqkv, rows, 3 * kEncH), false)) return -1;
+      CKL(launch_rope_enc<T>(qkv, h->rope_enc_cos, h->rope_enc_sin, rows, kEncT, kEncHeads, kEncHd, kEncRot, h->stream), 1);
+      {
+        AttnArgs a;
+        memset(&a, 0, sizeof(a));
+        a.q = qkv; a.q_row_stride = 3 * kEncH;
+        a.k = qkv + kEncH; a.k_tok_stride = 3 * kEncH; a.k_head_stride = kEncHd; a.k_seg_stride = (long long)kEncT * 3 * kEncH;
+        a.v = qkv + 2 * kEncH; a.v_tok_stride = 3 * kEncH; a.v_head_stride = kEncHd; a.v_seg_stride = (long long)kEncT * 3 * kEncH;
+        a.o = attn; a.o_row_stride = kEncH;
+        a.q_len_fixed = kEncT; a.kv_len_fixed = kEncT; a.causal = 0; a.decode = 0;
+        a.heads = kEncHeads; a.kv_heads = kEncHeads; a.hd = kEncHd; a.batch = B; a.max_q = kEncT; a.scale = 0.125f;
+        CKL(launch_attention_simt<T>(a, h->stream), 1);
+      }
+      if (gemm(h, lin(attn, kEncH, w.wo, kEncH, x, kEncH, w.bo, rows, kEncH, ACT_NONE, x, kEncH), false)) return -1;
+      CKL(launch_layernorm<T>(x, u, w.ln2_g, w.ln2_b, rows, kEncH, kLnEps, h->stream), 1);
+      if (gemm(h, lin(u, kEncH, w.fc1, kEncH, mlp, kEncInter, w.b1, rows, kEncInter, ACT_GELU), false)) return -1;
+      if (gemm(h, lin(mlp, kEncInter, w.fc2, kEncInter, x, kEncH, w.b2, rows, kEncH, ACT_NONE, x, kEncH), false)) return -1;
+      if (l == 0 && probe(h, "enc_layer0", x, (size_t)rows * kEncH)) return -1;
+    }
+    CKL(launch_layernorm<T>(x, u, h->enc_norm_g, h->enc_norm_b, rows, kEncH, kLnEps, h->stream), 1);
+    if (probe(h, "enc_out", u, (size_t)rows * kEncH)) return -1;
+    // adapter: [B*375, 5120] -> 4096 (GELU) -> 2048 (modeling_glmasr.py:412-415, 333-349)
+    const int mrows = B * kMerged;
+    if (gemm(h, lin(u, kEncInter, h->proj1_w, kEncInter, h->a1, 2 * kDecH, h->proj1_b, mrows, 2 * kDecH, ACT_GELU), false)) return -1;
+    if (gemm(h, lin(h->a1, 2 * kDecH, h->proj2_w, 2 * kDecH, h->audio, kDecH, h->proj2_b, mrows, kDecH), false)) return -1;
+    if (probe(h, "audio_embeds", h->audio, (size_t)mrows * kDecH)) return -1;
+    return 0;
+  }
+
+  // one decoder layer over `rows` token rows; prefill (row_seg != null) or decode step
+  static int dec_layer(sonic_ctx* h, int l, int rows, int B, bool prefill, int max_q) {
+    const DecLayerW& w = h->dec[l];
+    T *x = reinterpret_cast<T*>(h->dx), *u = reinterpret_cast<T*>(h->du), *qkv = reinterpret_cast<T*>(h->dqkv);
+    T *attn = reinterpret_cast<T*>(h->dattn), *act = reinterpret_cast<T*>(h->dact);
+    const size_t layer_kv = (size_t)h->cfg.max_batch * kDecKv * h->max_ctx * kDecHd;
+    T* kc = reinterpret_cast<T*>(h->kcache) + (size_t)l * layer_kv;
+    T* vc = reinterpret_cast<T*>(h->vcache) + (size_t)l * layer_kv;
+    const bool swap = !prefill;
+    CKL(launch_rmsnorm<T>(x, u, w.rms1, rows, kDecH, kRmsEps, h->stream), 1);
+    if (gemm(h, lin(u, kDecH, w.wqkv, kDecH, qkv, kQkvDec, nullptr, rows, kQkvDec), swap)) return -1;
+    CKL(launch_rope_dec_kv<T>(qkv, h->rope_dec_cos, h->rope_dec_sin, prefill ? h->d_row_seg : nullptr, prefill ? h->d_row_pos : nullptr,
+                              h->gs.ctx_len, kc, vc, rows, kDecHeads, kDecKv, kDecHd, h->max_ctx, h->stream), 1);
+    {
+      AttnArgs a;
+      memset(&a, 0, sizeof(a));
+      a.q = qkv; a.q_row_stride = kQkvDec;
+      a.k = kc; a.k_tok_stride = kDecHd; a.k_head_stride = (long long)h->max_ctx * kDecHd; a.k_seg_stride = (long long)kDecKv * h->max_ctx * kDecHd;
+      a.v = vc; a.v_tok_stride = kDecHd; a.v_head_stride = a.k_head_stride; a.v_seg_stride = a.k_seg_stride;
+      a.o = attn; a.o_row_stride = kDecH;
+      a.q_off = prefill ? h->d_tok_off : nullptr;
+      a.kv_len = h->gs.ctx_len;
+      a.causal = 1; a.decode = prefill ? 0 : 1;
+      a.heads = kDecHeads; a.kv_heads = kDecKv; a.hd = kDecHd; a.batch = B; a.max_q = max_q;
+      a.scale = 0.08838834764831845f;   // 128^-1/2
+      CKL(launch_attention_simt<T>(a, h->stream), 1);
+    }
+    if (gemm(h, lin(attn, kDecH, w.wo, kDecH, x, kDecH, nullptr, rows, kDecH, ACT_NONE, x, kDecH), swap)) return -1;
+    CKL(launch_rmsnorm<T>(x, u, w.rms2, rows, kDecH, kRmsEps, h->stream), 1);
+    if (gemm(h, lin(u, kDecH, w.wgu, kDecH, act, kDecInter, nullptr, rows, 2 * kDecInter, ACT_SWIGLU), swap)) return -1;
+    if (gemm(h, lin(act, kDecInter, w.wdown, kDecInter, x, kDecH, nullptr, rows, kDecH, ACT_NONE, x, kDecH), swap)) return -1;
+    return 0;
+  }
+
+  static int lm_head(sonic_ctx* h, int B, const int* rows_idx, int advance) {
+    T *x = reinterpret_cast<T*>(h->dx), *u = reinterpret_cast<T*>(h->du);
+    CKL(launch_rmsnorm_rows<T>(x, rows_idx, u, h->final_norm, B, kDecH, kRmsEps, h->stream), 1);
+    GemmArgs g = lin(u, kDecH, h->lm_head, kDecH, h->logits, kVocab, nullptr, B, kVocab);
+    g.out_f32 = 1;
+    if (gemm(h, g, true)) return -1;
+    CKL(launch_greedy_pick(h->logits, B, kVocab, h->gs, advance, h->stream), 2);
+    return 0;
+  }
+
+  static int prefill(sonic_ctx* h, int B, int total_rows, int max_q) {
+    T* x = reinterpret_cast<T*>(h->dx);
+    CKL(launch_embed<T>(h->d_ids, h->d_audio_src, reinterpret_cast<const T*>(h->embed), reinterpret_cast<const T*>(h->audio), x,
+                        total_rows, kDecH, h->stream), 1);
+    for (int l = 0; l < h->cfg.dec_layers; ++l) {
+      if (dec_layer(h, l, total_rows, B, true, max_q)) return -1;
+      if (l == 0 && probe(h, "dec_layer0", x, (size_t)total_rows * kDecH)) return -1;
+    }
+    if (lm_head(h, B, h->d_last_rows, 0)) return -1;
+    if (h->cfg.debug) {
+      auto& pf = h->probes_f32["first_logits"];
+      if (!pf.first) { float* p = nullptr; if (dalloc(h, &p, (size_t)h->cfg.max_batch * kVocab * 4)) return -1; pf.first = p; }
+      pf.second = (size_t)B * kVocab;
+      CK(cudaMemcpyAsync(pf.first, h->logits, (size_t)B * kVocab * 4, cudaMemcpyDeviceToDevice, h->stream));
+    }
+    return 0;
+  }
+
+  static int decode_step(sonic_ctx* h, int B) {
+    T* x = reinterpret_cast<T*>(h->dx);
+    CKL(launch_embed_next<T>(h->gs.cur_tok, reinterpret_cast<const T*>(h->embed), x, B, kDecH, h->stream), 1);
+    for (int l = 0; l < h->cfg.dec_layers; ++l)
+      if (dec_layer(h, l, B, B, false, 1)) return -1;
+    return lm_head(h, B, nullptr, 1);
+  }
+};
+
+template <typename F32Fn, typename Bf16Fn>
+int dispatch(sonic_ctx* h, F32Fn f32, Bf16Fn b16) { return h->is_f32 ? f32() : b16(); }
+
+// ---- weight routing ------------------------------------------------------------------------------------------------------
+struct Dest {
+  enum Kind { MAT, CONV, VEC } kind;
+  void* ptr;                 // destination base
+  long long rows, cols;      // expected source shape (MAT: [rows, cols]; CONV: [co, ci(,3)]; VEC: [rows])
+  long long row0, row_step;  // MAT placement inside a fused destination
+};
+
+bool route(sonic_ctx* h, const std::string& name, Dest* d) {
+  auto mat = [&](void* p, long long r, long long c, long long row0 = 0, long long step = 1) { *d = {Dest::MAT, p, r, c, row0, step}; return true; };
+  auto vec = [&](float* p, long long n) { *d = {Dest::VEC, p, n, 1, 0, 1}; return true; };
+  int i = 0;
+  char tail[128];
+  if (name == "audio_tower.conv1.weight") { *d = {Dest::CONV, h->conv1_w, kEncH, kMels, 0, 1}; return true; }
+  if (name == "audio_tower.conv2.weight") { *d = {Dest::CONV, h->conv2_w, kEncH, kEncH, 0, 1}; return true; }
+  if (name == "audio_tower.conv1.bias") return vec(h->conv1_b, kEncH);
+  if (name == "audio_tower.conv2.bias") return vec(h->conv2_b, kEncH);
+  if (name == "audio_tower.norm.weight") return vec(h->enc_norm_g, kEncH);
+  if (name == "audio_tower.norm.bias") return vec(h->enc_norm_b, kEncH);
+  if (name == "multi_modal_projector.linear_1.weight") return mat(h->proj1_w, 2 * kDecH, kEncInter);
+  if (name == "multi_modal_projector.linear_1.bias") return vec(h->proj1_b, 2 * kDecH);
+  if (name == "multi_modal_projector.linear_2.weight") return mat(h->proj2_w, kDecH, 2 * kDecH);
+  if (name == "multi_modal_projector.linear_2.bias") return vec(h->proj2_b, kDecH);
+  if (name == "language_model.model.embed_tokens.weight") return mat(h->embed, kVocab, kDecH);
+  if (name == "language_model.lm_head.weight") return mat(h->lm_head, kVocab, kDecH);
+  if (name == "language_model.model.norm.weight") return vec(h->final_norm, kDecH);
+  if (sscanf(name.c_str(), "audio_tower.layers.%d.%127s", &i, tail) == 2) {
+    if (i < 0 || i >= h->cfg.enc_layers) return false;
+    EncLayerW& w = h->enc[i];
+    const std::string t = tail;
+    if (t == "self_attn.q_proj.weight") return mat(w.wqkv, kEncH, kEncH, 0);
+    if (t == "self_attn.k_proj.weight") return mat(w.wqkv, kEncH, kEncH, kEncH);
+    if (t == "self_attn.v_proj.weight") return mat(w.wqkv, kEncH, kEncH, 2 * kEncH);
+    if (t == "self_attn.q_proj.bias") return vec(w.bqkv, kEncH);
+    if (t == "self_attn.v_proj.bias") return vec(w.bqkv + 2 * kEncH, kEncH);
+    if (t == "self_attn.o_proj.weight") return mat(w.wo, kEncH, kEncH);
+    if (t == "self_attn.o_proj.bias") return vec(w.bo, kEncH);
+    if (t == "mlp.fc1.weight") return mat(w.fc1, kEncInter, kEncH);
+    if (t == "mlp.fc1.bias") return vec(w.b1, kEncInter);
+    if (t == "mlp.fc2.weight") return mat(w.fc2, kEncH, kEncInter);
+    if (t == "mlp.fc2.bias") return vec(w.b2, kEncH);
+    if (t == "input_layernorm.weight") return vec(w.ln1_g, kEncH);
+    if (t == "input_layernorm.bias") return vec(w.ln1_b, kEncH);
+    if (t == "post_attention_layernorm.weight") return vec(w.ln2_g, kEncH);
+    if (t == "post_attention_layernorm.bias") return vec(w.ln2_b, kEncH);
+    return false;
+  }
+  if (sscanf(name.c_str(), "language_model.model.layers.%d.%127s", &i, tail) == 2) {
+    if (i < 0 || i >= h->cfg.dec_layers) return false;
+    DecLayerW& w = h->dec[i];
+    const std::string t = tail;
+    if (t == "self_attn.q_proj.weight") return mat(w.wqkv, kDecHeads * kDecHd, kDecH, 0);
+    if (t == "self_attn.k_proj.weight") return mat(w.wqkv, kDecKv * kDecHd, kDecH, kDecHeads * kDecHd);
+    if (t == "self_attn.v_proj.weight") return mat(w.wqkv, kDecKv * kDecHd, kDecH, (kDecHeads + kDecKv) * kDecHd);
+    if (t == "self_attn.o_proj.weight") return mat(w.wo, kDecH, kDecH);
+    if (t == "mlp.gate_proj.weight") return mat(w.wgu, kDecInter, kDecH, 0, 2);   // rows interleaved (gate, up) for the SwiGLU epilogue
+    if (t == "mlp.up_proj.weight") return mat(w.wgu, kDecInter, kDecH, 1, 2);
+    if (t == "mlp.down_proj.weight") return mat(w.wdown, kDecH, kDecInter);
+    if (t == "input_layernorm.weight") return vec(w.rms1, kDecH);
+    if (t == "post_attention_layernorm.weight") return vec(w.rms2, kDecH);
+    return false;
+  }
+  return false;
+}
+
+size_t expected_tensor_count(const sonic_config& c) { return 4 + c.enc_layers * 15 + 2 + 4 + 1 + c.dec_layers * 9 + 2; }
+
+int alloc_all(sonic_ctx* h) {
+  const sonic_config& c = h->cfg;
+  const size_t E = h->esz;
+  const int B = c.max_batch;
+  h->max_ctx = c.max_prompt + c.max_new;
+  // weights
+  DA(h->conv1_w, (size_t)kEncH * 3 * kMels * E); DA(h->conv2_w, (size_t)kEncH * 3 * kEncH * E);
+  DA(h->conv1_b, kEncH * 4); DA(h->conv2_b, kEncH * 4); DA(h->enc_norm_g, kEncH * 4); DA(h->enc_norm_b, kEncH * 4);
+  DA(h->proj1_w, (size_t)2 * kDecH * kEncInter * E); DA(h->proj1_b, 2 * kDecH * 4);
+  DA(h->proj2_w, (size_t)kDecH * 2 * kDecH * E); DA(h->proj2_b, kDecH * 4);
+  DA(h->embed, (size_t)kVocab * kDecH * E); DA(h->lm_head, (size_t)kVocab * kDecH * E); DA(h->final_norm, kDecH * 4);
+  h->enc.resize(c.enc_layers);
+  for (auto& w : h->enc) {
+    DA(w.ln1_g, kEncH * 4); DA(w.ln1_b, kEncH * 4); DA(w.ln2_g, kEncH * 4); DA(w.ln2_b, kEncH * 4);
+    DAZ(w.bqkv, 3 * kEncH * 4); DA(w.bo, kEncH * 4); DA(w.b1, kEncInter * 4); DA(w.b2, kEncH * 4);
+    DA(w.wqkv, (size_t)3 * kEncH * kEncH * E); DA(w.wo, (size_t)kEncH * kEncH * E);
+    DA(w.fc1, (size_t)kEncInter * kEncH * E); DA(w.fc2, (size_t)kEncH * kEncInter * E);
+  }
+  h->dec.resize(c.dec_layers);
+  for (auto& w : h->dec) {
+    DA(w.rms1, kDecH * 4); DA(w.rms2, kDecH * 4);
+    DA(w.wqkv, (size_t)kQkvDec * kDecH * E); DA(w.wo, (size_t)kDecH * kDecH * E);
+    DA(w.wgu, (size_t)2 * kDecInter * kDecH * E); DA(w.wdown, (size_t)kDecH * kDecInter * E);
+  }
+  // tables
+  {
+    std::vector<int> ts, tc; std::vector<float> tw;
+    build_mel_taps(ts, tc, tw);
+    std::vector<char> host(mel_tables_bytes());
+    mel_build_tables(host.data(), ts.data(), tc.data(), tw.data());
+    DA(h->mel_tables, host.size());
+    CK(cudaMemcpyAsync(h->mel_tables, host.data(), host.size(), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    std::vector<float> cs((size_t)kEncT * kEncRot / 2), sn(cs.size());
+    rope_table_host(cs.data(), sn.data(), kEncT, kEncRot, kTheta);
+    DA(h->rope_enc_cos, cs.size() * 4); DA(h->rope_enc_sin, cs.size() * 4);
+    CK(cudaMemcpy(h->rope_enc_cos, cs.data(), cs.size() * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(h->rope_enc_sin, sn.data(), cs.size() * 4, cudaMemcpyHostToDevice));
+    std::vector<float> dc((size_t)h->max_ctx * kDecHd / 2), ds(dc.size());
+    rope_table_host(dc.data(), ds.data(), h->max_ctx, kDecHd, kTheta);
+    DA(h->rope_dec_cos, dc.size() * 4); DA(h->rope_dec_sin, dc.size() * 4);
+    CK(cudaMemcpy(h->rope_dec_cos, dc.data(), dc.size() * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(h->rope_dec_sin, ds.data(), dc.size() * 4, cudaMemcpyHostToDevice));
+  }
+  // mel
+  DA(h->pcm_dev, (size_t)B * kWinSamples * 4); DA(h->offs_dev, B * 8); DA(h->lens_dev, B * 4);
+  DA(h->peak_bits, B * 4); DA(h->gmax_bits, B * 4);
+  DA(h->mel_raw, (size_t)B * kMels * kFrames * 4); DA(h->mel_feat, (size_t)B * kMels * kFrames * 4);
+  DAZ(h->mel_tm, (size_t)B * (kFrames + 2) * kMels * E);
+  // encoder
+  DAZ(h->h1, (size_t)B * (kFrames + 2) * kEncH * E);     // pad rows 0 / 3001 stay zero forever
+  DA(h->ex, (size_t)B * kEncT * kEncH * E); DA(h->eu, (size_t)B * kEncT * kEncH * E);
+  DA(h->eqkv, (size_t)B * kEncT * 3 * kEncH * E); DA(h->eattn, (size_t)B * kEncT * kEncH * E);
+  DA(h->emlp, (size_t)B * kEncT * kEncInter * E);
+  DA(h->a1, (size_t)B * kMerged * 2 * kDecH * E); DA(h->audio, (size_t)B * kMerged * kDecH * E);
+  // decoder
+  const size_t rows = (size_t)B * c.max_prompt;
+  DA(h->dx, rows * kDecH * E); DA(h->du, rows * kDecH * E); DA(h->dqkv, rows * kQkvDec * E); DA(h->dattn, rows * kDecH * E);
+  DA(h->dact, rows * kDecInter * E);
+  const size_t kv = (size_t)c.dec_layers * B * kDecKv * h->max_ctx * kDecHd * E;
+  DAZ(h->kcache, kv); DAZ(h->vcache, kv);
+  DA(h->logits, (size_t)B * kVocab * 4);
+  DA(h->d_ids, rows * 4); DA(h->d_audio_src, rows * 4); DA(h->d_row_seg, rows * 4); DA(h->d_row_pos, rows * 4);
+  DA(h->d_tok_off, (B + 1) * 4); DA(h->d_last_rows, B * 4);
+  DA(h->gs.cur_tok, B * 4); DA(h->gs.ctx_len, B * 4); DA(h->gs.finished, B * 4); DA(h->gs.n_out, B * 4);
+  DA(h->gs.out_ids, (size_t)B * c.max_new * 4); DA(h->gs.margins, (size_t)B * c.max_new * 4);
+  DA(h->gs.step, 4); DA(h->gs.n_unfinished, 4);
+  h->gs.eos[0] = 59246; h->gs.eos[1] = 59253; h->gs.eos[2] = 59255; h->gs.n_eos = 3;
+  h->h_pinned_ints = rows * 4 + 8 * (size_t)B + 64;
+  CK(cudaMallocHost(&h->h_pinned, h->h_pinned_ints * sizeof(int)));
+  for (auto& e : h->ev) CK(cudaEventCreate(&e));
+  for (auto& e : h->ev_user) CK(cudaEventCreate(&e));
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int do_mel(sonic_ctx* h, const float* pcm, const int64_t* offsets, const int32_t* lengths, int batch, int flags, float* features,
+           int32_t* n_frames) {
+  if (batch <= 0 || batch > h->cfg.max_batch) return fail(h, "sonic_mel: batch out of range");
+  // stage metadata (and PCM, when it lives on the host) on the device
+  long long* h_offs = reinterpret_cast<long long*>(h->h_pinned);          // mel metadata region: 3*max_batch ints
+  int* h_lens = h->h_pinned + 2 * h->cfg.max_batch;
+  int max_len = 0;
+  h->last_lens.assign(batch, 0);
+  const float* pcm_dev = nullptr;
+  if (flags & SONIC_FLAG_PCM_DEVICE) {
+    for (int b = 0; b < batch; ++b) { h_offs[b] = offsets[b]; h_lens[b] = lengths[b]; }
+    pcm_dev = pcm;
+  } else {
+    for (int b = 0; b < batch; ++b) {
+      // only the first 30 s window is consumed; the peak of the reference pre-step is over the whole segment, so
+      // longer inputs are rejected rather than silently changing semantics (callers cap segments at 30 s, config.py:41)
+      if (lengths[b] > kWinSamples) return fail(h, "sonic_mel: segment longer than 30 s (480000 samples)");
+      h_offs[b] = (long long)b * kWinSamples;
+      h_lens[b] = lengths[b];
+      CK(cudaMemcpyAsync(h->pcm_dev + (size_t)b * kWinSamples, pcm + offsets[b], (size_t)lengths[b] * 4, cudaMemcpyHostToDevice, h->stream));
+    }
+    pcm_dev = h->pcm_dev;
+  }
+  for (int b = 0; b < batch; ++b) {
+    if (lengths[b] <= 0) return fail(h, "sonic_mel: empty segment");
+    if (lengths[b] > max_len) max_len = lengths[b];
+    h->last_lens[b] = lengths[b];
+    if (n_frames) n_frames[b] = n_valid_frames(lengths[b]);
+  }
+  h->last_batch = batch;
+  CK(cudaMemcpyAsync(h->offs_dev, h_offs, batch * 8, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->lens_dev, h_lens, batch * 4, cudaMemcpyHostToDevice, h->stream));
+  float* feat_dev = nullptr;
+  if (features) feat_dev = (flags & SONIC_FLAG_OUT_DEVICE) ? features : h->mel_feat;
+  int rc = dispatch(h, [&] { return Engine<float>::mel(h, pcm_dev, batch, max_len, flags, feat_dev); },
+                    [&] { return Engine<bf16>::mel(h, pcm_dev, batch, max_len, flags, feat_dev); });
+  if (rc) return rc;
+  if (features && !(flags & SONIC_FLAG_OUT_DEVICE)) {
+    CK(cudaMemcpyAsync(features, h->mel_feat, (size_t)batch * kMels * kFrames * 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+  }
+  return 0;
+}
+
+int do_encode(sonic_ctx* h, int batch, float* audio_embeds, int32_t* n_audio) {
+  if (!h->finalized) return fail(h, "sonic_encode: weights not finalized");
+  if (batch <= 0 || batch != h->last_batch) return fail(h, "sonic_encode: batch does not match the preceding sonic_mel");
+  int rc = dispatch(h, [&] { return Engine<float>::encode(h, batch); }, [&] { return Engine<bf16>::encode(h, batch); });
+  if (rc) return rc;
+  if (n_audio) for (int b = 0; b < batch; ++b) n_audio[b] = n_audio_tokens(h->last_lens[b]);
+  if (audio_embeds) {
+    const size_t n = (size_t)batch * kMerged * kDecH;
+    if (h->is_f32) {
+      CK(cudaMemcpyAsync(audio_embeds, h->audio, n * 4, cudaMemcpyDeviceToHost, h->stream));
+    } else {
+      float* tmp = reinterpret_cast<float*>(h->emlp);   // free scratch at this point
+      convert_flat_kernel<bf16, float><<<1024, 256, 0, h->stream>>>(reinterpret_cast<const bf16*>(h->audio), tmp, (long long)n);
+      CK(cudaGetLastError());
+      CK(cudaMemcpyAsync(audio_embeds, tmp, n * 4, cudaMemcpyDeviceToHost, h->stream));
+    }
+    CK(cudaStreamSynchronize(h->stream));
+  }
+  return 0;
+}
+
+int do_generate(sonic_ctx* h, const int32_t* ids, const int32_t* id_offsets, int batch, int max_new, int32_t* out_ids, int32_t* n_out,
+                float* margins) {
+  if (!h->finalized) return fail(h, "sonic_generate: weights not finalized");
+  if (batch <= 0 || batch > h->cfg.max_batch) return fail(h, "sonic_generate: batch out of range");
+  if (max_new <= 0 || max_new > h->cfg.max_new) return fail(h, "sonic_generate: max_new_tokens out of range");
+  const int total = id_offsets[batch] - id_offsets[0];
+  int max_q = 0;
+  // host metadata: ids, audio_src, row_seg, row_pos | tok_off | last_rows | ctx_len
+  int* p = h->h_pinned + 4 * h->cfg.max_batch;                             // generate metadata region
+  int *m_ids = p, *m_src = p + total, *m_seg = p + 2 * total, *m_pos = p + 3 * total;
+  int *m_off = p + 4 * total, *m_last = m_off + batch + 1, *m_ctx = m_last + batch;
+  if ((size_t)(4 * h->cfg.max_batch + 4 * total + 3 * batch + 1 + 16) > h->h_pinned_ints) return fail(h, "sonic_generate: prompt longer than max_prompt");
+  for (int b = 0; b < batch; ++b) {
+    const int s = id_offsets[b + 1] - id_offsets[b];
+    if (s <= 0 || s > h->cfg.max_prompt) return fail(h, "sonic_generate: prompt length out of range");
+    if (s > max_q) max_q = s;
+    int na = 0;
+    const int r0 = id_offsets[b] - id_offsets[0];
+    for (int i = 0; i < s; ++i) {
+      const int id = ids[id_offsets[b] + i];
+      if (id < 0 || id >= kVocab) return fail(h, "sonic_generate: token id out of range");
+      m_ids[r0 + i] = id;
+      m_src[r0 + i] = (id == kAudioTok) ? (b * kMerged + na++) : -1;
+      m_seg[r0 + i] = b;
+      m_pos[r0 + i] = i;
+    }
+    if (na > 0) {
+      const int expect = (b < (int)h->last_lens.size()) ? n_audio_tokens(h->last_lens[b]) : -1;
+      if (na != expect) return fail(h, "sonic_generate: number of audio placeholder tokens does not match the encoded audio");
+    }
+    m_off[b] = r0;
+    m_last[b] = r0 + s - 1;
+    m_ctx[b] = s;
+  }
+  m_off[batch] = total;
+  cudaStream_t st = h->stream;
+  CK(cudaMemcpyAsync(h->d_ids, m_ids, total * 4, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(h->d_audio_src, m_src, total * 4, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(h->d_row_seg, m_seg, total * 4, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(h->d_row_pos, m_pos, total * 4, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(h->d_tok_off, m_off, (batch + 1) * 4, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(h->d_last_rows, m_last, batch * 4, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(h->gs.ctx_len, m_ctx, batch * 4, cudaMemcpyHostToDevice, st));
+  CK(cudaMemsetAsync(h->gs.finished, 0, batch * 4, st));
+  CK(cudaMemsetAsync(h->gs.n_out, 0, batch * 4, st));
+  CK(cudaMemsetAsync(h->gs.step, 0, 4, st));
+  set_int_kernel<<<1, 32, 0, st>>>(h->gs.n_unfinished, batch, 1);
+  CK(cudaGetLastError());
+  h->gs.max_new = max_new;
+
+  CK(cudaEventRecord(h->ev[2], st));
+  int rc = dispatch(h, [&] { return Engine<float>::prefill(h, batch, total, max_q); }, [&] { return Engine<bf16>::prefill(h, batch, total, max_q); });
+  if (rc) return rc;
+  CK(cudaEventRecord(h->ev[3], st));
+
+  // greedy steps 2..max_new: one CUDA graph per (batch, max_new) replayed; no per-token host sync.
+  if (max_new > 1) {
+    const int key = batch * 100000 + max_new;
+    auto it = h->decode_graphs.find(key);
+    if (it == h->decode_graphs.end()) {
+      const int64_t before = h->launches;
+      cudaGraph_t graph = nullptr;
+      CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+      rc = dispatch(h, [&] { return Engine<float>::decode_step(h, batch); }, [&] { return Engine<bf16>::decode_step(h, batch); });
+      cudaError_t ce = cudaStreamEndCapture(st, &graph);
+      if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+      if (ce != cudaSuccess) return fail_cuda(h, ce, "cudaStreamEndCapture");
+      cudaGraphExec_t exec = nullptr;
+      CK(cudaGraphInstantiate(&exec, graph, 0));
+      cudaGraphDestroy(graph);
+      h->decode_graph_kernels[key] = h->launches - before;
+      h->launches = before;
+      h->decode_graphs[key] = exec;
+      it = h->decode_graphs.find(key);
+    }
+    const int64_t per = h->decode_graph_kernels[key];
+    int* flag = h->h_pinned + h->h_pinned_ints - 16;
+    for (int step = 1; step < max_new; ++step) {
+      CK(cudaGraphLaunch(it->second, st));
+      h->launches += per;
+      if ((step % 16) == 0 && step + 1 < max_new) {       // early exit once every segment hit EOS
+        CK(cudaMemcpyAsync(flag, h->gs.n_unfinished, 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        if (*flag <= 0) break;
+      }
+    }
+  }
+  CK(cudaEventRecord(h->ev[4], st));
+  // results
+  CK(cudaMemcpyAsync(out_ids, h->gs.out_ids, (size_t)batch * max_new * 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(n_out, h->gs.n_out, batch * 4, cudaMemcpyDeviceToHost, st));
+  if (margins) CK(cudaMemcpyAsync(margins, h->gs.margins, (size_t)batch * max_new * 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return 0;
+}
+
+template <typename TS>
+int upload(sonic_ctx* h, const Dest& d, const void* data, size_t n_elems) {
+  const size_t bytes = n_elems * sizeof(TS);
+  if (bytes > h->staging_bytes) {
+    if (h->staging) { cudaFree(h->staging); h->bytes -= (int64_t)h->staging_bytes; }
+    h->staging = nullptr;
+    h->staging_bytes = 0;
+    CK(cudaMalloc(&h->staging, bytes));
+    h->staging_bytes = bytes;
+    h->bytes += (int64_t)bytes;
+  }
+  cudaStream_t st = h->stream;
+  CK(cudaMemcpyAsync(h->staging, data, bytes, cudaMemcpyHostToDevice, st));
+  const TS* src = reinterpret_cast<const TS*>(h->staging);
+  const int grid = 2048;
+  if (d.kind == Dest::VEC) {
+    convert_vec_kernel<TS><<<64, 256, 0, st>>>(src, reinterpret_cast<float*>(d.ptr), d.rows, h->is_f32 ? 0 : 1);
+  } else if (d.kind == Dest::CONV) {
+    if (h->is_f32) convert_conv_kernel<TS, float><<<grid, 256, 0, st>>>(src, reinterpret_cast<float*>(d.ptr), d.rows, d.cols);
+    else convert_conv_kernel<TS, bf16><<<grid, 256, 0, st>>>(src, reinterpret_cast<bf16*>(d.ptr), d.rows, d.cols);
+  } else {
+    if (h->is_f32) convert_rows_kernel<TS, float><<<grid, 256, 0, st>>>(src, reinterpret_cast<float*>(d.ptr), d.rows, d.cols, d.row0, d.row_step);
+    else convert_rows_kernel<TS, bf16><<<grid, 256, 0, st>>>(src, reinterpret_cast<bf16*>(d.ptr), d.rows, d.cols, d.row0, d.row_step);
+  }
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(st));     // the caller may free `data` on return
+  return 0;
+}
+
+}  // namespace
+
+// =========================================================================================================================
+extern "C" {
+
+const char* sonic_version(void) { return "sonicscribe_b200 0.1 (sm_100a)"; }
+
+const char* sonic_last_error(sonic_handle h) { return h ? h->err.c_str() : g_last_error.c_str(); }
+
+int32_t sonic_num_audio_tokens(int64_t n_samples) { return n_audio_tokens(n_samples); }
+
+int sonic_create(const sonic_config* cfg, sonic_handle* out) {
+  if (!cfg || !out) return fail(nullptr, "sonic_create: null argument");
+  *out = nullptr;
+  if (cfg->mode != SONIC_MODE_BF16 && cfg->mode != SONIC_MODE_FP32) return fail(nullptr, "sonic_create: unsupported mode");
+  if (cfg->enc_layers < 1 || cfg->enc_layers > 64 || cfg->dec_layers < 1 || cfg->dec_layers > 64 || cfg->max_batch < 1 ||
+      cfg->max_batch > 256 || cfg->max_prompt < 8 || cfg->max_new < 1)
+    return fail(nullptr, "sonic_create: bad configuration");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) return fail(nullptr, "sonic_create: no CUDA device available (this library has no CPU path)");
+  if (cfg->device < 0 || cfg->device >= ndev) return fail(nullptr, "sonic_create: device ordinal out of range");
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, cfg->device);
+  if (prop.major != 10) return fail(nullptr, std::string("sonic_create: sm_100a required, found sm_") + std::to_string(prop.major * 10 + prop.minor));
+  sonic_ctx* h = new sonic_ctx();
+  h->cfg = *cfg;
+  h->is_f32 = cfg->mode == SONIC_MODE_FP32;
+  h->esz = h->is_f32 ? 4 : 2;
+  const char* fs = getenv("SONIC_FORCE_SIMT");
+  h->force_simt = fs && fs[0] == '1';
+  auto bail = [&](int) { g_last_error = h->err; for (void* p : h->allocs) cudaFree(p); delete h; return -1; };
+  if (cudaSetDevice(cfg->device) != cudaSuccess) { h->err = "cudaSetDevice failed"; return bail(0); }
+  if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { h->err = "cudaStreamCreate failed"; return bail(0); }
+  if (mel_setup() != cudaSuccess) { h->err = "mel_setup failed"; return bail(0); }
+  if (!h->is_f32 && gemm_tc_init() != cudaSuccess) { h->err = "cuTensorMapEncodeTiled entry point unavailable"; return bail(0); }
+  if (!h->is_f32 && gemm_tc_configure() != cudaSuccess) { h->err = "gemm_tc_configure failed"; return bail(0); }
+  if (alloc_all(h)) return bail(0);
+  *out = h;
+  return 0;
+}
+
+int sonic_destroy(sonic_handle h) {
+  if (!h) return 0;
+  cudaSetDevice(h->cfg.device);
+  cudaStreamSynchronize(h->stream);
+  for (auto& kv : h->decode_graphs) cudaGraphExecDestroy(kv.second);
+  for (void* p : h->allocs) cudaFree(p);
+  if (h->staging) cudaFree(h->staging);
+  if (h->h_pinned) cudaFreeHost(h->h_pinned);
+  for (auto& e : h->ev) if (e) cudaEventDestroy(e);
+  for (auto& e : h->ev_user) if (e) cudaEventDestroy(e);
+  cudaStreamDestroy(h->stream);
+  delete h;
+  return 0;
+}
+
+#define ENTER()                                          \
+  if (!h) return fail(nullptr, "null handle");           \
+  std::lock_guard<std::mutex> _lk(h->mu);                \
+  if (cudaSetDevice(h->cfg.device) != cudaSuccess) return fail(h, "cudaSetDevice failed")
+
+int sonic_load_tensor(sonic_handle h, const char* name, const void* data, int32_t dtype, const int64_t* shape, int32_t ndim) {
+  ENTER();
+  if (!name || !data || !shape) return fail(h, "sonic_load_tensor: null argument");
+  Dest d;
+  if (!route(h, name, &d)) return fail(h, std::string("sonic_load_tensor: unknown tensor ") + name);
+  size_t n = 1;
+  for (int i = 0; i < ndim; ++i) n *= (size_t)shape[i];
+  bool ok = false;
+  if (d.kind == Dest::VEC) ok = ndim == 1 && shape[0] == d.rows;
+  if (d.kind == Dest::MAT) ok = ndim == 2 && shape[0] == d.rows && shape[1] == d.cols;
+  if (d.kind == Dest::CONV) ok = ndim == 3 && shape[0] == d.rows && shape[1] == d.cols && shape[2] == 3;
+  if (!ok) return fail(h, std::string("sonic_load_tensor: shape mismatch for ") + name);
+  int rc = (dtype == SONIC_DTYPE_F32) ? upload<float>(h, d, data, n) : (dtype == SONIC_DTYPE_BF16) ? upload<bf16>(h, d, data, n) : fail(h, "bad dtype");
+  if (rc == 0) h->loaded.insert(name);
+  return rc;
+}
+
+int sonic_finalize_weights(sonic_handle h) {
+  ENTER();
+  if (h->loaded.size() != expected_tensor_count(h->cfg))
+    return fail(h, "sonic_finalize_weights: " + std::to_string(h->loaded.size()) + " tensors loaded, expected " +
+                       std::to_string(expected_tensor_count(h->cfg)));
+  if (h->staging) { cudaFree(h->staging); h->bytes -= (int64_t)h->staging_bytes; h->staging = nullptr; h->staging_bytes = 0; }
+  h->finalized = true;
+  return 0;
+}
+
+int sonic_mel(sonic_handle h, const float* pcm, const int64_t* offsets, const int32_t* lengths, int32_t batch, int32_t flags,
+              float* features, int32_t* n_frames) {
+  ENTER();
+  if (!pcm || !offsets || !lengths) return fail(h, "sonic_mel: null argument");
+  int rc = do_mel(h, pcm, offsets, lengths, batch, flags, features, n_frames);
+  if (rc == 0 && cudaStreamSynchronize(h->stream) != cudaSuccess) return fail(h, "sonic_mel: stream sync failed");
+  return rc;
+}
+
+int sonic_encode(sonic_handle h, int32_t batch, float* audio_embeds, int32_t* n_audio) {
+  ENTER();
+  int rc = do_encode(h, batch, audio_embeds, n_audio);
+  if (rc == 0) { cudaError_t e = cudaStreamSynchronize(h->stream); if (e != cudaSuccess) return fail_cuda(h, e, "sonic_encode"); }
+  return rc;
+}
+
+int sonic_generate(sonic_handle h, const int32_t* ids, const int32_t* id_offsets, int32_t batch, int32_t max_new_tokens,
+                   int32_t* out_ids, int32_t* n_out, float* margins) {
+  ENTER();
+  if (!ids || !id_offsets || !out_ids || !n_out) return fail(h, "sonic_generate: null argument");
+  return do_generate(h, ids, id_offsets, batch, max_new_tokens, out_ids, n_out, margins);
+}
+
+int sonic_transcribe_batch(sonic_handle h, const float* pcm, const int64_t* offsets, const int32_t* lengths, int32_t batch,
+                           int32_t flags, const int32_t* ids, const int32_t* id_offsets, int32_t max_new_tokens, int32_t* out_ids,
+                           int32_t* n_out, float* margins) {
+  ENTER();
+  if (!pcm || !offsets || !lengths || !ids || !id_offsets || !out_ids || !n_out) return fail(h, "sonic_transcribe_batch: null argument");
+  CK(cudaEventRecord(h->ev[0], h->stream));
+  if (do_mel(h, pcm, offsets, lengths, batch, flags, nullptr, nullptr)) return -1;
+  CK(cudaEventRecord(h->ev[1], h->stream));
+  if (do_encode(h, batch, nullptr, nullptr)) return -1;
+  if (do_generate(h, ids, id_offsets, batch, max_new_tokens, out_ids, n_out, margins)) return -1;
+  cudaEventElapsedTime(&h->stage_ms[0], h->ev[0], h->ev[1]);
+  cudaEventElapsedTime(&h->stage_ms[1], h->ev[1], h->ev[2]);
+  cudaEventElapsedTime(&h->stage_ms[2], h->ev[2], h->ev[3]);
+  cudaEventElapsedTime(&h->stage_ms[3], h->ev[3], h->ev[4]);
+  return 0;
+}
+
+int sonic_sync(sonic_handle h) {
+  ENTER();
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+int sonic_timer_begin(sonic_handle h) {
+  ENTER();
+  CK(cudaEventRecord(h->ev_user[0], h->stream));
+  return 0;
+}
+int sonic_timer_end(sonic_handle h, float* ms) {
+  ENTER();
+  CK(cudaEventRecord(h->ev_user[1], h->stream));
+  CK(cudaEventSynchronize(h->ev_user[1]));
+  CK(cudaEventElapsedTime(ms, h->ev_user[0], h->ev_user[1]));
+  return 0;
+}
+int sonic_stage_times(sonic_handle h, float* ms4) {
+  ENTER();
+  for (int i = 0; i < 4; ++i) ms4[i] = h->stage_ms[i];
+  return 0;
+}
+int64_t sonic_launch_count(sonic_handle h) { return h ? h->launches : -1; }
+int64_t sonic_device_bytes(sonic_handle h) { return h ? h->bytes : -1; }
+
+int sonic_debug_read(sonic_handle h, const char* name, float* out, size_t max_elems, size_t* n_elems) {
+  ENTER();
+  if (!name || !out) return fail(h, "sonic_debug_read: null argument");
+  const std::string nm = name;
+  const float* src_f32 = nullptr;
+  const void* src_t = nullptr;
+  size_t n = 0;
+  if (nm == "rope_enc_cos") { src_f32 = h->rope_enc_cos; n = (size_t)kEncT * kEncRot / 2; }
+  else if (nm == "rope_dec_cos") { src_f32 = h->rope_dec_cos; n = (size_t)h->max_ctx * kDecHd / 2; }
+  else if (nm == "mel_raw") { src_f32 = h->mel_raw; n = (size_t)h->last_batch * kMels * kFrames; }
+  else if (h->probes_f32.count(nm)) { src_f32 = h->probes_f32[nm].first; n = h->probes_f32[nm].second; }
+  else if (h->probes.count(nm)) { src_t = h->probes[nm].first; n = h->probes[nm].second; }
+  else return fail(h, "sonic_debug_read: no such probe (create the handle with debug=1): " + nm);
+  if (n > max_elems) return fail(h, "sonic_debug_read: output buffer too small");
+  if (n_elems) *n_elems = n;
+  if (src_t && !h->is_f32) {
+    float* tmp = nullptr;
+    CK(cudaMalloc(&tmp, n * 4));
+    convert_flat_kernel<bf16, float><<<1024, 256, 0, h->stream>>>(reinterpret_cast<const bf16*>(src_t), tmp, (long long)n);
+    cudaError_t e = cudaMemcpyAsync(out, tmp, n * 4, cudaMemcpyDeviceToHost, h->stream);
+    cudaStreamSynchronize(h->stream);
+    cudaFree(tmp);
+    if (e != cudaSuccess) return fail_cuda(h, e, "debug copy");
+  } else {
+    CK(cudaMemcpyAsync(out, src_f32 ? (const void*)src_f32 : src_t, n * 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+  }
+  return 0;
+}
+
+int sonic_test_gemm(sonic_handle h, int32_t impl, int32_t swap, const float* A, const float* W, const float* bias, const float* resid,
+                    float* C, int32_t M, int32_t N, int32_t K, int32_t act) {
+  ENTER();
+  const int outN = (act == ACT_SWIGLU) ? N / 2 : N;
+  bf16 *dA = nullptr, *dW = nullptr, *dC = nullptr;
+  float *fA = nullptr, *fW = nullptr, *fC = nullptr, *dB = nullptr;
+  cudaStream_t st = h->stream;
+  auto cleanup = [&]() { cudaFree(dA); cudaFree(dW); cudaFree(dC); cudaFree(fA); cudaFree(fW); cudaFree(fC); cudaFree(dB); };
+  const size_t nA = (size_t)M * K, nW = (size_t)N * K, nC = (size_t)M * outN;
+  const size_t nbig = nA > nW ? (nA > nC ? nA : nC) : (nW > nC ? nW : nC);
+  cudaError_t e = cudaSuccess;
+  if ((e = cudaMalloc(&dA, nA * 2)) || (e = cudaMalloc(&dW, nW * 2)) || (e = cudaMalloc(&dC, nC * 2)) || (e = cudaMalloc(&fA, nbig * 4)) ||
+      (e = cudaMalloc(&dB, (size_t)N * 4))) { cleanup(); return fail_cuda(h, e, "sonic_test_gemm alloc"); }
+  cudaMemcpyAsync(fA, A, nA * 4, cudaMemcpyHostToDevice, st);
+  convert_flat_kernel<float, bf16><<<1024, 256, 0, st>>>(fA, dA, (long long)nA);
+  cudaMemcpyAsync(fA, W, nW * 4, cudaMemcpyHostToDevice, st);
+  convert_flat_kernel<float, bf16><<<1024, 256, 0, st>>>(fA, dW, (long long)nW);
+  if (resid) {
+    cudaMemcpyAsync(fA, resid, nC * 4, cudaMemcpyHostToDevice, st);
+    convert_flat_kernel<float, bf16><<<1024, 256, 0, st>>>(fA, dC, (long long)nC);
+  }
+  if (bias) cudaMemcpyAsync(dB, bias, (size_t)N * 4, cudaMemcpyHostToDevice, st);
+  GemmArgs g;
+  memset(&g, 0, sizeof(g));
+  g.A = dA; g.lda = K; g.W = dW; g.ldw = K; g.C = dC; g.ldc = outN; g.bias = bias ? dB : nullptr;
+  g.resid = resid ? dC : nullptr; g.ldr = outN; g.M = M; g.N = N; g.K = K; g.batch = 1; g.act = act;
+  e = (impl == 0) ? launch_gemm_tc(g, swap != 0, st) : launch_gemm_simt<bf16>(g, st);
+  if (e != cudaSuccess) { cleanup(); return fail_cuda(h, e, "sonic_test_gemm launch"); }
+  h->launches += 1;
+  convert_flat_kernel<bf16, float><<<1024, 256, 0, st>>>(dC, fA, (long long)nC);
+  cudaMemcpyAsync(C, fA, nC * 4, cudaMemcpyDeviceToHost, st);
+  e = cudaStreamSynchronize(st);
+  cleanup();
+  if (e != cudaSuccess) return fail_cuda(h, e, "sonic_test_gemm");
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,432 @@
+// bf16 GEMM on the 5th-generation tensor cores (tcgen05) for sm_100a:
+//   TMA (cp.async.bulk.tensor, 128B swizzle) -> shared-memory ring -> tcgen05.mma (single issuing thread,
+//   fp32 accumulators in TMEM) -> tcgen05.ld epilogue (bias / GELU / SwiGLU / residual / dtype) -> global.
+//
+//   normal mode: D[m,n] = A[m,:].W[n,:]   A = activations [M,K] (tile 128 rows), W = weights [N,K] (tile BN rows)
+//   swap mode  : D[f,t] = W[f,:].X[t,:]   the 128-row MMA operand is the WEIGHT tile, the N operand the (few) token
+//                rows; the epilogue stores D transposed so the output is still [tokens, features].  This is the
+//                weight-streaming shape of the greedy decode step (HBM-bound, tokens <= 64).
+//
+// Replaces the cuBLAS bf16 GEMMs behind every nn.Linear / nn.Conv1d of GlmAsrEncoder, the projector and the Llama
+// decoder (transformers/models/glmasr/modeling_glmasr.py:175-349, transformers/models/llama/modeling_llama.py:171-289).
+// Warp roles (256 threads): w0 TMA producer, w1 MMA issuer, w2 TMEM allocator, w4-7 epilogue (TMEM lane quadrants).
+#include <cuda.h>
+#include "common.cuh"
+#include "kernels.h"
+#include "gemm_tc.h"
+
+namespace sonic {
+
+static constexpr int BM = 128;          // MMA M (rows of the A-side operand per CTA)
+static constexpr int BK = 64;           // 64 bf16 = 128 B = one swizzle atom row
+static constexpr int UMMA_K = 16;
+
+// ---- PTX wrappers ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+        "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+        "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute/arch/mma_sm100_desc.hpp SmemDescriptor):
+// start>>4 | LBO(ignored)=1 @16 | SBO = 8 rows * 128 B = 1024 B (>>4 = 64) @32 | version 1 @46 | layout SWIZZLE_128B (2) @61
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// kind::f16 instruction descriptor: D fp32 (1<<4), A bf16 (1<<7), B bf16 (1<<10), both K-major, N>>3 @17, M>>4 @24
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int m, int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+template <int BN> struct TcCfg {
+  static constexpr int kStageA = BM * BK * 2;                 // 16 KB
+  static constexpr int kStageB = BN * BK * 2;
+  static constexpr int kStages = (BN >= 256) ? 4 : (BN >= 128 ? 3 : 4);
+  static constexpr int kSmem = kStages * (kStageA + kStageB) + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kTmemCols = BN < 32 ? 32 : BN;
+};
+
+struct TcEpi {
+  void* C; long long ldc; long long c_bstride; long long c_row0;
+  const float* bias;
+  const void* resid; long long ldr; long long r_bstride;
+  int M, N, K;            // logical problem: M tokens, N features
+  int act;
+  // implicit conv1d (k=3, pad 1): K = 3*cin is walked tap by tap; tap t reads A-map coordinates
+  // {tap_col[t] + kc*64, a0 + tap_row[t]} (see launch_gemm_tc).  kb_per_tap = K/64 for a plain GEMM.
+  int kb_per_tap;
+  int tap_col[3];
+  int tap_row[3];
+};
+
+template <typename TC>
+__device__ __forceinline__ void store_chunk32(TC* dst, const float (&x)[32]);
+template <>
+__device__ __forceinline__ void store_chunk32<bf16>(bf16* dst, const float (&x)[32]) {
+  uint4* d = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    uint4 o;
+    __nv_bfloat162 p0 = __floats2bfloat162_rn(x[8 * i + 0], x[8 * i + 1]);
+    __nv_bfloat162 p1 = __floats2bfloat162_rn(x[8 * i + 2], x[8 * i + 3]);
+    __nv_bfloat162 p2 = __floats2bfloat162_rn(x[8 * i + 4], x[8 * i + 5]);
+    __nv_bfloat162 p3 = __floats2bfloat162_rn(x[8 * i + 6], x[8 * i + 7]);
+    o.x = *reinterpret_cast<uint32_t*>(&p0); o.y = *reinterpret_cast<uint32_t*>(&p1);
+    o.z = *reinterpret_cast<uint32_t*>(&p2); o.w = *reinterpret_cast<uint32_t*>(&p3);
+    d[i] = o;
+  }
+}
+template <>
+__device__ __forceinline__ void store_chunk32<float>(float* dst, const float (&x)[32]) {
+  float4* d = reinterpret_cast<float4*>(dst);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) d[i] = make_float4(x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]);
+}
+
+template <int BN, bool SWAP, typename TC>
+__global__ void __launch_bounds__(256, (BN <= 128 ? 2 : 1))
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TcEpi e) {
+  using Cfg = TcCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;                // SWIZZLE_128B tiles need 1024 B alignment
+  uint8_t* sgen = smem_raw + (base - raw);
+  const uint32_t sA = base, sB = base + Cfg::kStages * Cfg::kStageA;
+  const uint32_t bars = sB + Cfg::kStages * Cfg::kStageB;     // full[kStages], empty[kStages], tmem_full, tmem slot
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sgen + Cfg::kStages * (Cfg::kStageA + Cfg::kStageB) + 8 * (2 * Cfg::kStages + 1));
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (Cfg::kStages + s); };
+  const uint32_t tmem_full_bar = bars + 8u * (2 * Cfg::kStages);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int a0 = blockIdx.y * BM;            // first row of the 128-row operand (tokens, or features when SWAP)
+  const int b0 = blockIdx.x * BN;            // first row of the BN-row operand (features, or tokens when SWAP)
+  const int batch = blockIdx.z;
+  const int num_kb = e.K / BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(Cfg::kTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int s = 0; uint32_t ph = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(empty_bar(s), ph ^ 1u);
+        mbar_expect_tx(full_bar(s), Cfg::kStageA + Cfg::kStageB);
+        const int tap = kb / e.kb_per_tap, kc = kb - tap * e.kb_per_tap;
+        tma_load_3d(sA + s * Cfg::kStageA, &tmA, full_bar(s), (SWAP ? kb : kc) * BK + (SWAP ? 0 : e.tap_col[tap]),
+                    a0 + (SWAP ? 0 : e.tap_row[tap]), SWAP ? 0 : batch);
+        tma_load_3d(sB + s * Cfg::kStageB, &tmB, full_bar(s), kb * BK, b0, SWAP ? batch : 0);
+        if (++s == Cfg::kStages) { s = 0; ph ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
+      int s = 0; uint32_t ph = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(full_bar(s), ph);
+        tc_fence_after();
+        const uint64_t da = make_sw128_desc(sA + s * Cfg::kStageA);
+        const uint64_t db = make_sw128_desc(sB + s * Cfg::kStageB);
+#pragma unroll
+        for (int k = 0; k < BK / UMMA_K; ++k) {
+          // advancing 16 bf16 = 32 B along K inside the 128 B swizzle atom: +2 in the (addr>>4) field
+          tc_mma_bf16(tmem_base, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+        }
+        tc_commit(empty_bar(s));                 // frees the smem stage once these MMAs retire
+        if (++s == Cfg::kStages) { s = 0; ph ^= 1u; }
+      }
+      tc_commit(tmem_full_bar);                  // accumulator complete
+    }
+  } else if (warp >= 4) {
+    const int q = warp - 4;                      // TMEM lane quadrant == warp % 4
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+    TC* Cb = reinterpret_cast<TC*>(e.C) + (size_t)batch * e.c_bstride + (size_t)e.c_row0 * e.ldc;
+    const TC* Rb = e.resid ? reinterpret_cast<const TC*>(e.resid) + (size_t)batch * e.r_bstride : nullptr;
+    if constexpr (!SWAP) {
+      const int m = a0 + q * 32 + lane;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld32(trow + c * 32, v);
+        tmem_ld_wait();
+        const int n = b0 + c * 32;
+        if (m < e.M && n < e.N) {
+          float x[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]);
+          if (e.bias) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 bv = __ldg(reinterpret_cast<const float4*>(e.bias + n + j));
+              x[j] += bv.x; x[j + 1] += bv.y; x[j + 2] += bv.z; x[j + 3] += bv.w;
+            }
+          }
+          if (e.act == ACT_GELU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) x[j] = gelu_erf(x[j]);
+          }
+          if (e.act == ACT_SWIGLU) {
+            float y[32];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) y[j] = silu(x[2 * j]) * x[2 * j + 1];
+            TC* dst = Cb + (size_t)m * e.ldc + (n >> 1);
+            if constexpr (sizeof(TC) == 2) {
+              uint4* d = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+              for (int i = 0; i < 2; ++i) {
+                __nv_bfloat162 p0 = __floats2bfloat162_rn(y[8 * i + 0], y[8 * i + 1]);
+                __nv_bfloat162 p1 = __floats2bfloat162_rn(y[8 * i + 2], y[8 * i + 3]);
+                __nv_bfloat162 p2 = __floats2bfloat162_rn(y[8 * i + 4], y[8 * i + 5]);
+                __nv_bfloat162 p3 = __floats2bfloat162_rn(y[8 * i + 6], y[8 * i + 7]);
+                uint4 o;
+                o.x = *reinterpret_cast<uint32_t*>(&p0); o.y = *reinterpret_cast<uint32_t*>(&p1);
+                o.z = *reinterpret_cast<uint32_t*>(&p2); o.w = *reinterpret_cast<uint32_t*>(&p3);
+                d[i] = o;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) dst[j] = from_f32<TC>(y[j]);
+            }
+          } else {
+            if (Rb) {
+              const TC* r = Rb + (size_t)m * e.ldr + n;
+              if constexpr (sizeof(TC) == 2) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const uint4 rv = *reinterpret_cast<const uint4*>(r + 8 * i);
+                  const uint32_t w[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+                  for (int t = 0; t < 4; ++t) {
+                    x[8 * i + 2 * t] += __uint_as_float(w[t] << 16);
+                    x[8 * i + 2 * t + 1] += __uint_as_float(w[t] & 0xffff0000u);
+                  }
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) x[j] += to_f32(r[j]);
+              }
+            }
+            store_chunk32<TC>(Cb + (size_t)m * e.ldc + n, x);
+          }
+        }
+      }
+    } else {
+      // rows of D are features, columns are tokens; store transposed
+      const int f = a0 + q * 32 + lane;
+      const int ntok = min(BN, e.M - b0);
+      const float bias = (e.bias && f < e.N) ? e.bias[f] : 0.f;
+#pragma unroll 1
+      for (int c = 0; c < BN / 16; ++c) {
+        uint32_t v[16];
+        tmem_ld16(trow + c * 16, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int t = c * 16 + j;
+          float x = __uint_as_float(v[j]) + bias;
+          if (e.act == ACT_GELU) x = gelu_erf(x);
+          if (e.act == ACT_SWIGLU) {
+            const float other = __shfl_xor_sync(0xffffffffu, x, 1);
+            if (t < ntok && f < e.N && (lane & 1) == 0) Cb[(size_t)(b0 + t) * e.ldc + (f >> 1)] = from_f32<TC>(silu(x) * other);
+          } else if (t < ntok && f < e.N) {
+            if (Rb) x += to_f32(Rb[(size_t)(b0 + t) * e.ldr + f]);
+            Cb[(size_t)(b0 + t) * e.ldc + f] = from_f32<TC>(x);
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(Cfg::kTmemCols) : "memory");
+  }
+}
+
+// ---- host side --------------------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_encodeTiled g_encode = nullptr;
+
+cudaError_t gemm_tc_init() {
+  if (g_encode) return cudaSuccess;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  SONIC_CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+  if (qres != cudaDriverEntryPointSuccess || !fn) return cudaErrorNotSupported;
+  g_encode = reinterpret_cast<PFN_encodeTiled>(fn);
+  return cudaSuccess;
+}
+
+// 3-D bf16 tensor map {K, rows, batch} with a {64, box_rows, 1} box and 128B swizzle; OOB reads return zeros.
+static cudaError_t make_map(CUtensorMap* map, const void* ptr, long long K, long long rows, long long ld, long long batch,
+                            long long bstride, int box_rows) {
+  cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)rows, (cuuint64_t)(batch > 0 ? batch : 1)};
+  cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)(bstride > 0 ? bstride : ld * rows) * 2};
+  cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
+}
+
+template <int BN, bool SWAP, typename TC>
+static cudaError_t launch_one(const CUtensorMap& ma, const CUtensorMap& mb, const TcEpi& e, dim3 grid, cudaStream_t st) {
+  using Cfg = TcCfg<BN>;
+  gemm_tc_kernel<BN, SWAP, TC><<<grid, 256, Cfg::kSmem, st>>>(ma, mb, e);
+  return cudaGetLastError();
+}
+
+template <int BN, bool SWAP, typename TC>
+static cudaError_t configure_one() {
+  return cudaFuncSetAttribute(gemm_tc_kernel<BN, SWAP, TC>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<BN>::kSmem);
+}
+// opt every instantiation into its dynamic shared memory up front (must not happen lazily inside a stream capture)
+cudaError_t gemm_tc_configure() {
+  SONIC_CUDA_TRY((configure_one<128, false, bf16>()));
+  SONIC_CUDA_TRY((configure_one<128, false, float>()));
+  SONIC_CUDA_TRY((configure_one<16, true, bf16>()));
+  SONIC_CUDA_TRY((configure_one<16, true, float>()));
+  SONIC_CUDA_TRY((configure_one<32, true, bf16>()));
+  SONIC_CUDA_TRY((configure_one<32, true, float>()));
+  SONIC_CUDA_TRY((configure_one<64, true, bf16>()));
+  SONIC_CUDA_TRY((configure_one<64, true, float>()));
+  return cudaSuccess;
+}
+
+int gemm_tc_pick_bn(const GemmArgs& g, bool swap) {
+  if (swap) return g.M <= 16 ? 16 : (g.M <= 32 ? 32 : 64);
+  return 128;
+}
+
+cudaError_t launch_gemm_tc(const GemmArgs& g, bool swap, cudaStream_t st) {
+  if (g.M <= 0 || g.N <= 0 || g.batch <= 0) return cudaSuccess;
+  SONIC_CUDA_TRY(gemm_tc_init());
+  if (g.K % BK != 0 || g.lda % 8 != 0 || g.ldw % 8 != 0 || g.N % 32 != 0) return cudaErrorInvalidValue;
+  if ((reinterpret_cast<uintptr_t>(g.A) & 15) || (reinterpret_cast<uintptr_t>(g.W) & 15)) return cudaErrorInvalidValue;
+  TcEpi e;
+  e.C = g.C; e.ldc = g.ldc; e.c_bstride = g.c_bstride; e.c_row0 = g.c_row0;
+  e.bias = g.bias; e.resid = g.resid; e.ldr = g.ldr; e.r_bstride = g.r_bstride;
+  e.M = g.M; e.N = g.N; e.K = g.K; e.act = g.act;
+  e.kb_per_tap = g.K / BK;
+  for (int t = 0; t < 3; ++t) { e.tap_col[t] = 0; e.tap_row[t] = 0; }
+  CUtensorMap ma, mb;
+  const int bn = gemm_tc_pick_bn(g, swap);
+  if (!swap && g.conv_cin > 0) {
+    // A = padded time-major input [batch][rows_pad, cin]; output row m reads input rows stride*m + {0,1,2}
+    if (g.conv_cin % BK != 0 || g.K != 3 * g.conv_cin) return cudaErrorInvalidValue;
+    e.kb_per_tap = g.conv_cin / BK;
+    if (g.conv_stride == 1) {
+      SONIC_CUDA_TRY(make_map(&ma, g.A, g.conv_cin, g.conv_rows_pad, g.conv_cin, g.batch, g.a_bstride, BM));
+      for (int t = 0; t < 3; ++t) e.tap_row[t] = t;
+    } else if (g.conv_stride == 2) {
+      if (g.conv_rows_pad % 2) return cudaErrorInvalidValue;
+      SONIC_CUDA_TRY(make_map(&ma, g.A, 2 * g.conv_cin, g.conv_rows_pad / 2, 2 * g.conv_cin, g.batch, g.a_bstride, BM));
+      e.tap_col[1] = g.conv_cin;
+      e.tap_row[2] = 1;
+    } else return cudaErrorInvalidValue;
+    SONIC_CUDA_TRY(make_map(&mb, g.W, g.K, g.N, g.ldw, 1, 0, bn));
+    dim3 grid(cdiv(g.N, bn), cdiv(g.M, BM), g.batch);
+    return g.out_f32 ? launch_one<128, false, float>(ma, mb, e, grid, st) : launch_one<128, false, bf16>(ma, mb, e, grid, st);
+  }
+  if (!swap) {
+    SONIC_CUDA_TRY(make_map(&ma, g.A, g.K, g.M, g.lda, g.batch, g.a_bstride, BM));
+    SONIC_CUDA_TRY(make_map(&mb, g.W, g.K, g.N, g.ldw, 1, 0, bn));
+    dim3 grid(cdiv(g.N, bn), cdiv(g.M, BM), g.batch);
+    return g.out_f32 ? launch_one<128, false, float>(ma, mb, e, grid, st) : launch_one<128, false, bf16>(ma, mb, e, grid, st);
+  }
+  // swap: the 128-row operand is the weight matrix
+  SONIC_CUDA_TRY(make_map(&ma, g.W, g.K, g.N, g.ldw, 1, 0, BM));
+  SONIC_CUDA_TRY(make_map(&mb, g.A, g.K, g.M, g.lda, g.batch, g.a_bstride, bn));
+  dim3 grid(cdiv(g.M, bn), cdiv(g.N, BM), g.batch);
+#define SWAP_CASE(BN_)                                                                                         \
+  case BN_:                                                                                                    \
+    return g.out_f32 ? launch_one<BN_, true, float>(ma, mb, e, grid, st) : launch_one<BN_, true, bf16>(ma, mb, e, grid, st);
+  switch (bn) {
+    SWAP_CASE(16)
+    SWAP_CASE(32)
+    SWAP_CASE(64)
+  }
+#undef SWAP_CASE
+  return cudaErrorInvalidValue;
+}
+
+}  // namespace sonic

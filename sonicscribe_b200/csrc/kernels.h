@@ -1,0 +1,97 @@
+// Internal launcher prototypes (device code lives in the .cu files next to this header).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stddef.h>
+
+#define SONIC_MEL_PEAK_NORM 1
+#define SONIC_MEL_PCM16 2
+
+namespace sonic {
+
+typedef __nv_bfloat16 bf16;
+
+// ---- mel.cu ------------------------------------------------------------------------------------------------------
+size_t mel_tables_bytes();
+void mel_build_tables(void* host_out, const int* tap_start, const int* tap_count, const float* tapw);
+cudaError_t mel_setup();
+template <typename T>
+cudaError_t launch_mel(const float* pcm, const long long* offs, const int* lens, int batch, int max_len, int flags,
+                       const void* tables, unsigned* peak_bits, unsigned* gmax_bits, float* raw, float* feat, T* feat_tm,
+                       cudaStream_t st);
+
+// ---- gemm: C[b][M,N] = epilogue(A[b][M,K] * W[N,K]^T) ---------------------------------------------------------------
+enum { ACT_NONE = 0, ACT_GELU = 1, ACT_SWIGLU = 2 };   // SWIGLU: columns are (gate,up) pairs; writes N/2 columns
+struct GemmArgs {
+  const void* A; long long lda; long long a_bstride;       // elements
+  const void* W; long long ldw;                             // [N,K] row-major ("K-major")
+  void* C; long long ldc; long long c_bstride; long long c_row0;   // output row offset inside each batch slab
+  const float* bias;                                        // [N] or null (fp32)
+  const void* resid; long long ldr; long long r_bstride;    // same dtype as C; may alias C
+  int M, N, K, batch;
+  int act;
+  int out_f32;                                              // 1: C is float regardless of the activation dtype
+  // implicit conv1d(k=3, pad=1, stride 1|2) over a zero-padded time-major input [batch][conv_rows_pad, conv_cin]:
+  // A points at padded row 0, K = 3*conv_cin, lda = conv_stride*conv_cin (the overlapping-row view the SIMT kernel uses
+  // directly; the TMA kernel walks the three taps with a non-overlapping tensor map).  conv_cin = 0 => plain GEMM.
+  int conv_cin, conv_stride, conv_rows_pad;
+};
+template <typename T> cudaError_t launch_gemm_simt(const GemmArgs& g, cudaStream_t st);       // gemm_simt.cu
+
+// ---- ops.cu ------------------------------------------------------------------------------------------------------
+template <typename T>
+cudaError_t launch_layernorm(const T* x, T* y, const float* gamma, const float* beta, int rows, int H, float eps, cudaStream_t st);
+template <typename T>
+cudaError_t launch_rmsnorm(const T* x, T* y, const float* gamma, int rows, int H, float eps, cudaStream_t st);
+// rows_idx: optional gather of input rows (used for the last-position final norm)
+template <typename T>
+cudaError_t launch_rmsnorm_rows(const T* x, const int* rows_idx, T* y, const float* gamma, int rows, int H, float eps, cudaStream_t st);
+
+// encoder RoPE on the fused QKV buffer [rows, 3*H]: rotate the first rot dims of every q and k head. pos = row % T.
+template <typename T>
+cudaError_t launch_rope_enc(T* qkv, const float* cos_t, const float* sin_t, int rows, int T_len, int heads, int hd, int rot, cudaStream_t st);
+// decoder RoPE + KV append. qkv [rows, (H + 2*KV)*hd]; row r belongs to segment row_seg[r] at position row_pos[r]
+// (null row_seg => decode step: segment = r, position = ctx_len[r]). q rotated in place; k (rotated) and v stored into the caches.
+template <typename T>
+cudaError_t launch_rope_dec_kv(T* qkv, const float* cos_t, const float* sin_t, const int* row_seg, const int* row_pos,
+                               const int* ctx_len, T* kcache, T* vcache, int rows, int heads, int kv_heads, int hd,
+                               int max_ctx, cudaStream_t st);
+template <typename T>
+cudaError_t launch_embed(const int* ids, const int* audio_src, const T* table, const T* audio_embeds, T* x, int rows, int H, cudaStream_t st);
+template <typename T>
+cudaError_t launch_embed_next(const int* cur_tok, const T* table, T* x, int rows, int H, cudaStream_t st);
+// greedy step bookkeeping: argmax(+top-2 margin) over logits [B,V]; appends to out_ids unless finished; updates state.
+struct GreedyState {
+  int* cur_tok;      // [B] next input token
+  int* ctx_len;      // [B] tokens in the KV cache
+  int* finished;     // [B]
+  int* n_out;        // [B]
+  int* out_ids;      // [B][max_new]
+  float* margins;    // [B][max_new]
+  int* step;         // [1]
+  int* n_unfinished; // [1]
+  int max_new;
+  int eos[4];
+  int n_eos;
+};
+cudaError_t launch_greedy_pick(const float* logits, int B, int V, GreedyState gs, int advance_ctx, cudaStream_t st);
+void rope_table_host(float* cos_t, float* sin_t, int positions, int rot_dim, float theta);
+
+// ---- attention.cu ---------------------------------------------------------------------------------------------
+struct AttnArgs {
+  const void* q; long long q_row_stride;                 // q[(row)*q_row_stride + h*hd + d]
+  const void* k; long long k_tok_stride, k_head_stride, k_seg_stride;
+  const void* v; long long v_tok_stride, v_head_stride, v_seg_stride;
+  void* o; long long o_row_stride;
+  const int* q_off;     // [B+1] first q row of each segment (null => b*q_len_fixed)
+  const int* kv_len;    // [B] keys visible per segment (null => kv_len_fixed)
+  int q_len_fixed, kv_len_fixed;
+  int causal;           // 1: key j visible to the i-th query of a segment iff j <= (kv_len - q_len + i)
+  int decode;           // 1: one query per segment (row b), kv_len read AFTER the append (ctx_len+1 handled by caller)
+  int heads, kv_heads, hd, batch, max_q;
+  float scale;
+};
+template <typename T> cudaError_t launch_attention_simt(const AttnArgs& a, cudaStream_t st);
+
+}  // namespace sonic

@@ -1,0 +1,237 @@
+// Row-wise and bookkeeping kernels of the GLM-ASR path: LayerNorm, RMSNorm, RoPE (+KV append), embedding gather with
+// audio-embedding scatter, greedy pick.  All math in fp32; T is the activation storage type (float or bf16).
+#include "common.cuh"
+#include "kernels.h"
+#include <math.h>
+
+namespace sonic {
+
+// ---- LayerNorm (modeling_glmasr.py:250-251,308; eps 1e-5, affine) ----------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) layernorm_kernel(const T* __restrict__ x, T* __restrict__ y, const float* __restrict__ gamma,
+                                                        const float* __restrict__ beta, int H, float eps) {
+  __shared__ float red[32];
+  const size_t row = blockIdx.x;
+  const T* xr = x + row * H;
+  float v[8];                                             // H <= 2048 with 256 threads
+  float s = 0.f;
+  int cnt = 0;
+  for (int i = threadIdx.x; i < H; i += 256) { v[cnt] = to_f32(xr[i]); s += v[cnt]; ++cnt; }
+  const float mean = block_sum(s, red) / H;
+  float q = 0.f;
+  for (int c = 0; c < cnt; ++c) { const float d = v[c] - mean; q += d * d; }
+  const float var = block_sum(q, red) / H;
+  const float rstd = rsqrtf(var + eps);
+  cnt = 0;
+  for (int i = threadIdx.x; i < H; i += 256) { y[row * H + i] = from_f32<T>((v[cnt] - mean) * rstd * gamma[i] + beta[i]); ++cnt; }
+}
+template <typename T>
+cudaError_t launch_layernorm(const T* x, T* y, const float* gamma, const float* beta, int rows, int H, float eps, cudaStream_t st) {
+  if (rows <= 0) return cudaSuccess;
+  if (H > 2048) return cudaErrorInvalidValue;
+  layernorm_kernel<T><<<rows, 256, 0, st>>>(x, y, gamma, beta, H, eps);
+  return cudaGetLastError();
+}
+
+// ---- RMSNorm (modeling_llama.py:62-67): w * (x_f32 * rsqrt(mean(x_f32^2)+eps)).to(dtype) -------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) rmsnorm_kernel(const T* __restrict__ x, const int* __restrict__ rows_idx, T* __restrict__ y,
+                                                      const float* __restrict__ gamma, int H, float eps) {
+  __shared__ float red[32];
+  const size_t row = blockIdx.x;
+  const size_t src = rows_idx ? (size_t)rows_idx[row] : row;
+  const T* xr = x + src * H;
+  float v[8];
+  float s = 0.f;
+  int cnt = 0;
+  for (int i = threadIdx.x; i < H; i += 256) { v[cnt] = to_f32(xr[i]); s += v[cnt] * v[cnt]; ++cnt; }
+  const float rstd = rsqrtf(block_sum(s, red) / H + eps);
+  cnt = 0;
+  for (int i = threadIdx.x; i < H; i += 256) {
+    const float n = to_f32(from_f32<T>(v[cnt] * rstd));   // the reference rounds to the model dtype before the weight
+    y[row * H + i] = from_f32<T>(gamma[i] * n);
+    ++cnt;
+  }
+}
+template <typename T>
+cudaError_t launch_rmsnorm_rows(const T* x, const int* rows_idx, T* y, const float* gamma, int rows, int H, float eps, cudaStream_t st) {
+  if (rows <= 0) return cudaSuccess;
+  if (H > 2048) return cudaErrorInvalidValue;
+  rmsnorm_kernel<T><<<rows, 256, 0, st>>>(x, rows_idx, y, gamma, H, eps);
+  return cudaGetLastError();
+}
+template <typename T>
+cudaError_t launch_rmsnorm(const T* x, T* y, const float* gamma, int rows, int H, float eps, cudaStream_t st) {
+  return launch_rmsnorm_rows<T>(x, nullptr, y, gamma, rows, H, eps, st);
+}
+
+// ---- RoPE tables (modeling_glmasr.py:66-109 / modeling_llama.py:96-136): fp32, angle = pos * inv_freq -------------------
+void rope_table_host(float* cos_t, float* sin_t, int positions, int rot_dim, float theta) {
+  const int half = rot_dim / 2;
+  for (int j = 0; j < half; ++j) {
+    const float e = (float)(2 * j) / (float)rot_dim;
+    const float inv = 1.0f / (float)pow((double)theta, (double)e);
+    for (int p = 0; p < positions; ++p) {
+      const float a = (float)p * inv;
+      cos_t[(size_t)p * half + j] = (float)cos((double)a);
+      sin_t[(size_t)p * half + j] = (float)sin((double)a);
+    }
+  }
+}
+
+// encoder: rotate first `rot` dims of each q/k head in the fused [rows, 3*heads*hd] buffer (NeoX halves: j <-> j+rot/2)
+template <typename T>
+__global__ void rope_enc_kernel(T* __restrict__ qkv, const float* __restrict__ cos_t, const float* __restrict__ sin_t, int rows,
+                                int T_len, int heads, int hd, int rot) {
+  const int half = rot / 2;
+  const int per_row = 2 * heads * half;                 // q and k
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)rows * per_row) return;
+  const int row = (int)(idx / per_row);
+  int r = (int)(idx - (long long)row * per_row);
+  const int which = r / (heads * half);                 // 0 q, 1 k
+  r -= which * heads * half;
+  const int h = r / half, j = r - h * half;
+  const int pos = row % T_len;
+  // the reference casts cos/sin to the model dtype (modeling_glmasr.py:109)
+  const float c = to_f32(from_f32<T>(cos_t[pos * half + j])), s = to_f32(from_f32<T>(sin_t[pos * half + j]));
+  T* p = qkv + (size_t)row * (3 * heads * hd) + (size_t)which * heads * hd + h * hd;
+  const float a = to_f32(p[j]), b = to_f32(p[j + half]);
+  p[j] = from_f32<T>(a * c - b * s);
+  p[j + half] = from_f32<T>(b * c + a * s);
+}
+template <typename T>
+cudaError_t launch_rope_enc(T* qkv, const float* cos_t, const float* sin_t, int rows, int T_len, int heads, int hd, int rot, cudaStream_t st) {
+  const long long total = (long long)rows * 2 * heads * (rot / 2);
+  if (total <= 0) return cudaSuccess;
+  rope_enc_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(qkv, cos_t, sin_t, rows, T_len, heads, hd, rot);
+  return cudaGetLastError();
+}
+
+// decoder: full-dim RoPE on q (in place) and k; k,v appended to the caches [seg][kv_head][pos][hd]
+template <typename T>
+__global__ void rope_dec_kv_kernel(T* __restrict__ qkv, const float* __restrict__ cos_t, const float* __restrict__ sin_t,
+                                   const int* __restrict__ row_seg, const int* __restrict__ row_pos, const int* __restrict__ ctx_len,
+                                   T* __restrict__ kcache, T* __restrict__ vcache, int heads, int kv_heads, int hd, int max_ctx) {
+  const int row = blockIdx.x;
+  const int seg = row_seg ? row_seg[row] : row;
+  const int pos = row_seg ? row_pos[row] : ctx_len[row];
+  const int half = hd / 2;
+  const int width = (heads + 2 * kv_heads) * hd;
+  T* base = qkv + (size_t)row * width;
+  const int n_rot = (heads + kv_heads) * half;
+  for (int i = threadIdx.x; i < n_rot; i += blockDim.x) {
+    const int h = i / half, j = i - h * half;              // h < heads: q head, else k head
+    const float c = to_f32(from_f32<T>(cos_t[(size_t)pos * half + j])), s = to_f32(from_f32<T>(sin_t[(size_t)pos * half + j]));
+    T* p = base + (size_t)h * hd;
+    const float a = to_f32(p[j]), b = to_f32(p[j + half]);
+    const T ra = from_f32<T>(a * c - b * s), rb = from_f32<T>(b * c + a * s);
+    if (h < heads) {
+      p[j] = ra;
+      p[j + half] = rb;
+    } else {
+      T* kc = kcache + (((size_t)seg * kv_heads + (h - heads)) * max_ctx + pos) * hd;
+      kc[j] = ra;
+      kc[j + half] = rb;
+    }
+  }
+  const T* vsrc = base + (size_t)(heads + kv_heads) * hd;
+  for (int i = threadIdx.x; i < kv_heads * hd; i += blockDim.x) {
+    const int h = i / hd, d = i - h * hd;
+    vcache[(((size_t)seg * kv_heads + h) * max_ctx + pos) * hd + d] = vsrc[i];
+  }
+}
+template <typename T>
+cudaError_t launch_rope_dec_kv(T* qkv, const float* cos_t, const float* sin_t, const int* row_seg, const int* row_pos,
+                               const int* ctx_len, T* kcache, T* vcache, int rows, int heads, int kv_heads, int hd,
+                               int max_ctx, cudaStream_t st) {
+  if (rows <= 0) return cudaSuccess;
+  rope_dec_kv_kernel<T><<<rows, 256, 0, st>>>(qkv, cos_t, sin_t, row_seg, row_pos, ctx_len, kcache, vcache, heads, kv_heads, hd, max_ctx);
+  return cudaGetLastError();
+}
+
+// ---- embedding gather + audio scatter (modeling_glmasr.py:473-483) ------------------------------------------------------
+template <typename T>
+__global__ void embed_kernel(const int* __restrict__ ids, const int* __restrict__ audio_src, const T* __restrict__ table,
+                             const T* __restrict__ audio, T* __restrict__ x, int H) {
+  const int row = blockIdx.x;
+  const int a = audio_src ? audio_src[row] : -1;
+  const T* src = (a >= 0) ? audio + (size_t)a * H : table + (size_t)ids[row] * H;
+  for (int i = threadIdx.x; i < H; i += blockDim.x) x[(size_t)row * H + i] = src[i];
+}
+template <typename T>
+cudaError_t launch_embed(const int* ids, const int* audio_src, const T* table, const T* audio_embeds, T* x, int rows, int H, cudaStream_t st) {
+  if (rows <= 0) return cudaSuccess;
+  embed_kernel<T><<<rows, 256, 0, st>>>(ids, audio_src, table, audio_embeds, x, H);
+  return cudaGetLastError();
+}
+template <typename T>
+cudaError_t launch_embed_next(const int* cur_tok, const T* table, T* x, int rows, int H, cudaStream_t st) {
+  return launch_embed<T>(cur_tok, nullptr, table, nullptr, x, rows, H, st);
+}
+
+// ---- greedy pick (generation/utils.py:2793-2805): argmax of fp32 logits, first index on ties; EOS bookkeeping ---------
+__global__ void __launch_bounds__(1024) greedy_pick_kernel(const float* __restrict__ logits, int V, GreedyState gs, int advance_ctx) {
+  const int b = blockIdx.x;
+  const float* l = logits + (size_t)b * V;
+  float best = -INFINITY, second = -INFINITY;
+  int bi = 0x7fffffff;
+  for (int i = threadIdx.x; i < V; i += blockDim.x) {
+    const float v = l[i];
+    if (v > best) { second = best; best = v; bi = i; }
+    else if (v > second) second = v;
+  }
+  __shared__ float s_best[1024], s_second[1024];
+  __shared__ int s_idx[1024];
+  s_best[threadIdx.x] = best; s_second[threadIdx.x] = second; s_idx[threadIdx.x] = bi;
+  __syncthreads();
+  for (int o = 512; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) {
+      const float ob = s_best[threadIdx.x + o], os = s_second[threadIdx.x + o];
+      const int oi = s_idx[threadIdx.x + o];
+      float mb = s_best[threadIdx.x], ms = s_second[threadIdx.x];
+      int mi = s_idx[threadIdx.x];
+      if (ob > mb || (ob == mb && oi < mi)) { ms = fmaxf(fmaxf(ms, os), mb); mb = ob; mi = oi; }
+      else { ms = fmaxf(ms, ob); }
+      s_best[threadIdx.x] = mb; s_second[threadIdx.x] = ms; s_idx[threadIdx.x] = mi;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const int tok = s_idx[0];
+    const int step = *gs.step;
+    if (advance_ctx) gs.ctx_len[b] += 1;                 // the token just consumed is now in the cache
+    if (!gs.finished[b]) {
+      gs.out_ids[(size_t)b * gs.max_new + step] = tok;
+      if (gs.margins) gs.margins[(size_t)b * gs.max_new + step] = s_best[0] - s_second[0];
+      gs.n_out[b] = step + 1;
+      bool eos = false;
+      for (int e = 0; e < gs.n_eos; ++e) eos |= (tok == gs.eos[e]);
+      if (eos || step + 1 >= gs.max_new) { gs.finished[b] = 1; atomicSub(gs.n_unfinished, 1); }
+    }
+    gs.cur_tok[b] = tok;
+  }
+}
+__global__ void greedy_step_inc_kernel(int* step) { *step += 1; }
+
+cudaError_t launch_greedy_pick(const float* logits, int B, int V, GreedyState gs, int advance_ctx, cudaStream_t st) {
+  if (B <= 0) return cudaSuccess;
+  greedy_pick_kernel<<<B, 1024, 0, st>>>(logits, V, gs, advance_ctx);
+  SONIC_LAUNCH_CHECK();
+  greedy_step_inc_kernel<<<1, 1, 0, st>>>(gs.step);
+  return cudaGetLastError();
+}
+
+#define INST(T)                                                                                                           \
+  template cudaError_t launch_layernorm<T>(const T*, T*, const float*, const float*, int, int, float, cudaStream_t);       \
+  template cudaError_t launch_rmsnorm<T>(const T*, T*, const float*, int, int, float, cudaStream_t);                        \
+  template cudaError_t launch_rmsnorm_rows<T>(const T*, const int*, T*, const float*, int, int, float, cudaStream_t);       \
+  template cudaError_t launch_rope_enc<T>(T*, const float*, const float*, int, int, int, int, int, cudaStream_t);           \
+  template cudaError_t launch_rope_dec_kv<T>(T*, const float*, const float*, const int*, const int*, const int*, T*, T*,    \
+                                             int, int, int, int, int, cudaStream_t);                                       \
+  template cudaError_t launch_embed<T>(const int*, const int*, const T*, const T*, T*, int, int, cudaStream_t);             \
+  template cudaError_t launch_embed_next<T>(const int*, const T*, T*, int, int, cudaStream_t);
+INST(float)
+INST(bf16)
+
+}  // namespace sonic
