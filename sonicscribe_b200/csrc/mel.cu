@@ -197,7 +197,6 @@ mel_frames_kernel(const float* __restrict__ pcm, const long long* __restrict__ o
       const float zr = s_re[a0], zi = s_im[a0], yr = s_re[a1], yi = s_im[a1];
       const float ar = zr + yr, ai = zi - yi;        // 2*X_A
       const float br = zr - yr, bi = zi + yi;        // 2*i*X_B (same modulus)
-      __syncwarp();
       // in-place is safe: a1 addresses bins >= 200, which no item writes (k = 200 maps to itself)
       s_re[a0] = 0.25f * (ar * ar + ai * ai);
       s_im[a0] = 0.25f * (br * br + bi * bi);
