@@ -103,6 +103,12 @@ SONIC_API int sonic_timer_end(sonic_handle h, float* ms);        /* records, syn
 SONIC_API int sonic_stage_times(sonic_handle h, float* ms4);     /* device ms of the last transcribe: mel, encode, prefill, decode */
 SONIC_API int64_t sonic_launch_count(sonic_handle h);            /* kernels launched through this handle so far                */
 SONIC_API int64_t sonic_device_bytes(sonic_handle h);            /* device memory held by the handle                           */
+/* Per-launch-class device-time breakdown: between begin and end every kernel launch of the handle is bracketed by an event
+ * pair on its stream (the decode loop runs eagerly instead of as a CUDA graph).  Classes: sonic_profile_class_name(i). */
+SONIC_API int sonic_profile_begin(sonic_handle h);
+SONIC_API int sonic_profile_end(sonic_handle h, float* ms_per_class, int64_t* launches_per_class, int32_t n_classes);
+SONIC_API int32_t sonic_profile_num_classes(void);
+SONIC_API const char* sonic_profile_class_name(int32_t c);
 /* Copy an intermediate tensor as float32 (handle created with debug=1):
  * "mel_tm", "conv_out", "enc_layer0", "enc_out", "audio_embeds", "first_logits", "dec_layer0", "rope_enc_cos", ... */
 SONIC_API int sonic_debug_read(sonic_handle h, const char* name, float* out, size_t max_elems, size_t* n_elems);

@@ -139,6 +139,12 @@ struct sonic_ctx {
   std::map<std::string, std::pair<void*, size_t>> probes;   // name -> (device ptr in activation dtype, elems)
   std::map<std::string, std::pair<float*, size_t>> probes_f32;
 
+  // per-launch-class profiling (sonic_profile_*): eager execution with an event pair around every launch
+  bool prof_on = false;
+  int prof_cls = 0;
+  std::vector<cudaEvent_t> prof_pool;
+  std::vector<int> prof_tags;           // class of pair i (events 2i, 2i+1)
+  size_t prof_used = 0;
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t ev_user[2] = {nullptr, nullptr};
   float stage_ms[4] = {0, 0, 0, 0};
@@ -159,12 +165,28 @@ int fail_cuda(sonic_ctx* h, cudaError_t e, const char* what) {
     cudaError_t _e = (expr);                                       \
     if (_e != cudaSuccess) return fail_cuda(h, _e, #expr);         \
   } while (0)
+enum ProfClass { PC_MEL = 0, PC_ENC_GEMM, PC_ENC_ATTN, PC_ENC_OTHER, PC_PRE_GEMM, PC_PRE_ATTN, PC_PRE_OTHER, PC_DEC_QKV, PC_DEC_O,
+                 PC_DEC_GU, PC_DEC_DOWN, PC_DEC_LMHEAD, PC_DEC_ATTN, PC_DEC_OTHER, PC_COUNT };
+const char* const kProfNames[PC_COUNT] = {"mel", "enc_gemm", "enc_attn", "enc_other", "prefill_gemm", "prefill_attn", "prefill_other",
+                                          "dec_gemm_qkv", "dec_gemm_o", "dec_gemm_gateup", "dec_gemm_down", "dec_gemm_lmhead",
+                                          "dec_attn", "dec_other"};
+cudaEvent_t prof_event(sonic_ctx* h) {
+  if (h->prof_used == h->prof_pool.size()) {
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    h->prof_pool.push_back(e);
+  }
+  return h->prof_pool[h->prof_used++];
+}
 #define CKL(expr, nk)                                              \
   do {                                                             \
+    if (h->prof_on) { cudaEventRecord(prof_event(h), h->stream); h->prof_tags.push_back(h->prof_cls); } \
     cudaError_t _e = (expr);                                       \
     if (_e != cudaSuccess) return fail_cuda(h, _e, #expr);         \
+    if (h->prof_on) cudaEventRecord(prof_event(h), h->stream);     \
     h->launches += (nk);                                           \
   } while (0)
+#define TAG(c) h->prof_cls = (c)
 
 template <typename P>
 int dalloc(sonic_ctx* h, P** p, size_t bytes, bool zero = false) {
@@ -223,7 +245,8 @@ int n_audio_tokens(long long n) {
 // ---- typed pipeline -------------------------------------------------------------------------------------------------------
 template <typename T>
 struct Engine {
-  static int gemm(sonic_ctx* h, GemmArgs g, bool swap) {
+  static int gemm(sonic_ctx* h, GemmArgs g, bool swap, int cls) {
+    TAG(cls);
     if (std::is_same<T, float>::value) { CKL(launch_gemm_simt<float>(g, h->stream), 1); return 0; }
     if (h->force_simt) { CKL(launch_gemm_simt<bf16>(g, h->stream), 1); return 0; }
     CKL(launch_gemm_tc(g, swap, h->stream), 1);
@@ -252,6 +275,7 @@ struct Engine {
   }
 
   static int mel(sonic_ctx* h, const float* pcm_dev, int batch, int max_len, int flags, float* feat_dev) {
+    TAG(PC_MEL);
     CKL(launch_mel<T>(pcm_dev, h->offs_dev, h->lens_dev, batch, max_len, flags & 3, h->mel_tables, h->peak_bits, h->gmax_bits,
                       h->mel_raw, feat_dev, reinterpret_cast<T*>(h->mel_tm), h->stream),
         (flags & SONIC_FLAG_PEAK_NORM) ? 4 : 3);
@@ -268,19 +292,21 @@ struct Engine {
       GemmArgs g = lin(mel_tm, kMels, h->conv1_w, 3 * kMels, h1, kEncH, h->conv1_b, kFrames, kEncH, ACT_GELU);
       g.batch = B; g.a_bstride = (long long)(kFrames + 2) * kMels; g.c_bstride = (long long)(kFrames + 2) * kEncH; g.c_row0 = 1;
       g.conv_cin = kMels; g.conv_stride = 1; g.conv_rows_pad = kFrames + 2;
-      if (gemm(h, g, false)) return -1;
+      if (gemm(h, g, false, PC_ENC_GEMM)) return -1;
     }
     {  // conv2 (stride 2) + GELU (modeling_glmasr.py:318)
       GemmArgs g = lin(h1, 2 * kEncH, h->conv2_w, 3 * kEncH, x, kEncH, h->conv2_b, kEncT, kEncH, ACT_GELU);
       g.batch = B; g.a_bstride = (long long)(kFrames + 2) * kEncH; g.c_bstride = (long long)kEncT * kEncH;
       g.conv_cin = kEncH; g.conv_stride = 2; g.conv_rows_pad = kFrames + 2;
-      if (gemm(h, g, false)) return -1;
+      if (gemm(h, g, false, PC_ENC_GEMM)) return -1;
     }
     if (probe(h, "conv_out", x, (size_t)rows * kEncH)) return -1;
     for (int l = 0; l < h->cfg.enc_layers; ++l) {
       const EncLayerW& w = h->enc[l];
+      TAG(PC_ENC_OTHER);
       CKL(launch_layernorm<T>(x, u, w.ln1_g, w.ln1_b, rows, kEncH, kLnEps, h->stream), 1);
-      if (gemm(h, lin(u, kEncH, w.wqkv, kEncH, qkv, 3 * kEncH, w.bqkv, rows, 3 * kEncH), false)) return -1;
+      if (gemm(h, lin(u, kEncH, w.wqkv, kEncH, qkv, 3 * kEncH, w.bqkv, rows, 3 * kEncH), false, PC_ENC_GEMM)) return -1;
+      TAG(PC_ENC_OTHER);
       CKL(launch_rope_enc<T>(qkv, h->rope_enc_cos, h->rope_enc_sin, rows, kEncT, kEncHeads, kEncHd, kEncRot, h->stream), 1);
       {
         AttnArgs a;
@@ -291,20 +317,23 @@ struct Engine {
         a.o = attn; a.o_row_stride = kEncH;
         a.q_len_fixed = kEncT; a.kv_len_fixed = kEncT; a.causal = 0; a.decode = 0;
         a.heads = kEncHeads; a.kv_heads = kEncHeads; a.hd = kEncHd; a.batch = B; a.max_q = kEncT; a.scale = 0.125f;
+        TAG(PC_ENC_ATTN);
         CKL(launch_attention_simt<T>(a, h->stream), 1);
       }
-      if (gemm(h, lin(attn, kEncH, w.wo, kEncH, x, kEncH, w.bo, rows, kEncH, ACT_NONE, x, kEncH), false)) return -1;
+      if (gemm(h, lin(attn, kEncH, w.wo, kEncH, x, kEncH, w.bo, rows, kEncH, ACT_NONE, x, kEncH), false, PC_ENC_GEMM)) return -1;
+      TAG(PC_ENC_OTHER);
       CKL(launch_layernorm<T>(x, u, w.ln2_g, w.ln2_b, rows, kEncH, kLnEps, h->stream), 1);
-      if (gemm(h, lin(u, kEncH, w.fc1, kEncH, mlp, kEncInter, w.b1, rows, kEncInter, ACT_GELU), false)) return -1;
-      if (gemm(h, lin(mlp, kEncInter, w.fc2, kEncInter, x, kEncH, w.b2, rows, kEncH, ACT_NONE, x, kEncH), false)) return -1;
+      if (gemm(h, lin(u, kEncH, w.fc1, kEncH, mlp, kEncInter, w.b1, rows, kEncInter, ACT_GELU), false, PC_ENC_GEMM)) return -1;
+      if (gemm(h, lin(mlp, kEncInter, w.fc2, kEncInter, x, kEncH, w.b2, rows, kEncH, ACT_NONE, x, kEncH), false, PC_ENC_GEMM)) return -1;
       if (l == 0 && probe(h, "enc_layer0", x, (size_t)rows * kEncH)) return -1;
     }
+    TAG(PC_ENC_OTHER);
     CKL(launch_layernorm<T>(x, u, h->enc_norm_g, h->enc_norm_b, rows, kEncH, kLnEps, h->stream), 1);
     if (probe(h, "enc_out", u, (size_t)rows * kEncH)) return -1;
     // adapter: [B*375, 5120] -> 4096 (GELU) -> 2048 (modeling_glmasr.py:412-415, 333-349)
     const int mrows = B * kMerged;
-    if (gemm(h, lin(u, kEncInter, h->proj1_w, kEncInter, h->a1, 2 * kDecH, h->proj1_b, mrows, 2 * kDecH, ACT_GELU), false)) return -1;
-    if (gemm(h, lin(h->a1, 2 * kDecH, h->proj2_w, 2 * kDecH, h->audio, kDecH, h->proj2_b, mrows, kDecH), false)) return -1;
+    if (gemm(h, lin(u, kEncInter, h->proj1_w, kEncInter, h->a1, 2 * kDecH, h->proj1_b, mrows, 2 * kDecH, ACT_GELU), false, PC_ENC_GEMM)) return -1;
+    if (gemm(h, lin(h->a1, 2 * kDecH, h->proj2_w, 2 * kDecH, h->audio, kDecH, h->proj2_b, mrows, kDecH), false, PC_ENC_GEMM)) return -1;
     if (probe(h, "audio_embeds", h->audio, (size_t)mrows * kDecH)) return -1;
     return 0;
   }
@@ -318,8 +347,10 @@ struct Engine {
     T* kc = reinterpret_cast<T*>(h->kcache) + (size_t)l * layer_kv;
     T* vc = reinterpret_cast<T*>(h->vcache) + (size_t)l * layer_kv;
     const bool swap = !prefill;
+    TAG(prefill ? PC_PRE_OTHER : PC_DEC_OTHER);
     CKL(launch_rmsnorm<T>(x, u, w.rms1, rows, kDecH, kRmsEps, h->stream), 1);
-    if (gemm(h, lin(u, kDecH, w.wqkv, kDecH, qkv, kQkvDec, nullptr, rows, kQkvDec), swap)) return -1;
+    if (gemm(h, lin(u, kDecH, w.wqkv, kDecH, qkv, kQkvDec, nullptr, rows, kQkvDec), swap, prefill ? PC_PRE_GEMM : PC_DEC_QKV)) return -1;
+    TAG(prefill ? PC_PRE_OTHER : PC_DEC_OTHER);
     CKL(launch_rope_dec_kv<T>(qkv, h->rope_dec_cos, h->rope_dec_sin, prefill ? h->d_row_seg : nullptr, prefill ? h->d_row_pos : nullptr,
                               h->gs.ctx_len, kc, vc, rows, kDecHeads, kDecKv, kDecHd, h->max_ctx, h->stream), 1);
     {
@@ -334,27 +365,32 @@ struct Engine {
       a.causal = 1; a.decode = prefill ? 0 : 1;
       a.heads = kDecHeads; a.kv_heads = kDecKv; a.hd = kDecHd; a.batch = B; a.max_q = max_q;
       a.scale = 0.08838834764831845f;   // 128^-1/2
+      TAG(prefill ? PC_PRE_ATTN : PC_DEC_ATTN);
       CKL(launch_attention_simt<T>(a, h->stream), 1);
     }
-    if (gemm(h, lin(attn, kDecH, w.wo, kDecH, x, kDecH, nullptr, rows, kDecH, ACT_NONE, x, kDecH), swap)) return -1;
+    if (gemm(h, lin(attn, kDecH, w.wo, kDecH, x, kDecH, nullptr, rows, kDecH, ACT_NONE, x, kDecH), swap, prefill ? PC_PRE_GEMM : PC_DEC_O)) return -1;
+    TAG(prefill ? PC_PRE_OTHER : PC_DEC_OTHER);
     CKL(launch_rmsnorm<T>(x, u, w.rms2, rows, kDecH, kRmsEps, h->stream), 1);
-    if (gemm(h, lin(u, kDecH, w.wgu, kDecH, act, kDecInter, nullptr, rows, 2 * kDecInter, ACT_SWIGLU), swap)) return -1;
-    if (gemm(h, lin(act, kDecInter, w.wdown, kDecInter, x, kDecH, nullptr, rows, kDecH, ACT_NONE, x, kDecH), swap)) return -1;
+    if (gemm(h, lin(u, kDecH, w.wgu, kDecH, act, kDecInter, nullptr, rows, 2 * kDecInter, ACT_SWIGLU), swap, prefill ? PC_PRE_GEMM : PC_DEC_GU)) return -1;
+    if (gemm(h, lin(act, kDecInter, w.wdown, kDecInter, x, kDecH, nullptr, rows, kDecH, ACT_NONE, x, kDecH), swap, prefill ? PC_PRE_GEMM : PC_DEC_DOWN)) return -1;
     return 0;
   }
 
   static int lm_head(sonic_ctx* h, int B, const int* rows_idx, int advance) {
     T *x = reinterpret_cast<T*>(h->dx), *u = reinterpret_cast<T*>(h->du);
+    TAG(PC_DEC_OTHER);
     CKL(launch_rmsnorm_rows<T>(x, rows_idx, u, h->final_norm, B, kDecH, kRmsEps, h->stream), 1);
     GemmArgs g = lin(u, kDecH, h->lm_head, kDecH, h->logits, kVocab, nullptr, B, kVocab);
     g.out_f32 = 1;
-    if (gemm(h, g, true)) return -1;
+    if (gemm(h, g, true, PC_DEC_LMHEAD)) return -1;
+    TAG(PC_DEC_OTHER);
     CKL(launch_greedy_pick(h->logits, B, kVocab, h->gs, advance, h->stream), 2);
     return 0;
   }
 
   static int prefill(sonic_ctx* h, int B, int total_rows, int max_q) {
     T* x = reinterpret_cast<T*>(h->dx);
+    TAG(PC_PRE_OTHER);
     CKL(launch_embed<T>(h->d_ids, h->d_audio_src, reinterpret_cast<const T*>(h->embed), reinterpret_cast<const T*>(h->audio), x,
                         total_rows, kDecH, h->stream), 1);
     for (int l = 0; l < h->cfg.dec_layers; ++l) {
@@ -373,6 +409,7 @@ struct Engine {
 
   static int decode_step(sonic_ctx* h, int B) {
     T* x = reinterpret_cast<T*>(h->dx);
+    TAG(PC_DEC_OTHER);
     CKL(launch_embed_next<T>(h->gs.cur_tok, reinterpret_cast<const T*>(h->embed), x, B, kDecH, h->stream), 1);
     for (int l = 0; l < h->cfg.dec_layers; ++l)
       if (dec_layer(h, l, B, B, false, 1)) return -1;
@@ -647,7 +684,12 @@ int do_generate(sonic_ctx* h, const int32_t* ids, const int32_t* id_offsets, int
   CK(cudaEventRecord(h->ev[3], st));
 
   // greedy steps 2..max_new: one CUDA graph per (batch, max_new) replayed; no per-token host sync.
-  if (max_new > 1) {
+  if (max_new > 1 && h->prof_on) {
+    for (int step = 1; step < max_new; ++step) {
+      rc = dispatch(h, [&] { return Engine<float>::decode_step(h, batch); }, [&] { return Engine<bf16>::decode_step(h, batch); });
+      if (rc) return rc;
+    }
+  } else if (max_new > 1) {
     const int key = batch * 100000 + max_new;
     auto it = h->decode_graphs.find(key);
     if (it == h->decode_graphs.end()) {
@@ -768,6 +810,7 @@ int sonic_destroy(sonic_handle h) {
   if (h->h_pinned) cudaFreeHost(h->h_pinned);
   for (auto& e : h->ev) if (e) cudaEventDestroy(e);
   for (auto& e : h->ev_user) if (e) cudaEventDestroy(e);
+  for (auto& e : h->prof_pool) cudaEventDestroy(e);
   cudaStreamDestroy(h->stream);
   delete h;
   return 0;
@@ -869,6 +912,31 @@ int sonic_stage_times(sonic_handle h, float* ms4) {
 }
 int64_t sonic_launch_count(sonic_handle h) { return h ? h->launches : -1; }
 int64_t sonic_device_bytes(sonic_handle h) { return h ? h->bytes : -1; }
+
+int sonic_profile_begin(sonic_handle h) {
+  ENTER();
+  h->prof_on = true;
+  h->prof_used = 0;
+  h->prof_tags.clear();
+  return 0;
+}
+int sonic_profile_end(sonic_handle h, float* ms_per_class, int64_t* launches_per_class, int32_t n_classes) {
+  ENTER();
+  h->prof_on = false;
+  CK(cudaStreamSynchronize(h->stream));
+  for (int c = 0; c < n_classes; ++c) { ms_per_class[c] = 0.f; launches_per_class[c] = 0; }
+  for (size_t i = 0; i < h->prof_tags.size(); ++i) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, h->prof_pool[2 * i], h->prof_pool[2 * i + 1]) != cudaSuccess) continue;
+    const int c = h->prof_tags[i];
+    if (c < n_classes) { ms_per_class[c] += ms; launches_per_class[c] += 1; }
+  }
+  h->prof_used = 0;
+  h->prof_tags.clear();
+  return 0;
+}
+int32_t sonic_profile_num_classes(void) { return PC_COUNT; }
+const char* sonic_profile_class_name(int32_t c) { return (c >= 0 && c < PC_COUNT) ? kProfNames[c] : ""; }
 
 int sonic_debug_read(sonic_handle h, const char* name, float* out, size_t max_elems, size_t* n_elems) {
   ENTER();

@@ -63,6 +63,10 @@ def load_library():
         "sonic_stage_times": (C.c_int, [H, f32p]),
         "sonic_launch_count": (C.c_int64, [H]),
         "sonic_device_bytes": (C.c_int64, [H]),
+        "sonic_profile_begin": (C.c_int, [H]),
+        "sonic_profile_end": (C.c_int, [H, f32p, i64p, C.c_int32]),
+        "sonic_profile_num_classes": (C.c_int32, []),
+        "sonic_profile_class_name": (C.c_char_p, [C.c_int32]),
         "sonic_debug_read": (C.c_int, [H, C.c_char_p, f32p, C.c_size_t, C.POINTER(C.c_size_t)]),
         "sonic_test_gemm": (C.c_int, [H, C.c_int32, C.c_int32, f32p, f32p, f32p, f32p, f32p, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
     }
@@ -221,6 +225,16 @@ class Engine:
         a = (C.c_float * 4)()
         self._ck(self.lib.sonic_stage_times(self.h, a))
         return dict(zip(("mel_ms", "encode_ms", "prefill_ms", "decode_ms"), [float(v) for v in a]))
+
+    def profile_begin(self):
+        self._ck(self.lib.sonic_profile_begin(self.h))
+
+    def profile_end(self) -> dict:
+        n = int(self.lib.sonic_profile_num_classes())
+        ms = (C.c_float * n)()
+        cnt = (C.c_int64 * n)()
+        self._ck(self.lib.sonic_profile_end(self.h, ms, cnt, n))
+        return {self.lib.sonic_profile_class_name(i).decode(): {"ms": float(ms[i]), "launches": int(cnt[i])} for i in range(n)}
 
     def launch_count(self) -> int:
         return int(self.lib.sonic_launch_count(self.h))
