@@ -318,7 +318,12 @@ struct Engine {
         a.q_len_fixed = kEncT; a.kv_len_fixed = kEncT; a.causal = 0; a.decode = 0;
         a.heads = kEncHeads; a.kv_heads = kEncHeads; a.hd = kEncHd; a.batch = B; a.max_q = kEncT; a.scale = 0.125f;
         TAG(PC_ENC_ATTN);
-        CKL(launch_attention_simt<T>(a, h->stream), 1);
+        if (std::is_same<T, bf16>::value && !h->force_simt) {
+          CKL(launch_attention_tc(reinterpret_cast<const bf16*>(qkv), 3 * kEncH, 0, kEncH, 2 * kEncH, reinterpret_cast<bf16*>(attn), kEncH, B,
+                                  kEncT, kEncHeads, 0.125f, h->stream), 1);
+        } else {
+          CKL(launch_attention_simt<T>(a, h->stream), 1);
+        }
       }
       if (gemm(h, lin(attn, kEncH, w.wo, kEncH, x, kEncH, w.bo, rows, kEncH, ACT_NONE, x, kEncH), false, PC_ENC_GEMM)) return -1;
       TAG(PC_ENC_OTHER);
@@ -795,6 +800,7 @@ int sonic_create(const sonic_config* cfg, sonic_handle* out) {
   if (mel_setup() != cudaSuccess) { h->err = "mel_setup failed"; return bail(0); }
   if (!h->is_f32 && gemm_tc_init() != cudaSuccess) { h->err = "cuTensorMapEncodeTiled entry point unavailable"; return bail(0); }
   if (!h->is_f32 && gemm_tc_configure() != cudaSuccess) { h->err = "gemm_tc_configure failed"; return bail(0); }
+  if (!h->is_f32 && attention_tc_configure() != cudaSuccess) { h->err = "attention_tc_configure failed"; return bail(0); }
   if (alloc_all(h)) return bail(0);
   *out = h;
   return 0;
@@ -1002,6 +1008,39 @@ int sonic_test_gemm(sonic_handle h, int32_t impl, int32_t swap, const float* A, 
   e = cudaStreamSynchronize(st);
   cleanup();
   if (e != cudaSuccess) return fail_cuda(h, e, "sonic_test_gemm");
+  return 0;
+}
+
+int sonic_test_enc_attention(sonic_handle h, int32_t impl, const float* qkv, float* out, int32_t segments, int32_t T) {
+  ENTER();
+  const size_t rows = (size_t)segments * T, nq = rows * 3 * kEncH, no = rows * kEncH;
+  bf16 *dq = nullptr, *dout = nullptr;
+  float* f = nullptr;
+  cudaStream_t st = h->stream;
+  auto cleanup = [&]() { cudaFree(dq); cudaFree(dout); cudaFree(f); };
+  cudaError_t e;
+  if ((e = cudaMalloc(&dq, nq * 2)) || (e = cudaMalloc(&dout, no * 2)) || (e = cudaMalloc(&f, nq * 4))) { cleanup(); return fail_cuda(h, e, "alloc"); }
+  cudaMemcpyAsync(f, qkv, nq * 4, cudaMemcpyHostToDevice, st);
+  convert_flat_kernel<float, bf16><<<1024, 256, 0, st>>>(f, dq, (long long)nq);
+  if (impl == 0) {
+    e = launch_attention_tc(dq, 3 * kEncH, 0, kEncH, 2 * kEncH, dout, kEncH, segments, T, kEncHeads, 0.125f, st);
+  } else {
+    AttnArgs a;
+    memset(&a, 0, sizeof(a));
+    a.q = dq; a.q_row_stride = 3 * kEncH;
+    a.k = dq + kEncH; a.k_tok_stride = 3 * kEncH; a.k_head_stride = kEncHd; a.k_seg_stride = (long long)T * 3 * kEncH;
+    a.v = dq + 2 * kEncH; a.v_tok_stride = 3 * kEncH; a.v_head_stride = kEncHd; a.v_seg_stride = (long long)T * 3 * kEncH;
+    a.o = dout; a.o_row_stride = kEncH; a.q_len_fixed = T; a.kv_len_fixed = T; a.heads = kEncHeads; a.kv_heads = kEncHeads;
+    a.hd = kEncHd; a.batch = segments; a.max_q = T; a.scale = 0.125f;
+    e = launch_attention_simt<bf16>(a, st);
+  }
+  if (e != cudaSuccess) { cleanup(); return fail_cuda(h, e, "sonic_test_enc_attention launch"); }
+  h->launches += 1;
+  convert_flat_kernel<bf16, float><<<1024, 256, 0, st>>>(dout, f, (long long)no);
+  cudaMemcpyAsync(out, f, no * 4, cudaMemcpyDeviceToHost, st);
+  e = cudaStreamSynchronize(st);
+  cleanup();
+  if (e != cudaSuccess) return fail_cuda(h, e, "sonic_test_enc_attention");
   return 0;
 }
 

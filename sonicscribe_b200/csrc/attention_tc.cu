@@ -1,0 +1,223 @@
+// Non-causal multi-head attention for the audio encoder on tcgen05 (sm_100a): head_dim 64, T = 1500 keys, no mask
+// (GlmAsrAttention, transformers/models/glmasr/modeling_glmasr.py:175-225 via sdpa_attention.py:40-104).
+//
+// One CTA = one (segment, head, 128-query tile).  Per 128-key tile:
+//   S = Q.K^T   tcgen05.mma 128x128x64 (Q, K tiles K-major, TMA 128B swizzle)            -> TMEM cols [0,128)
+//   softmax     4 warps, one query row per thread: tcgen05.ld S, running max / sum in registers (exp2),
+//               P written as bf16 into shared memory in the K-major SW128 operand layout
+//   O_t = P.V   tcgen05.mma 128x64x128, V tile used as an MN-major SW128 B operand (no transpose)  -> TMEM cols [128,192)
+//   O = O*corr + O_t accumulated in registers (exact online softmax, fp32)
+// Two CTAs fit per SM (112 KB smem, 256 TMEM columns each) so one CTA's softmax overlaps the other's MMAs.
+// Warp roles (192 threads): w0 TMA producer, w1 MMA issuer + TMEM owner, w2..5 softmax (TMEM lane quadrant = warp % 4).
+#include "common.cuh"
+#include "kernels.h"
+#include "gemm_tc.h"
+#include "tc_ptx.cuh"
+
+namespace sonic {
+
+static constexpr int AQ = 128, AK = 128, AD = 64;
+static constexpr int kTileBytes = AQ * AD * 2;          // 16 KB: a [128 x 64] bf16 tile
+static constexpr int kKvStages = 2;                     // K tiles are double-buffered; V needs one buffer (it is consumed a
+                                                        // whole softmax later than it is requested)
+static constexpr int kPBytes = AQ * AK * 2;             // 32 KB: P as two K-major SW128 atoms of 64 keys
+static constexpr int kAttnSmem = kTileBytes * (1 + kKvStages + 1) + kPBytes + 1024 + 256;   // ~97 KB -> 2 CTAs / SM
+static constexpr int kAttnTmemCols = 256;
+
+struct AttnTcArgs {
+  bf16* out; long long out_stride;    // out[(seg*T + q) * out_stride + h*64 + d]
+  int T;                              // queries == keys per segment
+  int q_col, k_col, v_col;            // column offsets of head 0 inside the fused QKV row
+  float scale_log2;                   // softmax scale * log2(e)
+};
+
+__global__ void __launch_bounds__(192, 2)
+attention_tc_kernel(const __grid_constant__ CUtensorMap tm, AttnTcArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* sgen = smem_raw + (base - raw);
+  const uint32_t sQ = base, sK = sQ + kTileBytes, sV = sK + kKvStages * kTileBytes, sP = sV + kTileBytes;
+  const uint32_t bars = sP + kPBytes;
+  // barriers: 0 q_full | 1,2 k_full | 3,4 k_empty | 5 v_full | 7 v_empty | 9 s_full | 10 p_full | 11 o_full
+  auto bar = [&](int i) { return bars + 8u * i; };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sgen + (bars - base) + 8 * 12);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * AQ, h = blockIdx.y, seg = blockIdx.z;
+  const int row0 = seg * a.T;
+  const int n_kt = (a.T + AK - 1) / AK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm);
+    for (int i = 0; i < 12; ++i) mbar_init(bar(i), i == 10 ? 128 : 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<kAttnTmemCols>(smem_u32(tmem_slot));
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tS = tmem_base, tO = tmem_base + 128;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(bar(0), kTileBytes);
+      tma_load_2d(sQ, &tm, bar(0), a.q_col + h * AD, row0 + q0);
+      for (int j = 0; j < n_kt; ++j) {
+        const int s = j & 1;
+        const uint32_t ph = (uint32_t)((j >> 1) & 1);
+        mbar_wait(bar(3 + s), ph ^ 1u);
+        mbar_expect_tx(bar(1 + s), kTileBytes);
+        tma_load_2d(sK + s * kTileBytes, &tm, bar(1 + s), a.k_col + h * AD, row0 + j * AK);
+        mbar_wait(bar(7), (uint32_t)(j & 1) ^ 1u);
+        mbar_expect_tx(bar(5), kTileBytes);
+        tma_load_2d(sV, &tm, bar(5), a.v_col + h * AD, row0 + j * AK);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = make_idesc_bf16_major(AQ, AK, 0, 0);     // S: A = Q (K-major), B = K (K-major)
+      constexpr uint32_t idesc_o = make_idesc_bf16_major(AQ, AD, 0, 1);     // O: A = P (K-major), B = V (MN-major)
+      auto issue_s = [&](int j) {
+        const int s = j & 1;
+        mbar_wait(bar(1 + s), (uint32_t)((j >> 1) & 1));
+        tc_fence_after();
+        const uint64_t dq = make_sw128_desc(sQ), dk = make_sw128_desc(sK + s * kTileBytes);
+#pragma unroll
+        for (int k = 0; k < AD / 16; ++k) tc_mma_bf16(tS, dq + (uint64_t)(2 * k), dk + (uint64_t)(2 * k), idesc_s, k != 0 ? 1u : 0u);
+        tc_commit(bar(3 + s));       // K stage free once the MMAs retire
+        tc_commit(bar(9));           // S ready
+      };
+      mbar_wait(bar(0), 0);
+      issue_s(0);
+      for (int j = 0; j < n_kt; ++j) {
+        mbar_wait(bar(10), (uint32_t)(j & 1));                       // P_j in smem, S_j and O_{j-1} drained from TMEM
+        mbar_wait(bar(5), (uint32_t)(j & 1));                        // V_j landed
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < AK / 16; ++k) {
+          const uint64_t dp = make_sw128_desc(sP + (k >> 2) * (kPBytes / 2) + (k & 3) * 32);
+          const uint64_t dv = make_sw128_mn_desc(sV + k * 16 * 128, 16);
+          tc_mma_bf16(tO, dp, dv, idesc_o, k != 0 ? 1u : 0u);
+        }
+        tc_commit(bar(7));           // V buffer free
+        tc_commit(bar(11));          // O_t ready (also: P buffer free)
+        if (j + 1 < n_kt) issue_s(j + 1);
+      }
+    }
+  } else {
+    const int quad = warp & 3;                       // TMEM lanes [32*quad, 32*quad+32)
+    const int r = quad * 32 + lane;                  // query row inside the tile
+    const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
+    float o[AD];
+#pragma unroll
+    for (int d = 0; d < AD; ++d) o[d] = 0.f;
+    float m = -INFINITY, l = 0.f;
+    uint8_t* pP = sgen + (sP - base);
+    for (int j = 0; j < n_kt; ++j) {
+      mbar_wait(bar(9), (uint32_t)(j & 1));
+      tc_fence_after();
+      // pass 1: row max of this tile
+      const int kv_left = a.T - j * AK;              // keys >= kv_left are outside the segment
+      float tmax = -INFINITY;
+#pragma unroll 1
+      for (int c = 0; c < AK / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld32(tS + lane_off + c * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const float s = (c * 32 + i < kv_left) ? __uint_as_float(v[i]) : -INFINITY;
+          tmax = fmaxf(tmax, s);
+        }
+      }
+      const float m_new = fmaxf(m, tmax);
+      const float corr = exp2f((m - m_new) * a.scale_log2);          // m = -inf on the first tile -> 0
+      const float mb = m_new * a.scale_log2;
+      float psum = 0.f;
+      // pass 2: p = exp2(s*scale - m*scale) -> bf16 -> shared memory (K-major SW128: 16 B chunk c8 of row r at (c8 ^ (r & 7)))
+#pragma unroll 1
+      for (int c = 0; c < AK / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld32(tS + lane_off + c * 32, v);
+        tmem_ld_wait();
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          float p0 = (c * 32 + i < kv_left) ? exp2f(fmaf(__uint_as_float(v[i]), a.scale_log2, -mb)) : 0.f;
+          float p1 = (c * 32 + i + 1 < kv_left) ? exp2f(fmaf(__uint_as_float(v[i + 1]), a.scale_log2, -mb)) : 0.f;
+          __nv_bfloat162 pb = __floats2bfloat162_rn(p0, p1);
+          // the denominator sums what the tensor core will actually multiply (bf16-rounded P), like the reference's
+          // softmax-then-cast only up to rounding; keeps rows normalised exactly
+          psum += __low2float(pb) + __high2float(pb);
+          pk[i >> 1] = *reinterpret_cast<uint32_t*>(&pb);
+        }
+        const int atom = c >> 1;                                       // 64 keys per atom
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int chunk = (c & 1) * 4 + q;                           // 16 B chunk index inside the 128 B row
+          uint4 val = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+          *reinterpret_cast<uint4*>(pP + atom * (kPBytes / 2) + r * 128 + ((chunk ^ (r & 7)) << 4)) = val;
+        }
+      }
+      l = l * corr + psum;
+      m = m_new;
+      fence_proxy_async_smem();          // generic-proxy writes of P -> visible to the tensor core (async proxy)
+      tc_fence_before();
+      mbar_arrive(bar(10));
+      // O accumulate
+      mbar_wait(bar(11), (uint32_t)(j & 1));
+      tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < AD / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld32(tO + lane_off + c * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o[c * 32 + i] = fmaf(o[c * 32 + i], corr, __uint_as_float(v[i]));
+      }
+      tc_fence_before();
+    }
+    const int q = q0 + r;
+    if (q < a.T) {
+      const float inv = 1.0f / l;
+      bf16* dst = a.out + (size_t)(row0 + q) * a.out_stride + h * AD;
+#pragma unroll
+      for (int c = 0; c < AD / 8; ++c) {
+        uint4 val;
+        __nv_bfloat162 p0 = __floats2bfloat162_rn(o[8 * c] * inv, o[8 * c + 1] * inv);
+        __nv_bfloat162 p1 = __floats2bfloat162_rn(o[8 * c + 2] * inv, o[8 * c + 3] * inv);
+        __nv_bfloat162 p2 = __floats2bfloat162_rn(o[8 * c + 4] * inv, o[8 * c + 5] * inv);
+        __nv_bfloat162 p3 = __floats2bfloat162_rn(o[8 * c + 6] * inv, o[8 * c + 7] * inv);
+        val.x = *reinterpret_cast<uint32_t*>(&p0); val.y = *reinterpret_cast<uint32_t*>(&p1);
+        val.z = *reinterpret_cast<uint32_t*>(&p2); val.w = *reinterpret_cast<uint32_t*>(&p3);
+        reinterpret_cast<uint4*>(dst)[c] = val;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<kAttnTmemCols>(tmem_base);
+}
+
+cudaError_t attention_tc_configure() {
+  return cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem);
+}
+
+// qkv: fused [segments*T, row_width] bf16 (q | k | v column blocks), out: [segments*T, out_stride]
+cudaError_t launch_attention_tc(const bf16* qkv, int row_width, int q_col, int k_col, int v_col, bf16* out, int out_stride, int segments,
+                                int T, int heads, float scale, cudaStream_t st) {
+  if (segments <= 0) return cudaSuccess;
+  SONIC_CUDA_TRY(gemm_tc_init());
+  CUtensorMap tm;
+  SONIC_CUDA_TRY(make_tensor_map_2d(&tm, qkv, row_width, (long long)segments * T, row_width, AD, AQ));
+  AttnTcArgs a;
+  a.out = out; a.out_stride = out_stride; a.T = T; a.q_col = q_col; a.k_col = k_col; a.v_col = v_col;
+  a.scale_log2 = scale * 1.4426950408889634f;
+  dim3 grid(cdiv(T, AQ), heads, segments);
+  attention_tc_kernel<<<grid, 192, kAttnSmem, st>>>(tm, a);
+  return cudaGetLastError();
+}
+
+}  // namespace sonic

@@ -68,6 +68,7 @@ def load_library():
         "sonic_profile_num_classes": (C.c_int32, []),
         "sonic_profile_class_name": (C.c_char_p, [C.c_int32]),
         "sonic_debug_read": (C.c_int, [H, C.c_char_p, f32p, C.c_size_t, C.POINTER(C.c_size_t)]),
+        "sonic_test_enc_attention": (C.c_int, [H, C.c_int32, f32p, f32p, C.c_int32, C.c_int32]),
         "sonic_test_gemm": (C.c_int, [H, C.c_int32, C.c_int32, f32p, f32p, f32p, f32p, f32p, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
     }
     for name, (res, args) in protos.items():
@@ -259,3 +260,9 @@ class Engine:
         r = np.ascontiguousarray(resid, dtype=np.float32) if resid is not None else None
         self._ck(self.lib.sonic_test_gemm(self.h, impl, 1 if swap else 0, _f32p(A), _f32p(W), _f32p(b), _f32p(r), _f32p(Cm), M, N, K, act))
         return Cm
+
+    def test_enc_attention(self, qkv, segments, T, impl=0):
+        qkv = np.ascontiguousarray(qkv, dtype=np.float32)
+        out = np.zeros((segments * T, 1280), dtype=np.float32)
+        self._ck(self.lib.sonic_test_enc_attention(self.h, impl, _f32p(qkv), _f32p(out), segments, T))
+        return out

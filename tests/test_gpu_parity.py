@@ -255,3 +255,24 @@ def test_full_model_fp32_ids_identical_to_hf(golden_dir):
     assert rel_l2(enc, g["c0_enc_out_sub"]) < 3e-2
     assert got[0][0] == int(g["c0_new_ids"][0])
     eng.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# tcgen05 encoder attention against a float64 softmax attention on the same bf16-rounded inputs
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("segments,T", [(1, 1500), (2, 1500), (3, 200), (1, 128)])
+def test_enc_attention_tc(eng_bf16, segments, T):
+    rng = np.random.default_rng(T + segments)
+    qkv = bf16_round(rng.standard_normal((segments * T, 3840)) * 1.5)
+    got = eng_bf16.test_enc_attention(qkv, segments, T, impl=0)
+    simt = eng_bf16.test_enc_attention(qkv, segments, T, impl=1)
+    for s in range(segments):
+        blk = qkv[s * T:(s + 1) * T].astype(np.float64)
+        for h in (0, 7, 19):
+            q, k, v = (blk[:, o + 64 * h:o + 64 * h + 64] for o in (0, 1280, 2560))
+            sc = q @ k.T / 8.0
+            p = np.exp(sc - sc.max(axis=1, keepdims=True))
+            ref = (p / p.sum(axis=1, keepdims=True)) @ v
+            g = got[s * T:(s + 1) * T, 64 * h:64 * h + 64]
+            assert np.abs(g - ref).max() < 3e-2 * max(1.0, np.abs(ref).max()), (s, h, float(np.abs(g - ref).max()))
+    assert np.abs(got - simt).max() < 5e-2
