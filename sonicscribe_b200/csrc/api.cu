@@ -132,6 +132,13 @@ struct sonic_ctx {
   GreedyState gs{};
   int* h_pinned = nullptr;              // pinned scratch for metadata upload / flags
   size_t h_pinned_ints = 0;
+  float* dattn_ws = nullptr;
+  int* dattn_counters = nullptr;
+  int dattn_max_chunks = 0;
+  int decode_chunks = 1;                // key chunks of 64 the current generate call may reach
+  float* splitk_ws = nullptr;
+  size_t splitk_ws_bytes = 0;
+  int* splitk_counters = nullptr;
   std::map<int, cudaGraphExec_t> decode_graphs;
   std::map<int, int64_t> decode_graph_kernels;
 
@@ -247,6 +254,7 @@ template <typename T>
 struct Engine {
   static int gemm(sonic_ctx* h, GemmArgs g, bool swap, int cls) {
     TAG(cls);
+    g.splitk_ws = h->splitk_ws; g.splitk_ws_bytes = h->splitk_ws_bytes; g.splitk_counters = h->splitk_counters;
     if (std::is_same<T, float>::value) { CKL(launch_gemm_simt<float>(g, h->stream), 1); return 0; }
     if (h->force_simt) { CKL(launch_gemm_simt<bf16>(g, h->stream), 1); return 0; }
     CKL(launch_gemm_tc(g, swap, h->stream), 1);
@@ -355,23 +363,33 @@ struct Engine {
     TAG(prefill ? PC_PRE_OTHER : PC_DEC_OTHER);
     CKL(launch_rmsnorm<T>(x, u, w.rms1, rows, kDecH, kRmsEps, h->stream), 1);
     if (gemm(h, lin(u, kDecH, w.wqkv, kDecH, qkv, kQkvDec, nullptr, rows, kQkvDec), swap, prefill ? PC_PRE_GEMM : PC_DEC_QKV)) return -1;
-    TAG(prefill ? PC_PRE_OTHER : PC_DEC_OTHER);
-    CKL(launch_rope_dec_kv<T>(qkv, h->rope_dec_cos, h->rope_dec_sin, prefill ? h->d_row_seg : nullptr, prefill ? h->d_row_pos : nullptr,
-                              h->gs.ctx_len, kc, vc, rows, kDecHeads, kDecKv, kDecHd, h->max_ctx, h->stream), 1);
-    {
-      AttnArgs a;
-      memset(&a, 0, sizeof(a));
-      a.q = qkv; a.q_row_stride = kQkvDec;
-      a.k = kc; a.k_tok_stride = kDecHd; a.k_head_stride = (long long)h->max_ctx * kDecHd; a.k_seg_stride = (long long)kDecKv * h->max_ctx * kDecHd;
-      a.v = vc; a.v_tok_stride = kDecHd; a.v_head_stride = a.k_head_stride; a.v_seg_stride = a.k_seg_stride;
-      a.o = attn; a.o_row_stride = kDecH;
-      a.q_off = prefill ? h->d_tok_off : nullptr;
-      a.kv_len = h->gs.ctx_len;
-      a.causal = 1; a.decode = prefill ? 0 : 1;
-      a.heads = kDecHeads; a.kv_heads = kDecKv; a.hd = kDecHd; a.batch = B; a.max_q = max_q;
-      a.scale = 0.08838834764831845f;   // 128^-1/2
-      TAG(prefill ? PC_PRE_ATTN : PC_DEC_ATTN);
-      CKL(launch_attention_simt<T>(a, h->stream), 1);
+    if (!prefill && std::is_same<T, bf16>::value && !h->force_simt) {
+      DecodeAttnArgs d;
+      d.qkv = reinterpret_cast<const bf16*>(qkv); d.cos_t = h->rope_dec_cos; d.sin_t = h->rope_dec_sin; d.ctx_len = h->gs.ctx_len;
+      d.kcache = reinterpret_cast<bf16*>(kc); d.vcache = reinterpret_cast<bf16*>(vc); d.out = reinterpret_cast<bf16*>(attn);
+      d.ws = h->dattn_ws; d.counters = h->dattn_counters; d.kv_heads = kDecKv; d.max_ctx = h->max_ctx; d.max_chunks = h->dattn_max_chunks;
+      d.scale = 0.08838834764831845f;
+      TAG(PC_DEC_ATTN);
+      CKL(launch_decode_attn(d, B, h->decode_chunks, h->stream), 1);
+    } else {
+      TAG(prefill ? PC_PRE_OTHER : PC_DEC_OTHER);
+      CKL(launch_rope_dec_kv<T>(qkv, h->rope_dec_cos, h->rope_dec_sin, prefill ? h->d_row_seg : nullptr, prefill ? h->d_row_pos : nullptr,
+                                h->gs.ctx_len, kc, vc, rows, kDecHeads, kDecKv, kDecHd, h->max_ctx, h->stream), 1);
+      {
+        AttnArgs a;
+        memset(&a, 0, sizeof(a));
+        a.q = qkv; a.q_row_stride = kQkvDec;
+        a.k = kc; a.k_tok_stride = kDecHd; a.k_head_stride = (long long)h->max_ctx * kDecHd; a.k_seg_stride = (long long)kDecKv * h->max_ctx * kDecHd;
+        a.v = vc; a.v_tok_stride = kDecHd; a.v_head_stride = a.k_head_stride; a.v_seg_stride = a.k_seg_stride;
+        a.o = attn; a.o_row_stride = kDecH;
+        a.q_off = prefill ? h->d_tok_off : nullptr;
+        a.kv_len = h->gs.ctx_len;
+        a.causal = 1; a.decode = prefill ? 0 : 1;
+        a.heads = kDecHeads; a.kv_heads = kDecKv; a.hd = kDecHd; a.batch = B; a.max_q = max_q;
+        a.scale = 0.08838834764831845f;   // 128^-1/2
+        TAG(prefill ? PC_PRE_ATTN : PC_DEC_ATTN);
+        CKL(launch_attention_simt<T>(a, h->stream), 1);
+      }
     }
     if (gemm(h, lin(attn, kDecH, w.wo, kDecH, x, kDecH, nullptr, rows, kDecH, ACT_NONE, x, kDecH), swap, prefill ? PC_PRE_GEMM : PC_DEC_O)) return -1;
     TAG(prefill ? PC_PRE_OTHER : PC_DEC_OTHER);
@@ -554,6 +572,12 @@ int alloc_all(sonic_ctx* h) {
   const size_t kv = (size_t)c.dec_layers * B * kDecKv * h->max_ctx * kDecHd * E;
   DAZ(h->kcache, kv); DAZ(h->vcache, kv);
   DA(h->logits, (size_t)B * kVocab * 4);
+  h->dattn_max_chunks = (h->max_ctx + 63) / 64;
+  DA(h->dattn_ws, (size_t)B * kDecKv * h->dattn_max_chunks * 4 * 130 * 4);
+  DAZ(h->dattn_counters, (size_t)B * kDecKv * 4);
+  h->splitk_ws_bytes = 24u << 20;
+  DA(h->splitk_ws, h->splitk_ws_bytes);
+  DAZ(h->splitk_counters, 2048 * 4);
   DA(h->d_ids, rows * 4); DA(h->d_audio_src, rows * 4); DA(h->d_row_seg, rows * 4); DA(h->d_row_pos, rows * 4);
   DA(h->d_tok_off, (B + 1) * 4); DA(h->d_last_rows, B * 4);
   DA(h->gs.cur_tok, B * 4); DA(h->gs.ctx_len, B * 4); DA(h->gs.finished, B * 4); DA(h->gs.n_out, B * 4);
@@ -689,13 +713,17 @@ int do_generate(sonic_ctx* h, const int32_t* ids, const int32_t* id_offsets, int
   CK(cudaEventRecord(h->ev[3], st));
 
   // greedy steps 2..max_new: one CUDA graph per (batch, max_new) replayed; no per-token host sync.
+  h->decode_chunks = (max_q + max_new + 63) / 64;
+  if (h->decode_chunks > h->dattn_max_chunks) h->decode_chunks = h->dattn_max_chunks;
   if (max_new > 1 && h->prof_on) {
     for (int step = 1; step < max_new; ++step) {
       rc = dispatch(h, [&] { return Engine<float>::decode_step(h, batch); }, [&] { return Engine<bf16>::decode_step(h, batch); });
       if (rc) return rc;
     }
   } else if (max_new > 1) {
-    const int key = batch * 100000 + max_new;
+    h->decode_chunks = (max_q + max_new + 63) / 64;
+    if (h->decode_chunks > h->dattn_max_chunks) h->decode_chunks = h->dattn_max_chunks;
+    const int key = (batch * 1024 + max_new) * 64 + h->decode_chunks;
     auto it = h->decode_graphs.find(key);
     if (it == h->decode_graphs.end()) {
       const int64_t before = h->launches;
@@ -1000,6 +1028,7 @@ int sonic_test_gemm(sonic_handle h, int32_t impl, int32_t swap, const float* A, 
   memset(&g, 0, sizeof(g));
   g.A = dA; g.lda = K; g.W = dW; g.ldw = K; g.C = dC; g.ldc = outN; g.bias = bias ? dB : nullptr;
   g.resid = resid ? dC : nullptr; g.ldr = outN; g.M = M; g.N = N; g.K = K; g.batch = 1; g.act = act;
+  g.splitk_ws = h->splitk_ws; g.splitk_ws_bytes = h->splitk_ws_bytes; g.splitk_counters = h->splitk_counters;
   e = (impl == 0) ? launch_gemm_tc(g, swap != 0, st) : launch_gemm_simt<bf16>(g, st);
   if (e != cudaSuccess) { cleanup(); return fail_cuda(h, e, "sonic_test_gemm launch"); }
   h->launches += 1;

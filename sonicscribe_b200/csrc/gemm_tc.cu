@@ -25,7 +25,7 @@ static constexpr int UMMA_K = 16;
 template <int BN> struct TcCfg {
   static constexpr int kStageA = BM * BK * 2;                 // 16 KB
   static constexpr int kStageB = BN * BK * 2;
-  static constexpr int kStages = (BN >= 256) ? 4 : (BN >= 128 ? 3 : 4);
+  static constexpr int kStages = (BN >= 256) ? 4 : (BN >= 128 ? 3 : (BN <= 32 ? 6 : 4));   // <= ~110 KB: two CTAs per SM
   static constexpr int kSmem = kStages * (kStageA + kStageB) + 1024 /*align slack*/ + 256 /*barriers*/;
   static constexpr int kTmemCols = BN < 32 ? 32 : BN;
 };
@@ -41,6 +41,11 @@ struct TcEpi {
   int kb_per_tap;
   int tap_col[3];
   int tap_row[3];
+  // split-K (swap mode): gridDim.z CTAs share one output tile; fp32 partials go to `ws`, the CTA that arrives last at
+  // `counters[tile]` sums them in split order (deterministic) and runs the epilogue.
+  int splits;
+  float* ws;
+  int* counters;
 };
 
 template <typename TC>
@@ -85,8 +90,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int a0 = blockIdx.y * BM;            // first row of the 128-row operand (tokens, or features when SWAP)
   const int b0 = blockIdx.x * BN;            // first row of the BN-row operand (features, or tokens when SWAP)
-  const int batch = blockIdx.z;
-  const int num_kb = e.K / BK;
+  const int batch = SWAP ? 0 : blockIdx.z;
+  const int split = SWAP ? blockIdx.z : 0;
+  const int total_kb = e.K / BK;
+  const int kb_begin = SWAP ? (split * total_kb) / e.splits : 0;
+  const int kb_end = SWAP ? ((split + 1) * total_kb) / e.splits : total_kb;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -109,7 +117,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0) {
     if (lane == 0) {
       int s = 0; uint32_t ph = 0;
-      for (int kb = 0; kb < num_kb; ++kb) {
+      for (int kb = kb_begin; kb < kb_end; ++kb) {
         mbar_wait(empty_bar(s), ph ^ 1u);
         mbar_expect_tx(full_bar(s), Cfg::kStageA + Cfg::kStageB);
         const int tap = kb / e.kb_per_tap, kc = kb - tap * e.kb_per_tap;
@@ -123,7 +131,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
       int s = 0; uint32_t ph = 0;
-      for (int kb = 0; kb < num_kb; ++kb) {
+      for (int kb = kb_begin; kb < kb_end; ++kb) {
         mbar_wait(full_bar(s), ph);
         tc_fence_after();
         const uint64_t da = make_sw128_desc(sA + s * Cfg::kStageA);
@@ -131,7 +139,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
         for (int k = 0; k < BK / UMMA_K; ++k) {
           // advancing 16 bf16 = 32 B along K inside the 128 B swizzle atom: +2 in the (addr>>4) field
-          tc_mma_bf16(tmem_base, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+          tc_mma_bf16(tmem_base, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb > kb_begin || k != 0) ? 1u : 0u);
         }
         tc_commit(empty_bar(s));                 // frees the smem stage once these MMAs retire
         if (++s == Cfg::kStages) { s = 0; ph ^= 1u; }
@@ -218,11 +226,49 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int f = a0 + q * 32 + lane;
       const int ntok = min(BN, e.M - b0);
       const float bias = (e.bias && f < e.N) ? e.bias[f] : 0.f;
+      const float* wsum = nullptr;                 // != null: this CTA reduces the split-K partials
+      if (e.splits > 1) {
+        __shared__ int s_last;
+        const int tile = blockIdx.y * gridDim.x + blockIdx.x;
+        float* wsp = e.ws + ((size_t)(tile * e.splits + split) * BN) * BM + q * 32 + lane;
+#pragma unroll 1
+        for (int c = 0; c < BN / 16; ++c) {
+          uint32_t v[16];
+          tmem_ld16(trow + c * 16, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (c * 16 + j < ntok) wsp[(size_t)(c * 16 + j) * BM] = __uint_as_float(v[j]);
+        }
+        __threadfence();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (threadIdx.x == 128) {
+          const int prev = atomicAdd(e.counters + tile, 1);
+          s_last = (prev == e.splits - 1) ? 1 : 0;
+          if (s_last) e.counters[tile] = 0;        // ready for the next launch
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (s_last) {
+          __threadfence();
+          wsum = e.ws + ((size_t)(tile * e.splits) * BN) * BM + q * 32 + lane;
+        }
+      }
+      if (e.splits == 1 || wsum != nullptr) {
 #pragma unroll 1
       for (int c = 0; c < BN / 16; ++c) {
         uint32_t v[16];
-        tmem_ld16(trow + c * 16, v);
-        tmem_ld_wait();
+        if (wsum == nullptr) {
+          tmem_ld16(trow + c * 16, v);
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            float acc = 0.f;
+            if (c * 16 + j < ntok)
+              for (int z = 0; z < e.splits; ++z) acc += __ldcg(wsum + ((size_t)z * BN + c * 16 + j) * BM);
+            v[j] = __float_as_uint(acc);
+          }
+        }
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           const int t = c * 16 + j;
@@ -236,6 +282,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             Cb[(size_t)(b0 + t) * e.ldc + f] = from_f32<TC>(x);
           }
         }
+      }
       }
     }
   }
@@ -312,6 +359,8 @@ cudaError_t gemm_tc_configure() {
   return cudaSuccess;
 }
 
+static constexpr int kMaxTiles = 2048;
+
 int gemm_tc_pick_bn(const GemmArgs& g, bool swap) {
   if (swap) return g.M <= 16 ? 16 : (g.M <= 32 ? 32 : 64);
   return 128;
@@ -327,6 +376,7 @@ cudaError_t launch_gemm_tc(const GemmArgs& g, bool swap, cudaStream_t st) {
   e.bias = g.bias; e.resid = g.resid; e.ldr = g.ldr; e.r_bstride = g.r_bstride;
   e.M = g.M; e.N = g.N; e.K = g.K; e.act = g.act;
   e.kb_per_tap = g.K / BK;
+  e.splits = 1; e.ws = nullptr; e.counters = nullptr;
   for (int t = 0; t < 3; ++t) { e.tap_col[t] = 0; e.tap_row[t] = 0; }
   CUtensorMap ma, mb;
   const int bn = gemm_tc_pick_bn(g, swap);
@@ -356,7 +406,18 @@ cudaError_t launch_gemm_tc(const GemmArgs& g, bool swap, cudaStream_t st) {
   // swap: the 128-row operand is the weight matrix
   SONIC_CUDA_TRY(make_map(&ma, g.W, g.K, g.N, g.ldw, 1, 0, BM));
   SONIC_CUDA_TRY(make_map(&mb, g.A, g.K, g.M, g.lda, g.batch, g.a_bstride, bn));
-  dim3 grid(cdiv(g.M, bn), cdiv(g.N, BM), g.batch);
+  if (g.batch != 1) return cudaErrorInvalidValue;
+  const int tiles = cdiv(g.M, bn) * cdiv(g.N, BM);
+  const int num_kb = g.K / BK;
+  int splits = 296 / tiles;                                     // aim at two resident CTAs per SM
+  if (splits > num_kb / 4) splits = num_kb / 4;
+  if (splits < 1) splits = 1;
+  if (!g.splitk_ws || !g.splitk_counters || tiles > kMaxTiles) splits = 1;
+  while (splits > 1 && (size_t)tiles * splits * bn * BM * 4 > g.splitk_ws_bytes) --splits;
+  e.splits = splits;
+  e.ws = g.splitk_ws;
+  e.counters = g.splitk_counters;
+  dim3 grid(cdiv(g.M, bn), cdiv(g.N, BM), splits);
 #define SWAP_CASE(BN_)                                                                                         \
   case BN_:                                                                                                    \
     return g.out_f32 ? launch_one<BN_, true, float>(ma, mb, e, grid, st) : launch_one<BN_, true, bf16>(ma, mb, e, grid, st);

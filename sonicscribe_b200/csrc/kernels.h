@@ -36,6 +36,9 @@ struct GemmArgs {
   // A points at padded row 0, K = 3*conv_cin, lda = conv_stride*conv_cin (the overlapping-row view the SIMT kernel uses
   // directly; the TMA kernel walks the three taps with a non-overlapping tensor map).  conv_cin = 0 => plain GEMM.
   int conv_cin, conv_stride, conv_rows_pad;
+  // split-K scratch of the tcgen05 decode orientation: fp32 partials + per-tile arrival counters (zero-initialised,
+  // >= 2048 ints).  Null => no split.  One scratch per stream: launches that share it must be stream-ordered.
+  float* splitk_ws; size_t splitk_ws_bytes; int* splitk_counters;
 };
 template <typename T> cudaError_t launch_gemm_simt(const GemmArgs& g, cudaStream_t st);       // gemm_simt.cu
 
@@ -93,5 +96,18 @@ struct AttnArgs {
   float scale;
 };
 template <typename T> cudaError_t launch_attention_simt(const AttnArgs& a, cudaStream_t st);
+
+// ---- decode_attn.cu: fused RoPE + KV append + split-KV attention + combine for one new token per segment (bf16) -----
+struct DecodeAttnArgs {
+  const bf16* qkv;            // [segments, (heads + 2*kv_heads) * 128] un-rotated q | k | v of the new token
+  const float* cos_t; const float* sin_t;   // [max_ctx, 64]
+  const int* ctx_len;         // [segments] tokens already in the cache == position of the new token
+  bf16* kcache; bf16* vcache; // this layer: [segments(max_batch stride)][kv_heads][max_ctx][128]
+  bf16* out;                  // [segments, heads*128]
+  float* ws; int* counters;   // partials [segments*kv_heads][max_chunks][4][130], arrival counters [segments*kv_heads]
+  int kv_heads, max_ctx, max_chunks;
+  float scale;
+};
+cudaError_t launch_decode_attn(const DecodeAttnArgs& a, int batch, int n_chunks, cudaStream_t st);
 
 }  // namespace sonic

@@ -276,3 +276,53 @@ def test_enc_attention_tc(eng_bf16, segments, T):
             g = got[s * T:(s + 1) * T, 64 * h:64 * h + 64]
             assert np.abs(g - ref).max() < 3e-2 * max(1.0, np.abs(ref).max()), (s, h, float(np.abs(g - ref).max()))
     assert np.abs(got - simt).max() < 5e-2
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# decode orientation with split-K (deterministic last-arriver reduction) and the fused decode attention
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("M,N,K,act", [(16, 2048, 2048, 0), (40, 2048, 6144, 0), (8, 12288, 2048, 2), (1, 3072, 2048, 0),
+                                       (64, 2048, 2048, 1), (33, 59264, 2048, 0)])
+def test_gemm_swap_splitk(eng_bf16, M, N, K, act):
+    rng = np.random.default_rng(M + N + K)
+    A = bf16_round(rng.standard_normal((M, K)) * 0.5)
+    W = bf16_round(rng.standard_normal((N, K)) * 0.05)
+    acc = A.astype(np.float64) @ W.astype(np.float64).T
+    resid = None
+    if act == 1:
+        ref = 0.5 * acc * (1 + np.vectorize(__import__("math").erf)(acc / np.sqrt(2)))
+    elif act == 2:
+        g, u = acc[:, 0::2], acc[:, 1::2]
+        ref = g / (1 + np.exp(-g)) * u
+    else:
+        resid = bf16_round(rng.standard_normal((M, N)))
+        ref = acc + resid
+    got = eng_bf16.test_gemm(A, W, resid=resid, act=act, impl=0, swap=True)
+    again = eng_bf16.test_gemm(A, W, resid=resid, act=act, impl=0, swap=True)
+    assert np.array_equal(got, again)                               # split-K reduction order is fixed
+    assert np.abs(got - ref).max() < 2e-2 * max(1.0, np.abs(ref).max())
+
+
+def test_bf16_tensor_core_path_vs_cuda_core_path(tiny_sd, eng_bf16):
+    """Same bf16 weights through (tcgen05 GEMMs + tcgen05 attention + fused decode attention) and through the CUDA-core
+    kernels (SONIC_FORCE_SIMT=1): logits agree to bf16 noise and the greedy ids agree while margins are healthy."""
+    os.environ["SONIC_FORCE_SIMT"] = "1"
+    try:
+        ref_eng = Engine(2, 2, mode="bf16", device=0, max_batch=4, max_prompt=300, max_new=40, debug=True)
+    finally:
+        del os.environ["SONIC_FORCE_SIMT"]
+    ref_eng.load_state_dict(tiny_sd)
+    segs = [mo.synth_audio("speech", 163840, 11), mo.synth_audio("noise", 20480, 3)]
+    prompts = [synthetic_prompt_ids(num_audio_tokens(s.shape[0])) for s in segs]
+    a, ma = eng_bf16.transcribe_ids(segs, prompts, 24, want_margins=True)
+    la = eng_bf16.debug_read("first_logits", 2 * 59264)
+    b, mb = ref_eng.transcribe_ids(segs, prompts, 24, want_margins=True)
+    lb = ref_eng.debug_read("first_logits", 2 * 59264)
+    ref_eng.close()
+    assert rel_l2(la, lb) < 2e-2
+    for s in range(2):
+        for t, (x, y) in enumerate(zip(a[s], b[s])):
+            if x != y:
+                assert min(ma[s][t], mb[s][t]) < 0.2, (s, t, ma[s][t], mb[s][t])
+                break
+        assert a[s][:4] == b[s][:4]
