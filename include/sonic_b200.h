@@ -119,6 +119,9 @@ SONIC_API int sonic_debug_read(sonic_handle h, const char* name, float* out, siz
 SONIC_API int sonic_test_gemm(sonic_handle h, int32_t impl, int32_t swap, const float* A, const float* W, const float* bias,
                     const float* resid, float* C, int32_t M, int32_t N, int32_t K, int32_t act);
 
+/* back-to-back launches of one tcgen05 GEMM shape (zero-filled bf16 operands, weights rotated through > 126 MB so L2
+ * never holds them); returns the average device time per launch in microseconds (CUDA events on the handle's stream). */
+SONIC_API int sonic_bench_gemm(sonic_handle h, int32_t swap, int32_t M, int32_t N, int32_t K, int32_t act, int32_t iters, float* avg_us);
 /* encoder attention alone (20 heads x 64, non-causal, scale 1/8) on a fused [segments*T, 3840] q|k|v buffer (host float32,
  * rounded to bf16 on the device): impl 0 = tcgen05 kernel, impl 1 = CUDA-core cross-check.  out: [segments*T, 1280]. */
 SONIC_API int sonic_test_enc_attention(sonic_handle h, int32_t impl, const float* qkv, float* out, int32_t segments, int32_t T);

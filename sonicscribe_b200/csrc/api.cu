@@ -407,7 +407,7 @@ struct Engine {
     g.out_f32 = 1;
     if (gemm(h, g, true, PC_DEC_LMHEAD)) return -1;
     TAG(PC_DEC_OTHER);
-    CKL(launch_greedy_pick(h->logits, B, kVocab, h->gs, advance, h->stream), 2);
+    CKL(launch_greedy_pick(h->logits, B, kVocab, h->gs, advance, h->stream), 1);
     return 0;
   }
 
@@ -582,7 +582,8 @@ int alloc_all(sonic_ctx* h) {
   DA(h->d_tok_off, (B + 1) * 4); DA(h->d_last_rows, B * 4);
   DA(h->gs.cur_tok, B * 4); DA(h->gs.ctx_len, B * 4); DA(h->gs.finished, B * 4); DA(h->gs.n_out, B * 4);
   DA(h->gs.out_ids, (size_t)B * c.max_new * 4); DA(h->gs.margins, (size_t)B * c.max_new * 4);
-  DA(h->gs.step, 4); DA(h->gs.n_unfinished, 4);
+  DA(h->gs.step, 4); DA(h->gs.n_unfinished, 4); DAZ(h->gs.step_arrivals, 4);
+  DA(h->gs.pick_partials, greedy_pick_scratch_bytes(B)); DAZ(h->gs.pick_counters, (B + 1) * 4);
   h->gs.eos[0] = 59246; h->gs.eos[1] = 59253; h->gs.eos[2] = 59255; h->gs.n_eos = 3;
   h->h_pinned_ints = rows * 4 + 8 * (size_t)B + 64;
   CK(cudaMallocHost(&h->h_pinned, h->h_pinned_ints * sizeof(int)));
@@ -1037,6 +1038,55 @@ int sonic_test_gemm(sonic_handle h, int32_t impl, int32_t swap, const float* A, 
   e = cudaStreamSynchronize(st);
   cleanup();
   if (e != cudaSuccess) return fail_cuda(h, e, "sonic_test_gemm");
+  return 0;
+}
+
+int sonic_bench_gemm(sonic_handle h, int32_t swap, int32_t M, int32_t N, int32_t K, int32_t act, int32_t iters, float* avg_us) {
+  ENTER();
+  bf16 *dA = nullptr, *dW = nullptr, *dC = nullptr;
+  cudaStream_t st = h->stream;
+  const int outN = (act == ACT_SWIGLU) ? N / 2 : N;
+  auto cleanup = [&]() { cudaFree(dA); cudaFree(dW); cudaFree(dC); };
+  cudaError_t e;
+  // several weight copies so that consecutive launches never find their weights in the 126 MB L2
+  const size_t wbytes = (size_t)N * K * 2;
+  int copies = (int)((400u << 20) / wbytes) + 1;
+  if (copies > 64) copies = 64;
+  if ((e = cudaMalloc(&dA, (size_t)M * K * 2)) || (e = cudaMalloc(&dW, wbytes * copies)) || (e = cudaMalloc(&dC, (size_t)M * outN * 2))) {
+    cleanup();
+    return fail_cuda(h, e, "sonic_bench_gemm alloc");
+  }
+  cudaMemsetAsync(dA, 0, (size_t)M * K * 2, st);
+  cudaMemsetAsync(dW, 0, wbytes * copies, st);
+  GemmArgs g;
+  memset(&g, 0, sizeof(g));
+  g.A = dA; g.lda = K; g.ldw = K; g.C = dC; g.ldc = outN; g.M = M; g.N = N; g.K = K; g.batch = 1; g.act = act;
+  g.splitk_ws = h->splitk_ws; g.splitk_ws_bytes = h->splitk_ws_bytes; g.splitk_counters = h->splitk_counters;
+  // capture the launches into a CUDA graph so the measurement holds no host-side launch or tensor-map-encode time
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  if ((e = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal)) != cudaSuccess) { cleanup(); return fail_cuda(h, e, "capture"); }
+  cudaError_t le = cudaSuccess;
+  for (int it = 0; it < iters && le == cudaSuccess; ++it) {
+    g.W = dW + (size_t)(it % copies) * N * K;
+    le = launch_gemm_tc(g, swap != 0, st);
+  }
+  e = cudaStreamEndCapture(st, &graph);
+  if (le != cudaSuccess || e != cudaSuccess) { if (graph) cudaGraphDestroy(graph); cleanup(); return fail_cuda(h, le != cudaSuccess ? le : e, "sonic_bench_gemm launch"); }
+  if ((e = cudaGraphInstantiate(&exec, graph, 0)) != cudaSuccess) { cudaGraphDestroy(graph); cleanup(); return fail_cuda(h, e, "instantiate"); }
+  cudaGraphLaunch(exec, st);                       // warm-up
+  cudaEventRecord(h->ev_user[0], st);
+  cudaGraphLaunch(exec, st);
+  cudaEventRecord(h->ev_user[1], st);
+  e = cudaEventSynchronize(h->ev_user[1]);
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, h->ev_user[0], h->ev_user[1]);
+  cudaGraphExecDestroy(exec);
+  cudaGraphDestroy(graph);
+  cleanup();
+  if (e != cudaSuccess) return fail_cuda(h, e, "sonic_bench_gemm");
+  *avg_us = ms * 1000.f / iters;
+  h->launches += 2 * iters;
   return 0;
 }
 

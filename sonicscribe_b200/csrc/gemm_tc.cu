@@ -11,6 +11,7 @@
 // decoder (transformers/models/glmasr/modeling_glmasr.py:175-349, transformers/models/llama/modeling_llama.py:171-289).
 // Warp roles (256 threads): w0 TMA producer, w1 MMA issuer, w2 TMEM allocator, w4-7 epilogue (TMEM lane quadrants).
 #include <cuda.h>
+#include <stdlib.h>
 #include "common.cuh"
 #include "kernels.h"
 #include "gemm_tc.h"
@@ -261,13 +262,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           tmem_ld16(trow + c * 16, v);
           tmem_ld_wait();
         } else {
+          // sum the partials in split order; 64 independent L2 loads are in flight per thread (latency-bound otherwise)
+          float acc[16];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            float acc = 0.f;
-            if (c * 16 + j < ntok)
-              for (int z = 0; z < e.splits; ++z) acc += __ldcg(wsum + ((size_t)z * BN + c * 16 + j) * BM);
-            v[j] = __float_as_uint(acc);
+          for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+#pragma unroll 1
+          for (int z0 = 0; z0 < e.splits; z0 += 4) {
+            float tmp[4][16];
+#pragma unroll
+            for (int zz = 0; zz < 4; ++zz)
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                tmp[zz][j] = (z0 + zz < e.splits && c * 16 + j < ntok) ? __ldcg(wsum + ((size_t)(z0 + zz) * BN + c * 16 + j) * BM) : 0.f;
+#pragma unroll
+            for (int zz = 0; zz < 4; ++zz)
+#pragma unroll
+              for (int j = 0; j < 16; ++j) acc[j] += tmp[zz][j];
           }
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(acc[j]);
         }
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
@@ -409,9 +422,11 @@ cudaError_t launch_gemm_tc(const GemmArgs& g, bool swap, cudaStream_t st) {
   if (g.batch != 1) return cudaErrorInvalidValue;
   const int tiles = cdiv(g.M, bn) * cdiv(g.N, BM);
   const int num_kb = g.K / BK;
-  int splits = 296 / tiles;                                     // aim at two resident CTAs per SM
+  int splits = 128 / tiles;                                     // measured optimum: ~100-150 CTAs streaming (bench_gemm.py)
   if (splits > num_kb / 4) splits = num_kb / 4;
+  if (splits > g.K / (8 * g.M)) splits = g.K / (8 * g.M);      // keep the fp32 partial traffic well below the weight bytes
   if (splits < 1) splits = 1;
+  if (const char* fs = getenv("SONIC_SPLITS")) { const int v = atoi(fs); if (v >= 1 && v <= num_kb) splits = v; }   // tuning override
   if (!g.splitk_ws || !g.splitk_counters || tiles > kMaxTiles) splits = 1;
   while (splits > 1 && (size_t)tiles * splits * bn * BM * 4 > g.splitk_ws_bytes) --splits;
   e.splits = splits;

@@ -74,10 +74,14 @@ struct GreedyState {
   float* margins;    // [B][max_new]
   int* step;         // [1]
   int* n_unfinished; // [1]
+  int* step_arrivals;   // [1] zero-initialised
+  void* pick_partials;  // greedy_pick_scratch_bytes(max_batch)
+  int* pick_counters;   // [max_batch + 1] zero-initialised
   int max_new;
   int eos[4];
   int n_eos;
 };
+size_t greedy_pick_scratch_bytes(int max_batch);
 cudaError_t launch_greedy_pick(const float* logits, int B, int V, GreedyState gs, int advance_ctx, cudaStream_t st);
 void rope_table_host(float* cos_t, float* sin_t, int positions, int rot_dim, float theta);
 

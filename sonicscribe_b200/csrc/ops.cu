@@ -171,56 +171,84 @@ cudaError_t launch_embed_next(const int* cur_tok, const T* table, T* x, int rows
 }
 
 // ---- greedy pick (generation/utils.py:2793-2805): argmax of fp32 logits, first index on ties; EOS bookkeeping ---------
-__global__ void __launch_bounds__(1024) greedy_pick_kernel(const float* __restrict__ logits, int V, GreedyState gs, int advance_ctx) {
-  const int b = blockIdx.x;
+// grid (kPickSlices, B): every CTA scans one slice of the vocabulary; the CTA arriving last at the segment's counter merges
+// the slice results in slice order and does the bookkeeping (also advances the step counter once per launch).
+static constexpr int kPickSlices = 16;
+struct PickPartial { float best, second; int idx; int pad; };
+
+__device__ __forceinline__ void pick_merge(float& mb, float& ms, int& mi, float ob, float os, int oi) {
+  if (ob > mb || (ob == mb && oi < mi)) { ms = fmaxf(fmaxf(ms, os), mb); mb = ob; mi = oi; }
+  else { ms = fmaxf(ms, ob); }
+}
+
+__global__ void __launch_bounds__(256) greedy_pick_kernel(const float* __restrict__ logits, int V, GreedyState gs, int advance_ctx,
+                                                          PickPartial* __restrict__ partials, int* __restrict__ counters) {
+  const int b = blockIdx.y, slice = blockIdx.x;
+  const int per = (V + kPickSlices - 1) / kPickSlices;
+  const int lo = slice * per, hi = min(V, lo + per);
   const float* l = logits + (size_t)b * V;
   float best = -INFINITY, second = -INFINITY;
   int bi = 0x7fffffff;
-  for (int i = threadIdx.x; i < V; i += blockDim.x) {
+  for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) {
     const float v = l[i];
     if (v > best) { second = best; best = v; bi = i; }
     else if (v > second) second = v;
   }
-  __shared__ float s_best[1024], s_second[1024];
-  __shared__ int s_idx[1024];
-  s_best[threadIdx.x] = best; s_second[threadIdx.x] = second; s_idx[threadIdx.x] = bi;
+  // warp then block merge
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, o), os = __shfl_xor_sync(0xffffffffu, second, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    pick_merge(best, second, bi, ob, os, oi);
+  }
+  __shared__ float s_best[8], s_second[8];
+  __shared__ int s_idx[8], s_last;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) { s_best[warp] = best; s_second[warp] = second; s_idx[warp] = bi; }
   __syncthreads();
-  for (int o = 512; o > 0; o >>= 1) {
-    if ((int)threadIdx.x < o) {
-      const float ob = s_best[threadIdx.x + o], os = s_second[threadIdx.x + o];
-      const int oi = s_idx[threadIdx.x + o];
-      float mb = s_best[threadIdx.x], ms = s_second[threadIdx.x];
-      int mi = s_idx[threadIdx.x];
-      if (ob > mb || (ob == mb && oi < mi)) { ms = fmaxf(fmaxf(ms, os), mb); mb = ob; mi = oi; }
-      else { ms = fmaxf(ms, ob); }
-      s_best[threadIdx.x] = mb; s_second[threadIdx.x] = ms; s_idx[threadIdx.x] = mi;
-    }
-    __syncthreads();
-  }
   if (threadIdx.x == 0) {
-    const int tok = s_idx[0];
-    const int step = *gs.step;
-    if (advance_ctx) gs.ctx_len[b] += 1;                 // the token just consumed is now in the cache
-    if (!gs.finished[b]) {
-      gs.out_ids[(size_t)b * gs.max_new + step] = tok;
-      if (gs.margins) gs.margins[(size_t)b * gs.max_new + step] = s_best[0] - s_second[0];
-      gs.n_out[b] = step + 1;
-      bool eos = false;
-      for (int e = 0; e < gs.n_eos; ++e) eos |= (tok == gs.eos[e]);
-      if (eos || step + 1 >= gs.max_new) { gs.finished[b] = 1; atomicSub(gs.n_unfinished, 1); }
-    }
-    gs.cur_tok[b] = tok;
+    for (int w = 1; w < 8; ++w) pick_merge(best, second, bi, s_best[w], s_second[w], s_idx[w]);
+    PickPartial p; p.best = best; p.second = second; p.idx = bi; p.pad = 0;
+    partials[b * kPickSlices + slice] = p;
+    __threadfence();
+    const int prev = atomicAdd(counters + b, 1);
+    s_last = (prev == kPickSlices - 1);
+    if (s_last) counters[b] = 0;
   }
+  __syncthreads();
+  if (!s_last || threadIdx.x != 0) return;
+  __threadfence();
+  float mb = -INFINITY, ms = -INFINITY;
+  int mi = 0x7fffffff;
+  for (int s = 0; s < kPickSlices; ++s) {
+    const volatile PickPartial* p = partials + b * kPickSlices + s;
+    pick_merge(mb, ms, mi, p->best, p->second, p->idx);
+  }
+  const int tok = mi;
+  const int step = *gs.step;
+  if (advance_ctx) gs.ctx_len[b] += 1;                 // the token just consumed is now in the cache
+  if (!gs.finished[b]) {
+    gs.out_ids[(size_t)b * gs.max_new + step] = tok;
+    if (gs.margins) gs.margins[(size_t)b * gs.max_new + step] = mb - ms;
+    gs.n_out[b] = step + 1;
+    bool eos = false;
+    for (int e = 0; e < gs.n_eos; ++e) eos |= (tok == gs.eos[e]);
+    if (eos || step + 1 >= gs.max_new) { gs.finished[b] = 1; atomicSub(gs.n_unfinished, 1); }
+  }
+  gs.cur_tok[b] = tok;
+  // the segment finishing last in this launch advances the shared step counter
+  __threadfence();
+  const int arrived = atomicAdd(gs.step_arrivals, 1);
+  if (arrived == (int)gridDim.y - 1) { *gs.step_arrivals = 0; *gs.step = step + 1; }
 }
-__global__ void greedy_step_inc_kernel(int* step) { *step += 1; }
 
 cudaError_t launch_greedy_pick(const float* logits, int B, int V, GreedyState gs, int advance_ctx, cudaStream_t st) {
   if (B <= 0) return cudaSuccess;
-  greedy_pick_kernel<<<B, 1024, 0, st>>>(logits, V, gs, advance_ctx);
-  SONIC_LAUNCH_CHECK();
-  greedy_step_inc_kernel<<<1, 1, 0, st>>>(gs.step);
+  greedy_pick_kernel<<<dim3(kPickSlices, B), 256, 0, st>>>(logits, V, gs, advance_ctx, reinterpret_cast<PickPartial*>(gs.pick_partials),
+                                                          gs.pick_counters);
   return cudaGetLastError();
 }
+size_t greedy_pick_scratch_bytes(int max_batch) { return (size_t)max_batch * kPickSlices * sizeof(PickPartial); }
 
 #define INST(T)                                                                                                           \
   template cudaError_t launch_layernorm<T>(const T*, T*, const float*, const float*, int, int, float, cudaStream_t);       \

@@ -69,6 +69,7 @@ def load_library():
         "sonic_profile_class_name": (C.c_char_p, [C.c_int32]),
         "sonic_debug_read": (C.c_int, [H, C.c_char_p, f32p, C.c_size_t, C.POINTER(C.c_size_t)]),
         "sonic_test_enc_attention": (C.c_int, [H, C.c_int32, f32p, f32p, C.c_int32, C.c_int32]),
+        "sonic_bench_gemm": (C.c_int, [H, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, f32p]),
         "sonic_test_gemm": (C.c_int, [H, C.c_int32, C.c_int32, f32p, f32p, f32p, f32p, f32p, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
     }
     for name, (res, args) in protos.items():
@@ -266,3 +267,8 @@ class Engine:
         out = np.zeros((segments * T, 1280), dtype=np.float32)
         self._ck(self.lib.sonic_test_enc_attention(self.h, impl, _f32p(qkv), _f32p(out), segments, T))
         return out
+
+    def bench_gemm(self, M, N, K, swap=False, act=0, iters=50) -> float:
+        us = C.c_float()
+        self._ck(self.lib.sonic_bench_gemm(self.h, 1 if swap else 0, M, N, K, act, iters, C.byref(us)))
+        return float(us.value)
