@@ -6,8 +6,8 @@ shapes = {"qkv": (3072, 2048, 0), "o": (2048, 2048, 0), "gateup": (12288, 2048, 
 for M in (16, 64):
     for name, (N, K, act) in shapes.items():
         res = []
-        for sp in ([1, 2, 4, 8, 16] if name != "lmhead" else [1]):
-            os.environ["SONIC_SPLITS"] = str(sp)
+        for sp in ([0, 1, 2, 4, 8, 16] if name != "lmhead" else [0]):
+            os.environ["SONIC_SPLITS"] = str(sp)   # 0 = library heuristic
             us = eng.bench_gemm(M, N, K, swap=True, act=act, iters=40)
             res.append(f"s{sp}:{us:6.1f}us({N*K*2/us/1e3:5.0f}GB/s)")
         print(f"M={M:3d} {name:7s}", " ".join(res), flush=True)

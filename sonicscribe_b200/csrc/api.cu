@@ -96,6 +96,8 @@ struct sonic_ctx {
   size_t esz = 2;                       // activation / weight element size
   bool is_f32 = false;
   bool force_simt = false;
+  bool use_pdl = true;                  // SONIC_NO_PDL=1 disables programmatic dependent launch in the decode step
+  bool pdl_now = false;
 
   // weights
   void *conv1_w = nullptr, *conv2_w = nullptr, *proj1_w = nullptr, *proj2_w = nullptr, *embed = nullptr, *lm_head = nullptr;
@@ -255,6 +257,7 @@ struct Engine {
   static int gemm(sonic_ctx* h, GemmArgs g, bool swap, int cls) {
     TAG(cls);
     g.splitk_ws = h->splitk_ws; g.splitk_ws_bytes = h->splitk_ws_bytes; g.splitk_counters = h->splitk_counters;
+    g.pdl = h->pdl_now ? 1 : 0;
     if (std::is_same<T, float>::value) { CKL(launch_gemm_simt<float>(g, h->stream), 1); return 0; }
     if (h->force_simt) { CKL(launch_gemm_simt<bf16>(g, h->stream), 1); return 0; }
     CKL(launch_gemm_tc(g, swap, h->stream), 1);
@@ -361,7 +364,7 @@ struct Engine {
     T* vc = reinterpret_cast<T*>(h->vcache) + (size_t)l * layer_kv;
     const bool swap = !prefill;
     TAG(prefill ? PC_PRE_OTHER : PC_DEC_OTHER);
-    CKL(launch_rmsnorm<T>(x, u, w.rms1, rows, kDecH, kRmsEps, h->stream), 1);
+    CKL(launch_rmsnorm<T>(x, u, w.rms1, rows, kDecH, kRmsEps, h->stream, h->pdl_now), 1);
     if (gemm(h, lin(u, kDecH, w.wqkv, kDecH, qkv, kQkvDec, nullptr, rows, kQkvDec), swap, prefill ? PC_PRE_GEMM : PC_DEC_QKV)) return -1;
     if (!prefill && std::is_same<T, bf16>::value && !h->force_simt) {
       DecodeAttnArgs d;
@@ -370,7 +373,7 @@ struct Engine {
       d.ws = h->dattn_ws; d.counters = h->dattn_counters; d.kv_heads = kDecKv; d.max_ctx = h->max_ctx; d.max_chunks = h->dattn_max_chunks;
       d.scale = 0.08838834764831845f;
       TAG(PC_DEC_ATTN);
-      CKL(launch_decode_attn(d, B, h->decode_chunks, h->stream), 1);
+      CKL(launch_decode_attn(d, B, h->decode_chunks, h->stream, h->pdl_now), 1);
     } else {
       TAG(prefill ? PC_PRE_OTHER : PC_DEC_OTHER);
       CKL(launch_rope_dec_kv<T>(qkv, h->rope_dec_cos, h->rope_dec_sin, prefill ? h->d_row_seg : nullptr, prefill ? h->d_row_pos : nullptr,
@@ -393,7 +396,7 @@ struct Engine {
     }
     if (gemm(h, lin(attn, kDecH, w.wo, kDecH, x, kDecH, nullptr, rows, kDecH, ACT_NONE, x, kDecH), swap, prefill ? PC_PRE_GEMM : PC_DEC_O)) return -1;
     TAG(prefill ? PC_PRE_OTHER : PC_DEC_OTHER);
-    CKL(launch_rmsnorm<T>(x, u, w.rms2, rows, kDecH, kRmsEps, h->stream), 1);
+    CKL(launch_rmsnorm<T>(x, u, w.rms2, rows, kDecH, kRmsEps, h->stream, h->pdl_now), 1);
     if (gemm(h, lin(u, kDecH, w.wgu, kDecH, act, kDecInter, nullptr, rows, 2 * kDecInter, ACT_SWIGLU), swap, prefill ? PC_PRE_GEMM : PC_DEC_GU)) return -1;
     if (gemm(h, lin(act, kDecInter, w.wdown, kDecInter, x, kDecH, nullptr, rows, kDecH, ACT_NONE, x, kDecH), swap, prefill ? PC_PRE_GEMM : PC_DEC_DOWN)) return -1;
     return 0;
@@ -402,12 +405,12 @@ struct Engine {
   static int lm_head(sonic_ctx* h, int B, const int* rows_idx, int advance) {
     T *x = reinterpret_cast<T*>(h->dx), *u = reinterpret_cast<T*>(h->du);
     TAG(PC_DEC_OTHER);
-    CKL(launch_rmsnorm_rows<T>(x, rows_idx, u, h->final_norm, B, kDecH, kRmsEps, h->stream), 1);
+    CKL(launch_rmsnorm_rows<T>(x, rows_idx, u, h->final_norm, B, kDecH, kRmsEps, h->stream, h->pdl_now), 1);
     GemmArgs g = lin(u, kDecH, h->lm_head, kDecH, h->logits, kVocab, nullptr, B, kVocab);
     g.out_f32 = 1;
     if (gemm(h, g, true, PC_DEC_LMHEAD)) return -1;
     TAG(PC_DEC_OTHER);
-    CKL(launch_greedy_pick(h->logits, B, kVocab, h->gs, advance, h->stream), 1);
+    CKL(launch_greedy_pick(h->logits, B, kVocab, h->gs, advance, h->stream, h->pdl_now), 1);
     return 0;
   }
 
@@ -433,10 +436,19 @@ struct Engine {
   static int decode_step(sonic_ctx* h, int B) {
     T* x = reinterpret_cast<T*>(h->dx);
     TAG(PC_DEC_OTHER);
-    CKL(launch_embed_next<T>(h->gs.cur_tok, reinterpret_cast<const T*>(h->embed), x, B, kDecH, h->stream), 1);
-    for (int l = 0; l < h->cfg.dec_layers; ++l)
-      if (dec_layer(h, l, B, B, false, 1)) return -1;
-    return lm_head(h, B, nullptr, 1);
+    // every kernel of the step is launched with programmatic stream serialization (bf16 tensor-core path only): the next
+    // kernel's CTAs are scheduled, and its weight tiles are in flight, while the current one drains
+    h->pdl_now = h->use_pdl && std::is_same<T, bf16>::value && !h->force_simt;
+    int rc = 0;
+    do {
+      cudaError_t _e = launch_embed_next<T>(h->gs.cur_tok, reinterpret_cast<const T*>(h->embed), x, B, kDecH, h->stream, h->pdl_now);
+      if (_e != cudaSuccess) { h->pdl_now = false; return fail_cuda(h, _e, "launch_embed_next"); }
+      h->launches += 1;
+      for (int l = 0; l < h->cfg.dec_layers && rc == 0; ++l) rc = dec_layer(h, l, B, B, false, 1);
+      if (rc == 0) rc = lm_head(h, B, nullptr, 1);
+    } while (0);
+    h->pdl_now = false;
+    return rc;
   }
 };
 
@@ -823,6 +835,8 @@ int sonic_create(const sonic_config* cfg, sonic_handle* out) {
   h->esz = h->is_f32 ? 4 : 2;
   const char* fs = getenv("SONIC_FORCE_SIMT");
   h->force_simt = fs && fs[0] == '1';
+  const char* np = getenv("SONIC_NO_PDL");
+  h->use_pdl = !(np && np[0] == '1');
   auto bail = [&](int) { g_last_error = h->err; for (void* p : h->allocs) cudaFree(p); delete h; return -1; };
   if (cudaSetDevice(cfg->device) != cudaSuccess) { h->err = "cudaSetDevice failed"; return bail(0); }
   if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { h->err = "cudaStreamCreate failed"; return bail(0); }

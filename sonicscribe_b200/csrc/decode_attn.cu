@@ -23,6 +23,8 @@ decode_attn_kernel(DecodeAttnArgs a) {
   __shared__ float sM[DG], sL[DG];
   __shared__ int s_last;
 
+  pdl_launch_dependents();
+  pdl_wait();
   const int chunk = blockIdx.x, kvh = blockIdx.y, seg = blockIdx.z;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int pos = a.ctx_len[seg];                       // position of the token being decoded
@@ -148,12 +150,11 @@ decode_attn_kernel(DecodeAttnArgs a) {
   }
 }
 
-cudaError_t launch_decode_attn(const DecodeAttnArgs& a, int batch, int n_chunks, cudaStream_t st) {
+cudaError_t launch_decode_attn(const DecodeAttnArgs& a, int batch, int n_chunks, cudaStream_t st, bool pdl) {
   if (batch <= 0) return cudaSuccess;
   if (n_chunks < 1 || n_chunks > a.max_chunks) return cudaErrorInvalidValue;
   dim3 grid(n_chunks, a.kv_heads, batch);
-  decode_attn_kernel<<<grid, 128, 0, st>>>(a);
-  return cudaGetLastError();
+  return launch_ex(decode_attn_kernel, grid, dim3(128), 0, st, pdl, a);
 }
 
 }  // namespace sonic

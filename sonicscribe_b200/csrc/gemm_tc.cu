@@ -26,8 +26,12 @@ static constexpr int UMMA_K = 16;
 template <int BN> struct TcCfg {
   static constexpr int kStageA = BM * BK * 2;                 // 16 KB
   static constexpr int kStageB = BN * BK * 2;
-  static constexpr int kStages = (BN >= 256) ? 4 : (BN >= 128 ? 3 : (BN <= 32 ? 6 : 4));   // <= ~110 KB: two CTAs per SM
-  static constexpr int kSmem = kStages * (kStageA + kStageB) + 1024 /*align slack*/ + 256 /*barriers*/;
+  // stage count is a launch-time choice: "two CTAs per SM" (<= ~110 KB each) when the grid has more CTAs than SMs, otherwise
+  // the whole 227 KB of one SM so a lone CTA keeps as many TMA loads in flight as possible (HBM latency ~2 us per box)
+  static constexpr int kStagesDual = (BN >= 128 ? 3 : (BN <= 32 ? 6 : 4));
+  static constexpr int kMaxStages = 12;
+  static constexpr int kStagesSolo = ((227 * 1024 - 1024 - 512) / (kStageA + kStageB)) > kMaxStages ? kMaxStages : ((227 * 1024 - 1024 - 512) / (kStageA + kStageB));
+  static constexpr int smem_bytes(int stages) { return stages * (kStageA + kStageB) + 1024 /*align slack*/ + 512 /*barriers*/; }
   static constexpr int kTmemCols = BN < 32 ? 32 : BN;
 };
 
@@ -47,6 +51,7 @@ struct TcEpi {
   int splits;
   float* ws;
   int* counters;
+  int stages;             // shared-memory ring depth chosen at launch
 };
 
 template <typename TC>
@@ -74,19 +79,20 @@ __device__ __forceinline__ void store_chunk32<float>(float* dst, const float (&x
 }
 
 template <int BN, bool SWAP, typename TC>
-__global__ void __launch_bounds__(256, (BN <= 128 ? 2 : 1))
+__global__ void __launch_bounds__(256, 2)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TcEpi e) {
   using Cfg = TcCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;                // SWIZZLE_128B tiles need 1024 B alignment
   uint8_t* sgen = smem_raw + (base - raw);
-  const uint32_t sA = base, sB = base + Cfg::kStages * Cfg::kStageA;
-  const uint32_t bars = sB + Cfg::kStages * Cfg::kStageB;     // full[kStages], empty[kStages], tmem_full, tmem slot
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sgen + Cfg::kStages * (Cfg::kStageA + Cfg::kStageB) + 8 * (2 * Cfg::kStages + 1));
+  const int kStages = e.stages;
+  const uint32_t sA = base, sB = base + kStages * Cfg::kStageA;
+  const uint32_t bars = sB + kStages * Cfg::kStageB;          // full[kStages], empty[kStages], tmem_full, tmem slot
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sgen + kStages * (Cfg::kStageA + Cfg::kStageB) + 8 * (2 * kStages + 1));
   auto full_bar = [&](int s) { return bars + 8u * s; };
-  auto empty_bar = [&](int s) { return bars + 8u * (Cfg::kStages + s); };
-  const uint32_t tmem_full_bar = bars + 8u * (2 * Cfg::kStages);
+  auto empty_bar = [&](int s) { return bars + 8u * (kStages + s); };
+  const uint32_t tmem_full_bar = bars + 8u * (2 * kStages);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int a0 = blockIdx.y * BM;            // first row of the 128-row operand (tokens, or features when SWAP)
@@ -102,7 +108,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tma_prefetch_desc(&tmB);
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     mbar_init(tmem_full_bar, 1);
     fence_barrier_init();
   }
@@ -115,17 +121,35 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  pdl_launch_dependents();
   if (warp == 0) {
     if (lane == 0) {
       int s = 0; uint32_t ph = 0;
-      for (int kb = kb_begin; kb < kb_end; ++kb) {
+      int kb = kb_begin;
+      if constexpr (SWAP) {
+        // the weight operand does not depend on the predecessor kernel: stream the first ring of weight tiles before the
+        // dependency wait, then add the activation tiles of those stages
+        const int pre = min(kb_end - kb_begin, kStages);
+        for (int i = 0; i < pre; ++i) {
+          mbar_expect_tx(full_bar(i), Cfg::kStageA + Cfg::kStageB);
+          tma_load_3d(sA + i * Cfg::kStageA, &tmA, full_bar(i), (kb_begin + i) * BK, a0, 0);
+        }
+        pdl_wait();
+        for (int i = 0; i < pre; ++i) tma_load_3d(sB + i * Cfg::kStageB, &tmB, full_bar(i), (kb_begin + i) * BK, b0, 0);
+        kb = kb_begin + pre;
+        s = pre % kStages;
+        ph = (pre == kStages) ? 1u : 0u;
+      } else {
+        pdl_wait();
+      }
+      for (; kb < kb_end; ++kb) {
         mbar_wait(empty_bar(s), ph ^ 1u);
         mbar_expect_tx(full_bar(s), Cfg::kStageA + Cfg::kStageB);
         const int tap = kb / e.kb_per_tap, kc = kb - tap * e.kb_per_tap;
         tma_load_3d(sA + s * Cfg::kStageA, &tmA, full_bar(s), (SWAP ? kb : kc) * BK + (SWAP ? 0 : e.tap_col[tap]),
                     a0 + (SWAP ? 0 : e.tap_row[tap]), SWAP ? 0 : batch);
         tma_load_3d(sB + s * Cfg::kStageB, &tmB, full_bar(s), kb * BK, b0, SWAP ? batch : 0);
-        if (++s == Cfg::kStages) { s = 0; ph ^= 1u; }
+        if (++s == kStages) { s = 0; ph ^= 1u; }
       }
     }
   } else if (warp == 1) {
@@ -143,12 +167,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           tc_mma_bf16(tmem_base, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb > kb_begin || k != 0) ? 1u : 0u);
         }
         tc_commit(empty_bar(s));                 // frees the smem stage once these MMAs retire
-        if (++s == Cfg::kStages) { s = 0; ph ^= 1u; }
+        if (++s == kStages) { s = 0; ph ^= 1u; }
       }
       tc_commit(tmem_full_bar);                  // accumulator complete
     }
   } else if (warp >= 4) {
     const int q = warp - 4;                      // TMEM lane quadrant == warp % 4
+    pdl_wait();                                  // residual / output buffers belong to the predecessor until it completes
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
     const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
@@ -349,15 +374,21 @@ cudaError_t make_tensor_map_2d(CUtensorMap* map, const void* ptr, long long cols
 }
 
 template <int BN, bool SWAP, typename TC>
-static cudaError_t launch_one(const CUtensorMap& ma, const CUtensorMap& mb, const TcEpi& e, dim3 grid, cudaStream_t st) {
+static cudaError_t launch_one(const CUtensorMap& ma, const CUtensorMap& mb, const TcEpi& e, dim3 grid, cudaStream_t st, bool pdl = false) {
   using Cfg = TcCfg<BN>;
-  gemm_tc_kernel<BN, SWAP, TC><<<grid, 256, Cfg::kSmem, st>>>(ma, mb, e);
-  return cudaGetLastError();
+  TcEpi ee = e;
+  const long long ctas = (long long)grid.x * grid.y * grid.z;
+  // measured (scripts/bench_gemm.py): a deeper ring does not speed up the weight stream — one SM sustains ~40 GB/s of
+  // DRAM-missing TMA traffic whatever the ring depth — so the two-CTAs-per-SM depth is used throughout
+  (void)ctas;
+  ee.stages = Cfg::kStagesDual;
+  return launch_ex(gemm_tc_kernel<BN, SWAP, TC>, grid, dim3(256), (size_t)Cfg::smem_bytes(ee.stages), st, pdl, ma, mb, ee);
 }
 
 template <int BN, bool SWAP, typename TC>
 static cudaError_t configure_one() {
-  return cudaFuncSetAttribute(gemm_tc_kernel<BN, SWAP, TC>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<BN>::kSmem);
+  return cudaFuncSetAttribute(gemm_tc_kernel<BN, SWAP, TC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              TcCfg<BN>::smem_bytes(SWAP ? TcCfg<BN>::kStagesSolo : TcCfg<BN>::kStagesDual));
 }
 // opt every instantiation into its dynamic shared memory up front (must not happen lazily inside a stream capture)
 cudaError_t gemm_tc_configure() {
@@ -435,7 +466,7 @@ cudaError_t launch_gemm_tc(const GemmArgs& g, bool swap, cudaStream_t st) {
   dim3 grid(cdiv(g.M, bn), cdiv(g.N, BM), splits);
 #define SWAP_CASE(BN_)                                                                                         \
   case BN_:                                                                                                    \
-    return g.out_f32 ? launch_one<BN_, true, float>(ma, mb, e, grid, st) : launch_one<BN_, true, bf16>(ma, mb, e, grid, st);
+    return g.out_f32 ? launch_one<BN_, true, float>(ma, mb, e, grid, st, g.pdl != 0) : launch_one<BN_, true, bf16>(ma, mb, e, grid, st, g.pdl != 0);
   switch (bn) {
     SWAP_CASE(16)
     SWAP_CASE(32)

@@ -39,6 +39,7 @@ struct GemmArgs {
   // split-K scratch of the tcgen05 decode orientation: fp32 partials + per-tile arrival counters (zero-initialised,
   // >= 2048 ints).  Null => no split.  One scratch per stream: launches that share it must be stream-ordered.
   float* splitk_ws; size_t splitk_ws_bytes; int* splitk_counters;
+  int pdl;   // launch with programmatic stream serialization (weights are prefetched before the dependency wait)
 };
 template <typename T> cudaError_t launch_gemm_simt(const GemmArgs& g, cudaStream_t st);       // gemm_simt.cu
 
@@ -46,10 +47,10 @@ template <typename T> cudaError_t launch_gemm_simt(const GemmArgs& g, cudaStream
 template <typename T>
 cudaError_t launch_layernorm(const T* x, T* y, const float* gamma, const float* beta, int rows, int H, float eps, cudaStream_t st);
 template <typename T>
-cudaError_t launch_rmsnorm(const T* x, T* y, const float* gamma, int rows, int H, float eps, cudaStream_t st);
+cudaError_t launch_rmsnorm(const T* x, T* y, const float* gamma, int rows, int H, float eps, cudaStream_t st, bool pdl = false);
 // rows_idx: optional gather of input rows (used for the last-position final norm)
 template <typename T>
-cudaError_t launch_rmsnorm_rows(const T* x, const int* rows_idx, T* y, const float* gamma, int rows, int H, float eps, cudaStream_t st);
+cudaError_t launch_rmsnorm_rows(const T* x, const int* rows_idx, T* y, const float* gamma, int rows, int H, float eps, cudaStream_t st, bool pdl = false);
 
 // encoder RoPE on the fused QKV buffer [rows, 3*H]: rotate the first rot dims of every q and k head. pos = row % T.
 template <typename T>
@@ -61,9 +62,9 @@ cudaError_t launch_rope_dec_kv(T* qkv, const float* cos_t, const float* sin_t, c
                                const int* ctx_len, T* kcache, T* vcache, int rows, int heads, int kv_heads, int hd,
                                int max_ctx, cudaStream_t st);
 template <typename T>
-cudaError_t launch_embed(const int* ids, const int* audio_src, const T* table, const T* audio_embeds, T* x, int rows, int H, cudaStream_t st);
+cudaError_t launch_embed(const int* ids, const int* audio_src, const T* table, const T* audio_embeds, T* x, int rows, int H, cudaStream_t st, bool pdl = false);
 template <typename T>
-cudaError_t launch_embed_next(const int* cur_tok, const T* table, T* x, int rows, int H, cudaStream_t st);
+cudaError_t launch_embed_next(const int* cur_tok, const T* table, T* x, int rows, int H, cudaStream_t st, bool pdl = false);
 // greedy step bookkeeping: argmax(+top-2 margin) over logits [B,V]; appends to out_ids unless finished; updates state.
 struct GreedyState {
   int* cur_tok;      // [B] next input token
@@ -82,7 +83,7 @@ struct GreedyState {
   int n_eos;
 };
 size_t greedy_pick_scratch_bytes(int max_batch);
-cudaError_t launch_greedy_pick(const float* logits, int B, int V, GreedyState gs, int advance_ctx, cudaStream_t st);
+cudaError_t launch_greedy_pick(const float* logits, int B, int V, GreedyState gs, int advance_ctx, cudaStream_t st, bool pdl = false);
 void rope_table_host(float* cos_t, float* sin_t, int positions, int rot_dim, float theta);
 
 // ---- attention.cu ---------------------------------------------------------------------------------------------
@@ -112,6 +113,6 @@ struct DecodeAttnArgs {
   int kv_heads, max_ctx, max_chunks;
   float scale;
 };
-cudaError_t launch_decode_attn(const DecodeAttnArgs& a, int batch, int n_chunks, cudaStream_t st);
+cudaError_t launch_decode_attn(const DecodeAttnArgs& a, int batch, int n_chunks, cudaStream_t st, bool pdl = false);
 
 }  // namespace sonic

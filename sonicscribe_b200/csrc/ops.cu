@@ -38,6 +38,8 @@ template <typename T>
 __global__ void __launch_bounds__(256) rmsnorm_kernel(const T* __restrict__ x, const int* __restrict__ rows_idx, T* __restrict__ y,
                                                       const float* __restrict__ gamma, int H, float eps) {
   __shared__ float red[32];
+  pdl_launch_dependents();
+  pdl_wait();
   const size_t row = blockIdx.x;
   const size_t src = rows_idx ? (size_t)rows_idx[row] : row;
   const T* xr = x + src * H;
@@ -54,15 +56,14 @@ __global__ void __launch_bounds__(256) rmsnorm_kernel(const T* __restrict__ x, c
   }
 }
 template <typename T>
-cudaError_t launch_rmsnorm_rows(const T* x, const int* rows_idx, T* y, const float* gamma, int rows, int H, float eps, cudaStream_t st) {
+cudaError_t launch_rmsnorm_rows(const T* x, const int* rows_idx, T* y, const float* gamma, int rows, int H, float eps, cudaStream_t st, bool pdl) {
   if (rows <= 0) return cudaSuccess;
   if (H > 2048) return cudaErrorInvalidValue;
-  rmsnorm_kernel<T><<<rows, 256, 0, st>>>(x, rows_idx, y, gamma, H, eps);
-  return cudaGetLastError();
+  return launch_ex(rmsnorm_kernel<T>, dim3(rows), dim3(256), 0, st, pdl, x, rows_idx, y, gamma, H, eps);
 }
 template <typename T>
-cudaError_t launch_rmsnorm(const T* x, T* y, const float* gamma, int rows, int H, float eps, cudaStream_t st) {
-  return launch_rmsnorm_rows<T>(x, nullptr, y, gamma, rows, H, eps, st);
+cudaError_t launch_rmsnorm(const T* x, T* y, const float* gamma, int rows, int H, float eps, cudaStream_t st, bool pdl) {
+  return launch_rmsnorm_rows<T>(x, nullptr, y, gamma, rows, H, eps, st, pdl);
 }
 
 // ---- RoPE tables (modeling_glmasr.py:66-109 / modeling_llama.py:96-136): fp32, angle = pos * inv_freq -------------------
@@ -154,20 +155,21 @@ cudaError_t launch_rope_dec_kv(T* qkv, const float* cos_t, const float* sin_t, c
 template <typename T>
 __global__ void embed_kernel(const int* __restrict__ ids, const int* __restrict__ audio_src, const T* __restrict__ table,
                              const T* __restrict__ audio, T* __restrict__ x, int H) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int row = blockIdx.x;
   const int a = audio_src ? audio_src[row] : -1;
   const T* src = (a >= 0) ? audio + (size_t)a * H : table + (size_t)ids[row] * H;
   for (int i = threadIdx.x; i < H; i += blockDim.x) x[(size_t)row * H + i] = src[i];
 }
 template <typename T>
-cudaError_t launch_embed(const int* ids, const int* audio_src, const T* table, const T* audio_embeds, T* x, int rows, int H, cudaStream_t st) {
+cudaError_t launch_embed(const int* ids, const int* audio_src, const T* table, const T* audio_embeds, T* x, int rows, int H, cudaStream_t st, bool pdl) {
   if (rows <= 0) return cudaSuccess;
-  embed_kernel<T><<<rows, 256, 0, st>>>(ids, audio_src, table, audio_embeds, x, H);
-  return cudaGetLastError();
+  return launch_ex(embed_kernel<T>, dim3(rows), dim3(256), 0, st, pdl, ids, audio_src, table, audio_embeds, x, H);
 }
 template <typename T>
-cudaError_t launch_embed_next(const int* cur_tok, const T* table, T* x, int rows, int H, cudaStream_t st) {
-  return launch_embed<T>(cur_tok, nullptr, table, nullptr, x, rows, H, st);
+cudaError_t launch_embed_next(const int* cur_tok, const T* table, T* x, int rows, int H, cudaStream_t st, bool pdl) {
+  return launch_embed<T>(cur_tok, nullptr, table, nullptr, x, rows, H, st, pdl);
 }
 
 // ---- greedy pick (generation/utils.py:2793-2805): argmax of fp32 logits, first index on ties; EOS bookkeeping ---------
@@ -183,6 +185,8 @@ __device__ __forceinline__ void pick_merge(float& mb, float& ms, int& mi, float 
 
 __global__ void __launch_bounds__(256) greedy_pick_kernel(const float* __restrict__ logits, int V, GreedyState gs, int advance_ctx,
                                                           PickPartial* __restrict__ partials, int* __restrict__ counters) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int b = blockIdx.y, slice = blockIdx.x;
   const int per = (V + kPickSlices - 1) / kPickSlices;
   const int lo = slice * per, hi = min(V, lo + per);
@@ -242,23 +246,22 @@ __global__ void __launch_bounds__(256) greedy_pick_kernel(const float* __restric
   if (arrived == (int)gridDim.y - 1) { *gs.step_arrivals = 0; *gs.step = step + 1; }
 }
 
-cudaError_t launch_greedy_pick(const float* logits, int B, int V, GreedyState gs, int advance_ctx, cudaStream_t st) {
+cudaError_t launch_greedy_pick(const float* logits, int B, int V, GreedyState gs, int advance_ctx, cudaStream_t st, bool pdl) {
   if (B <= 0) return cudaSuccess;
-  greedy_pick_kernel<<<dim3(kPickSlices, B), 256, 0, st>>>(logits, V, gs, advance_ctx, reinterpret_cast<PickPartial*>(gs.pick_partials),
-                                                          gs.pick_counters);
-  return cudaGetLastError();
+  return launch_ex(greedy_pick_kernel, dim3(kPickSlices, B), dim3(256), 0, st, pdl, logits, V, gs, advance_ctx,
+                   reinterpret_cast<PickPartial*>(gs.pick_partials), gs.pick_counters);
 }
 size_t greedy_pick_scratch_bytes(int max_batch) { return (size_t)max_batch * kPickSlices * sizeof(PickPartial); }
 
 #define INST(T)                                                                                                           \
   template cudaError_t launch_layernorm<T>(const T*, T*, const float*, const float*, int, int, float, cudaStream_t);       \
-  template cudaError_t launch_rmsnorm<T>(const T*, T*, const float*, int, int, float, cudaStream_t);                        \
-  template cudaError_t launch_rmsnorm_rows<T>(const T*, const int*, T*, const float*, int, int, float, cudaStream_t);       \
+  template cudaError_t launch_rmsnorm<T>(const T*, T*, const float*, int, int, float, cudaStream_t, bool);                        \
+  template cudaError_t launch_rmsnorm_rows<T>(const T*, const int*, T*, const float*, int, int, float, cudaStream_t, bool);       \
   template cudaError_t launch_rope_enc<T>(T*, const float*, const float*, int, int, int, int, int, cudaStream_t);           \
   template cudaError_t launch_rope_dec_kv<T>(T*, const float*, const float*, const int*, const int*, const int*, T*, T*,    \
                                              int, int, int, int, int, cudaStream_t);                                       \
-  template cudaError_t launch_embed<T>(const int*, const int*, const T*, const T*, T*, int, int, cudaStream_t);             \
-  template cudaError_t launch_embed_next<T>(const int*, const T*, T*, int, int, cudaStream_t);
+  template cudaError_t launch_embed<T>(const int*, const int*, const T*, const T*, T*, int, int, cudaStream_t, bool);             \
+  template cudaError_t launch_embed_next<T>(const int*, const T*, T*, int, int, cudaStream_t, bool);
 INST(float)
 INST(bf16)
 
