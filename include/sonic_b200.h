@@ -119,6 +119,10 @@ SONIC_API int sonic_debug_read(sonic_handle h, const char* name, float* out, siz
 SONIC_API int sonic_test_gemm(sonic_handle h, int32_t impl, int32_t swap, const float* A, const float* W, const float* bias,
                     const float* resid, float* C, int32_t M, int32_t N, int32_t K, int32_t act);
 
+/* same as sonic_test_gemm for the int8 weight-only operand path: W (host float32) is quantised per output row on the device
+ * (s = max|row|, q = rint(127 w / s)) and expanded to bf16 inside the kernel; C = (A . q^T) * s/127 (+bias, act, resid). */
+SONIC_API int sonic_test_gemm_int8(sonic_handle h, int32_t swap, const float* A, const float* W, const float* bias, const float* resid,
+                                   float* C, int32_t M, int32_t N, int32_t K, int32_t act);
 /* back-to-back launches of one tcgen05 GEMM shape (zero-filled bf16 operands, weights rotated through > 126 MB so L2
  * never holds them); returns the average device time per launch in microseconds (CUDA events on the handle's stream). */
 SONIC_API int sonic_bench_gemm(sonic_handle h, int32_t swap, int32_t M, int32_t N, int32_t K, int32_t act, int32_t iters, float* avg_us);

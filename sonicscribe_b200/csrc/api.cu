@@ -69,6 +69,25 @@ __global__ void convert_flat_kernel(const TS* __restrict__ src, TD* __restrict__
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     dst[i] = from_f32<TD>(to_f32(src[i]));
 }
+// per-output-row absmax int8 quantisation (weight-only): s = max|w_row|, q = rint(127 w / s); scale[row] = s / 127.
+// One CTA per source row; destination row = row0 + r*row_step inside a fused matrix (same placement rule as convert_rows).
+template <typename TS>
+__global__ void __launch_bounds__(256) quantize_rows_kernel(const TS* __restrict__ src, int8_t* __restrict__ dst, float* __restrict__ scale,
+                                                            long long cols, long long row0, long long row_step) {
+  __shared__ float red[32];
+  const long long r = blockIdx.x;
+  const TS* s = src + r * cols;
+  float m = 0.f;
+  for (long long c = threadIdx.x; c < cols; c += 256) m = fmaxf(m, fabsf(src_f32<TS>(s, (size_t)c)));
+  m = block_max(m, red);
+  const float sc = fmaxf(m, 1e-30f);
+  const long long dr = row0 + r * row_step;
+  for (long long c = threadIdx.x; c < cols; c += 256) {
+    const float q = rintf(src_f32<TS>(s, (size_t)c) * (127.0f / sc));
+    dst[dr * cols + c] = (int8_t)fminf(fmaxf(q, -127.f), 127.f);
+  }
+  if (threadIdx.x == 0) scale[dr] = sc / 127.0f;
+}
 __global__ void set_int_kernel(int* p, int v, int n) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = v;
@@ -77,10 +96,12 @@ __global__ void set_int_kernel(int* p, int v, int n) {
 struct EncLayerW {
   float *ln1_g, *ln1_b, *ln2_g, *ln2_b, *bqkv, *bo, *b1, *b2;
   void *wqkv, *wo, *fc1, *fc2;
+  float *s_qkv = nullptr, *s_o = nullptr, *s_fc1 = nullptr, *s_fc2 = nullptr;      // int8 mode: per-row scales
 };
 struct DecLayerW {
   float *rms1, *rms2;
   void *wqkv, *wo, *wgu, *wdown;
+  float *s_qkv = nullptr, *s_o = nullptr, *s_gu = nullptr, *s_down = nullptr;
 };
 
 }  // namespace
@@ -95,6 +116,8 @@ struct sonic_ctx {
   int64_t launches = 0;
   size_t esz = 2;                       // activation / weight element size
   bool is_f32 = false;
+  bool is_int8 = false;                 // bf16 activations, int8 weight-only linears (lm_head / embedding / convs stay bf16)
+  float *s_proj1 = nullptr, *s_proj2 = nullptr;
   bool force_simt = false;
   bool use_pdl = true;                  // SONIC_NO_PDL=1 disables programmatic dependent launch in the decode step
   bool pdl_now = false;
@@ -264,11 +287,12 @@ struct Engine {
     return 0;
   }
   static GemmArgs lin(const void* A, long long lda, const void* W, int K, void* C, long long ldc, const float* bias, int M, int N,
-                      int act = ACT_NONE, const void* resid = nullptr, long long ldr = 0) {
+                      int act = ACT_NONE, const void* resid = nullptr, long long ldr = 0, const float* wscale = nullptr) {
     GemmArgs g;
     memset(&g, 0, sizeof(g));
     g.A = A; g.lda = lda; g.a_bstride = 0; g.W = W; g.ldw = K; g.C = C; g.ldc = ldc; g.c_bstride = 0; g.c_row0 = 0;
     g.bias = bias; g.resid = resid; g.ldr = ldr; g.r_bstride = 0; g.M = M; g.N = N; g.K = K; g.batch = 1; g.act = act; g.out_f32 = 0;
+    g.wscale = wscale; g.w_int8 = wscale ? 1 : 0;
     return g;
   }
   static int probe(sonic_ctx* h, const char* name, const void* src, size_t elems) {
@@ -316,7 +340,7 @@ struct Engine {
       const EncLayerW& w = h->enc[l];
       TAG(PC_ENC_OTHER);
       CKL(launch_layernorm<T>(x, u, w.ln1_g, w.ln1_b, rows, kEncH, kLnEps, h->stream), 1);
-      if (gemm(h, lin(u, kEncH, w.wqkv, kEncH, qkv, 3 * kEncH, w.bqkv, rows, 3 * kEncH), false, PC_ENC_GEMM)) return -1;
+      if (gemm(h, lin(u, kEncH, w.wqkv, kEncH, qkv, 3 * kEncH, w.bqkv, rows, 3 * kEncH, ACT_NONE, nullptr, 0, w.s_qkv), false, PC_ENC_GEMM)) return -1;
       TAG(PC_ENC_OTHER);
       CKL(launch_rope_enc<T>(qkv, h->rope_enc_cos, h->rope_enc_sin, rows, kEncT, kEncHeads, kEncHd, kEncRot, h->stream), 1);
       {
@@ -336,11 +360,11 @@ struct Engine {
           CKL(launch_attention_simt<T>(a, h->stream), 1);
         }
       }
-      if (gemm(h, lin(attn, kEncH, w.wo, kEncH, x, kEncH, w.bo, rows, kEncH, ACT_NONE, x, kEncH), false, PC_ENC_GEMM)) return -1;
+      if (gemm(h, lin(attn, kEncH, w.wo, kEncH, x, kEncH, w.bo, rows, kEncH, ACT_NONE, x, kEncH, w.s_o), false, PC_ENC_GEMM)) return -1;
       TAG(PC_ENC_OTHER);
       CKL(launch_layernorm<T>(x, u, w.ln2_g, w.ln2_b, rows, kEncH, kLnEps, h->stream), 1);
-      if (gemm(h, lin(u, kEncH, w.fc1, kEncH, mlp, kEncInter, w.b1, rows, kEncInter, ACT_GELU), false, PC_ENC_GEMM)) return -1;
-      if (gemm(h, lin(mlp, kEncInter, w.fc2, kEncInter, x, kEncH, w.b2, rows, kEncH, ACT_NONE, x, kEncH), false, PC_ENC_GEMM)) return -1;
+      if (gemm(h, lin(u, kEncH, w.fc1, kEncH, mlp, kEncInter, w.b1, rows, kEncInter, ACT_GELU, nullptr, 0, w.s_fc1), false, PC_ENC_GEMM)) return -1;
+      if (gemm(h, lin(mlp, kEncInter, w.fc2, kEncInter, x, kEncH, w.b2, rows, kEncH, ACT_NONE, x, kEncH, w.s_fc2), false, PC_ENC_GEMM)) return -1;
       if (l == 0 && probe(h, "enc_layer0", x, (size_t)rows * kEncH)) return -1;
     }
     TAG(PC_ENC_OTHER);
@@ -348,8 +372,8 @@ struct Engine {
     if (probe(h, "enc_out", u, (size_t)rows * kEncH)) return -1;
     // adapter: [B*375, 5120] -> 4096 (GELU) -> 2048 (modeling_glmasr.py:412-415, 333-349)
     const int mrows = B * kMerged;
-    if (gemm(h, lin(u, kEncInter, h->proj1_w, kEncInter, h->a1, 2 * kDecH, h->proj1_b, mrows, 2 * kDecH, ACT_GELU), false, PC_ENC_GEMM)) return -1;
-    if (gemm(h, lin(h->a1, 2 * kDecH, h->proj2_w, 2 * kDecH, h->audio, kDecH, h->proj2_b, mrows, kDecH), false, PC_ENC_GEMM)) return -1;
+    if (gemm(h, lin(u, kEncInter, h->proj1_w, kEncInter, h->a1, 2 * kDecH, h->proj1_b, mrows, 2 * kDecH, ACT_GELU, nullptr, 0, h->s_proj1), false, PC_ENC_GEMM)) return -1;
+    if (gemm(h, lin(h->a1, 2 * kDecH, h->proj2_w, 2 * kDecH, h->audio, kDecH, h->proj2_b, mrows, kDecH, ACT_NONE, nullptr, 0, h->s_proj2), false, PC_ENC_GEMM)) return -1;
     if (probe(h, "audio_embeds", h->audio, (size_t)mrows * kDecH)) return -1;
     return 0;
   }
@@ -365,7 +389,7 @@ struct Engine {
     const bool swap = !prefill;
     TAG(prefill ? PC_PRE_OTHER : PC_DEC_OTHER);
     CKL(launch_rmsnorm<T>(x, u, w.rms1, rows, kDecH, kRmsEps, h->stream, h->pdl_now), 1);
-    if (gemm(h, lin(u, kDecH, w.wqkv, kDecH, qkv, kQkvDec, nullptr, rows, kQkvDec), swap, prefill ? PC_PRE_GEMM : PC_DEC_QKV)) return -1;
+    if (gemm(h, lin(u, kDecH, w.wqkv, kDecH, qkv, kQkvDec, nullptr, rows, kQkvDec, ACT_NONE, nullptr, 0, w.s_qkv), swap, prefill ? PC_PRE_GEMM : PC_DEC_QKV)) return -1;
     if (!prefill && std::is_same<T, bf16>::value && !h->force_simt) {
       DecodeAttnArgs d;
       d.qkv = reinterpret_cast<const bf16*>(qkv); d.cos_t = h->rope_dec_cos; d.sin_t = h->rope_dec_sin; d.ctx_len = h->gs.ctx_len;
@@ -394,11 +418,11 @@ struct Engine {
         CKL(launch_attention_simt<T>(a, h->stream), 1);
       }
     }
-    if (gemm(h, lin(attn, kDecH, w.wo, kDecH, x, kDecH, nullptr, rows, kDecH, ACT_NONE, x, kDecH), swap, prefill ? PC_PRE_GEMM : PC_DEC_O)) return -1;
+    if (gemm(h, lin(attn, kDecH, w.wo, kDecH, x, kDecH, nullptr, rows, kDecH, ACT_NONE, x, kDecH, w.s_o), swap, prefill ? PC_PRE_GEMM : PC_DEC_O)) return -1;
     TAG(prefill ? PC_PRE_OTHER : PC_DEC_OTHER);
     CKL(launch_rmsnorm<T>(x, u, w.rms2, rows, kDecH, kRmsEps, h->stream, h->pdl_now), 1);
-    if (gemm(h, lin(u, kDecH, w.wgu, kDecH, act, kDecInter, nullptr, rows, 2 * kDecInter, ACT_SWIGLU), swap, prefill ? PC_PRE_GEMM : PC_DEC_GU)) return -1;
-    if (gemm(h, lin(act, kDecInter, w.wdown, kDecInter, x, kDecH, nullptr, rows, kDecH, ACT_NONE, x, kDecH), swap, prefill ? PC_PRE_GEMM : PC_DEC_DOWN)) return -1;
+    if (gemm(h, lin(u, kDecH, w.wgu, kDecH, act, kDecInter, nullptr, rows, 2 * kDecInter, ACT_SWIGLU, nullptr, 0, w.s_gu), swap, prefill ? PC_PRE_GEMM : PC_DEC_GU)) return -1;
+    if (gemm(h, lin(act, kDecInter, w.wdown, kDecInter, x, kDecH, nullptr, rows, kDecH, ACT_NONE, x, kDecH, w.s_down), swap, prefill ? PC_PRE_GEMM : PC_DEC_DOWN)) return -1;
     return 0;
   }
 
@@ -461,10 +485,15 @@ struct Dest {
   void* ptr;                 // destination base
   long long rows, cols;      // expected source shape (MAT: [rows, cols]; CONV: [co, ci(,3)]; VEC: [rows])
   long long row0, row_step;  // MAT placement inside a fused destination
+  float* qscale = nullptr;   // int8 mode: this matrix is stored as int8 with per-row scales here (indexed like the rows)
 };
 
 bool route(sonic_ctx* h, const std::string& name, Dest* d) {
-  auto mat = [&](void* p, long long r, long long c, long long row0 = 0, long long step = 1) { *d = {Dest::MAT, p, r, c, row0, step}; return true; };
+  auto mat = [&](void* p, long long r, long long c, long long row0 = 0, long long step = 1, float* qs = nullptr) {
+    *d = {Dest::MAT, p, r, c, row0, step};
+    d->qscale = h->is_int8 ? qs : nullptr;
+    return true;
+  };
   auto vec = [&](float* p, long long n) { *d = {Dest::VEC, p, n, 1, 0, 1}; return true; };
   int i = 0;
   char tail[128];
@@ -474,9 +503,9 @@ bool route(sonic_ctx* h, const std::string& name, Dest* d) {
   if (name == "audio_tower.conv2.bias") return vec(h->conv2_b, kEncH);
   if (name == "audio_tower.norm.weight") return vec(h->enc_norm_g, kEncH);
   if (name == "audio_tower.norm.bias") return vec(h->enc_norm_b, kEncH);
-  if (name == "multi_modal_projector.linear_1.weight") return mat(h->proj1_w, 2 * kDecH, kEncInter);
+  if (name == "multi_modal_projector.linear_1.weight") return mat(h->proj1_w, 2 * kDecH, kEncInter, 0, 1, h->s_proj1);
   if (name == "multi_modal_projector.linear_1.bias") return vec(h->proj1_b, 2 * kDecH);
-  if (name == "multi_modal_projector.linear_2.weight") return mat(h->proj2_w, kDecH, 2 * kDecH);
+  if (name == "multi_modal_projector.linear_2.weight") return mat(h->proj2_w, kDecH, 2 * kDecH, 0, 1, h->s_proj2);
   if (name == "multi_modal_projector.linear_2.bias") return vec(h->proj2_b, kDecH);
   if (name == "language_model.model.embed_tokens.weight") return mat(h->embed, kVocab, kDecH);
   if (name == "language_model.lm_head.weight") return mat(h->lm_head, kVocab, kDecH);
@@ -485,16 +514,16 @@ bool route(sonic_ctx* h, const std::string& name, Dest* d) {
     if (i < 0 || i >= h->cfg.enc_layers) return false;
     EncLayerW& w = h->enc[i];
     const std::string t = tail;
-    if (t == "self_attn.q_proj.weight") return mat(w.wqkv, kEncH, kEncH, 0);
-    if (t == "self_attn.k_proj.weight") return mat(w.wqkv, kEncH, kEncH, kEncH);
-    if (t == "self_attn.v_proj.weight") return mat(w.wqkv, kEncH, kEncH, 2 * kEncH);
+    if (t == "self_attn.q_proj.weight") return mat(w.wqkv, kEncH, kEncH, 0, 1, w.s_qkv);
+    if (t == "self_attn.k_proj.weight") return mat(w.wqkv, kEncH, kEncH, kEncH, 1, w.s_qkv);
+    if (t == "self_attn.v_proj.weight") return mat(w.wqkv, kEncH, kEncH, 2 * kEncH, 1, w.s_qkv);
     if (t == "self_attn.q_proj.bias") return vec(w.bqkv, kEncH);
     if (t == "self_attn.v_proj.bias") return vec(w.bqkv + 2 * kEncH, kEncH);
-    if (t == "self_attn.o_proj.weight") return mat(w.wo, kEncH, kEncH);
+    if (t == "self_attn.o_proj.weight") return mat(w.wo, kEncH, kEncH, 0, 1, w.s_o);
     if (t == "self_attn.o_proj.bias") return vec(w.bo, kEncH);
-    if (t == "mlp.fc1.weight") return mat(w.fc1, kEncInter, kEncH);
+    if (t == "mlp.fc1.weight") return mat(w.fc1, kEncInter, kEncH, 0, 1, w.s_fc1);
     if (t == "mlp.fc1.bias") return vec(w.b1, kEncInter);
-    if (t == "mlp.fc2.weight") return mat(w.fc2, kEncH, kEncInter);
+    if (t == "mlp.fc2.weight") return mat(w.fc2, kEncH, kEncInter, 0, 1, w.s_fc2);
     if (t == "mlp.fc2.bias") return vec(w.b2, kEncH);
     if (t == "input_layernorm.weight") return vec(w.ln1_g, kEncH);
     if (t == "input_layernorm.bias") return vec(w.ln1_b, kEncH);
@@ -506,13 +535,13 @@ bool route(sonic_ctx* h, const std::string& name, Dest* d) {
     if (i < 0 || i >= h->cfg.dec_layers) return false;
     DecLayerW& w = h->dec[i];
     const std::string t = tail;
-    if (t == "self_attn.q_proj.weight") return mat(w.wqkv, kDecHeads * kDecHd, kDecH, 0);
-    if (t == "self_attn.k_proj.weight") return mat(w.wqkv, kDecKv * kDecHd, kDecH, kDecHeads * kDecHd);
-    if (t == "self_attn.v_proj.weight") return mat(w.wqkv, kDecKv * kDecHd, kDecH, (kDecHeads + kDecKv) * kDecHd);
-    if (t == "self_attn.o_proj.weight") return mat(w.wo, kDecH, kDecH);
-    if (t == "mlp.gate_proj.weight") return mat(w.wgu, kDecInter, kDecH, 0, 2);   // rows interleaved (gate, up) for the SwiGLU epilogue
-    if (t == "mlp.up_proj.weight") return mat(w.wgu, kDecInter, kDecH, 1, 2);
-    if (t == "mlp.down_proj.weight") return mat(w.wdown, kDecH, kDecInter);
+    if (t == "self_attn.q_proj.weight") return mat(w.wqkv, kDecHeads * kDecHd, kDecH, 0, 1, w.s_qkv);
+    if (t == "self_attn.k_proj.weight") return mat(w.wqkv, kDecKv * kDecHd, kDecH, kDecHeads * kDecHd, 1, w.s_qkv);
+    if (t == "self_attn.v_proj.weight") return mat(w.wqkv, kDecKv * kDecHd, kDecH, (kDecHeads + kDecKv) * kDecHd, 1, w.s_qkv);
+    if (t == "self_attn.o_proj.weight") return mat(w.wo, kDecH, kDecH, 0, 1, w.s_o);
+    if (t == "mlp.gate_proj.weight") return mat(w.wgu, kDecInter, kDecH, 0, 2, w.s_gu);   // rows interleaved (gate, up) for the SwiGLU epilogue
+    if (t == "mlp.up_proj.weight") return mat(w.wgu, kDecInter, kDecH, 1, 2, w.s_gu);
+    if (t == "mlp.down_proj.weight") return mat(w.wdown, kDecH, kDecInter, 0, 1, w.s_down);
     if (t == "input_layernorm.weight") return vec(w.rms1, kDecH);
     if (t == "post_attention_layernorm.weight") return vec(w.rms2, kDecH);
     return false;
@@ -525,26 +554,30 @@ size_t expected_tensor_count(const sonic_config& c) { return 4 + c.enc_layers * 
 int alloc_all(sonic_ctx* h) {
   const sonic_config& c = h->cfg;
   const size_t E = h->esz;
+  const size_t Q = h->is_int8 ? 1 : E;      // element size of the quantisable linears
   const int B = c.max_batch;
   h->max_ctx = c.max_prompt + c.max_new;
   // weights
   DA(h->conv1_w, (size_t)kEncH * 3 * kMels * E); DA(h->conv2_w, (size_t)kEncH * 3 * kEncH * E);
   DA(h->conv1_b, kEncH * 4); DA(h->conv2_b, kEncH * 4); DA(h->enc_norm_g, kEncH * 4); DA(h->enc_norm_b, kEncH * 4);
-  DA(h->proj1_w, (size_t)2 * kDecH * kEncInter * E); DA(h->proj1_b, 2 * kDecH * 4);
-  DA(h->proj2_w, (size_t)kDecH * 2 * kDecH * E); DA(h->proj2_b, kDecH * 4);
+  DA(h->proj1_w, (size_t)2 * kDecH * kEncInter * Q); DA(h->proj1_b, 2 * kDecH * 4);
+  DA(h->proj2_w, (size_t)kDecH * 2 * kDecH * Q); DA(h->proj2_b, kDecH * 4);
+  if (h->is_int8) { DA(h->s_proj1, 2 * kDecH * 4); DA(h->s_proj2, kDecH * 4); }
   DA(h->embed, (size_t)kVocab * kDecH * E); DA(h->lm_head, (size_t)kVocab * kDecH * E); DA(h->final_norm, kDecH * 4);
   h->enc.resize(c.enc_layers);
   for (auto& w : h->enc) {
     DA(w.ln1_g, kEncH * 4); DA(w.ln1_b, kEncH * 4); DA(w.ln2_g, kEncH * 4); DA(w.ln2_b, kEncH * 4);
     DAZ(w.bqkv, 3 * kEncH * 4); DA(w.bo, kEncH * 4); DA(w.b1, kEncInter * 4); DA(w.b2, kEncH * 4);
-    DA(w.wqkv, (size_t)3 * kEncH * kEncH * E); DA(w.wo, (size_t)kEncH * kEncH * E);
-    DA(w.fc1, (size_t)kEncInter * kEncH * E); DA(w.fc2, (size_t)kEncH * kEncInter * E);
+    DA(w.wqkv, (size_t)3 * kEncH * kEncH * Q); DA(w.wo, (size_t)kEncH * kEncH * Q);
+    DA(w.fc1, (size_t)kEncInter * kEncH * Q); DA(w.fc2, (size_t)kEncH * kEncInter * Q);
+    if (h->is_int8) { DA(w.s_qkv, 3 * kEncH * 4); DA(w.s_o, kEncH * 4); DA(w.s_fc1, kEncInter * 4); DA(w.s_fc2, kEncH * 4); }
   }
   h->dec.resize(c.dec_layers);
   for (auto& w : h->dec) {
     DA(w.rms1, kDecH * 4); DA(w.rms2, kDecH * 4);
-    DA(w.wqkv, (size_t)kQkvDec * kDecH * E); DA(w.wo, (size_t)kDecH * kDecH * E);
-    DA(w.wgu, (size_t)2 * kDecInter * kDecH * E); DA(w.wdown, (size_t)kDecH * kDecInter * E);
+    DA(w.wqkv, (size_t)kQkvDec * kDecH * Q); DA(w.wo, (size_t)kDecH * kDecH * Q);
+    DA(w.wgu, (size_t)2 * kDecInter * kDecH * Q); DA(w.wdown, (size_t)kDecH * kDecInter * Q);
+    if (h->is_int8) { DA(w.s_qkv, kQkvDec * 4); DA(w.s_o, kDecH * 4); DA(w.s_gu, 2 * kDecInter * 4); DA(w.s_down, kDecH * 4); }
   }
   // tables
   {
@@ -795,6 +828,8 @@ int upload(sonic_ctx* h, const Dest& d, const void* data, size_t n_elems) {
   } else if (d.kind == Dest::CONV) {
     if (h->is_f32) convert_conv_kernel<TS, float><<<grid, 256, 0, st>>>(src, reinterpret_cast<float*>(d.ptr), d.rows, d.cols);
     else convert_conv_kernel<TS, bf16><<<grid, 256, 0, st>>>(src, reinterpret_cast<bf16*>(d.ptr), d.rows, d.cols);
+  } else if (d.qscale) {
+    quantize_rows_kernel<TS><<<(unsigned)d.rows, 256, 0, st>>>(src, reinterpret_cast<int8_t*>(d.ptr), d.qscale, d.cols, d.row0, d.row_step);
   } else {
     if (h->is_f32) convert_rows_kernel<TS, float><<<grid, 256, 0, st>>>(src, reinterpret_cast<float*>(d.ptr), d.rows, d.cols, d.row0, d.row_step);
     else convert_rows_kernel<TS, bf16><<<grid, 256, 0, st>>>(src, reinterpret_cast<bf16*>(d.ptr), d.rows, d.cols, d.row0, d.row_step);
@@ -818,7 +853,7 @@ int32_t sonic_num_audio_tokens(int64_t n_samples) { return n_audio_tokens(n_samp
 int sonic_create(const sonic_config* cfg, sonic_handle* out) {
   if (!cfg || !out) return fail(nullptr, "sonic_create: null argument");
   *out = nullptr;
-  if (cfg->mode != SONIC_MODE_BF16 && cfg->mode != SONIC_MODE_FP32) return fail(nullptr, "sonic_create: unsupported mode");
+  if (cfg->mode != SONIC_MODE_BF16 && cfg->mode != SONIC_MODE_FP32 && cfg->mode != SONIC_MODE_INT8) return fail(nullptr, "sonic_create: unsupported mode");
   if (cfg->enc_layers < 1 || cfg->enc_layers > 64 || cfg->dec_layers < 1 || cfg->dec_layers > 64 || cfg->max_batch < 1 ||
       cfg->max_batch > 256 || cfg->max_prompt < 8 || cfg->max_new < 1)
     return fail(nullptr, "sonic_create: bad configuration");
@@ -832,11 +867,13 @@ int sonic_create(const sonic_config* cfg, sonic_handle* out) {
   sonic_ctx* h = new sonic_ctx();
   h->cfg = *cfg;
   h->is_f32 = cfg->mode == SONIC_MODE_FP32;
+  h->is_int8 = cfg->mode == SONIC_MODE_INT8;
   h->esz = h->is_f32 ? 4 : 2;
   const char* fs = getenv("SONIC_FORCE_SIMT");
   h->force_simt = fs && fs[0] == '1';
   const char* np = getenv("SONIC_NO_PDL");
   h->use_pdl = !(np && np[0] == '1');
+  if (h->is_int8 && h->force_simt) { delete h; return fail(nullptr, "sonic_create: SONIC_FORCE_SIMT is not available in int8 mode"); }
   auto bail = [&](int) { g_last_error = h->err; for (void* p : h->allocs) cudaFree(p); delete h; return -1; };
   if (cudaSetDevice(cfg->device) != cudaSuccess) { h->err = "cudaSetDevice failed"; return bail(0); }
   if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { h->err = "cudaStreamCreate failed"; return bail(0); }
@@ -1052,6 +1089,46 @@ int sonic_test_gemm(sonic_handle h, int32_t impl, int32_t swap, const float* A, 
   e = cudaStreamSynchronize(st);
   cleanup();
   if (e != cudaSuccess) return fail_cuda(h, e, "sonic_test_gemm");
+  return 0;
+}
+
+int sonic_test_gemm_int8(sonic_handle h, int32_t swap, const float* A, const float* W, const float* bias, const float* resid, float* C,
+                         int32_t M, int32_t N, int32_t K, int32_t act) {
+  ENTER();
+  const int outN = (act == ACT_SWIGLU) ? N / 2 : N;
+  bf16 *dA = nullptr, *dC = nullptr;
+  int8_t* dW = nullptr;
+  float *fA = nullptr, *dB = nullptr, *dS = nullptr;
+  cudaStream_t st = h->stream;
+  auto cleanup = [&]() { cudaFree(dA); cudaFree(dW); cudaFree(dC); cudaFree(fA); cudaFree(dB); cudaFree(dS); };
+  const size_t nA = (size_t)M * K, nW = (size_t)N * K, nC = (size_t)M * outN;
+  const size_t nbig = nA > nW ? (nA > nC ? nA : nC) : (nW > nC ? nW : nC);
+  cudaError_t e = cudaSuccess;
+  if ((e = cudaMalloc(&dA, nA * 2)) || (e = cudaMalloc(&dW, nW)) || (e = cudaMalloc(&dC, nC * 2)) || (e = cudaMalloc(&fA, nbig * 4)) ||
+      (e = cudaMalloc(&dB, (size_t)N * 4)) || (e = cudaMalloc(&dS, (size_t)N * 4))) { cleanup(); return fail_cuda(h, e, "alloc"); }
+  cudaMemcpyAsync(fA, A, nA * 4, cudaMemcpyHostToDevice, st);
+  convert_flat_kernel<float, bf16><<<1024, 256, 0, st>>>(fA, dA, (long long)nA);
+  cudaMemcpyAsync(fA, W, nW * 4, cudaMemcpyHostToDevice, st);
+  quantize_rows_kernel<float><<<(unsigned)N, 256, 0, st>>>(fA, dW, dS, K, 0, 1);
+  if (resid) {
+    cudaMemcpyAsync(fA, resid, nC * 4, cudaMemcpyHostToDevice, st);
+    convert_flat_kernel<float, bf16><<<1024, 256, 0, st>>>(fA, dC, (long long)nC);
+  }
+  if (bias) cudaMemcpyAsync(dB, bias, (size_t)N * 4, cudaMemcpyHostToDevice, st);
+  GemmArgs g;
+  memset(&g, 0, sizeof(g));
+  g.A = dA; g.lda = K; g.W = dW; g.ldw = K; g.C = dC; g.ldc = outN; g.bias = bias ? dB : nullptr;
+  g.resid = resid ? dC : nullptr; g.ldr = outN; g.M = M; g.N = N; g.K = K; g.batch = 1; g.act = act;
+  g.w_int8 = 1; g.wscale = dS;
+  g.splitk_ws = h->splitk_ws; g.splitk_ws_bytes = h->splitk_ws_bytes; g.splitk_counters = h->splitk_counters;
+  e = launch_gemm_tc(g, swap != 0, st);
+  if (e != cudaSuccess) { cleanup(); return fail_cuda(h, e, "sonic_test_gemm_int8 launch"); }
+  h->launches += 1;
+  convert_flat_kernel<bf16, float><<<1024, 256, 0, st>>>(dC, fA, (long long)nC);
+  cudaMemcpyAsync(C, fA, nC * 4, cudaMemcpyDeviceToHost, st);
+  e = cudaStreamSynchronize(st);
+  cleanup();
+  if (e != cudaSuccess) return fail_cuda(h, e, "sonic_test_gemm_int8");
   return 0;
 }
 

@@ -23,15 +23,19 @@ static constexpr int BM = 128;          // MMA M (rows of the A-side operand per
 static constexpr int BK = 64;           // 64 bf16 = 128 B = one swizzle atom row
 static constexpr int UMMA_K = 16;
 
-template <int BN> struct TcCfg {
-  static constexpr int kStageA = BM * BK * 2;                 // 16 KB
-  static constexpr int kStageB = BN * BK * 2;
+template <int BN, bool SWAP = false, bool W8 = false> struct TcCfg {
+  // bytes per ring stage of the two TMA-loaded operands.  With W8 the weight operand (A when SWAP, else B; always 128
+  // rows) arrives as int8 (64 B rows, no swizzle) and is expanded to bf16 into one of kConv SW128 buffers by warps 4-7.
+  static constexpr int kStageA = (W8 && SWAP) ? BM * BK : BM * BK * 2;
+  static constexpr int kStageB = (W8 && !SWAP) ? BN * BK : BN * BK * 2;
+  static constexpr int kConv = W8 ? 2 : 0;
+  static constexpr int kConvBytes = 128 * BK * 2;             // 16 KB
   // stage count is a launch-time choice: "two CTAs per SM" (<= ~110 KB each) when the grid has more CTAs than SMs, otherwise
   // the whole 227 KB of one SM so a lone CTA keeps as many TMA loads in flight as possible (HBM latency ~2 us per box)
   static constexpr int kStagesDual = (BN >= 128 ? 3 : (BN <= 32 ? 6 : 4));
   static constexpr int kMaxStages = 12;
   static constexpr int kStagesSolo = ((227 * 1024 - 1024 - 512) / (kStageA + kStageB)) > kMaxStages ? kMaxStages : ((227 * 1024 - 1024 - 512) / (kStageA + kStageB));
-  static constexpr int smem_bytes(int stages) { return stages * (kStageA + kStageB) + 1024 /*align slack*/ + 512 /*barriers*/; }
+  static constexpr int smem_bytes(int stages) { return stages * (kStageA + kStageB) + kConv * kConvBytes + 1024 /*align slack*/ + 512 /*barriers*/; }
   static constexpr int kTmemCols = BN < 32 ? 32 : BN;
 };
 
@@ -52,6 +56,7 @@ struct TcEpi {
   float* ws;
   int* counters;
   int stages;             // shared-memory ring depth chosen at launch
+  const float* wscale;    // W8: per-output-feature dequantisation scale (absmax / 127)
 };
 
 template <typename TC>
@@ -78,21 +83,25 @@ __device__ __forceinline__ void store_chunk32<float>(float* dst, const float (&x
   for (int i = 0; i < 8; ++i) d[i] = make_float4(x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]);
 }
 
-template <int BN, bool SWAP, typename TC>
+template <int BN, bool SWAP, typename TC, bool W8>
 __global__ void __launch_bounds__(256, 2)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TcEpi e) {
-  using Cfg = TcCfg<BN>;
+  using Cfg = TcCfg<BN, SWAP, W8>;
+  static_assert(!W8 || SWAP || BN == 128, "int8 weight tiles are 128 rows");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;                // SWIZZLE_128B tiles need 1024 B alignment
   uint8_t* sgen = smem_raw + (base - raw);
   const int kStages = e.stages;
   const uint32_t sA = base, sB = base + kStages * Cfg::kStageA;
-  const uint32_t bars = sB + kStages * Cfg::kStageB;          // full[kStages], empty[kStages], tmem_full, tmem slot
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sgen + kStages * (Cfg::kStageA + Cfg::kStageB) + 8 * (2 * kStages + 1));
+  const uint32_t sConv = sB + kStages * Cfg::kStageB;         // W8: bf16 images of the weight tile
+  const uint32_t bars = sConv + Cfg::kConv * Cfg::kConvBytes; // full[kStages], empty[kStages], tmem_full, conv_full[2], conv_empty[2], tmem slot
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sgen + (bars - base) + 8 * (2 * kStages + 5));
   auto full_bar = [&](int s) { return bars + 8u * s; };
   auto empty_bar = [&](int s) { return bars + 8u * (kStages + s); };
   const uint32_t tmem_full_bar = bars + 8u * (2 * kStages);
+  auto conv_full_bar = [&](int c) { return bars + 8u * (2 * kStages + 1 + c); };
+  auto conv_empty_bar = [&](int c) { return bars + 8u * (2 * kStages + 3 + c); };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int a0 = blockIdx.y * BM;            // first row of the 128-row operand (tokens, or features when SWAP)
@@ -110,6 +119,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     mbar_init(tmem_full_bar, 1);
+    if constexpr (W8) {
+      for (int c = 0; c < 2; ++c) { mbar_init(conv_full_bar(c), 128); mbar_init(conv_empty_bar(c), 1); }
+    }
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -156,23 +168,65 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
       int s = 0; uint32_t ph = 0;
+      int c = 0; uint32_t cph = 0;
       for (int kb = kb_begin; kb < kb_end; ++kb) {
         mbar_wait(full_bar(s), ph);
+        if constexpr (W8) mbar_wait(conv_full_bar(c), cph);
         tc_fence_after();
-        const uint64_t da = make_sw128_desc(sA + s * Cfg::kStageA);
-        const uint64_t db = make_sw128_desc(sB + s * Cfg::kStageB);
+        const uint64_t da = make_sw128_desc((W8 && SWAP) ? sConv + c * Cfg::kConvBytes : sA + s * Cfg::kStageA);
+        const uint64_t db = make_sw128_desc((W8 && !SWAP) ? sConv + c * Cfg::kConvBytes : sB + s * Cfg::kStageB);
 #pragma unroll
         for (int k = 0; k < BK / UMMA_K; ++k) {
           // advancing 16 bf16 = 32 B along K inside the 128 B swizzle atom: +2 in the (addr>>4) field
           tc_mma_bf16(tmem_base, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb > kb_begin || k != 0) ? 1u : 0u);
         }
         tc_commit(empty_bar(s));                 // frees the smem stage once these MMAs retire
+        if constexpr (W8) {
+          tc_commit(conv_empty_bar(c));
+          if (++c == 2) { c = 0; cph ^= 1u; }
+        }
         if (++s == kStages) { s = 0; ph ^= 1u; }
       }
       tc_commit(tmem_full_bar);                  // accumulator complete
     }
   } else if (warp >= 4) {
     const int q = warp - 4;                      // TMEM lane quadrant == warp % 4
+    if constexpr (W8) {
+      // int8 -> bf16 expansion of the weight tile: thread r owns weight row r (64 int8 = 64 B in, 128 B out in the
+      // K-major SWIZZLE_128B operand layout: 16 B chunk c8 of row r lives at chunk (c8 ^ (r & 7)))
+      const int r = threadIdx.x - 128;
+      const uint32_t raw0 = SWAP ? sA : sB;
+      const int raw_stride = SWAP ? Cfg::kStageA : Cfg::kStageB;
+      int s = 0; uint32_t ph = 0;
+      int c = 0; uint32_t cph = 0;
+      for (int kb = kb_begin; kb < kb_end; ++kb) {
+        mbar_wait(full_bar(s), ph);
+        mbar_wait(conv_empty_bar(c), cph ^ 1u);
+        const uint8_t* src = sgen + (raw0 - base) + s * raw_stride + r * 64;
+        uint8_t* dst = sgen + (sConv - base) + c * Cfg::kConvBytes + r * 128;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const uint4 w = *reinterpret_cast<const uint4*>(src + 16 * i);
+          const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+          uint32_t o[8];
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const int b0i = (int)(int8_t)(ww[t] & 0xff), b1i = (int)(int8_t)((ww[t] >> 8) & 0xff);
+            const int b2i = (int)(int8_t)((ww[t] >> 16) & 0xff), b3i = (int)(int8_t)(ww[t] >> 24);
+            __nv_bfloat162 lo = __floats2bfloat162_rn((float)b0i, (float)b1i);
+            __nv_bfloat162 hi = __floats2bfloat162_rn((float)b2i, (float)b3i);
+            o[2 * t] = *reinterpret_cast<uint32_t*>(&lo);
+            o[2 * t + 1] = *reinterpret_cast<uint32_t*>(&hi);
+          }
+          *reinterpret_cast<uint4*>(dst + (((2 * i) ^ (r & 7)) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
+          *reinterpret_cast<uint4*>(dst + (((2 * i + 1) ^ (r & 7)) << 4)) = make_uint4(o[4], o[5], o[6], o[7]);
+        }
+        fence_proxy_async_smem();
+        mbar_arrive(conv_full_bar(c));
+        if (++c == 2) { c = 0; cph ^= 1u; }
+        if (++s == kStages) { s = 0; ph ^= 1u; }
+      }
+    }
     pdl_wait();                                  // residual / output buffers belong to the predecessor until it completes
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
@@ -191,6 +245,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           float x[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]);
+          if constexpr (W8) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 sv = __ldg(reinterpret_cast<const float4*>(e.wscale + n + j));
+              x[j] *= sv.x; x[j + 1] *= sv.y; x[j + 2] *= sv.z; x[j + 3] *= sv.w;
+            }
+          }
           if (e.bias) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
@@ -252,6 +313,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int f = a0 + q * 32 + lane;
       const int ntok = min(BN, e.M - b0);
       const float bias = (e.bias && f < e.N) ? e.bias[f] : 0.f;
+      const float wsc = (W8 && f < e.N) ? e.wscale[f] : 1.f;
       const float* wsum = nullptr;                 // != null: this CTA reduces the split-K partials
       if (e.splits > 1) {
         __shared__ int s_last;
@@ -310,7 +372,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           const int t = c * 16 + j;
-          float x = __uint_as_float(v[j]) + bias;
+          float x = __uint_as_float(v[j]) * wsc + bias;
           if (e.act == ACT_GELU) x = gelu_erf(x);
           if (e.act == ACT_SWIGLU) {
             const float other = __shfl_xor_sync(0xffffffffu, x, 1);
@@ -360,6 +422,18 @@ static cudaError_t make_map(CUtensorMap* map, const void* ptr, long long K, long
   return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
 }
 
+// 3-D int8 tensor map {K, rows, 1} with a {64, box_rows, 1} box, no swizzle (the converter warps read it row by row)
+static cudaError_t make_map_i8(CUtensorMap* map, const void* ptr, long long K, long long rows, long long ld, int box_rows) {
+  cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)rows, 1};
+  cuuint64_t strides[2] = {(cuuint64_t)ld, (cuuint64_t)ld * rows};
+  cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
+}
+
 // 2-D bf16 tensor map {cols, rows} (row stride ld elements) with a {box_cols, box_rows} box and 128B swizzle
 cudaError_t make_tensor_map_2d(CUtensorMap* map, const void* ptr, long long cols, long long rows, long long ld, int box_cols, int box_rows) {
   SONIC_CUDA_TRY(gemm_tc_init());
@@ -373,22 +447,23 @@ cudaError_t make_tensor_map_2d(CUtensorMap* map, const void* ptr, long long cols
   return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
 }
 
-template <int BN, bool SWAP, typename TC>
+template <int BN, bool SWAP, typename TC, bool W8 = false>
 static cudaError_t launch_one(const CUtensorMap& ma, const CUtensorMap& mb, const TcEpi& e, dim3 grid, cudaStream_t st, bool pdl = false) {
-  using Cfg = TcCfg<BN>;
+  using Cfg = TcCfg<BN, SWAP, W8>;
   TcEpi ee = e;
   const long long ctas = (long long)grid.x * grid.y * grid.z;
   // measured (scripts/bench_gemm.py): a deeper ring does not speed up the weight stream — one SM sustains ~40 GB/s of
   // DRAM-missing TMA traffic whatever the ring depth — so the two-CTAs-per-SM depth is used throughout
   (void)ctas;
   ee.stages = Cfg::kStagesDual;
-  return launch_ex(gemm_tc_kernel<BN, SWAP, TC>, grid, dim3(256), (size_t)Cfg::smem_bytes(ee.stages), st, pdl, ma, mb, ee);
+  return launch_ex(gemm_tc_kernel<BN, SWAP, TC, W8>, grid, dim3(256), (size_t)Cfg::smem_bytes(ee.stages), st, pdl, ma, mb, ee);
 }
 
-template <int BN, bool SWAP, typename TC>
+template <int BN, bool SWAP, typename TC, bool W8 = false>
 static cudaError_t configure_one() {
-  return cudaFuncSetAttribute(gemm_tc_kernel<BN, SWAP, TC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                              TcCfg<BN>::smem_bytes(SWAP ? TcCfg<BN>::kStagesSolo : TcCfg<BN>::kStagesDual));
+  using Cfg = TcCfg<BN, SWAP, W8>;
+  return cudaFuncSetAttribute(gemm_tc_kernel<BN, SWAP, TC, W8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              Cfg::smem_bytes(SWAP ? Cfg::kStagesSolo : Cfg::kStagesDual));
 }
 // opt every instantiation into its dynamic shared memory up front (must not happen lazily inside a stream capture)
 cudaError_t gemm_tc_configure() {
@@ -400,6 +475,10 @@ cudaError_t gemm_tc_configure() {
   SONIC_CUDA_TRY((configure_one<32, true, float>()));
   SONIC_CUDA_TRY((configure_one<64, true, bf16>()));
   SONIC_CUDA_TRY((configure_one<64, true, float>()));
+  SONIC_CUDA_TRY((configure_one<128, false, bf16, true>()));
+  SONIC_CUDA_TRY((configure_one<16, true, bf16, true>()));
+  SONIC_CUDA_TRY((configure_one<32, true, bf16, true>()));
+  SONIC_CUDA_TRY((configure_one<64, true, bf16, true>()));
   return cudaSuccess;
 }
 
@@ -413,14 +492,17 @@ int gemm_tc_pick_bn(const GemmArgs& g, bool swap) {
 cudaError_t launch_gemm_tc(const GemmArgs& g, bool swap, cudaStream_t st) {
   if (g.M <= 0 || g.N <= 0 || g.batch <= 0) return cudaSuccess;
   SONIC_CUDA_TRY(gemm_tc_init());
-  if (g.K % BK != 0 || g.lda % 8 != 0 || g.ldw % 8 != 0 || g.N % 32 != 0) return cudaErrorInvalidValue;
+  if (g.K % BK != 0 || g.lda % 8 != 0 || g.ldw % 16 != 0 || g.N % 32 != 0) return cudaErrorInvalidValue;
   if ((reinterpret_cast<uintptr_t>(g.A) & 15) || (reinterpret_cast<uintptr_t>(g.W) & 15)) return cudaErrorInvalidValue;
   TcEpi e;
   e.C = g.C; e.ldc = g.ldc; e.c_bstride = g.c_bstride; e.c_row0 = g.c_row0;
   e.bias = g.bias; e.resid = g.resid; e.ldr = g.ldr; e.r_bstride = g.r_bstride;
   e.M = g.M; e.N = g.N; e.K = g.K; e.act = g.act;
   e.kb_per_tap = g.K / BK;
-  e.splits = 1; e.ws = nullptr; e.counters = nullptr;
+  e.splits = 1; e.ws = nullptr; e.counters = nullptr; e.stages = 0;
+  e.wscale = g.wscale;
+  const bool w8 = g.w_int8 != 0;
+  if (w8 && (g.out_f32 || g.conv_cin > 0 || !g.wscale)) return cudaErrorInvalidValue;
   for (int t = 0; t < 3; ++t) { e.tap_col[t] = 0; e.tap_row[t] = 0; }
   CUtensorMap ma, mb;
   const int bn = gemm_tc_pick_bn(g, swap);
@@ -443,12 +525,15 @@ cudaError_t launch_gemm_tc(const GemmArgs& g, bool swap, cudaStream_t st) {
   }
   if (!swap) {
     SONIC_CUDA_TRY(make_map(&ma, g.A, g.K, g.M, g.lda, g.batch, g.a_bstride, BM));
-    SONIC_CUDA_TRY(make_map(&mb, g.W, g.K, g.N, g.ldw, 1, 0, bn));
+    if (w8) SONIC_CUDA_TRY(make_map_i8(&mb, g.W, g.K, g.N, g.ldw, bn));
+    else SONIC_CUDA_TRY(make_map(&mb, g.W, g.K, g.N, g.ldw, 1, 0, bn));
     dim3 grid(cdiv(g.N, bn), cdiv(g.M, BM), g.batch);
+    if (w8) return launch_one<128, false, bf16, true>(ma, mb, e, grid, st);
     return g.out_f32 ? launch_one<128, false, float>(ma, mb, e, grid, st) : launch_one<128, false, bf16>(ma, mb, e, grid, st);
   }
   // swap: the 128-row operand is the weight matrix
-  SONIC_CUDA_TRY(make_map(&ma, g.W, g.K, g.N, g.ldw, 1, 0, BM));
+  if (w8) SONIC_CUDA_TRY(make_map_i8(&ma, g.W, g.K, g.N, g.ldw, BM));
+  else SONIC_CUDA_TRY(make_map(&ma, g.W, g.K, g.N, g.ldw, 1, 0, BM));
   SONIC_CUDA_TRY(make_map(&mb, g.A, g.K, g.M, g.lda, g.batch, g.a_bstride, bn));
   if (g.batch != 1) return cudaErrorInvalidValue;
   const int tiles = cdiv(g.M, bn) * cdiv(g.N, BM);
@@ -466,6 +551,7 @@ cudaError_t launch_gemm_tc(const GemmArgs& g, bool swap, cudaStream_t st) {
   dim3 grid(cdiv(g.M, bn), cdiv(g.N, BM), splits);
 #define SWAP_CASE(BN_)                                                                                         \
   case BN_:                                                                                                    \
+    if (w8) return launch_one<BN_, true, bf16, true>(ma, mb, e, grid, st, g.pdl != 0);                         \
     return g.out_f32 ? launch_one<BN_, true, float>(ma, mb, e, grid, st, g.pdl != 0) : launch_one<BN_, true, bf16>(ma, mb, e, grid, st, g.pdl != 0);
   switch (bn) {
     SWAP_CASE(16)

@@ -69,6 +69,7 @@ def load_library():
         "sonic_profile_class_name": (C.c_char_p, [C.c_int32]),
         "sonic_debug_read": (C.c_int, [H, C.c_char_p, f32p, C.c_size_t, C.POINTER(C.c_size_t)]),
         "sonic_test_enc_attention": (C.c_int, [H, C.c_int32, f32p, f32p, C.c_int32, C.c_int32]),
+        "sonic_test_gemm_int8": (C.c_int, [H, C.c_int32, f32p, f32p, f32p, f32p, f32p, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
         "sonic_bench_gemm": (C.c_int, [H, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, f32p]),
         "sonic_test_gemm": (C.c_int, [H, C.c_int32, C.c_int32, f32p, f32p, f32p, f32p, f32p, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
     }
@@ -272,3 +273,15 @@ class Engine:
         us = C.c_float()
         self._ck(self.lib.sonic_bench_gemm(self.h, 1 if swap else 0, M, N, K, act, iters, C.byref(us)))
         return float(us.value)
+
+    def test_gemm_int8(self, A, W, bias=None, resid=None, act=0, swap=False):
+        A = np.ascontiguousarray(A, dtype=np.float32)
+        W = np.ascontiguousarray(W, dtype=np.float32)
+        M, K = A.shape
+        N = W.shape[0]
+        outN = N // 2 if act == 2 else N
+        Cm = np.zeros((M, outN), dtype=np.float32)
+        b = np.ascontiguousarray(bias, dtype=np.float32) if bias is not None else None
+        r = np.ascontiguousarray(resid, dtype=np.float32) if resid is not None else None
+        self._ck(self.lib.sonic_test_gemm_int8(self.h, 1 if swap else 0, _f32p(A), _f32p(W), _f32p(b), _f32p(r), _f32p(Cm), M, N, K, act))
+        return Cm

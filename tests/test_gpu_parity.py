@@ -326,3 +326,51 @@ def test_bf16_tensor_core_path_vs_cuda_core_path(tiny_sd, eng_bf16):
                 assert min(ma[s][t], mb[s][t]) < 0.2, (s, t, ma[s][t], mb[s][t])
                 break
         assert a[s][:4] == b[s][:4]
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# INT8 weight-only variant: per-output-row absmax int8 weights expanded to bf16 inside the tcgen05 GEMM
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("swap,M,N,K,act", [(False, 300, 1280, 1280, 0), (False, 1500, 5120, 1280, 1), (False, 77, 3840, 1280, 0),
+                                            (True, 1, 3072, 2048, 0), (True, 16, 2048, 6144, 0), (True, 40, 12288, 2048, 2),
+                                            (True, 64, 2048, 2048, 1)])
+def test_gemm_int8_weights(eng_bf16, swap, M, N, K, act):
+    rng = np.random.default_rng(N + K + M)
+    A = bf16_round(rng.standard_normal((M, K)) * 0.5)
+    W = (rng.standard_normal((N, K)) * 0.05).astype(np.float32)
+    q, s = ora.quantize_rowwise_int8(torch.from_numpy(W))
+    Wd = q.double().numpy() * (s.double().numpy() / 127.0)[:, None]
+    bias = rng.standard_normal(N).astype(np.float32) * 0.1
+    acc = A.astype(np.float64) @ Wd.T + bias
+    resid = None
+    if act == 1:
+        ref = 0.5 * acc * (1 + np.vectorize(__import__("math").erf)(acc / np.sqrt(2)))
+    elif act == 2:
+        g, u = acc[:, 0::2], acc[:, 1::2]
+        ref = g / (1 + np.exp(-g)) * u
+    else:
+        resid = bf16_round(rng.standard_normal((M, N)))
+        ref = acc + resid
+    got = eng_bf16.test_gemm_int8(A, W, bias=bias, resid=resid, act=act, swap=swap)
+    assert np.abs(got - ref).max() < 2e-2 * max(1.0, np.abs(ref).max())
+
+
+def test_int8_mode_matches_dequantised_oracle(tiny_sd):
+    """mode="int8": the path with int8 linears vs the fp32 oracle run on the de-quantised weights (same quantiser)."""
+    eng = Engine(2, 2, mode="int8", device=0, max_batch=2, max_prompt=300, max_new=40, debug=True)
+    eng.load_state_dict(tiny_sd)
+    sdq = ora.int8_weight_only_state(tiny_sd)
+    x = mo.synth_audio("speech", 163840, 11)
+    ids, ref_new, margins, ref_logits, probes = _oracle_run(sdq, TINY, x, 16)
+    got = eng.transcribe_ids([x], [ids], 16)
+    enc = eng.debug_read("enc_out", 1500 * 1280).reshape(1500, 1280)
+    assert rel_l2(enc, probes["enc_out"].numpy()) < 3e-2
+    fl = eng.debug_read("first_logits", 59264)
+    assert rel_l2(fl, ref_logits) < 5e-2
+    assert got[0][0] == ref_new[0]
+    for t, (a, b) in enumerate(zip(got[0], ref_new)):
+        if a != b:
+            assert margins[t] < 0.25, (t, margins[t])
+            break
+    assert eng.device_bytes() > 0
+    eng.close()
