@@ -340,9 +340,16 @@ struct Engine {
       const EncLayerW& w = h->enc[l];
       TAG(PC_ENC_OTHER);
       CKL(launch_layernorm<T>(x, u, w.ln1_g, w.ln1_b, rows, kEncH, kLnEps, h->stream), 1);
-      if (gemm(h, lin(u, kEncH, w.wqkv, kEncH, qkv, 3 * kEncH, w.bqkv, rows, 3 * kEncH, ACT_NONE, nullptr, 0, w.s_qkv), false, PC_ENC_GEMM)) return -1;
-      TAG(PC_ENC_OTHER);
-      CKL(launch_rope_enc<T>(qkv, h->rope_enc_cos, h->rope_enc_sin, rows, kEncT, kEncHeads, kEncHd, kEncRot, h->stream), 1);
+      {
+        GemmArgs g = lin(u, kEncH, w.wqkv, kEncH, qkv, 3 * kEncH, w.bqkv, rows, 3 * kEncH, ACT_NONE, nullptr, 0, w.s_qkv);
+        const bool fused_rope = std::is_same<T, bf16>::value && !h->force_simt;     // tcgen05 epilogue rotates q and k
+        if (fused_rope) { g.rope_cos = h->rope_enc_cos; g.rope_sin = h->rope_enc_sin; g.rope_T = kEncT; g.rope_ncols = 2 * kEncH; }
+        if (gemm(h, g, false, PC_ENC_GEMM)) return -1;
+        if (!fused_rope) {
+          TAG(PC_ENC_OTHER);
+          CKL(launch_rope_enc<T>(qkv, h->rope_enc_cos, h->rope_enc_sin, rows, kEncT, kEncHeads, kEncHd, kEncRot, h->stream), 1);
+        }
+      }
       {
         AttnArgs a;
         memset(&a, 0, sizeof(a));

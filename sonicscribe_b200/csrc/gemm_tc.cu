@@ -57,6 +57,9 @@ struct TcEpi {
   int* counters;
   int stages;             // shared-memory ring depth chosen at launch
   const float* wscale;    // W8: per-output-feature dequantisation scale (absmax / 127)
+  // fused partial RoPE of the encoder QKV projection (normal mode): for columns < rope_ncols, the first 32 dims of every
+  // 64-dim head are rotated (pairs j, j+16) with the angle table [rope_T][16] indexed by (row % rope_T)
+  const float* rope_cos; const float* rope_sin; int rope_T; int rope_ncols;
 };
 
 template <typename TC>
@@ -262,6 +265,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (e.act == ACT_GELU) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) x[j] = gelu_erf(x[j]);
+          }
+          if (e.rope_cos != nullptr && n < e.rope_ncols && (n & 63) == 0) {
+            const int pos = m % e.rope_T;
+            const float4* cp = reinterpret_cast<const float4*>(e.rope_cos + (size_t)pos * 16);
+            const float4* sp = reinterpret_cast<const float4*>(e.rope_sin + (size_t)pos * 16);
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4) {
+              const float4 c4 = __ldg(cp + q4), s4 = __ldg(sp + q4);
+              const float cc[4] = {c4.x, c4.y, c4.z, c4.w}, ss[4] = {s4.x, s4.y, s4.z, s4.w};
+#pragma unroll
+              for (int t = 0; t < 4; ++t) {
+                const int j = 4 * q4 + t;
+                // the reference casts cos/sin to the model dtype (modeling_glmasr.py:109)
+                const float c = __bfloat162float(__float2bfloat16_rn(cc[t])), s = __bfloat162float(__float2bfloat16_rn(ss[t]));
+                const float a = x[j], b = x[j + 16];
+                x[j] = a * c - b * s;
+                x[j + 16] = b * c + a * s;
+              }
+            }
           }
           if (e.act == ACT_SWIGLU) {
             float y[32];
@@ -501,6 +523,7 @@ cudaError_t launch_gemm_tc(const GemmArgs& g, bool swap, cudaStream_t st) {
   e.kb_per_tap = g.K / BK;
   e.splits = 1; e.ws = nullptr; e.counters = nullptr; e.stages = 0;
   e.wscale = g.wscale;
+  e.rope_cos = swap ? nullptr : g.rope_cos; e.rope_sin = g.rope_sin; e.rope_T = g.rope_T; e.rope_ncols = g.rope_ncols;
   const bool w8 = g.w_int8 != 0;
   if (w8 && (g.out_f32 || g.conv_cin > 0 || !g.wscale)) return cudaErrorInvalidValue;
   for (int t = 0; t < 3; ++t) { e.tap_col[t] = 0; e.tap_row[t] = 0; }

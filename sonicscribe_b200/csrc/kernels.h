@@ -40,6 +40,7 @@ struct GemmArgs {
   // >= 2048 ints).  Null => no split.  One scratch per stream: launches that share it must be stream-ordered.
   float* splitk_ws; size_t splitk_ws_bytes; int* splitk_counters;
   int w_int8; const float* wscale;   // tcgen05 path: W is int8 [N,K] with per-row fp32 scale (weight-only quantisation)
+  const float* rope_cos; const float* rope_sin; int rope_T; int rope_ncols;   // tcgen05 normal mode: fused encoder RoPE (see gemm_tc.cu)
   int pdl;   // launch with programmatic stream serialization (weights are prefetched before the dependency wait)
 };
 template <typename T> cudaError_t launch_gemm_simt(const GemmArgs& g, cudaStream_t st);       // gemm_simt.cu
