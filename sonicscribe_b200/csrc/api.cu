@@ -157,6 +157,11 @@ struct sonic_ctx {
   GreedyState gs{};
   int* h_pinned = nullptr;              // pinned scratch for metadata upload / flags
   size_t h_pinned_ints = 0;
+  bool use_persist = false;            // one cooperative kernel per greedy step (bf16 mode; SONIC_DECODE=graph disables)
+  DecLayerDev* dev_layers = nullptr;
+  float* persist_part = nullptr;
+  unsigned* persist_bar = nullptr;
+  int num_sms = 0;
   float* dattn_ws = nullptr;
   int* dattn_counters = nullptr;
   int dattn_max_chunks = 0;
@@ -198,10 +203,10 @@ int fail_cuda(sonic_ctx* h, cudaError_t e, const char* what) {
     if (_e != cudaSuccess) return fail_cuda(h, _e, #expr);         \
   } while (0)
 enum ProfClass { PC_MEL = 0, PC_ENC_GEMM, PC_ENC_ATTN, PC_ENC_OTHER, PC_PRE_GEMM, PC_PRE_ATTN, PC_PRE_OTHER, PC_DEC_QKV, PC_DEC_O,
-                 PC_DEC_GU, PC_DEC_DOWN, PC_DEC_LMHEAD, PC_DEC_ATTN, PC_DEC_OTHER, PC_COUNT };
+                 PC_DEC_GU, PC_DEC_DOWN, PC_DEC_LMHEAD, PC_DEC_ATTN, PC_DEC_OTHER, PC_DEC_PERSIST, PC_COUNT };
 const char* const kProfNames[PC_COUNT] = {"mel", "enc_gemm", "enc_attn", "enc_other", "prefill_gemm", "prefill_attn", "prefill_other",
                                           "dec_gemm_qkv", "dec_gemm_o", "dec_gemm_gateup", "dec_gemm_down", "dec_gemm_lmhead",
-                                          "dec_attn", "dec_other"};
+                                          "dec_attn", "dec_other", "dec_persistent_step"};
 cudaEvent_t prof_event(sonic_ctx* h) {
   if (h->prof_used == h->prof_pool.size()) {
     cudaEvent_t e = nullptr;
@@ -467,6 +472,18 @@ struct Engine {
   static int decode_step(sonic_ctx* h, int B) {
     T* x = reinterpret_cast<T*>(h->dx);
     TAG(PC_DEC_OTHER);
+    if (h->use_persist && std::is_same<T, bf16>::value) {
+      DecodePersistArgs p;
+      p.layers = h->dev_layers; p.n_layers = h->cfg.dec_layers;
+      p.embed = reinterpret_cast<const bf16*>(h->embed); p.lm_head = reinterpret_cast<const bf16*>(h->lm_head); p.final_norm = h->final_norm;
+      p.cos_t = h->rope_dec_cos; p.sin_t = h->rope_dec_sin;
+      p.x = reinterpret_cast<bf16*>(h->dx); p.u = reinterpret_cast<bf16*>(h->du); p.attn = reinterpret_cast<bf16*>(h->dattn);
+      p.act = reinterpret_cast<bf16*>(h->dact); p.part = h->persist_part; p.logits_out = nullptr; p.gs = h->gs; p.bar = h->persist_bar;
+      p.B = B; p.Bpad = (B + 7) / 8 * 8; p.max_ctx = h->max_ctx; p.eps = kRmsEps; p.scale = 0.08838834764831845f;
+      TAG(PC_DEC_PERSIST);
+      CKL(launch_decode_persist(p, h->num_sms, h->stream), 1);
+      return 0;
+    }
     // every kernel of the step is launched with programmatic stream serialization (bf16 tensor-core path only): the next
     // kernel's CTAs are scheduled, and its weight tiles are in flight, while the current one drains
     h->pdl_now = h->use_pdl && std::is_same<T, bf16>::value && !h->force_simt;
@@ -624,6 +641,12 @@ int alloc_all(sonic_ctx* h) {
   const size_t kv = (size_t)c.dec_layers * B * kDecKv * h->max_ctx * kDecHd * E;
   DAZ(h->kcache, kv); DAZ(h->vcache, kv);
   DA(h->logits, (size_t)B * kVocab * 4);
+  if (h->use_persist) {
+    const int Bpad = (B + 7) / 8 * 8;
+    DA(h->persist_part, decode_persist_part_floats(Bpad) * 4);
+    DAZ(h->persist_bar, 16);
+    DA(h->dev_layers, (size_t)c.dec_layers * sizeof(DecLayerDev));
+  }
   h->dattn_max_chunks = (h->max_ctx + 63) / 64;
   DA(h->dattn_ws, (size_t)B * kDecKv * h->dattn_max_chunks * 4 * 130 * 4);
   DAZ(h->dattn_counters, (size_t)B * kDecKv * 4);
@@ -768,10 +791,16 @@ int do_generate(sonic_ctx* h, const int32_t* ids, const int32_t* id_offsets, int
   // greedy steps 2..max_new: one CUDA graph per (batch, max_new) replayed; no per-token host sync.
   h->decode_chunks = (max_q + max_new + 63) / 64;
   if (h->decode_chunks > h->dattn_max_chunks) h->decode_chunks = h->dattn_max_chunks;
-  if (max_new > 1 && h->prof_on) {
+  if (max_new > 1 && (h->prof_on || (h->use_persist && !h->is_f32))) {
+    int* flag = h->h_pinned + h->h_pinned_ints - 16;
     for (int step = 1; step < max_new; ++step) {
       rc = dispatch(h, [&] { return Engine<float>::decode_step(h, batch); }, [&] { return Engine<bf16>::decode_step(h, batch); });
       if (rc) return rc;
+      if (!h->prof_on && (step % 16) == 0 && step + 1 < max_new) {       // early exit once every segment hit EOS
+        CK(cudaMemcpyAsync(flag, h->gs.n_unfinished, 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        if (*flag <= 0) break;
+      }
     }
   } else if (max_new > 1) {
     h->decode_chunks = (max_q + max_new + 63) / 64;
@@ -880,6 +909,9 @@ int sonic_create(const sonic_config* cfg, sonic_handle* out) {
   h->force_simt = fs && fs[0] == '1';
   const char* np = getenv("SONIC_NO_PDL");
   h->use_pdl = !(np && np[0] == '1');
+  const char* dm = getenv("SONIC_DECODE");
+  h->use_persist = !h->is_f32 && !h->is_int8 && !h->force_simt && !(dm && std::string(dm) == "graph");
+  h->num_sms = prop.multiProcessorCount;
   if (h->is_int8 && h->force_simt) { delete h; return fail(nullptr, "sonic_create: SONIC_FORCE_SIMT is not available in int8 mode"); }
   auto bail = [&](int) { g_last_error = h->err; for (void* p : h->allocs) cudaFree(p); delete h; return -1; };
   if (cudaSetDevice(cfg->device) != cudaSuccess) { h->err = "cudaSetDevice failed"; return bail(0); }
@@ -887,6 +919,7 @@ int sonic_create(const sonic_config* cfg, sonic_handle* out) {
   if (mel_setup() != cudaSuccess) { h->err = "mel_setup failed"; return bail(0); }
   if (!h->is_f32 && gemm_tc_init() != cudaSuccess) { h->err = "cuTensorMapEncodeTiled entry point unavailable"; return bail(0); }
   if (!h->is_f32 && gemm_tc_configure() != cudaSuccess) { h->err = "gemm_tc_configure failed"; return bail(0); }
+  if (h->use_persist && decode_persist_configure() != cudaSuccess) { h->err = "decode_persist_configure failed"; return bail(0); }
   if (!h->is_f32 && attention_tc_configure() != cudaSuccess) { h->err = "attention_tc_configure failed"; return bail(0); }
   if (alloc_all(h)) return bail(0);
   *out = h;
@@ -937,6 +970,19 @@ int sonic_finalize_weights(sonic_handle h) {
     return fail(h, "sonic_finalize_weights: " + std::to_string(h->loaded.size()) + " tensors loaded, expected " +
                        std::to_string(expected_tensor_count(h->cfg)));
   if (h->staging) { cudaFree(h->staging); h->bytes -= (int64_t)h->staging_bytes; h->staging = nullptr; h->staging_bytes = 0; }
+  if (h->use_persist) {
+    std::vector<DecLayerDev> tab(h->cfg.dec_layers);
+    const size_t layer_kv = (size_t)h->cfg.max_batch * kDecKv * h->max_ctx * kDecHd;
+    for (int l = 0; l < h->cfg.dec_layers; ++l) {
+      const DecLayerW& w = h->dec[l];
+      tab[l].wqkv = reinterpret_cast<const bf16*>(w.wqkv); tab[l].wo = reinterpret_cast<const bf16*>(w.wo);
+      tab[l].wgu = reinterpret_cast<const bf16*>(w.wgu); tab[l].wdown = reinterpret_cast<const bf16*>(w.wdown);
+      tab[l].rms1 = w.rms1; tab[l].rms2 = w.rms2;
+      tab[l].kc = reinterpret_cast<bf16*>(h->kcache) + (size_t)l * layer_kv;
+      tab[l].vc = reinterpret_cast<bf16*>(h->vcache) + (size_t)l * layer_kv;
+    }
+    CK(cudaMemcpy(h->dev_layers, tab.data(), tab.size() * sizeof(DecLayerDev), cudaMemcpyHostToDevice));
+  }
   h->finalized = true;
   return 0;
 }

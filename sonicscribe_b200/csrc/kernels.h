@@ -117,4 +117,23 @@ struct DecodeAttnArgs {
 };
 cudaError_t launch_decode_attn(const DecodeAttnArgs& a, int batch, int n_chunks, cudaStream_t st, bool pdl = false);
 
+// ---- decode_persist.cu: one cooperative kernel per greedy step (all layers + lm_head + pick), bf16 ------------------------
+struct DecLayerDev { const bf16 *wqkv, *wo, *wgu, *wdown; const float *rms1, *rms2; bf16 *kc, *vc; };
+struct DecodePersistArgs {
+  const DecLayerDev* layers; int n_layers;
+  const bf16* embed; const bf16* lm_head; const float* final_norm;
+  const float* cos_t; const float* sin_t;
+  bf16 *x, *u, *attn, *act;       // [B][2048], [B][2048], [B][2048], [B][6144]
+  float* part;                    // split-K partials, decode_persist_part_floats(Bpad) floats
+  float* logits_out;              // optional [B][vocab]
+  GreedyState gs;
+  unsigned* bar;                  // grid barrier counter
+  int B, Bpad, max_ctx;
+  float eps, scale;
+};
+size_t decode_persist_smem_bytes();
+size_t decode_persist_part_floats(int Bpad);
+cudaError_t decode_persist_configure();
+cudaError_t launch_decode_persist(const DecodePersistArgs& a, int num_sms, cudaStream_t st);
+
 }  // namespace sonic
