@@ -161,6 +161,8 @@ struct sonic_ctx {
   DecLayerDev* dev_layers = nullptr;
   float* persist_part = nullptr;
   unsigned* persist_bar = nullptr;
+  unsigned long long* persist_ts = nullptr;
+  float* persist_pick = nullptr;
   int num_sms = 0;
   float* dattn_ws = nullptr;
   int* dattn_counters = nullptr;
@@ -478,7 +480,8 @@ struct Engine {
       p.embed = reinterpret_cast<const bf16*>(h->embed); p.lm_head = reinterpret_cast<const bf16*>(h->lm_head); p.final_norm = h->final_norm;
       p.cos_t = h->rope_dec_cos; p.sin_t = h->rope_dec_sin;
       p.x = reinterpret_cast<bf16*>(h->dx); p.u = reinterpret_cast<bf16*>(h->du); p.attn = reinterpret_cast<bf16*>(h->dattn);
-      p.act = reinterpret_cast<bf16*>(h->dact); p.part = h->persist_part; p.logits_out = nullptr; p.gs = h->gs; p.bar = h->persist_bar;
+      p.act = reinterpret_cast<bf16*>(h->dact); p.part = h->persist_part; p.logits_out = nullptr; p.pick_scratch = h->persist_pick; p.gs = h->gs; p.bar = h->persist_bar; p.timestamps = h->cfg.debug ? h->persist_ts : nullptr;
+      { const char* pf = getenv("SONIC_PERSIST_PREFETCH"); p.prefetch = (pf && pf[0] == '1') ? 1 : 0; }
       p.B = B; p.Bpad = (B + 7) / 8 * 8; p.max_ctx = h->max_ctx; p.eps = kRmsEps; p.scale = 0.08838834764831845f;
       TAG(PC_DEC_PERSIST);
       CKL(launch_decode_persist(p, h->num_sms, h->stream), 1);
@@ -645,6 +648,8 @@ int alloc_all(sonic_ctx* h) {
     const int Bpad = (B + 7) / 8 * 8;
     DA(h->persist_part, decode_persist_part_floats(Bpad) * 4);
     DAZ(h->persist_bar, 16);
+    DAZ(h->persist_ts, 2048 * 8);
+    DA(h->persist_pick, decode_persist_pick_floats(B, h->num_sms) * 4);
     DA(h->dev_layers, (size_t)c.dec_layers * sizeof(DecLayerDev));
   }
   h->dattn_max_chunks = (h->max_ctx + 63) / 64;
@@ -1086,6 +1091,17 @@ int sonic_debug_read(sonic_handle h, const char* name, float* out, size_t max_el
   size_t n = 0;
   if (nm == "rope_enc_cos") { src_f32 = h->rope_enc_cos; n = (size_t)kEncT * kEncRot / 2; }
   else if (nm == "rope_dec_cos") { src_f32 = h->rope_dec_cos; n = (size_t)h->max_ctx * kDecHd / 2; }
+  else if (nm == "persist_ts" && h->persist_ts) {
+    // phase timestamps of the last persistent decode step, returned as float32 microseconds relative to the first stamp
+    const int n = 2 + 7 * h->cfg.dec_layers + 3;
+    std::vector<unsigned long long> ts(n);
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaMemcpy(ts.data(), h->persist_ts, n * 8, cudaMemcpyDeviceToHost));
+    if ((size_t)n > max_elems) return fail(h, "sonic_debug_read: output buffer too small");
+    for (int i = 0; i < n; ++i) out[i] = (float)((double)(ts[i] - ts[0]) * 1e-3);
+    if (n_elems) *n_elems = n;
+    return 0;
+  }
   else if (nm == "mel_raw") { src_f32 = h->mel_raw; n = (size_t)h->last_batch * kMels * kFrames; }
   else if (h->probes_f32.count(nm)) { src_f32 = h->probes_f32[nm].first; n = h->probes_f32[nm].second; }
   else if (h->probes.count(nm)) { src_t = h->probes[nm].first; n = h->probes[nm].second; }

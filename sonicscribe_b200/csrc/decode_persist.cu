@@ -20,7 +20,7 @@ namespace sonic {
 
 static constexpr int PH = 2048, PQKV = 3072, PI = 6144, PV_ = 59264, PHD = 128, PKVH = 4, PG = 4;
 static constexpr int kPThreads = 512, kPWarps = 16;
-static constexpr int kSplitQkv = 16, kSplitO = 16, kSplitGu = 4, kSplitDown = 24, kSplitHead = 2;
+
 static constexpr int AKEYS = 128;                        // keys per attention chunk
 static constexpr int kAKRow = PHD * 2 + 16;              // padded K row in shared memory (bytes)
 
@@ -56,51 +56,91 @@ __device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& epoch)
 // ---- GEMM phase: part[s][tok][n] = sum_{k in slice s} W[n][k] * X[tok][k] ------------------------------------------------
 // item = (K-slice s, 16-row block rb); the warps of one CTA take consecutive row blocks of the same slice so that the
 // activation slice they all read stays in L1.
-template <int NT>
-__device__ __forceinline__ void gemm_phase(const bf16* __restrict__ W, int N, int K, int ksplit, const bf16* X, int B, int Bpad,
-                                           float* __restrict__ part) {
-  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-  const int gw = blockIdx.x * kPWarps + (threadIdx.x >> 5), GW = gridDim.x * kPWarps;
-  const int nrb = N >> 4, Ks = K / ksplit, n_items = nrb * ksplit;
-  for (int item = gw; item < n_items; item += GW) {
-    const int s = item / nrb, rb = item - s * nrb;
-    const bf16* w0 = W + (size_t)(rb * 16 + g) * K + (size_t)s * Ks + 8 * t;
+// L2 prefetch of a weight matrix that a LATER phase will stream: every warp asks for its 1/(grid*16) share with one bulk
+// prefetch, so HBM keeps streaming the next matrix while the current phase computes and while the grid sits in barriers.
+__device__ __forceinline__ void prefetch_weights_l2(const void* W, size_t bytes, int enable = 1) {
+  if (!enable || (threadIdx.x & 31) != 0) return;
+  const size_t nw = (size_t)gridDim.x * kPWarps, gw = (size_t)blockIdx.x * kPWarps + (threadIdx.x >> 5);
+  size_t chunk = ((bytes + nw - 1) / nw + 127) & ~(size_t)127;
+  const size_t off = gw * chunk;
+  if (off >= bytes) return;
+  if (off + chunk > bytes) chunk = (bytes - off) & ~(size_t)15;
+  if (chunk == 0) return;
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<const uint8_t*>(W) + off), "r"((uint32_t)chunk) : "memory");
+}
+
+// ---- GEMM phase ---------------------------------------------------------------------------------------------------------
+// item = (16-row block rb, 2048-wide K section gs).  The 16 warps of the CTA split the section (128 k each: one group of
+// 8 weight loads per lane), exchange their fp32 fragments through shared memory and sum them in warp order (deterministic),
+// so a finished 16 x tokens tile leaves the CTA and the epilogue can be fused: fp32 store (per section), residual add into
+// the bf16 stream, or SwiGLU of interleaved (gate, up) rows.  The next item's weight loads are issued before the exchange.
+enum { EPI_F32 = 0, EPI_RESID = 1, EPI_SWIGLU = 2 };
+
+template <int NT, int EPI>
+__device__ __forceinline__ void gemm_phase(const bf16* __restrict__ W, int N, int K, const bf16* X, int B, int Bpad,
+                                           float* __restrict__ out32, bf16* xres, bf16* act, float* sR) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+  const int nrb = N >> 4, gsplit = K >> 11, n_items = nrb * gsplit;
+  int item = blockIdx.x;
+  uint4 wa[4], wb[4];
+  auto load_item = [&](int it) {
+    const int gs = it / nrb, rb = it - gs * nrb;
+    const bf16* w0 = W + (size_t)(rb * 16 + g) * K + (size_t)gs * 2048 + warp * 128 + 8 * t;
     const bf16* w1 = w0 + (size_t)8 * K;
-    const bf16* xb = X + (size_t)s * Ks + 8 * t;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { wa[u] = ldg_stream(w0 + 32 * u); wb[u] = ldg_stream(w1 + 32 * u); }
+  };
+  if (item < n_items) load_item(item);
+  for (; item < n_items; item += gridDim.x) {
+    const int gs = item / nrb, rb = item - gs * nrb;
+    const bf16* xb = X + (size_t)gs * 2048 + warp * 128 + 8 * t;
     float acc[NT][4];
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) { acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f; }
-    for (int k0 = 0; k0 < Ks; k0 += 128) {
-      uint4 wa[4], wb[4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) { wa[u] = ldg_stream(w0 + k0 + 32 * u); wb[u] = ldg_stream(w1 + k0 + 32 * u); }
+    for (int u = 0; u < 4; ++u) {
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int nt = 0; nt < NT; ++nt) {
+        const int tok = nt * 8 + g;
+        uint4 xv = make_uint4(0, 0, 0, 0);
+        if (tok < B) xv = *reinterpret_cast<const uint4*>(xb + (size_t)tok * K + 32 * u);
+        mma16816(acc[nt], wa[u].x, wb[u].x, wa[u].y, wb[u].y, xv.x, xv.y);
+        mma16816(acc[nt], wa[u].z, wb[u].z, wa[u].w, wb[u].w, xv.z, xv.w);
+      }
+    }
+    if (item + (int)gridDim.x < n_items) load_item(item + gridDim.x);     // in flight during the exchange below
 #pragma unroll
-        for (int nt = 0; nt < NT; ++nt) {
-          const int tok = nt * 8 + g;
-          uint4 xv = make_uint4(0, 0, 0, 0);
-          if (tok < B) xv = *reinterpret_cast<const uint4*>(xb + (size_t)tok * K + k0 + 32 * u);
-          mma16816(acc[nt], wa[u].x, wb[u].x, wa[u].y, wb[u].y, xv.x, xv.y);
-          mma16816(acc[nt], wa[u].z, wb[u].z, wa[u].w, wb[u].w, xv.z, xv.w);
+    for (int nt = 0; nt < NT; ++nt)
+      *reinterpret_cast<float4*>(sR + ((size_t)(warp * NT + nt) * 32 + lane) * 4) = make_float4(acc[nt][0], acc[nt][1], acc[nt][2], acc[nt][3]);
+    __syncthreads();
+    for (int e = threadIdx.x; e < NT * 128; e += kPThreads) {
+      float v = 0.f;
+#pragma unroll
+      for (int w = 0; w < kPWarps; ++w) v += sR[(size_t)w * NT * 128 + e];
+      const int c = e & 3, ml = (e >> 2) & 31, nt = e >> 7;
+      const int row = rb * 16 + (ml >> 2) + 8 * (c >> 1), tok = nt * 8 + 2 * (ml & 3) + (c & 1);
+      if (EPI == EPI_SWIGLU) {
+        const float up = __shfl_down_sync(0xffffffffu, v, 16);            // row + 1 of the same token sits 16 threads up
+        if (((ml >> 2) & 1) == 0 && tok < B) act[(size_t)tok * (N >> 1) + (row >> 1)] = __float2bfloat16_rn(silu(v) * up);
+      } else if (tok < B) {
+        if (EPI == EPI_F32) out32[((size_t)gs * Bpad + tok) * N + row] = v;
+        else {
+          bf16* px = xres + (size_t)tok * N + row;
+          *px = __float2bfloat16_rn(__bfloat162float(*px) + v);
         }
       }
     }
-    float* p = part + (size_t)s * Bpad * N + rb * 16 + g;
-#pragma unroll
-    for (int nt = 0; nt < NT; ++nt) {
-      const int tok = nt * 8 + 2 * t;
-      if (tok < B) { p[(size_t)tok * N] = acc[nt][0]; p[(size_t)tok * N + 8] = acc[nt][2]; }
-      if (tok + 1 < B) { p[(size_t)(tok + 1) * N] = acc[nt][1]; p[(size_t)(tok + 1) * N + 8] = acc[nt][3]; }
-    }
+    __syncthreads();
   }
 }
 
-__device__ __forceinline__ void gemm_dispatch(const bf16* W, int N, int K, int ksplit, const bf16* X, int B, int Bpad, float* part) {
-  if (B <= 8) gemm_phase<1>(W, N, K, ksplit, X, B, Bpad, part);
-  else if (B <= 16) gemm_phase<2>(W, N, K, ksplit, X, B, Bpad, part);
-  else if (B <= 32) gemm_phase<4>(W, N, K, ksplit, X, B, Bpad, part);
-  else gemm_phase<8>(W, N, K, ksplit, X, B, Bpad, part);
+template <int EPI>
+__device__ __forceinline__ void gemm_dispatch(const bf16* W, int N, int K, const bf16* X, int B, int Bpad, float* out32, bf16* xres,
+                                              bf16* act, float* sR) {
+  if (B <= 8) gemm_phase<1, EPI>(W, N, K, X, B, Bpad, out32, xres, act, sR);
+  else if (B <= 16) gemm_phase<2, EPI>(W, N, K, X, B, Bpad, out32, xres, act, sR);
+  else if (B <= 32) gemm_phase<4, EPI>(W, N, K, X, B, Bpad, out32, xres, act, sR);
+  else gemm_phase<8, EPI>(W, N, K, X, B, Bpad, out32, xres, act, sR);
 }
 
 // fixed-order sum of the KS split-K partials of one element; fully unrolled so the KS L2 loads are in flight together
@@ -116,26 +156,28 @@ __device__ __forceinline__ float sum_partials(const float* part, size_t stride, 
 }
 
 // ---- row phase: x[b] (+)= sum of partials; u[b] = rmsnorm(x[b]) * gamma  (one CTA per token, 4 features per thread) -------
+// ---- row phase: x[b] += sum of KS fp32 sections (KS = 0: x is already final); u[b] = rmsnorm(x[b]) * gamma ------------------
 template <int KS>
 __device__ __forceinline__ void residual_norm_phase(const float* part, int B, int Bpad, bf16* x, bf16* u,
                                                     const float* __restrict__ gamma, float eps, float* red) {
   for (int b = blockIdx.x; b < B; b += gridDim.x) {
     const int c0 = threadIdx.x * 4;
     float v[4];
-    const uint2 xr = *reinterpret_cast<const uint2*>(x + (size_t)b * PH + c0);
+    const uint2 xr = __ldcg(reinterpret_cast<const uint2*>(x + (size_t)b * PH + c0));
     v[0] = __uint_as_float(xr.x << 16); v[1] = __uint_as_float(xr.x & 0xffff0000u);
     v[2] = __uint_as_float(xr.y << 16); v[3] = __uint_as_float(xr.y & 0xffff0000u);
     float ss = 0.f;
-    float add[4];
+    if (KS > 0) {
+      float add[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) add[i] = sum_partials<KS>(part, (size_t)Bpad * PH, (size_t)b * PH + c0 + i);
+      for (int i = 0; i < 4; ++i) add[i] = sum_partials<(KS > 0 ? KS : 1)>(part, (size_t)Bpad * PH, (size_t)b * PH + c0 + i);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      v[i] = bf16r(v[i] + add[i]);
-      ss += v[i] * v[i];
+      for (int i = 0; i < 4; ++i) v[i] = bf16r(v[i] + add[i]);
+      __nv_bfloat162 o0 = __floats2bfloat162_rn(v[0], v[1]), o1 = __floats2bfloat162_rn(v[2], v[3]);
+      *reinterpret_cast<uint2*>(x + (size_t)b * PH + c0) = make_uint2(*reinterpret_cast<uint32_t*>(&o0), *reinterpret_cast<uint32_t*>(&o1));
     }
-    __nv_bfloat162 o0 = __floats2bfloat162_rn(v[0], v[1]), o1 = __floats2bfloat162_rn(v[2], v[3]);
-    *reinterpret_cast<uint2*>(x + (size_t)b * PH + c0) = make_uint2(*reinterpret_cast<uint32_t*>(&o0), *reinterpret_cast<uint32_t*>(&o1));
+#pragma unroll
+    for (int i = 0; i < 4; ++i) ss += v[i] * v[i];
     const float rstd = rsqrtf(block_sum(ss, red) / PH + eps);
     const float4 gm = *reinterpret_cast<const float4*>(gamma + c0);
     __nv_bfloat162 u0 = __floats2bfloat162_rn(gm.x * bf16r(v[0] * rstd), gm.y * bf16r(v[1] * rstd));
@@ -155,7 +197,6 @@ __device__ __forceinline__ void attention_phase(const DecodePersistArgs& a, cons
   float* sRed = sKV + 2 * PHD;                                 // [4 heads][4 key groups] max, then sums
   float* sState = sRed + 32;                                   // m[4], l[4], corr[4]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const size_t pstride = (size_t)a.Bpad * PQKV;
   for (int item = blockIdx.x; item < a.B * PKVH; item += gridDim.x) {
     const int seg = item / PKVH, kvh = item - seg * PKVH;
     const int pos = a.gs.ctx_len[seg], kv_len = pos + 1;
@@ -165,8 +206,8 @@ __device__ __forceinline__ void attention_phase(const DecodePersistArgs& a, cons
     for (int i = tid; i < (PG + 2) * (PHD / 2); i += kPThreads) {
       const int hh = i / (PHD / 2), j = i - hh * (PHD / 2);     // hh < 4: query head; 4: key; 5: value (pair j, j+64)
       const int col = (hh < PG) ? (kvh * PG + hh) * PHD : (hh == PG ? (16 + kvh) * PHD : (16 + PKVH + kvh) * PHD);
-      const float x = bf16r(sum_partials<kSplitQkv>(a.part, pstride, (size_t)seg * PQKV + col + j));
-      const float y = bf16r(sum_partials<kSplitQkv>(a.part, pstride, (size_t)seg * PQKV + col + j + PHD / 2));
+      const float x = bf16r(__ldcg(a.part + (size_t)seg * PQKV + col + j));
+      const float y = bf16r(__ldcg(a.part + (size_t)seg * PQKV + col + j + PHD / 2));
       if (hh <= PG) {
         const float c = bf16r(a.cos_t[(size_t)pos * (PHD / 2) + j]), s = bf16r(a.sin_t[(size_t)pos * (PHD / 2) + j]);
         const float rx = bf16r(x * c - y * s), ry = bf16r(y * c + x * s);
@@ -259,10 +300,22 @@ __device__ __forceinline__ void attention_phase(const DecodePersistArgs& a, cons
   }
 }
 
+__device__ __forceinline__ unsigned long long gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+#define STAMP()                                                                      \
+  do {                                                                               \
+    if (a.timestamps && blockIdx.x == 0 && threadIdx.x == 0) a.timestamps[n_stamp++] = gtimer(); \
+  } while (0)
+
 __global__ void __launch_bounds__(kPThreads, 1) decode_persist_kernel(DecodePersistArgs a) {
   extern __shared__ __align__(16) uint8_t smem[];
   __shared__ float red[32];
   unsigned epoch = 0;
+  int n_stamp = 0;
+  STAMP();
   const int tid = threadIdx.x;
   const int B = a.B, Bpad = a.Bpad;
 
@@ -281,49 +334,39 @@ __global__ void __launch_bounds__(kPThreads, 1) decode_persist_kernel(DecodePers
     *reinterpret_cast<uint2*>(a.u + (size_t)b * PH + c0) = make_uint2(*reinterpret_cast<uint32_t*>(&u0), *reinterpret_cast<uint32_t*>(&u1));
     __syncthreads();
   }
-  grid_barrier(a.bar, epoch);
+  grid_barrier(a.bar, epoch); STAMP();
 
+  float* sR = reinterpret_cast<float*>(smem);                 // GEMM exchange buffer (aliases the attention staging area)
   for (int l = 0; l < a.n_layers; ++l) {
     const DecLayerDev L = a.layers[l];
-    gemm_dispatch(L.wqkv, PQKV, PH, kSplitQkv, a.u, B, Bpad, a.part);
-    grid_barrier(a.bar, epoch);
+    gemm_dispatch<EPI_F32>(L.wqkv, PQKV, PH, a.u, B, Bpad, a.part, nullptr, nullptr, sR);
+    grid_barrier(a.bar, epoch); STAMP();
     attention_phase(a, L, smem);
-    grid_barrier(a.bar, epoch);
-    gemm_dispatch(L.wo, PH, PH, kSplitO, a.attn, B, Bpad, a.part);
-    grid_barrier(a.bar, epoch);
-    residual_norm_phase<kSplitO>(a.part, B, Bpad, a.x, a.u, L.rms2, a.eps, red);
-    grid_barrier(a.bar, epoch);
-    gemm_dispatch(L.wgu, 2 * PI, PH, kSplitGu, a.u, B, Bpad, a.part);
-    grid_barrier(a.bar, epoch);
-    {  // SwiGLU over the interleaved (gate, up) columns
-      const size_t stride = (size_t)Bpad * 2 * PI;
-      const int total = B * PI;
-      for (int i = blockIdx.x * kPThreads + tid; i < total; i += gridDim.x * kPThreads) {
-        const int b = i / PI, j = i - b * PI;
-        const float gte = sum_partials<kSplitGu>(a.part, stride, (size_t)b * 2 * PI + 2 * j);
-        const float up = sum_partials<kSplitGu>(a.part, stride, (size_t)b * 2 * PI + 2 * j + 1);
-        a.act[(size_t)b * PI + j] = __float2bfloat16_rn(silu(gte) * up);
-      }
-    }
-    grid_barrier(a.bar, epoch);
-    gemm_dispatch(L.wdown, PH, PI, kSplitDown, a.act, B, Bpad, a.part);
-    grid_barrier(a.bar, epoch);
-    residual_norm_phase<kSplitDown>(a.part, B, Bpad, a.x, a.u, (l + 1 < a.n_layers) ? a.layers[l + 1].rms1 : a.final_norm, a.eps, red);
-    grid_barrier(a.bar, epoch);
+    grid_barrier(a.bar, epoch); STAMP();
+    gemm_dispatch<EPI_RESID>(L.wo, PH, PH, a.attn, B, Bpad, nullptr, a.x, nullptr, sR);
+    grid_barrier(a.bar, epoch); STAMP();
+    residual_norm_phase<0>(nullptr, B, Bpad, a.x, a.u, L.rms2, a.eps, red);
+    grid_barrier(a.bar, epoch); STAMP();
+    gemm_dispatch<EPI_SWIGLU>(L.wgu, 2 * PI, PH, a.u, B, Bpad, nullptr, nullptr, a.act, sR);
+    grid_barrier(a.bar, epoch); STAMP();
+    gemm_dispatch<EPI_F32>(L.wdown, PH, PI, a.act, B, Bpad, a.part, nullptr, nullptr, sR);
+    grid_barrier(a.bar, epoch); STAMP();
+    residual_norm_phase<3>(a.part, B, Bpad, a.x, a.u, (l + 1 < a.n_layers) ? a.layers[l + 1].rms1 : a.final_norm, a.eps, red);
+    grid_barrier(a.bar, epoch); STAMP();
   }
 
-  // ---- lm_head + greedy pick
-  gemm_dispatch(a.lm_head, PV_, PH, kSplitHead, a.u, B, Bpad, a.part);
-  grid_barrier(a.bar, epoch);
+  // ---- lm_head + greedy pick: every CTA scans its slice of the vocabulary for all tokens, CTA b merges token b
+  gemm_dispatch<EPI_F32>(a.lm_head, PV_, PH, a.u, B, Bpad, a.part, nullptr, nullptr, sR);
+  grid_barrier(a.bar, epoch); STAMP();
   {
-    __shared__ float s_best[kPWarps], s_second[kPWarps];
-    __shared__ int s_idx[kPWarps];
-    const size_t stride = (size_t)Bpad * PV_;
-    for (int b = blockIdx.x; b < B; b += gridDim.x) {
+    const int per = (PV_ + gridDim.x - 1) / gridDim.x;
+    const int lo = blockIdx.x * per, hi = min(PV_, lo + per);
+    const int lane = tid & 31, warp = tid >> 5;
+    for (int b = warp; b < B; b += kPWarps) {                       // one warp per token over this CTA's slice
       float best = -INFINITY, second = -INFINITY;
       int bi = 0x7fffffff;
-      for (int i = tid; i < PV_; i += kPThreads) {
-        const float v = __ldcg(a.part + (size_t)b * PV_ + i) + __ldcg(a.part + stride + (size_t)b * PV_ + i);
+      for (int i = lo + lane; i < hi; i += 32) {
+        const float v = __ldcg(a.part + (size_t)b * PV_ + i);
         if (a.logits_out) a.logits_out[(size_t)b * PV_ + i] = v;
         if (v > best) { second = best; best = v; bi = i; }
         else if (v > second) second = v;
@@ -335,15 +378,32 @@ __global__ void __launch_bounds__(kPThreads, 1) decode_persist_kernel(DecodePers
         if (ob > best || (ob == best && oi < bi)) { second = fmaxf(fmaxf(second, os), best); best = ob; bi = oi; }
         else { second = fmaxf(second, ob); }
       }
-      if ((tid & 31) == 0) { s_best[tid >> 5] = best; s_second[tid >> 5] = second; s_idx[tid >> 5] = bi; }
-      __syncthreads();
+      if (lane == 0) {
+        float* pp = a.pick_scratch + ((size_t)b * gridDim.x + blockIdx.x) * 4;
+        pp[0] = best; pp[1] = second; pp[2] = __int_as_float(bi);
+      }
+    }
+  }
+  grid_barrier(a.bar, epoch); STAMP();
+  for (int b = blockIdx.x; b < B; b += gridDim.x) {
+    if (tid < 32) {
+      float best = -INFINITY, second = -INFINITY;
+      int bi = 0x7fffffff;
+      for (int c = tid; c < (int)gridDim.x; c += 32) {
+        const float* pp = a.pick_scratch + ((size_t)b * gridDim.x + c) * 4;
+        const float ob = __ldcg(pp), os = __ldcg(pp + 1);
+        const int oi = __float_as_int(__ldcg(pp + 2));
+        if (ob > best || (ob == best && oi < bi)) { second = fmaxf(fmaxf(second, os), best); best = ob; bi = oi; }
+        else { second = fmaxf(second, ob); }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ob = __shfl_xor_sync(0xffffffffu, best, o), os = __shfl_xor_sync(0xffffffffu, second, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ob > best || (ob == best && oi < bi)) { second = fmaxf(fmaxf(second, os), best); best = ob; bi = oi; }
+        else { second = fmaxf(second, ob); }
+      }
       if (tid == 0) {
-        for (int w = 1; w < kPWarps; ++w) {
-          const float ob = s_best[w], os = s_second[w];
-          const int oi = s_idx[w];
-          if (ob > best || (ob == best && oi < bi)) { second = fmaxf(fmaxf(second, os), best); best = ob; bi = oi; }
-          else { second = fmaxf(second, ob); }
-        }
         const int step = *a.gs.step;
         a.gs.ctx_len[b] += 1;
         if (!a.gs.finished[b]) {
@@ -356,23 +416,20 @@ __global__ void __launch_bounds__(kPThreads, 1) decode_persist_kernel(DecodePers
         }
         a.gs.cur_tok[b] = bi;
       }
-      __syncthreads();
     }
   }
-  grid_barrier(a.bar, epoch);
+  grid_barrier(a.bar, epoch); STAMP();
   if (blockIdx.x == 0 && tid == 0) *a.gs.step += 1;
 }
 
-size_t decode_persist_smem_bytes() { return (size_t)AKEYS * kAKRow + (size_t)AKEYS * PHD * 2 + (PG * PHD + PG * AKEYS + 2 * PHD + 32 + 16) * 4; }
-
-size_t decode_persist_part_floats(int Bpad) {
-  size_t m = (size_t)kSplitQkv * PQKV;
-  if ((size_t)kSplitO * PH > m) m = (size_t)kSplitO * PH;
-  if ((size_t)kSplitGu * 2 * PI > m) m = (size_t)kSplitGu * 2 * PI;
-  if ((size_t)kSplitDown * PH > m) m = (size_t)kSplitDown * PH;
-  if ((size_t)kSplitHead * PV_ > m) m = (size_t)kSplitHead * PV_;
-  return m * Bpad;
+size_t decode_persist_smem_bytes() {
+  const size_t attn = (size_t)AKEYS * kAKRow + (size_t)AKEYS * PHD * 2 + (PG * PHD + PG * AKEYS + 2 * PHD + 32 + 16) * 4;
+  const size_t exch = (size_t)kPWarps * 8 * 128 * 4;          // 16 warps x NT(8) x 128 fp32
+  return attn > exch ? attn : exch;
 }
+
+size_t decode_persist_part_floats(int Bpad) { return (size_t)PV_ * Bpad; }     // >= qkv (3072) and 3 down sections (6144)
+size_t decode_persist_pick_floats(int max_batch, int num_sms) { return (size_t)max_batch * num_sms * 4; }
 
 cudaError_t decode_persist_configure() {
   return cudaFuncSetAttribute(decode_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)decode_persist_smem_bytes());

@@ -126,13 +126,17 @@ struct DecodePersistArgs {
   bf16 *x, *u, *attn, *act;       // [B][2048], [B][2048], [B][2048], [B][6144]
   float* part;                    // split-K partials, decode_persist_part_floats(Bpad) floats
   float* logits_out;              // optional [B][vocab]
+  float* pick_scratch;            // decode_persist_pick_floats(max_batch, num_sms)
   GreedyState gs;
   unsigned* bar;                  // grid barrier counter
+  unsigned long long* timestamps; // optional: %globaltimer after every grid barrier (CTA 0), 1 + 8*layers + 3 entries
   int B, Bpad, max_ctx;
+  int prefetch;                   // 1: L2-prefetch the next GEMM's weights at the start of every GEMM phase
   float eps, scale;
 };
 size_t decode_persist_smem_bytes();
 size_t decode_persist_part_floats(int Bpad);
+size_t decode_persist_pick_floats(int max_batch, int num_sms);
 cudaError_t decode_persist_configure();
 cudaError_t launch_decode_persist(const DecodePersistArgs& a, int num_sms, cudaStream_t st);
 
