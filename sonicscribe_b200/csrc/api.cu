@@ -480,7 +480,8 @@ struct Engine {
       p.embed = reinterpret_cast<const bf16*>(h->embed); p.lm_head = reinterpret_cast<const bf16*>(h->lm_head); p.final_norm = h->final_norm;
       p.cos_t = h->rope_dec_cos; p.sin_t = h->rope_dec_sin;
       p.x = reinterpret_cast<bf16*>(h->dx); p.u = reinterpret_cast<bf16*>(h->du); p.attn = reinterpret_cast<bf16*>(h->dattn);
-      p.act = reinterpret_cast<bf16*>(h->dact); p.part = h->persist_part; p.logits_out = nullptr; p.pick_scratch = h->persist_pick; p.gs = h->gs; p.bar = h->persist_bar; p.timestamps = h->cfg.debug ? h->persist_ts : nullptr;
+      p.act = reinterpret_cast<bf16*>(h->dact); p.part = h->persist_part; p.logits_out = nullptr; p.pick_scratch = h->persist_pick;
+      p.attn_ws = h->dattn_ws; p.attn_counters = h->dattn_counters; p.attn_chunks = (h->decode_chunks + 1) / 2;   // 128-key chunks p.gs = h->gs; p.bar = h->persist_bar; p.timestamps = h->cfg.debug ? h->persist_ts : nullptr;
       { const char* pf = getenv("SONIC_PERSIST_PREFETCH"); p.prefetch = (pf && pf[0] == '1') ? 1 : 0; }
       p.B = B; p.Bpad = (B + 7) / 8 * 8; p.max_ctx = h->max_ctx; p.eps = kRmsEps; p.scale = 0.08838834764831845f;
       TAG(PC_DEC_PERSIST);

@@ -187,48 +187,56 @@ __device__ __forceinline__ void residual_norm_phase(const float* part, int B, in
   }
 }
 
-// ---- attention phase: item = (segment, kv head): finish q/k/v from the partials, RoPE, append to the cache, attend ---------
+// ---- attention phase: item = (segment, kv head, chunk of 128 keys).  Every item finishes q (4 heads) from the fp32 qkv
+// section and rotates it; the item owning the newest position also rotates k and appends k, v to the cache.  Each item writes
+// an (m, l, o) partial; the item arriving last at the (segment, kv head) counter merges the partials in chunk order.
 __device__ __forceinline__ void attention_phase(const DecodePersistArgs& a, const DecLayerDev& L, uint8_t* smem) {
   uint8_t* sK = smem;                                          // AKEYS * kAKRow
   bf16* sV = reinterpret_cast<bf16*>(smem + AKEYS * kAKRow);   // AKEYS * 128
   float* sQ = reinterpret_cast<float*>(smem + AKEYS * kAKRow + AKEYS * PHD * 2);   // [4][128]
   float* sP = sQ + PG * PHD;                                   // [4][AKEYS]
   float* sKV = sP + PG * AKEYS;                                // new k (128) | new v (128)
-  float* sRed = sKV + 2 * PHD;                                 // [4 heads][4 key groups] max, then sums
-  float* sState = sRed + 32;                                   // m[4], l[4], corr[4]
+  float* sMax = sKV + 2 * PHD;                                 // [4 heads][4 key groups]
+  float* sSum = sMax + 16;                                     // [4 heads][4 key groups]
+  __shared__ int s_last;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int item = blockIdx.x; item < a.B * PKVH; item += gridDim.x) {
-    const int seg = item / PKVH, kvh = item - seg * PKVH;
+  const int C = a.attn_chunks;
+  const int n_items = a.B * PKVH * C;
+  for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    const int chunk = item % C, grp = item / C;                  // grp = seg * 4 + kvh
+    const int seg = grp / PKVH, kvh = grp - seg * PKVH;
     const int pos = a.gs.ctx_len[seg], kv_len = pos + 1;
-    bf16* kc = L.kc + ((size_t)seg * PKVH + kvh) * a.max_ctx * PHD;
-    bf16* vc = L.vc + ((size_t)seg * PKVH + kvh) * a.max_ctx * PHD;
-    // q (4 heads), k, v of the new token: sum the split-K partials, round to bf16 like the unfused path, rotate
-    for (int i = tid; i < (PG + 2) * (PHD / 2); i += kPThreads) {
-      const int hh = i / (PHD / 2), j = i - hh * (PHD / 2);     // hh < 4: query head; 4: key; 5: value (pair j, j+64)
-      const int col = (hh < PG) ? (kvh * PG + hh) * PHD : (hh == PG ? (16 + kvh) * PHD : (16 + PKVH + kvh) * PHD);
-      const float x = bf16r(__ldcg(a.part + (size_t)seg * PQKV + col + j));
-      const float y = bf16r(__ldcg(a.part + (size_t)seg * PQKV + col + j + PHD / 2));
-      if (hh <= PG) {
-        const float c = bf16r(a.cos_t[(size_t)pos * (PHD / 2) + j]), s = bf16r(a.sin_t[(size_t)pos * (PHD / 2) + j]);
-        const float rx = bf16r(x * c - y * s), ry = bf16r(y * c + x * s);
-        if (hh < PG) { sQ[hh * PHD + j] = rx * a.scale; sQ[hh * PHD + j + PHD / 2] = ry * a.scale; }
-        else { sKV[j] = rx; sKV[j + PHD / 2] = ry; }
-      } else { sKV[PHD + j] = x; sKV[PHD + j + PHD / 2] = y; }
-    }
-    if (tid < PG) { sState[tid] = -INFINITY; sState[4 + tid] = 0.f; }
-    __syncthreads();
-    if (tid < PHD) kc[(size_t)pos * PHD + tid] = __float2bfloat16_rn(sKV[tid]);
-    else if (tid < 2 * PHD) vc[(size_t)pos * PHD + tid - PHD] = __float2bfloat16_rn(sKV[tid]);
-    const int head = warp & 3, kgrp = warp >> 2;                 // scores: 4 heads x 4 groups of 32 keys
-    float o_acc = 0.f;                                           // PV: thread = (head = tid / 128, dim = tid % 128)
-    for (int k0 = 0; k0 < kv_len; k0 += AKEYS) {
+    const int n_chunks = (kv_len + AKEYS - 1) / AKEYS;
+    float* ws = a.attn_ws + ((size_t)grp * C + chunk) * PG * (PHD + 2);
+    if (chunk < n_chunks) {
+      bf16* kc = L.kc + ((size_t)seg * PKVH + kvh) * a.max_ctx * PHD;
+      bf16* vc = L.vc + ((size_t)seg * PKVH + kvh) * a.max_ctx * PHD;
+      const bool owner = (chunk == pos / AKEYS);
+      const int n_pairs = (owner ? PG + 2 : PG) * (PHD / 2);
+      for (int i = tid; i < n_pairs; i += kPThreads) {
+        const int hh = i / (PHD / 2), j = i - hh * (PHD / 2);     // hh < 4: query head; 4: key; 5: value (pair j, j+64)
+        const int col = (hh < PG) ? (kvh * PG + hh) * PHD : (hh == PG ? (16 + kvh) * PHD : (16 + PKVH + kvh) * PHD);
+        const float x = bf16r(__ldcg(a.part + (size_t)seg * PQKV + col + j));
+        const float y = bf16r(__ldcg(a.part + (size_t)seg * PQKV + col + j + PHD / 2));
+        if (hh <= PG) {
+          const float c = bf16r(a.cos_t[(size_t)pos * (PHD / 2) + j]), sn = bf16r(a.sin_t[(size_t)pos * (PHD / 2) + j]);
+          const float rx = bf16r(x * c - y * sn), ry = bf16r(y * c + x * sn);
+          if (hh < PG) { sQ[hh * PHD + j] = rx * a.scale; sQ[hh * PHD + j + PHD / 2] = ry * a.scale; }
+          else { sKV[j] = rx; sKV[j + PHD / 2] = ry; }
+        } else { sKV[PHD + j] = x; sKV[PHD + j + PHD / 2] = y; }
+      }
+      __syncthreads();
+      if (owner) {
+        if (tid < PHD) kc[(size_t)pos * PHD + tid] = __float2bfloat16_rn(sKV[tid]);
+        else if (tid < 2 * PHD) vc[(size_t)pos * PHD + tid - PHD] = __float2bfloat16_rn(sKV[tid]);
+      }
+      const int k0 = chunk * AKEYS;
       const int nk = min(AKEYS, kv_len - k0);
-      __syncthreads();                                           // previous chunk fully consumed; new k/v row written
       for (int i = tid; i < AKEYS * (PHD / 8); i += kPThreads) {
         const int r = i / (PHD / 8), c8 = i - r * (PHD / 8);
         uint4 kk = make_uint4(0, 0, 0, 0), vv = make_uint4(0, 0, 0, 0);
         if (r < nk) {
-          if (k0 + r == pos) {                                   // the row appended above by this CTA: take it from smem
+          if (k0 + r == pos) {                                   // the row this CTA appends: take it from shared memory
             uint32_t wk[4], wv[4];
 #pragma unroll
             for (int e2 = 0; e2 < 4; ++e2) {
@@ -246,7 +254,7 @@ __device__ __forceinline__ void attention_phase(const DecodePersistArgs& a, cons
         *reinterpret_cast<uint4*>(sV + r * PHD + c8 * 8) = vv;
       }
       __syncthreads();
-      // scores for (head, key = kgrp*32 + lane)
+      const int head = warp & 3, kgrp = warp >> 2;               // scores: 4 heads x 4 groups of 32 keys
       const int r = kgrp * 32 + lane;
       float sc = -INFINITY;
       if (r < nk) {
@@ -264,37 +272,49 @@ __device__ __forceinline__ void attention_phase(const DecodePersistArgs& a, cons
         sc = acc;
       }
       const float wmax = warp_max(sc);
-      if (lane == 0) sRed[head * 4 + kgrp] = wmax;
+      if (lane == 0) sMax[head * 4 + kgrp] = wmax;
       __syncthreads();
-      const float cmax = fmaxf(fmaxf(sRed[head * 4], sRed[head * 4 + 1]), fmaxf(sRed[head * 4 + 2], sRed[head * 4 + 3]));
-      const float m_old = sState[head];
-      const float m_new = fmaxf(m_old, cmax);
-      const float p = (sc == -INFINITY) ? 0.f : expf(sc - m_new);
+      const float cmax = fmaxf(fmaxf(sMax[head * 4], sMax[head * 4 + 1]), fmaxf(sMax[head * 4 + 2], sMax[head * 4 + 3]));
+      const float p = (sc == -INFINITY) ? 0.f : expf(sc - cmax);
       sP[head * AKEYS + r] = p;
       const float wsum = warp_sum(p);
-      __syncthreads();                                           // every thread has read the maxima and the running state
-      if (lane == 0) sRed[head * 4 + kgrp] = wsum;
-      __syncthreads();
-      if (kgrp == 0 && lane == 0) {                              // one thread per head advances the online-softmax state
-        const float corr = (m_old == -INFINITY) ? 0.f : expf(m_old - m_new);
-        const float lsum = sRed[head * 4] + sRed[head * 4 + 1] + sRed[head * 4 + 2] + sRed[head * 4 + 3];
-        sState[8 + head] = corr;
-        sState[head] = m_new;
-        sState[4 + head] = sState[4 + head] * corr + lsum;
-      }
+      if (lane == 0) sSum[head * 4 + kgrp] = wsum;
       __syncthreads();
       {
-        const int ph = tid >> 7, d = tid & 127;
-        float acc = o_acc * sState[8 + ph];
+        const int ph = tid >> 7, d = tid & 127;                  // PV: thread = (head, dim)
+        float acc = 0.f;
         const float* pp = sP + ph * AKEYS;
         for (int j = 0; j < nk; ++j) acc = fmaf(pp[j], __bfloat162float(sV[j * PHD + d]), acc);
-        o_acc = acc;
+        ws[(size_t)ph * (PHD + 2) + d] = acc;
+        if (d == 0) {
+          ws[(size_t)ph * (PHD + 2) + PHD] = fmaxf(fmaxf(sMax[ph * 4], sMax[ph * 4 + 1]), fmaxf(sMax[ph * 4 + 2], sMax[ph * 4 + 3]));
+          ws[(size_t)ph * (PHD + 2) + PHD + 1] = sSum[ph * 4] + sSum[ph * 4 + 1] + sSum[ph * 4 + 2] + sSum[ph * 4 + 3];
+        }
       }
     }
+    // arrival + last-arriver merge (chunk order => deterministic)
+    __threadfence();
     __syncthreads();
-    {
+    if (tid == 0) {
+      const int prev = atomicAdd(a.attn_counters + grp, 1);
+      s_last = (prev == C - 1) ? 1 : 0;
+      if (s_last) a.attn_counters[grp] = 0;
+    }
+    __syncthreads();
+    if (s_last) {
+      __threadfence();
       const int ph = tid >> 7, d = tid & 127;
-      a.attn[(size_t)seg * PH + (size_t)(kvh * PG + ph) * PHD + d] = __float2bfloat16_rn(o_acc / sState[4 + ph]);
+      const float* wg = a.attn_ws + (size_t)grp * C * PG * (PHD + 2);
+      float M = -INFINITY;
+      for (int c = 0; c < n_chunks; ++c) M = fmaxf(M, __ldcg(wg + ((size_t)c * PG + ph) * (PHD + 2) + PHD));
+      float Ls = 0.f, acc = 0.f;
+      for (int c = 0; c < n_chunks; ++c) {
+        const float* pc = wg + ((size_t)c * PG + ph) * (PHD + 2);
+        const float w = expf(__ldcg(pc + PHD) - M);
+        Ls += __ldcg(pc + PHD + 1) * w;
+        acc += __ldcg(pc + d) * w;
+      }
+      a.attn[(size_t)seg * PH + (size_t)(kvh * PG + ph) * PHD + d] = __float2bfloat16_rn(acc / Ls);
     }
     __syncthreads();
   }

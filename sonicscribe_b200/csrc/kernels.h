@@ -127,6 +127,7 @@ struct DecodePersistArgs {
   float* part;                    // split-K partials, decode_persist_part_floats(Bpad) floats
   float* logits_out;              // optional [B][vocab]
   float* pick_scratch;            // decode_persist_pick_floats(max_batch, num_sms)
+  float* attn_ws; int* attn_counters; int attn_chunks;   // split-KV partials [B*4][attn_chunks][4][130], counters [B*4] (zeroed)
   GreedyState gs;
   unsigned* bar;                  // grid barrier counter
   unsigned long long* timestamps; // optional: %globaltimer after every grid barrier (CTA 0), 1 + 8*layers + 3 entries
