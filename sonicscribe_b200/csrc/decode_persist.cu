@@ -76,49 +76,60 @@ __device__ __forceinline__ void prefetch_weights_l2(const void* W, size_t bytes,
 // the bf16 stream, or SwiGLU of interleaved (gate, up) rows.  The next item's weight loads are issued before the exchange.
 enum { EPI_F32 = 0, EPI_RESID = 1, EPI_SWIGLU = 2 };
 
-template <int NT, int EPI>
+template <int NT, int EPI, int RB>
 __device__ __forceinline__ void gemm_phase(const bf16* __restrict__ W, int N, int K, const bf16* X, int B, int Bpad,
                                            float* __restrict__ out32, bf16* xres, bf16* act, float* sR) {
+  // RB row blocks of 16 rows per item; the 16 warps form RB x (16/RB): warp -> (row block rw, k slice kw of 128*RB).
+  // Larger RB re-uses the activation slice for more weight rows (needed once the token count makes it the L2 bottleneck).
+  constexpr int KW = kPWarps / RB;                 // k slices per section
+  constexpr int GROUPS = RB;                       // 128-wide k groups per warp per item (2048 / KW / 128)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
-  const int nrb = N >> 4, gsplit = K >> 11, n_items = nrb * gsplit;
+  const int rw = warp % RB, kw = warp / RB;
+  const int nib = N / (16 * RB), gsplit = K >> 11, n_items = nib * gsplit;
   int item = blockIdx.x;
   uint4 wa[4], wb[4];
-  auto load_item = [&](int it) {
-    const int gs = it / nrb, rb = it - gs * nrb;
-    const bf16* w0 = W + (size_t)(rb * 16 + g) * K + (size_t)gs * 2048 + warp * 128 + 8 * t;
+  auto load_group = [&](int it, int grp) {
+    const int gs = it / nib, ib = it - gs * nib;
+    const bf16* w0 = W + (size_t)((ib * RB + rw) * 16 + g) * K + (size_t)gs * 2048 + (kw * GROUPS + grp) * 128 + 8 * t;
     const bf16* w1 = w0 + (size_t)8 * K;
 #pragma unroll
     for (int u = 0; u < 4; ++u) { wa[u] = ldg_stream(w0 + 32 * u); wb[u] = ldg_stream(w1 + 32 * u); }
   };
-  if (item < n_items) load_item(item);
+  if (item < n_items) load_group(item, 0);
   for (; item < n_items; item += gridDim.x) {
-    const int gs = item / nrb, rb = item - gs * nrb;
-    const bf16* xb = X + (size_t)gs * 2048 + warp * 128 + 8 * t;
+    const int gs = item / nib, ib = item - gs * nib;
     float acc[NT][4];
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) { acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f; }
+#pragma unroll 1
+    for (int grp = 0; grp < GROUPS; ++grp) {
+      const bf16* xb = X + (size_t)gs * 2048 + (kw * GROUPS + grp) * 128 + 8 * t;
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < 4; ++u) {
 #pragma unroll
-      for (int nt = 0; nt < NT; ++nt) {
-        const int tok = nt * 8 + g;
-        uint4 xv = make_uint4(0, 0, 0, 0);
-        if (tok < B) xv = *reinterpret_cast<const uint4*>(xb + (size_t)tok * K + 32 * u);
-        mma16816(acc[nt], wa[u].x, wb[u].x, wa[u].y, wb[u].y, xv.x, xv.y);
-        mma16816(acc[nt], wa[u].z, wb[u].z, wa[u].w, wb[u].w, xv.z, xv.w);
+        for (int nt = 0; nt < NT; ++nt) {
+          const int tok = nt * 8 + g;
+          uint4 xv = make_uint4(0, 0, 0, 0);
+          if (tok < B) xv = *reinterpret_cast<const uint4*>(xb + (size_t)tok * K + 32 * u);
+          mma16816(acc[nt], wa[u].x, wb[u].x, wa[u].y, wb[u].y, xv.x, xv.y);
+          mma16816(acc[nt], wa[u].z, wb[u].z, wa[u].w, wb[u].w, xv.z, xv.w);
+        }
       }
+      // next group of this item, or the first group of the next item (then in flight during the exchange below)
+      if (grp + 1 < GROUPS) load_group(item, grp + 1);
+      else if (item + (int)gridDim.x < n_items) load_group(item + gridDim.x, 0);
     }
-    if (item + (int)gridDim.x < n_items) load_item(item + gridDim.x);     // in flight during the exchange below
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt)
       *reinterpret_cast<float4*>(sR + ((size_t)(warp * NT + nt) * 32 + lane) * 4) = make_float4(acc[nt][0], acc[nt][1], acc[nt][2], acc[nt][3]);
     __syncthreads();
-    for (int e = threadIdx.x; e < NT * 128; e += kPThreads) {
+    for (int e = threadIdx.x; e < RB * NT * 128; e += kPThreads) {
+      const int rb_l = e / (NT * 128), e2 = e - rb_l * (NT * 128);       // row block inside the item, element inside its tile
       float v = 0.f;
 #pragma unroll
-      for (int w = 0; w < kPWarps; ++w) v += sR[(size_t)w * NT * 128 + e];
-      const int c = e & 3, ml = (e >> 2) & 31, nt = e >> 7;
-      const int row = rb * 16 + (ml >> 2) + 8 * (c >> 1), tok = nt * 8 + 2 * (ml & 3) + (c & 1);
+      for (int k = 0; k < KW; ++k) v += sR[(size_t)(k * RB + rb_l) * NT * 128 + e2];
+      const int c = e2 & 3, ml = (e2 >> 2) & 31, nt = e2 >> 7;
+      const int row = (ib * RB + rb_l) * 16 + (ml >> 2) + 8 * (c >> 1), tok = nt * 8 + 2 * (ml & 3) + (c & 1);
       if (EPI == EPI_SWIGLU) {
         const float up = __shfl_down_sync(0xffffffffu, v, 16);            // row + 1 of the same token sits 16 threads up
         if (((ml >> 2) & 1) == 0 && tok < B) act[(size_t)tok * (N >> 1) + (row >> 1)] = __float2bfloat16_rn(silu(v) * up);
@@ -137,10 +148,10 @@ __device__ __forceinline__ void gemm_phase(const bf16* __restrict__ W, int N, in
 template <int EPI>
 __device__ __forceinline__ void gemm_dispatch(const bf16* W, int N, int K, const bf16* X, int B, int Bpad, float* out32, bf16* xres,
                                               bf16* act, float* sR) {
-  if (B <= 8) gemm_phase<1, EPI>(W, N, K, X, B, Bpad, out32, xres, act, sR);
-  else if (B <= 16) gemm_phase<2, EPI>(W, N, K, X, B, Bpad, out32, xres, act, sR);
-  else if (B <= 32) gemm_phase<4, EPI>(W, N, K, X, B, Bpad, out32, xres, act, sR);
-  else gemm_phase<8, EPI>(W, N, K, X, B, Bpad, out32, xres, act, sR);
+  if (B <= 8) gemm_phase<1, EPI, 1>(W, N, K, X, B, Bpad, out32, xres, act, sR);
+  else if (B <= 16) gemm_phase<2, EPI, 1>(W, N, K, X, B, Bpad, out32, xres, act, sR);
+  else if (B <= 32) gemm_phase<4, EPI, 2>(W, N, K, X, B, Bpad, out32, xres, act, sR);
+  else gemm_phase<8, EPI, 4>(W, N, K, X, B, Bpad, out32, xres, act, sR);
 }
 
 // fixed-order sum of the KS split-K partials of one element; fully unrolled so the KS L2 loads are in flight together

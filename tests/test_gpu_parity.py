@@ -374,3 +374,36 @@ def test_int8_mode_matches_dequantised_oracle(tiny_sd):
             break
     assert eng.device_bytes() > 0
     eng.close()
+
+
+def test_persistent_decode_kernel_vs_graph_path(tiny_sd, eng_bf16):
+    """The cooperative one-launch-per-token decode kernel (default in bf16 mode) against the CUDA-graph path built from the
+    tcgen05 decode GEMMs + fused decode attention (SONIC_DECODE=graph): same bf16 arithmetic up to summation order."""
+    os.environ["SONIC_DECODE"] = "graph"
+    try:
+        ref_eng = Engine(2, 2, mode="bf16", device=0, max_batch=4, max_prompt=300, max_new=40, debug=True)
+    finally:
+        del os.environ["SONIC_DECODE"]
+    ref_eng.load_state_dict(tiny_sd)
+    segs = [mo.synth_audio("speech", 163840, 11), mo.synth_audio("noise", 20480, 3), mo.synth_audio("speech", 320000, 1)]
+    prompts = [synthetic_prompt_ids(num_audio_tokens(s.shape[0])) for s in segs]
+    a, ma = eng_bf16.transcribe_ids(segs, prompts, 32, want_margins=True)
+    b, mb = ref_eng.transcribe_ids(segs, prompts, 32, want_margins=True)
+    ref_eng.close()
+    for s in range(3):
+        assert len(a[s]) == len(b[s]) == 32
+        for t, (x, y) in enumerate(zip(a[s], b[s])):
+            if x != y:
+                assert min(ma[s][t], mb[s][t]) < 0.2, (s, t, ma[s][t], mb[s][t])
+                break
+        assert a[s][:6] == b[s][:6]
+        n = min(len(ma[s]), 6)
+        assert np.abs(np.array(ma[s][:n]) - np.array(mb[s][:n])).max() < 0.15
+
+
+def test_single_segment_long_generation_reaches_max_ctx(eng_bf16):
+    """max_new_tokens up to the handle's limit with a 20 s prompt: context 270 + 40 crosses the 64/128-key chunk borders."""
+    x = mo.synth_audio("speech", 320000, 1)
+    ids = synthetic_prompt_ids(num_audio_tokens(x.shape[0]))
+    out = eng_bf16.transcribe_ids([x], [ids], 40)
+    assert len(out[0]) == 40 and all(0 <= t < 59264 for t in out[0])
