@@ -164,6 +164,7 @@ struct sonic_ctx {
   unsigned long long* persist_ts = nullptr;
   float* persist_pick = nullptr;
   int num_sms = 0;
+  int persist_grid = 0;
   float* dattn_ws = nullptr;
   int* dattn_counters = nullptr;
   int dattn_max_chunks = 0;
@@ -476,17 +477,29 @@ struct Engine {
     TAG(PC_DEC_OTHER);
     if (h->use_persist && std::is_same<T, bf16>::value) {
       DecodePersistArgs p;
+      memset(&p, 0, sizeof(p));
       p.layers = h->dev_layers; p.n_layers = h->cfg.dec_layers;
       p.embed = reinterpret_cast<const bf16*>(h->embed); p.lm_head = reinterpret_cast<const bf16*>(h->lm_head); p.final_norm = h->final_norm;
       p.cos_t = h->rope_dec_cos; p.sin_t = h->rope_dec_sin;
       p.x = reinterpret_cast<bf16*>(h->dx); p.u = reinterpret_cast<bf16*>(h->du); p.attn = reinterpret_cast<bf16*>(h->dattn);
       p.act = reinterpret_cast<bf16*>(h->dact); p.part = h->persist_part; p.logits_out = nullptr; p.pick_scratch = h->persist_pick;
-      p.attn_ws = h->dattn_ws; p.attn_counters = h->dattn_counters; p.attn_chunks = (h->decode_chunks + 1) / 2;   // 128-key chunks p.gs = h->gs; p.bar = h->persist_bar; p.timestamps = h->cfg.debug ? h->persist_ts : nullptr;
+      p.attn_ws = h->dattn_ws; p.attn_counters = h->dattn_counters;
+      // 128-key chunks over separate CTAs while that still leaves CTAs idle; otherwise one CTA walks all chunks of a group
+      p.attn_chunks = (B * kDecKv * ((h->decode_chunks + 1) / 2) <= h->persist_grid) ? (h->decode_chunks + 1) / 2 : 1;
+      p.gs = h->gs; p.bar = h->persist_bar; p.timestamps = h->cfg.debug ? h->persist_ts : nullptr;
       { const char* pf = getenv("SONIC_PERSIST_PREFETCH"); p.prefetch = (pf && pf[0] == '1') ? 1 : 0; }
       p.B = B; p.Bpad = (B + 7) / 8 * 8; p.max_ctx = h->max_ctx; p.eps = kRmsEps; p.scale = 0.08838834764831845f;
       TAG(PC_DEC_PERSIST);
-      CKL(launch_decode_persist(p, h->num_sms, h->stream), 1);
-      return 0;
+      if (h->prof_on) { cudaEventRecord(prof_event(h), h->stream); h->prof_tags.push_back(h->prof_cls); }
+      cudaError_t pe = launch_decode_persist(p, h->persist_grid, h->stream);
+      if (h->prof_on) cudaEventRecord(prof_event(h), h->stream);
+      if (pe == cudaSuccess) { h->launches += 1; return 0; }
+      // a cooperative launch can be refused (co-residency not available on this device/driver state): fall back, for the
+      // rest of this handle's life, to the CUDA-graph decode path (still the GPU path) and say so once
+      cudaGetLastError();
+      fprintf(stderr, "[sonicscribe_b200] cooperative decode kernel refused (%s, grid %d, occupancy/SM now %d, B %d, smem %zu); using the graph decode path\n",
+              cudaGetErrorName(pe), h->persist_grid, decode_persist_occupancy(), B, decode_persist_smem_bytes());
+      h->use_persist = false;
     }
     // every kernel of the step is launched with programmatic stream serialization (bf16 tensor-core path only): the next
     // kernel's CTAs are scheduled, and its weight tiles are in flight, while the current one drains
@@ -926,6 +939,14 @@ int sonic_create(const sonic_config* cfg, sonic_handle* out) {
   if (!h->is_f32 && gemm_tc_init() != cudaSuccess) { h->err = "cuTensorMapEncodeTiled entry point unavailable"; return bail(0); }
   if (!h->is_f32 && gemm_tc_configure() != cudaSuccess) { h->err = "gemm_tc_configure failed"; return bail(0); }
   if (h->use_persist && decode_persist_configure() != cudaSuccess) { h->err = "decode_persist_configure failed"; return bail(0); }
+  if (h->use_persist) {
+    h->persist_grid = decode_persist_max_grid(h->num_sms);
+    if (const char* pg = getenv("SONIC_PERSIST_GRID")) { const int v = atoi(pg); if (v >= 1 && v <= h->num_sms) h->persist_grid = v; }
+    if (h->persist_grid < 1) {
+      fprintf(stderr, "[sonicscribe_b200] cooperative launch unavailable; using the graph decode path\n");
+      h->use_persist = false;
+    }
+  }
   if (!h->is_f32 && attention_tc_configure() != cudaSuccess) { h->err = "attention_tc_configure failed"; return bail(0); }
   if (alloc_all(h)) return bail(0);
   *out = h;

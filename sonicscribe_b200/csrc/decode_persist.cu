@@ -150,8 +150,8 @@ __device__ __forceinline__ void gemm_dispatch(const bf16* W, int N, int K, const
                                               bf16* act, float* sR) {
   if (B <= 8) gemm_phase<1, EPI, 1>(W, N, K, X, B, Bpad, out32, xres, act, sR);
   else if (B <= 16) gemm_phase<2, EPI, 1>(W, N, K, X, B, Bpad, out32, xres, act, sR);
-  else if (B <= 32) gemm_phase<4, EPI, 2>(W, N, K, X, B, Bpad, out32, xres, act, sR);
-  else gemm_phase<8, EPI, 4>(W, N, K, X, B, Bpad, out32, xres, act, sR);
+  else if (B <= 32) gemm_phase<4, EPI, 1>(W, N, K, X, B, Bpad, out32, xres, act, sR);   // RB > 1 measured slower: too few items
+  else gemm_phase<8, EPI, 1>(W, N, K, X, B, Bpad, out32, xres, act, sR);
 }
 
 // fixed-order sum of the KS split-K partials of one element; fully unrolled so the KS L2 loads are in flight together
@@ -331,6 +331,120 @@ __device__ __forceinline__ void attention_phase(const DecodePersistArgs& a, cons
   }
 }
 
+// ---- attention phase, large-batch variant: item = (segment, kv head), chunks walked in-CTA with an online softmax: finish q/k/v from the partials, RoPE, append to the cache, attend ---------
+__device__ __forceinline__ void attention_phase_serial(const DecodePersistArgs& a, const DecLayerDev& L, uint8_t* smem) {
+  uint8_t* sK = smem;                                          // AKEYS * kAKRow
+  bf16* sV = reinterpret_cast<bf16*>(smem + AKEYS * kAKRow);   // AKEYS * 128
+  float* sQ = reinterpret_cast<float*>(smem + AKEYS * kAKRow + AKEYS * PHD * 2);   // [4][128]
+  float* sP = sQ + PG * PHD;                                   // [4][AKEYS]
+  float* sKV = sP + PG * AKEYS;                                // new k (128) | new v (128)
+  float* sRed = sKV + 2 * PHD;                                 // [4 heads][4 key groups] max, then sums
+  float* sState = sRed + 32;                                   // m[4], l[4], corr[4]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int item = blockIdx.x; item < a.B * PKVH; item += gridDim.x) {
+    const int seg = item / PKVH, kvh = item - seg * PKVH;
+    const int pos = a.gs.ctx_len[seg], kv_len = pos + 1;
+    bf16* kc = L.kc + ((size_t)seg * PKVH + kvh) * a.max_ctx * PHD;
+    bf16* vc = L.vc + ((size_t)seg * PKVH + kvh) * a.max_ctx * PHD;
+    // q (4 heads), k, v of the new token: sum the split-K partials, round to bf16 like the unfused path, rotate
+    for (int i = tid; i < (PG + 2) * (PHD / 2); i += kPThreads) {
+      const int hh = i / (PHD / 2), j = i - hh * (PHD / 2);     // hh < 4: query head; 4: key; 5: value (pair j, j+64)
+      const int col = (hh < PG) ? (kvh * PG + hh) * PHD : (hh == PG ? (16 + kvh) * PHD : (16 + PKVH + kvh) * PHD);
+      const float x = bf16r(__ldcg(a.part + (size_t)seg * PQKV + col + j));
+      const float y = bf16r(__ldcg(a.part + (size_t)seg * PQKV + col + j + PHD / 2));
+      if (hh <= PG) {
+        const float c = bf16r(a.cos_t[(size_t)pos * (PHD / 2) + j]), s = bf16r(a.sin_t[(size_t)pos * (PHD / 2) + j]);
+        const float rx = bf16r(x * c - y * s), ry = bf16r(y * c + x * s);
+        if (hh < PG) { sQ[hh * PHD + j] = rx * a.scale; sQ[hh * PHD + j + PHD / 2] = ry * a.scale; }
+        else { sKV[j] = rx; sKV[j + PHD / 2] = ry; }
+      } else { sKV[PHD + j] = x; sKV[PHD + j + PHD / 2] = y; }
+    }
+    if (tid < PG) { sState[tid] = -INFINITY; sState[4 + tid] = 0.f; }
+    __syncthreads();
+    if (tid < PHD) kc[(size_t)pos * PHD + tid] = __float2bfloat16_rn(sKV[tid]);
+    else if (tid < 2 * PHD) vc[(size_t)pos * PHD + tid - PHD] = __float2bfloat16_rn(sKV[tid]);
+    const int head = warp & 3, kgrp = warp >> 2;                 // scores: 4 heads x 4 groups of 32 keys
+    float o_acc = 0.f;                                           // PV: thread = (head = tid / 128, dim = tid % 128)
+    for (int k0 = 0; k0 < kv_len; k0 += AKEYS) {
+      const int nk = min(AKEYS, kv_len - k0);
+      __syncthreads();                                           // previous chunk fully consumed; new k/v row written
+      for (int i = tid; i < AKEYS * (PHD / 8); i += kPThreads) {
+        const int r = i / (PHD / 8), c8 = i - r * (PHD / 8);
+        uint4 kk = make_uint4(0, 0, 0, 0), vv = make_uint4(0, 0, 0, 0);
+        if (r < nk) {
+          if (k0 + r == pos) {                                   // the row appended above by this CTA: take it from smem
+            uint32_t wk[4], wv[4];
+#pragma unroll
+            for (int e2 = 0; e2 < 4; ++e2) {
+              __nv_bfloat162 pk = __floats2bfloat162_rn(sKV[c8 * 8 + 2 * e2], sKV[c8 * 8 + 2 * e2 + 1]);
+              __nv_bfloat162 pv = __floats2bfloat162_rn(sKV[PHD + c8 * 8 + 2 * e2], sKV[PHD + c8 * 8 + 2 * e2 + 1]);
+              wk[e2] = *reinterpret_cast<uint32_t*>(&pk); wv[e2] = *reinterpret_cast<uint32_t*>(&pv);
+            }
+            kk = make_uint4(wk[0], wk[1], wk[2], wk[3]); vv = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+          } else {
+            kk = __ldcg(reinterpret_cast<const uint4*>(kc + (size_t)(k0 + r) * PHD + c8 * 8));
+            vv = __ldcg(reinterpret_cast<const uint4*>(vc + (size_t)(k0 + r) * PHD + c8 * 8));
+          }
+        }
+        *reinterpret_cast<uint4*>(sK + r * kAKRow + c8 * 16) = kk;
+        *reinterpret_cast<uint4*>(sV + r * PHD + c8 * 8) = vv;
+      }
+      __syncthreads();
+      // scores for (head, key = kgrp*32 + lane)
+      const int r = kgrp * 32 + lane;
+      float sc = -INFINITY;
+      if (r < nk) {
+        float acc = 0.f;
+#pragma unroll 4
+        for (int c8 = 0; c8 < PHD / 8; ++c8) {
+          const uint4 kv = *reinterpret_cast<const uint4*>(sK + r * kAKRow + c8 * 16);
+          const float4 q0 = *reinterpret_cast<const float4*>(sQ + head * PHD + c8 * 8);
+          const float4 q1 = *reinterpret_cast<const float4*>(sQ + head * PHD + c8 * 8 + 4);
+          acc = fmaf(__uint_as_float(kv.x << 16), q0.x, acc); acc = fmaf(__uint_as_float(kv.x & 0xffff0000u), q0.y, acc);
+          acc = fmaf(__uint_as_float(kv.y << 16), q0.z, acc); acc = fmaf(__uint_as_float(kv.y & 0xffff0000u), q0.w, acc);
+          acc = fmaf(__uint_as_float(kv.z << 16), q1.x, acc); acc = fmaf(__uint_as_float(kv.z & 0xffff0000u), q1.y, acc);
+          acc = fmaf(__uint_as_float(kv.w << 16), q1.z, acc); acc = fmaf(__uint_as_float(kv.w & 0xffff0000u), q1.w, acc);
+        }
+        sc = acc;
+      }
+      const float wmax = warp_max(sc);
+      if (lane == 0) sRed[head * 4 + kgrp] = wmax;
+      __syncthreads();
+      const float cmax = fmaxf(fmaxf(sRed[head * 4], sRed[head * 4 + 1]), fmaxf(sRed[head * 4 + 2], sRed[head * 4 + 3]));
+      const float m_old = sState[head];
+      const float m_new = fmaxf(m_old, cmax);
+      const float p = (sc == -INFINITY) ? 0.f : expf(sc - m_new);
+      sP[head * AKEYS + r] = p;
+      const float wsum = warp_sum(p);
+      __syncthreads();                                           // every thread has read the maxima and the running state
+      if (lane == 0) sRed[head * 4 + kgrp] = wsum;
+      __syncthreads();
+      if (kgrp == 0 && lane == 0) {                              // one thread per head advances the online-softmax state
+        const float corr = (m_old == -INFINITY) ? 0.f : expf(m_old - m_new);
+        const float lsum = sRed[head * 4] + sRed[head * 4 + 1] + sRed[head * 4 + 2] + sRed[head * 4 + 3];
+        sState[8 + head] = corr;
+        sState[head] = m_new;
+        sState[4 + head] = sState[4 + head] * corr + lsum;
+      }
+      __syncthreads();
+      {
+        const int ph = tid >> 7, d = tid & 127;
+        float acc = o_acc * sState[8 + ph];
+        const float* pp = sP + ph * AKEYS;
+        for (int j = 0; j < nk; ++j) acc = fmaf(pp[j], __bfloat162float(sV[j * PHD + d]), acc);
+        o_acc = acc;
+      }
+    }
+    __syncthreads();
+    {
+      const int ph = tid >> 7, d = tid & 127;
+      a.attn[(size_t)seg * PH + (size_t)(kvh * PG + ph) * PHD + d] = __float2bfloat16_rn(o_acc / sState[4 + ph]);
+    }
+    __syncthreads();
+  }
+}
+
+
 __device__ __forceinline__ unsigned long long gtimer() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
@@ -372,7 +486,8 @@ __global__ void __launch_bounds__(kPThreads, 1) decode_persist_kernel(DecodePers
     const DecLayerDev L = a.layers[l];
     gemm_dispatch<EPI_F32>(L.wqkv, PQKV, PH, a.u, B, Bpad, a.part, nullptr, nullptr, sR);
     grid_barrier(a.bar, epoch); STAMP();
-    attention_phase(a, L, smem);
+    if (a.attn_chunks > 1) attention_phase(a, L, smem);          // few segments: split the keys over CTAs
+    else attention_phase_serial(a, L, smem);
     grid_barrier(a.bar, epoch); STAMP();
     gemm_dispatch<EPI_RESID>(L.wo, PH, PH, a.attn, B, Bpad, nullptr, a.x, nullptr, sR);
     grid_barrier(a.bar, epoch); STAMP();
@@ -466,16 +581,59 @@ cudaError_t decode_persist_configure() {
   return cudaFuncSetAttribute(decode_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)decode_persist_smem_bytes());
 }
 
-cudaError_t launch_decode_persist(const DecodePersistArgs& a, int num_sms, cudaStream_t st) {
-  SONIC_CUDA_TRY(cudaMemsetAsync(a.bar, 0, sizeof(unsigned), st));
-  cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3(num_sms); cfg.blockDim = dim3(kPThreads); cfg.dynamicSmemBytes = decode_persist_smem_bytes(); cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeCooperative;
-  attr[0].val.cooperative = 1;
-  cfg.attrs = attr; cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, decode_persist_kernel, a);
+int decode_persist_occupancy() {
+  int per_sm = -1;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, decode_persist_kernel, kPThreads, decode_persist_smem_bytes());
+  return per_sm;
+}
+// largest cooperative grid (<= one CTA per SM) the device can hold for this kernel right now; 0 if it cannot be launched
+int decode_persist_max_grid(int num_sms) {
+  int per_sm = 0, coop = 0, dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+  if (!coop) return 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, decode_persist_kernel, kPThreads, decode_persist_smem_bytes()) != cudaSuccess) return 0;
+  if (per_sm < 1) return 0;
+  return num_sms;
+}
+
+cudaError_t launch_decode_persist(const DecodePersistArgs& a, int grid, cudaStream_t st) {
+  if (grid < 1) return cudaErrorInvalidConfiguration;
+  const int num_sms = grid;
+
+  {
+    cudaError_t me = cudaMemsetAsync(a.bar, 0, sizeof(unsigned), st);
+    if (me != cudaSuccess) { fprintf(stderr, "[sonicscribe_b200] barrier memset failed: %s\n", cudaGetErrorName(me)); return me; }
+  }
+  static int mode = 0;          // 0: cudaLaunchKernelEx + cooperative attribute, 1: cudaLaunchCooperativeKernel, 2: plain launch
+  cudaError_t e = cudaErrorUnknown;
+  for (; mode < 3; ++mode) {
+    if (mode == 0) {
+      cudaLaunchConfig_t cfg;
+      memset(&cfg, 0, sizeof(cfg));
+      cfg.gridDim = dim3(num_sms); cfg.blockDim = dim3(kPThreads); cfg.dynamicSmemBytes = decode_persist_smem_bytes(); cfg.stream = st;
+      cudaLaunchAttribute attr[1];
+      memset(attr, 0, sizeof(attr));
+      attr[0].id = cudaLaunchAttributeCooperative;
+      attr[0].val.cooperative = 1;
+      cfg.attrs = attr; cfg.numAttrs = 1;
+      e = cudaLaunchKernelEx(&cfg, decode_persist_kernel, a);
+    } else if (mode == 1) {
+      DecodePersistArgs copy = a;
+      void* args[1] = {&copy};
+      e = cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(decode_persist_kernel), dim3(num_sms), dim3(kPThreads), args,
+                                      decode_persist_smem_bytes(), st);
+    } else {
+      // grid <= SM count with one CTA per SM: co-resident on an otherwise idle device (stream order guarantees our own
+      // earlier kernels have drained); without the cooperative attribute this is not guaranteed by the programming model
+      decode_persist_kernel<<<dim3(num_sms), dim3(kPThreads), decode_persist_smem_bytes(), st>>>(a);
+      e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) return e;
+    fprintf(stderr, "[sonicscribe_b200] decode_persist launch mode %d failed: %s (%s)\n", mode, cudaGetErrorName(e), cudaGetErrorString(e));
+    cudaGetLastError();
+  }
+  return e;
 }
 
 }  // namespace sonic

@@ -139,6 +139,8 @@ size_t decode_persist_smem_bytes();
 size_t decode_persist_part_floats(int Bpad);
 size_t decode_persist_pick_floats(int max_batch, int num_sms);
 cudaError_t decode_persist_configure();
-cudaError_t launch_decode_persist(const DecodePersistArgs& a, int num_sms, cudaStream_t st);
+int decode_persist_max_grid(int num_sms);
+int decode_persist_occupancy();
+cudaError_t launch_decode_persist(const DecodePersistArgs& a, int grid, cudaStream_t st);
 
 }  // namespace sonic
