@@ -430,7 +430,13 @@ struct Engine {
         a.heads = kDecHeads; a.kv_heads = kDecKv; a.hd = kDecHd; a.batch = B; a.max_q = max_q;
         a.scale = 0.08838834764831845f;   // 128^-1/2
         TAG(prefill ? PC_PRE_ATTN : PC_DEC_ATTN);
-        CKL(launch_attention_simt<T>(a, h->stream), 1);
+        if (prefill && std::is_same<T, bf16>::value && !h->force_simt) {
+          CKL(launch_attention_prefill_tc(reinterpret_cast<const bf16*>(qkv), kQkvDec, rows, 0, reinterpret_cast<const bf16*>(kc),
+                                          reinterpret_cast<const bf16*>(vc), h->cfg.max_batch, kDecKv, kDecHeads, h->max_ctx, h->d_tok_off, B,
+                                          max_q, reinterpret_cast<bf16*>(attn), kDecH, 0.08838834764831845f, h->stream), 1);
+        } else {
+          CKL(launch_attention_simt<T>(a, h->stream), 1);
+        }
       }
     }
     if (gemm(h, lin(attn, kDecH, w.wo, kDecH, x, kDecH, nullptr, rows, kDecH, ACT_NONE, x, kDecH, w.s_o), swap, prefill ? PC_PRE_GEMM : PC_DEC_O)) return -1;
@@ -947,6 +953,7 @@ int sonic_create(const sonic_config* cfg, sonic_handle* out) {
       h->use_persist = false;
     }
   }
+  if (!h->is_f32 && attention_prefill_tc_configure() != cudaSuccess) { h->err = "attention_prefill_tc_configure failed"; return bail(0); }
   if (!h->is_f32 && attention_tc_configure() != cudaSuccess) { h->err = "attention_tc_configure failed"; return bail(0); }
   if (alloc_all(h)) return bail(0);
   *out = h;
