@@ -76,60 +76,74 @@ __device__ __forceinline__ void prefetch_weights_l2(const void* W, size_t bytes,
 // the bf16 stream, or SwiGLU of interleaved (gate, up) rows.  The next item's weight loads are issued before the exchange.
 enum { EPI_F32 = 0, EPI_RESID = 1, EPI_SWIGLU = 2 };
 
-template <int NT, int EPI, int RB>
-__device__ __forceinline__ void gemm_phase(const bf16* __restrict__ W, int N, int K, const bf16* X, int B, int Bpad,
-                                           float* __restrict__ out32, bf16* xres, bf16* act, float* sR) {
-  // RB row blocks of 16 rows per item; the 16 warps form RB x (16/RB): warp -> (row block rw, k slice kw of 128*RB).
-  // Larger RB re-uses the activation slice for more weight rows (needed once the token count makes it the L2 bottleneck).
-  constexpr int KW = kPWarps / RB;                 // k slices per section
-  constexpr int GROUPS = RB;                       // 128-wide k groups per warp per item (2048 / KW / 128)
+static constexpr int kXRowBytes = 2048 * 2 + 64;      // staged activation row: 2048 bf16 + 64 B pad (conflict-free 16 B reads)
+static constexpr int kXStageTok = 32;                 // tokens staged per pass
+static constexpr int kXStageBytes = kXStageTok * kXRowBytes;
+
+// NT: 8-token tiles per pass; EPI: fused epilogue; STAGE: copy the pass's activation rows for the current 2048-wide K
+// section into shared memory once and feed every item from there (at >= 9 tokens the per-item activation reads from L2
+// would otherwise exceed the weight bytes); tok0: first token of the pass.
+template <int NT, int EPI, bool STAGE>
+__device__ __forceinline__ void gemm_phase(const bf16* __restrict__ W, int N, int K, const bf16* X, int B, int Bpad, int tok0,
+                                           float* __restrict__ out32, bf16* xres, bf16* act, uint8_t* smem) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
-  const int rw = warp % RB, kw = warp / RB;
-  const int nib = N / (16 * RB), gsplit = K >> 11, n_items = nib * gsplit;
+  const int nib = N >> 4, gsplit = K >> 11, n_items = nib * gsplit;
+  uint8_t* sX = smem;
+  float* sR = reinterpret_cast<float*>(smem + (STAGE ? kXStageBytes : 0));
   int item = blockIdx.x;
+  int staged_gs = -1;
   uint4 wa[4], wb[4];
-  auto load_group = [&](int it, int grp) {
+  auto load_item = [&](int it) {
     const int gs = it / nib, ib = it - gs * nib;
-    const bf16* w0 = W + (size_t)((ib * RB + rw) * 16 + g) * K + (size_t)gs * 2048 + (kw * GROUPS + grp) * 128 + 8 * t;
+    const bf16* w0 = W + (size_t)(ib * 16 + g) * K + (size_t)gs * 2048 + warp * 128 + 8 * t;
     const bf16* w1 = w0 + (size_t)8 * K;
 #pragma unroll
     for (int u = 0; u < 4; ++u) { wa[u] = ldg_stream(w0 + 32 * u); wb[u] = ldg_stream(w1 + 32 * u); }
   };
-  if (item < n_items) load_group(item, 0);
+  if (item < n_items) load_item(item);
   for (; item < n_items; item += gridDim.x) {
     const int gs = item / nib, ib = item - gs * nib;
+    if (STAGE && gs != staged_gs) {                              // CTA-uniform
+      __syncthreads();
+      for (int i = threadIdx.x; i < NT * 8 * 256; i += kPThreads) {
+        const int row = i >> 8, c = i & 255;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (tok0 + row < B) v = __ldcg(reinterpret_cast<const uint4*>(X + (size_t)(tok0 + row) * K + (size_t)gs * 2048 + c * 8));
+        *reinterpret_cast<uint4*>(sX + (size_t)row * kXRowBytes + c * 16) = v;
+      }
+      __syncthreads();
+      staged_gs = gs;
+    }
     float acc[NT][4];
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) { acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f; }
-#pragma unroll 1
-    for (int grp = 0; grp < GROUPS; ++grp) {
-      const bf16* xb = X + (size_t)gs * 2048 + (kw * GROUPS + grp) * 128 + 8 * t;
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < 4; ++u) {
 #pragma unroll
-        for (int nt = 0; nt < NT; ++nt) {
-          const int tok = nt * 8 + g;
-          uint4 xv = make_uint4(0, 0, 0, 0);
-          if (tok < B) xv = *reinterpret_cast<const uint4*>(xb + (size_t)tok * K + 32 * u);
-          mma16816(acc[nt], wa[u].x, wb[u].x, wa[u].y, wb[u].y, xv.x, xv.y);
-          mma16816(acc[nt], wa[u].z, wb[u].z, wa[u].w, wb[u].w, xv.z, xv.w);
+      for (int nt = 0; nt < NT; ++nt) {
+        uint4 xv;
+        if (STAGE) {
+          xv = *reinterpret_cast<const uint4*>(sX + (size_t)(nt * 8 + g) * kXRowBytes + (warp * 128 + 32 * u + 8 * t) * 2);
+        } else {
+          const int tok = tok0 + nt * 8 + g;
+          xv = make_uint4(0, 0, 0, 0);
+          if (tok < B) xv = *reinterpret_cast<const uint4*>(X + (size_t)tok * K + (size_t)gs * 2048 + warp * 128 + 32 * u + 8 * t);
         }
+        mma16816(acc[nt], wa[u].x, wb[u].x, wa[u].y, wb[u].y, xv.x, xv.y);
+        mma16816(acc[nt], wa[u].z, wb[u].z, wa[u].w, wb[u].w, xv.z, xv.w);
       }
-      // next group of this item, or the first group of the next item (then in flight during the exchange below)
-      if (grp + 1 < GROUPS) load_group(item, grp + 1);
-      else if (item + (int)gridDim.x < n_items) load_group(item + gridDim.x, 0);
     }
+    if (item + (int)gridDim.x < n_items) load_item(item + gridDim.x);     // in flight during the exchange below
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt)
       *reinterpret_cast<float4*>(sR + ((size_t)(warp * NT + nt) * 32 + lane) * 4) = make_float4(acc[nt][0], acc[nt][1], acc[nt][2], acc[nt][3]);
     __syncthreads();
-    for (int e = threadIdx.x; e < RB * NT * 128; e += kPThreads) {
-      const int rb_l = e / (NT * 128), e2 = e - rb_l * (NT * 128);       // row block inside the item, element inside its tile
+    for (int e = threadIdx.x; e < NT * 128; e += kPThreads) {
       float v = 0.f;
 #pragma unroll
-      for (int k = 0; k < KW; ++k) v += sR[(size_t)(k * RB + rb_l) * NT * 128 + e2];
-      const int c = e2 & 3, ml = (e2 >> 2) & 31, nt = e2 >> 7;
-      const int row = (ib * RB + rb_l) * 16 + (ml >> 2) + 8 * (c >> 1), tok = nt * 8 + 2 * (ml & 3) + (c & 1);
+      for (int w = 0; w < kPWarps; ++w) v += sR[(size_t)w * NT * 128 + e];
+      const int c = e & 3, ml = (e >> 2) & 31, nt = e >> 7;
+      const int row = ib * 16 + (ml >> 2) + 8 * (c >> 1), tok = tok0 + nt * 8 + 2 * (ml & 3) + (c & 1);
       if (EPI == EPI_SWIGLU) {
         const float up = __shfl_down_sync(0xffffffffu, v, 16);            // row + 1 of the same token sits 16 threads up
         if (((ml >> 2) & 1) == 0 && tok < B) act[(size_t)tok * (N >> 1) + (row >> 1)] = __float2bfloat16_rn(silu(v) * up);
@@ -147,12 +161,13 @@ __device__ __forceinline__ void gemm_phase(const bf16* __restrict__ W, int N, in
 
 template <int EPI>
 __device__ __forceinline__ void gemm_dispatch(const bf16* W, int N, int K, const bf16* X, int B, int Bpad, float* out32, bf16* xres,
-                                              bf16* act, float* sR) {
-  if (B <= 8) gemm_phase<1, EPI, 1>(W, N, K, X, B, Bpad, out32, xres, act, sR);
-  else if (B <= 16) gemm_phase<2, EPI, 1>(W, N, K, X, B, Bpad, out32, xres, act, sR);
-  else if (B <= 32) gemm_phase<4, EPI, 1>(W, N, K, X, B, Bpad, out32, xres, act, sR);   // RB > 1 measured slower: too few items
-  else gemm_phase<8, EPI, 1>(W, N, K, X, B, Bpad, out32, xres, act, sR);
+                                              bf16* act, uint8_t* smem) {
+  if (B <= 8) gemm_phase<1, EPI, false>(W, N, K, X, B, Bpad, 0, out32, xres, act, smem);
+  else if (B <= 16) gemm_phase<2, EPI, true>(W, N, K, X, B, Bpad, 0, out32, xres, act, smem);
+  else if (B <= 32) gemm_phase<4, EPI, true>(W, N, K, X, B, Bpad, 0, out32, xres, act, smem);
+  else gemm_phase<8, EPI, false>(W, N, K, X, B, Bpad, 0, out32, xres, act, smem);   // measured: two staged 32-token passes are slower
 }
+
 
 // fixed-order sum of the KS split-K partials of one element; fully unrolled so the KS L2 loads are in flight together
 template <int KS>
@@ -481,28 +496,27 @@ __global__ void __launch_bounds__(kPThreads, 1) decode_persist_kernel(DecodePers
   }
   grid_barrier(a.bar, epoch); STAMP();
 
-  float* sR = reinterpret_cast<float*>(smem);                 // GEMM exchange buffer (aliases the attention staging area)
   for (int l = 0; l < a.n_layers; ++l) {
     const DecLayerDev L = a.layers[l];
-    gemm_dispatch<EPI_F32>(L.wqkv, PQKV, PH, a.u, B, Bpad, a.part, nullptr, nullptr, sR);
+    gemm_dispatch<EPI_F32>(L.wqkv, PQKV, PH, a.u, B, Bpad, a.part, nullptr, nullptr, smem);
     grid_barrier(a.bar, epoch); STAMP();
     if (a.attn_chunks > 1) attention_phase(a, L, smem);          // few segments: split the keys over CTAs
     else attention_phase_serial(a, L, smem);
     grid_barrier(a.bar, epoch); STAMP();
-    gemm_dispatch<EPI_RESID>(L.wo, PH, PH, a.attn, B, Bpad, nullptr, a.x, nullptr, sR);
+    gemm_dispatch<EPI_RESID>(L.wo, PH, PH, a.attn, B, Bpad, nullptr, a.x, nullptr, smem);
     grid_barrier(a.bar, epoch); STAMP();
     residual_norm_phase<0>(nullptr, B, Bpad, a.x, a.u, L.rms2, a.eps, red);
     grid_barrier(a.bar, epoch); STAMP();
-    gemm_dispatch<EPI_SWIGLU>(L.wgu, 2 * PI, PH, a.u, B, Bpad, nullptr, nullptr, a.act, sR);
+    gemm_dispatch<EPI_SWIGLU>(L.wgu, 2 * PI, PH, a.u, B, Bpad, nullptr, nullptr, a.act, smem);
     grid_barrier(a.bar, epoch); STAMP();
-    gemm_dispatch<EPI_F32>(L.wdown, PH, PI, a.act, B, Bpad, a.part, nullptr, nullptr, sR);
+    gemm_dispatch<EPI_F32>(L.wdown, PH, PI, a.act, B, Bpad, a.part, nullptr, nullptr, smem);
     grid_barrier(a.bar, epoch); STAMP();
     residual_norm_phase<3>(a.part, B, Bpad, a.x, a.u, (l + 1 < a.n_layers) ? a.layers[l + 1].rms1 : a.final_norm, a.eps, red);
     grid_barrier(a.bar, epoch); STAMP();
   }
 
   // ---- lm_head + greedy pick: every CTA scans its slice of the vocabulary for all tokens, CTA b merges token b
-  gemm_dispatch<EPI_F32>(a.lm_head, PV_, PH, a.u, B, Bpad, a.part, nullptr, nullptr, sR);
+  gemm_dispatch<EPI_F32>(a.lm_head, PV_, PH, a.u, B, Bpad, a.part, nullptr, nullptr, smem);
   grid_barrier(a.bar, epoch); STAMP();
   {
     const int per = (PV_ + gridDim.x - 1) / gridDim.x;
@@ -570,7 +584,7 @@ __global__ void __launch_bounds__(kPThreads, 1) decode_persist_kernel(DecodePers
 
 size_t decode_persist_smem_bytes() {
   const size_t attn = (size_t)AKEYS * kAKRow + (size_t)AKEYS * PHD * 2 + (PG * PHD + PG * AKEYS + 2 * PHD + 32 + 16) * 4;
-  const size_t exch = (size_t)kPWarps * 8 * 128 * 4;          // 16 warps x NT(8) x 128 fp32
+  const size_t exch = (size_t)kXStageBytes + (size_t)kPWarps * 4 * 128 * 4;    // staged activations + 16 warps x NT(4) x 128 fp32 (>= the unstaged NT = 8 exchange)
   return attn > exch ? attn : exch;
 }
 
