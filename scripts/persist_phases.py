@@ -11,7 +11,7 @@ dims = ModelDims(enc_layers=1, dec_layers=L)
 sd = synthetic_state_dict(dims, seed=0)
 names = ["qkv_gemm", "attention", "o_gemm+resid", "norm", "gateup+swiglu", "down_gemm", "resid_norm2"]
 for B in (1, 16, 64):
-    eng = Engine(1, L, mode="bf16", device=0, max_batch=B, max_prompt=320, max_new=64, debug=True)
+    eng = Engine(1, L, mode=os.environ.get("MODE", "bf16"), device=0, max_batch=B, max_prompt=320, max_new=64, debug=True)
     eng.load_state_dict(sd)
     segs = [synth_audio("speech", 320000, seed=i) for i in range(B)]
     prompts = [synthetic_prompt_ids(num_audio_tokens(320000)) for _ in range(B)]

@@ -494,6 +494,7 @@ struct Engine {
       p.attn_chunks = (B * kDecKv * ((h->decode_chunks + 1) / 2) <= h->persist_grid) ? (h->decode_chunks + 1) / 2 : 1;
       p.gs = h->gs; p.bar = h->persist_bar; p.timestamps = h->cfg.debug ? h->persist_ts : nullptr;
       { const char* pf = getenv("SONIC_PERSIST_PREFETCH"); p.prefetch = (pf && pf[0] == '1') ? 1 : 0; }
+      p.w8 = h->is_int8 ? 1 : 0;
       p.B = B; p.Bpad = (B + 7) / 8 * 8; p.max_ctx = h->max_ctx; p.eps = kRmsEps; p.scale = 0.08838834764831845f;
       TAG(PC_DEC_PERSIST);
       if (h->prof_on) { cudaEventRecord(prof_event(h), h->stream); h->prof_tags.push_back(h->prof_cls); }
@@ -935,7 +936,7 @@ int sonic_create(const sonic_config* cfg, sonic_handle* out) {
   const char* np = getenv("SONIC_NO_PDL");
   h->use_pdl = !(np && np[0] == '1');
   const char* dm = getenv("SONIC_DECODE");
-  h->use_persist = !h->is_f32 && !h->is_int8 && !h->force_simt && !(dm && std::string(dm) == "graph");
+  h->use_persist = !h->is_f32 && !h->force_simt && !(dm && std::string(dm) == "graph");
   h->num_sms = prop.multiProcessorCount;
   if (h->is_int8 && h->force_simt) { delete h; return fail(nullptr, "sonic_create: SONIC_FORCE_SIMT is not available in int8 mode"); }
   auto bail = [&](int) { g_last_error = h->err; for (void* p : h->allocs) cudaFree(p); delete h; return -1; };
@@ -1009,8 +1010,8 @@ int sonic_finalize_weights(sonic_handle h) {
     const size_t layer_kv = (size_t)h->cfg.max_batch * kDecKv * h->max_ctx * kDecHd;
     for (int l = 0; l < h->cfg.dec_layers; ++l) {
       const DecLayerW& w = h->dec[l];
-      tab[l].wqkv = reinterpret_cast<const bf16*>(w.wqkv); tab[l].wo = reinterpret_cast<const bf16*>(w.wo);
-      tab[l].wgu = reinterpret_cast<const bf16*>(w.wgu); tab[l].wdown = reinterpret_cast<const bf16*>(w.wdown);
+      tab[l].wqkv = w.wqkv; tab[l].wo = w.wo; tab[l].wgu = w.wgu; tab[l].wdown = w.wdown;
+      tab[l].sqkv = w.s_qkv; tab[l].so = w.s_o; tab[l].sgu = w.s_gu; tab[l].sdown = w.s_down;
       tab[l].rms1 = w.rms1; tab[l].rms2 = w.rms2;
       tab[l].kc = reinterpret_cast<bf16*>(h->kcache) + (size_t)l * layer_kv;
       tab[l].vc = reinterpret_cast<bf16*>(h->vcache) + (size_t)l * layer_kv;

@@ -83,9 +83,22 @@ static constexpr int kXStageBytes = kXStageTok * kXRowBytes;
 // NT: 8-token tiles per pass; EPI: fused epilogue; STAGE: copy the pass's activation rows for the current 2048-wide K
 // section into shared memory once and feed every item from there (at >= 9 tokens the per-item activation reads from L2
 // would otherwise exceed the weight bytes); tok0: first token of the pass.
-template <int NT, int EPI, bool STAGE>
-__device__ __forceinline__ void gemm_phase(const bf16* __restrict__ W, int N, int K, const bf16* X, int B, int Bpad, int tok0,
-                                           float* __restrict__ out32, bf16* xres, bf16* act, uint8_t* smem) {
+// W8: the weight matrix is int8 [N][K] with a per-row fp32 scale (weight-only quantisation): each lane
+// loads 16 int8 (16 B) per row and 64-k chunk, expands them to bf16 pairs in registers and the row scale is applied to the
+// summed tile in the epilogue.
+__device__ __forceinline__ void i8x4_to_bf16x2(uint32_t w, uint32_t& lo, uint32_t& hi) {
+  const float f0 = (float)(int)(int8_t)(w & 0xff), f1 = (float)(int)(int8_t)((w >> 8) & 0xff);
+  const float f2 = (float)(int)(int8_t)((w >> 16) & 0xff), f3 = (float)(int)(int8_t)(w >> 24);
+  __nv_bfloat162 a = __floats2bfloat162_rn(f0, f1), b = __floats2bfloat162_rn(f2, f3);
+  lo = *reinterpret_cast<uint32_t*>(&a);
+  hi = *reinterpret_cast<uint32_t*>(&b);
+}
+
+template <int NT, int EPI, bool STAGE, bool W8>
+__device__ __forceinline__ void gemm_phase(const void* __restrict__ Wv, const float* __restrict__ wscale, int N, int K, const bf16* X, int B,
+                                           int Bpad, int tok0, float* __restrict__ out32, bf16* xres, bf16* act, uint8_t* smem) {
+  const bf16* W = reinterpret_cast<const bf16*>(Wv);
+  const int8_t* W8p = reinterpret_cast<const int8_t*>(Wv);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
   const int nib = N >> 4, gsplit = K >> 11, n_items = nib * gsplit;
   uint8_t* sX = smem;
@@ -95,10 +108,17 @@ __device__ __forceinline__ void gemm_phase(const bf16* __restrict__ W, int N, in
   uint4 wa[4], wb[4];
   auto load_item = [&](int it) {
     const int gs = it / nib, ib = it - gs * nib;
-    const bf16* w0 = W + (size_t)(ib * 16 + g) * K + (size_t)gs * 2048 + warp * 128 + 8 * t;
-    const bf16* w1 = w0 + (size_t)8 * K;
+    if (W8) {                                                    // 2 x 16 B per row: k = 64 v + 16 t + [0, 16)
+      const int8_t* q0 = W8p + (size_t)(ib * 16 + g) * K + (size_t)gs * 2048 + warp * 128 + 16 * t;
+      const int8_t* q1 = q0 + (size_t)8 * K;
 #pragma unroll
-    for (int u = 0; u < 4; ++u) { wa[u] = ldg_stream(w0 + 32 * u); wb[u] = ldg_stream(w1 + 32 * u); }
+      for (int v = 0; v < 2; ++v) { wa[v] = ldg_stream(q0 + 64 * v); wb[v] = ldg_stream(q1 + 64 * v); }
+    } else {
+      const bf16* w0 = W + (size_t)(ib * 16 + g) * K + (size_t)gs * 2048 + warp * 128 + 8 * t;
+      const bf16* w1 = w0 + (size_t)8 * K;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { wa[u] = ldg_stream(w0 + 32 * u); wb[u] = ldg_stream(w1 + 32 * u); }
+    }
   };
   if (item < n_items) load_item(item);
   for (; item < n_items; item += gridDim.x) {
@@ -117,6 +137,36 @@ __device__ __forceinline__ void gemm_phase(const bf16* __restrict__ W, int N, in
     float acc[NT][4];
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) { acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f; }
+    if (W8) {
+#pragma unroll
+      for (int v = 0; v < 2; ++v) {
+        const uint32_t ra[4] = {wa[v].x, wa[v].y, wa[v].z, wa[v].w}, rb[4] = {wb[v].x, wb[v].y, wb[v].z, wb[v].w};
+        uint32_t a_lo[4], a_hi[4], b_lo[4], b_hi[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { i8x4_to_bf16x2(ra[q], a_lo[q], a_hi[q]); i8x4_to_bf16x2(rb[q], b_lo[q], b_hi[q]); }
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+          uint4 x0, x1;
+          if (STAGE) {
+            const uint8_t* px = sX + (size_t)(nt * 8 + g) * kXRowBytes + (warp * 128 + 64 * v + 16 * t) * 2;
+            x0 = *reinterpret_cast<const uint4*>(px);
+            x1 = *reinterpret_cast<const uint4*>(px + 16);
+          } else {
+            const int tok = tok0 + nt * 8 + g;
+            x0 = make_uint4(0, 0, 0, 0); x1 = x0;
+            if (tok < B) {
+              const bf16* px = X + (size_t)tok * K + (size_t)gs * 2048 + warp * 128 + 64 * v + 16 * t;
+              x0 = *reinterpret_cast<const uint4*>(px);
+              x1 = *reinterpret_cast<const uint4*>(px + 8);
+            }
+          }
+          mma16816(acc[nt], a_lo[0], b_lo[0], a_hi[0], b_hi[0], x0.x, x0.y);
+          mma16816(acc[nt], a_lo[1], b_lo[1], a_hi[1], b_hi[1], x0.z, x0.w);
+          mma16816(acc[nt], a_lo[2], b_lo[2], a_hi[2], b_hi[2], x1.x, x1.y);
+          mma16816(acc[nt], a_lo[3], b_lo[3], a_hi[3], b_hi[3], x1.z, x1.w);
+        }
+      }
+    } else {
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
 #pragma unroll
@@ -133,6 +183,7 @@ __device__ __forceinline__ void gemm_phase(const bf16* __restrict__ W, int N, in
         mma16816(acc[nt], wa[u].z, wb[u].z, wa[u].w, wb[u].w, xv.z, xv.w);
       }
     }
+    }
     if (item + (int)gridDim.x < n_items) load_item(item + gridDim.x);     // in flight during the exchange below
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt)
@@ -144,6 +195,7 @@ __device__ __forceinline__ void gemm_phase(const bf16* __restrict__ W, int N, in
       for (int w = 0; w < kPWarps; ++w) v += sR[(size_t)w * NT * 128 + e];
       const int c = e & 3, ml = (e >> 2) & 31, nt = e >> 7;
       const int row = ib * 16 + (ml >> 2) + 8 * (c >> 1), tok = tok0 + nt * 8 + 2 * (ml & 3) + (c & 1);
+      if (W8) v *= __ldg(wscale + row);
       if (EPI == EPI_SWIGLU) {
         const float up = __shfl_down_sync(0xffffffffu, v, 16);            // row + 1 of the same token sits 16 threads up
         if (((ml >> 2) & 1) == 0 && tok < B) act[(size_t)tok * (N >> 1) + (row >> 1)] = __float2bfloat16_rn(silu(v) * up);
@@ -159,15 +211,14 @@ __device__ __forceinline__ void gemm_phase(const bf16* __restrict__ W, int N, in
   }
 }
 
-template <int EPI>
-__device__ __forceinline__ void gemm_dispatch(const bf16* W, int N, int K, const bf16* X, int B, int Bpad, float* out32, bf16* xres,
-                                              bf16* act, uint8_t* smem) {
-  if (B <= 8) gemm_phase<1, EPI, false>(W, N, K, X, B, Bpad, 0, out32, xres, act, smem);
-  else if (B <= 16) gemm_phase<2, EPI, true>(W, N, K, X, B, Bpad, 0, out32, xres, act, smem);
-  else if (B <= 32) gemm_phase<4, EPI, true>(W, N, K, X, B, Bpad, 0, out32, xres, act, smem);
-  else gemm_phase<8, EPI, false>(W, N, K, X, B, Bpad, 0, out32, xres, act, smem);   // measured: two staged 32-token passes are slower
+template <int EPI, bool W8>
+__device__ __forceinline__ void gemm_dispatch(const void* W, const float* wscale, int N, int K, const bf16* X, int B, int Bpad, float* out32,
+                                              bf16* xres, bf16* act, uint8_t* smem) {
+  if (B <= 8) gemm_phase<1, EPI, false, W8>(W, wscale, N, K, X, B, Bpad, 0, out32, xres, act, smem);
+  else if (B <= 16) gemm_phase<2, EPI, true, W8>(W, wscale, N, K, X, B, Bpad, 0, out32, xres, act, smem);
+  else if (B <= 32) gemm_phase<4, EPI, true, W8>(W, wscale, N, K, X, B, Bpad, 0, out32, xres, act, smem);
+  else gemm_phase<8, EPI, false, W8>(W, wscale, N, K, X, B, Bpad, 0, out32, xres, act, smem);   // measured: two staged 32-token passes are slower
 }
-
 
 // fixed-order sum of the KS split-K partials of one element; fully unrolled so the KS L2 loads are in flight together
 template <int KS>
@@ -470,6 +521,7 @@ __device__ __forceinline__ unsigned long long gtimer() {
     if (a.timestamps && blockIdx.x == 0 && threadIdx.x == 0) a.timestamps[n_stamp++] = gtimer(); \
   } while (0)
 
+template <bool W8>
 __global__ void __launch_bounds__(kPThreads, 1) decode_persist_kernel(DecodePersistArgs a) {
   extern __shared__ __align__(16) uint8_t smem[];
   __shared__ float red[32];
@@ -498,25 +550,25 @@ __global__ void __launch_bounds__(kPThreads, 1) decode_persist_kernel(DecodePers
 
   for (int l = 0; l < a.n_layers; ++l) {
     const DecLayerDev L = a.layers[l];
-    gemm_dispatch<EPI_F32>(L.wqkv, PQKV, PH, a.u, B, Bpad, a.part, nullptr, nullptr, smem);
+    gemm_dispatch<EPI_F32, W8>(L.wqkv, L.sqkv, PQKV, PH, a.u, B, Bpad, a.part, nullptr, nullptr, smem);
     grid_barrier(a.bar, epoch); STAMP();
     if (a.attn_chunks > 1) attention_phase(a, L, smem);          // few segments: split the keys over CTAs
     else attention_phase_serial(a, L, smem);
     grid_barrier(a.bar, epoch); STAMP();
-    gemm_dispatch<EPI_RESID>(L.wo, PH, PH, a.attn, B, Bpad, nullptr, a.x, nullptr, smem);
+    gemm_dispatch<EPI_RESID, W8>(L.wo, L.so, PH, PH, a.attn, B, Bpad, nullptr, a.x, nullptr, smem);
     grid_barrier(a.bar, epoch); STAMP();
     residual_norm_phase<0>(nullptr, B, Bpad, a.x, a.u, L.rms2, a.eps, red);
     grid_barrier(a.bar, epoch); STAMP();
-    gemm_dispatch<EPI_SWIGLU>(L.wgu, 2 * PI, PH, a.u, B, Bpad, nullptr, nullptr, a.act, smem);
+    gemm_dispatch<EPI_SWIGLU, W8>(L.wgu, L.sgu, 2 * PI, PH, a.u, B, Bpad, nullptr, nullptr, a.act, smem);
     grid_barrier(a.bar, epoch); STAMP();
-    gemm_dispatch<EPI_F32>(L.wdown, PH, PI, a.act, B, Bpad, a.part, nullptr, nullptr, smem);
+    gemm_dispatch<EPI_F32, W8>(L.wdown, L.sdown, PH, PI, a.act, B, Bpad, a.part, nullptr, nullptr, smem);
     grid_barrier(a.bar, epoch); STAMP();
     residual_norm_phase<3>(a.part, B, Bpad, a.x, a.u, (l + 1 < a.n_layers) ? a.layers[l + 1].rms1 : a.final_norm, a.eps, red);
     grid_barrier(a.bar, epoch); STAMP();
   }
 
   // ---- lm_head + greedy pick: every CTA scans its slice of the vocabulary for all tokens, CTA b merges token b
-  gemm_dispatch<EPI_F32>(a.lm_head, PV_, PH, a.u, B, Bpad, a.part, nullptr, nullptr, smem);
+  gemm_dispatch<EPI_F32, false>(a.lm_head, nullptr, PV_, PH, a.u, B, Bpad, a.part, nullptr, nullptr, smem);
   grid_barrier(a.bar, epoch); STAMP();
   {
     const int per = (PV_ + gridDim.x - 1) / gridDim.x;
@@ -592,12 +644,13 @@ size_t decode_persist_part_floats(int Bpad) { return (size_t)PV_ * Bpad; }     /
 size_t decode_persist_pick_floats(int max_batch, int num_sms) { return (size_t)max_batch * num_sms * 4; }
 
 cudaError_t decode_persist_configure() {
-  return cudaFuncSetAttribute(decode_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)decode_persist_smem_bytes());
+  SONIC_CUDA_TRY(cudaFuncSetAttribute(decode_persist_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)decode_persist_smem_bytes()));
+  return cudaFuncSetAttribute(decode_persist_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)decode_persist_smem_bytes());
 }
 
 int decode_persist_occupancy() {
   int per_sm = -1;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, decode_persist_kernel, kPThreads, decode_persist_smem_bytes());
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, decode_persist_kernel<false>, kPThreads, decode_persist_smem_bytes());
   return per_sm;
 }
 // largest cooperative grid (<= one CTA per SM) the device can hold for this kernel right now; 0 if it cannot be launched
@@ -606,7 +659,10 @@ int decode_persist_max_grid(int num_sms) {
   if (cudaGetDevice(&dev) != cudaSuccess) return 0;
   cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
   if (!coop) return 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, decode_persist_kernel, kPThreads, decode_persist_smem_bytes()) != cudaSuccess) return 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, decode_persist_kernel<false>, kPThreads, decode_persist_smem_bytes()) != cudaSuccess) return 0;
+  int per_sm8 = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm8, decode_persist_kernel<true>, kPThreads, decode_persist_smem_bytes()) != cudaSuccess) return 0;
+  if (per_sm8 < per_sm) per_sm = per_sm8;
   if (per_sm < 1) return 0;
   return num_sms;
 }
@@ -631,16 +687,17 @@ cudaError_t launch_decode_persist(const DecodePersistArgs& a, int grid, cudaStre
       attr[0].id = cudaLaunchAttributeCooperative;
       attr[0].val.cooperative = 1;
       cfg.attrs = attr; cfg.numAttrs = 1;
-      e = cudaLaunchKernelEx(&cfg, decode_persist_kernel, a);
+      e = a.w8 ? cudaLaunchKernelEx(&cfg, decode_persist_kernel<true>, a) : cudaLaunchKernelEx(&cfg, decode_persist_kernel<false>, a);
     } else if (mode == 1) {
       DecodePersistArgs copy = a;
       void* args[1] = {&copy};
-      e = cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(decode_persist_kernel), dim3(num_sms), dim3(kPThreads), args,
+      e = cudaLaunchCooperativeKernel(a.w8 ? reinterpret_cast<const void*>(decode_persist_kernel<true>) : reinterpret_cast<const void*>(decode_persist_kernel<false>), dim3(num_sms), dim3(kPThreads), args,
                                       decode_persist_smem_bytes(), st);
     } else {
       // grid <= SM count with one CTA per SM: co-resident on an otherwise idle device (stream order guarantees our own
       // earlier kernels have drained); without the cooperative attribute this is not guaranteed by the programming model
-      decode_persist_kernel<<<dim3(num_sms), dim3(kPThreads), decode_persist_smem_bytes(), st>>>(a);
+      if (a.w8) decode_persist_kernel<true><<<dim3(num_sms), dim3(kPThreads), decode_persist_smem_bytes(), st>>>(a);
+      else decode_persist_kernel<false><<<dim3(num_sms), dim3(kPThreads), decode_persist_smem_bytes(), st>>>(a);
       e = cudaGetLastError();
     }
     if (e == cudaSuccess) return e;

@@ -118,7 +118,11 @@ struct DecodeAttnArgs {
 cudaError_t launch_decode_attn(const DecodeAttnArgs& a, int batch, int n_chunks, cudaStream_t st, bool pdl = false);
 
 // ---- decode_persist.cu: one cooperative kernel per greedy step (all layers + lm_head + pick), bf16 ------------------------
-struct DecLayerDev { const bf16 *wqkv, *wo, *wgu, *wdown; const float *rms1, *rms2; bf16 *kc, *vc; };
+struct DecLayerDev {
+  const void *wqkv, *wo, *wgu, *wdown;            // bf16 [N][K], or int8 [N][K] when DecodePersistArgs::w8
+  const float *sqkv, *so, *sgu, *sdown;           // int8 mode: per-row scales
+  const float *rms1, *rms2; bf16 *kc, *vc;
+};
 struct DecodePersistArgs {
   const DecLayerDev* layers; int n_layers;
   const bf16* embed; const bf16* lm_head; const float* final_norm;
@@ -132,6 +136,7 @@ struct DecodePersistArgs {
   unsigned* bar;                  // grid barrier counter
   unsigned long long* timestamps; // optional: %globaltimer after every grid barrier (CTA 0), 1 + 8*layers + 3 entries
   int B, Bpad, max_ctx;
+  int w8;                         // 1: decoder linears are int8 weight-only (lm_head / embedding stay bf16)
   int prefetch;                   // 1: L2-prefetch the next GEMM's weights at the start of every GEMM phase
   float eps, scale;
 };
