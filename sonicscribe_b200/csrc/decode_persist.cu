@@ -97,10 +97,13 @@ __device__ __forceinline__ void i8x4_to_bf16x2(uint32_t w, uint32_t& lo, uint32_
 template <int NT, int EPI, bool STAGE, bool W8>
 __device__ __forceinline__ void gemm_phase(const void* __restrict__ Wv, const float* __restrict__ wscale, int N, int K, const bf16* X, int B,
                                            int Bpad, int tok0, float* __restrict__ out32, bf16* xres, bf16* act, uint8_t* smem) {
+  // int8 rows are half as long in bytes: an int8 item covers two 16-row blocks per warp so that every lane still has eight
+  // 16 B weight loads in flight (and the activation fragments are shared by both blocks)
+  constexpr int RBW = (W8 && NT <= 4) ? 2 : 1;
   const bf16* W = reinterpret_cast<const bf16*>(Wv);
   const int8_t* W8p = reinterpret_cast<const int8_t*>(Wv);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
-  const int nib = N >> 4, gsplit = K >> 11, n_items = nib * gsplit;
+  const int nib = N / (16 * RBW), gsplit = K >> 11, n_items = nib * gsplit;
   uint8_t* sX = smem;
   float* sR = reinterpret_cast<float*>(smem + (STAGE ? kXStageBytes : 0));
   int item = blockIdx.x;
@@ -109,10 +112,13 @@ __device__ __forceinline__ void gemm_phase(const void* __restrict__ Wv, const fl
   auto load_item = [&](int it) {
     const int gs = it / nib, ib = it - gs * nib;
     if (W8) {                                                    // 2 x 16 B per row: k = 64 v + 16 t + [0, 16)
-      const int8_t* q0 = W8p + (size_t)(ib * 16 + g) * K + (size_t)gs * 2048 + warp * 128 + 16 * t;
-      const int8_t* q1 = q0 + (size_t)8 * K;
 #pragma unroll
-      for (int v = 0; v < 2; ++v) { wa[v] = ldg_stream(q0 + 64 * v); wb[v] = ldg_stream(q1 + 64 * v); }
+      for (int rbl = 0; rbl < RBW; ++rbl) {
+        const int8_t* q0 = W8p + (size_t)((ib * RBW + rbl) * 16 + g) * K + (size_t)gs * 2048 + warp * 128 + 16 * t;
+        const int8_t* q1 = q0 + (size_t)8 * K;
+#pragma unroll
+        for (int v = 0; v < 2; ++v) { wa[rbl * 2 + v] = ldg_stream(q0 + 64 * v); wb[rbl * 2 + v] = ldg_stream(q1 + 64 * v); }
+      }
     } else {
       const bf16* w0 = W + (size_t)(ib * 16 + g) * K + (size_t)gs * 2048 + warp * 128 + 8 * t;
       const bf16* w1 = w0 + (size_t)8 * K;
@@ -134,16 +140,22 @@ __device__ __forceinline__ void gemm_phase(const void* __restrict__ Wv, const fl
       __syncthreads();
       staged_gs = gs;
     }
-    float acc[NT][4];
+    float acc[RBW][NT][4];
 #pragma unroll
-    for (int nt = 0; nt < NT; ++nt) { acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f; }
+    for (int rbl = 0; rbl < RBW; ++rbl)
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) { acc[rbl][nt][0] = acc[rbl][nt][1] = acc[rbl][nt][2] = acc[rbl][nt][3] = 0.f; }
     if (W8) {
 #pragma unroll
       for (int v = 0; v < 2; ++v) {
-        const uint32_t ra[4] = {wa[v].x, wa[v].y, wa[v].z, wa[v].w}, rb[4] = {wb[v].x, wb[v].y, wb[v].z, wb[v].w};
-        uint32_t a_lo[4], a_hi[4], b_lo[4], b_hi[4];
+        uint32_t a_lo[RBW][4], a_hi[RBW][4], b_lo[RBW][4], b_hi[RBW][4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) { i8x4_to_bf16x2(ra[q], a_lo[q], a_hi[q]); i8x4_to_bf16x2(rb[q], b_lo[q], b_hi[q]); }
+        for (int rbl = 0; rbl < RBW; ++rbl) {
+          const uint4 qa = wa[rbl * 2 + v], qb = wb[rbl * 2 + v];
+          const uint32_t ra[4] = {qa.x, qa.y, qa.z, qa.w}, rb[4] = {qb.x, qb.y, qb.z, qb.w};
+#pragma unroll
+          for (int q = 0; q < 4; ++q) { i8x4_to_bf16x2(ra[q], a_lo[rbl][q], a_hi[rbl][q]); i8x4_to_bf16x2(rb[q], b_lo[rbl][q], b_hi[rbl][q]); }
+        }
 #pragma unroll
         for (int nt = 0; nt < NT; ++nt) {
           uint4 x0, x1;
@@ -160,41 +172,48 @@ __device__ __forceinline__ void gemm_phase(const void* __restrict__ Wv, const fl
               x1 = *reinterpret_cast<const uint4*>(px + 8);
             }
           }
-          mma16816(acc[nt], a_lo[0], b_lo[0], a_hi[0], b_hi[0], x0.x, x0.y);
-          mma16816(acc[nt], a_lo[1], b_lo[1], a_hi[1], b_hi[1], x0.z, x0.w);
-          mma16816(acc[nt], a_lo[2], b_lo[2], a_hi[2], b_hi[2], x1.x, x1.y);
-          mma16816(acc[nt], a_lo[3], b_lo[3], a_hi[3], b_hi[3], x1.z, x1.w);
+#pragma unroll
+          for (int rbl = 0; rbl < RBW; ++rbl) {
+            mma16816(acc[rbl][nt], a_lo[rbl][0], b_lo[rbl][0], a_hi[rbl][0], b_hi[rbl][0], x0.x, x0.y);
+            mma16816(acc[rbl][nt], a_lo[rbl][1], b_lo[rbl][1], a_hi[rbl][1], b_hi[rbl][1], x0.z, x0.w);
+            mma16816(acc[rbl][nt], a_lo[rbl][2], b_lo[rbl][2], a_hi[rbl][2], b_hi[rbl][2], x1.x, x1.y);
+            mma16816(acc[rbl][nt], a_lo[rbl][3], b_lo[rbl][3], a_hi[rbl][3], b_hi[rbl][3], x1.z, x1.w);
+          }
         }
       }
     } else {
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < 4; ++u) {
 #pragma unroll
-      for (int nt = 0; nt < NT; ++nt) {
-        uint4 xv;
-        if (STAGE) {
-          xv = *reinterpret_cast<const uint4*>(sX + (size_t)(nt * 8 + g) * kXRowBytes + (warp * 128 + 32 * u + 8 * t) * 2);
-        } else {
-          const int tok = tok0 + nt * 8 + g;
-          xv = make_uint4(0, 0, 0, 0);
-          if (tok < B) xv = *reinterpret_cast<const uint4*>(X + (size_t)tok * K + (size_t)gs * 2048 + warp * 128 + 32 * u + 8 * t);
+        for (int nt = 0; nt < NT; ++nt) {
+          uint4 xv;
+          if (STAGE) {
+            xv = *reinterpret_cast<const uint4*>(sX + (size_t)(nt * 8 + g) * kXRowBytes + (warp * 128 + 32 * u + 8 * t) * 2);
+          } else {
+            const int tok = tok0 + nt * 8 + g;
+            xv = make_uint4(0, 0, 0, 0);
+            if (tok < B) xv = *reinterpret_cast<const uint4*>(X + (size_t)tok * K + (size_t)gs * 2048 + warp * 128 + 32 * u + 8 * t);
+          }
+          mma16816(acc[0][nt], wa[u].x, wb[u].x, wa[u].y, wb[u].y, xv.x, xv.y);
+          mma16816(acc[0][nt], wa[u].z, wb[u].z, wa[u].w, wb[u].w, xv.z, xv.w);
         }
-        mma16816(acc[nt], wa[u].x, wb[u].x, wa[u].y, wb[u].y, xv.x, xv.y);
-        mma16816(acc[nt], wa[u].z, wb[u].z, wa[u].w, wb[u].w, xv.z, xv.w);
       }
-    }
     }
     if (item + (int)gridDim.x < n_items) load_item(item + gridDim.x);     // in flight during the exchange below
 #pragma unroll
-    for (int nt = 0; nt < NT; ++nt)
-      *reinterpret_cast<float4*>(sR + ((size_t)(warp * NT + nt) * 32 + lane) * 4) = make_float4(acc[nt][0], acc[nt][1], acc[nt][2], acc[nt][3]);
+    for (int rbl = 0; rbl < RBW; ++rbl)
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt)
+        *reinterpret_cast<float4*>(sR + ((size_t)((warp * RBW + rbl) * NT + nt) * 32 + lane) * 4) =
+            make_float4(acc[rbl][nt][0], acc[rbl][nt][1], acc[rbl][nt][2], acc[rbl][nt][3]);
     __syncthreads();
-    for (int e = threadIdx.x; e < NT * 128; e += kPThreads) {
+    for (int e = threadIdx.x; e < RBW * NT * 128; e += kPThreads) {
+      const int rbl = e / (NT * 128), e2 = e - rbl * (NT * 128);
       float v = 0.f;
 #pragma unroll
-      for (int w = 0; w < kPWarps; ++w) v += sR[(size_t)w * NT * 128 + e];
-      const int c = e & 3, ml = (e >> 2) & 31, nt = e >> 7;
-      const int row = ib * 16 + (ml >> 2) + 8 * (c >> 1), tok = tok0 + nt * 8 + 2 * (ml & 3) + (c & 1);
+      for (int w = 0; w < kPWarps; ++w) v += sR[(size_t)(w * RBW + rbl) * NT * 128 + e2];
+      const int c = e2 & 3, ml = (e2 >> 2) & 31, nt = e2 >> 7;
+      const int row = (ib * RBW + rbl) * 16 + (ml >> 2) + 8 * (c >> 1), tok = tok0 + nt * 8 + 2 * (ml & 3) + (c & 1);
       if (W8) v *= __ldg(wscale + row);
       if (EPI == EPI_SWIGLU) {
         const float up = __shfl_down_sync(0xffffffffu, v, 16);            // row + 1 of the same token sits 16 threads up
@@ -636,7 +655,7 @@ __global__ void __launch_bounds__(kPThreads, 1) decode_persist_kernel(DecodePers
 
 size_t decode_persist_smem_bytes() {
   const size_t attn = (size_t)AKEYS * kAKRow + (size_t)AKEYS * PHD * 2 + (PG * PHD + PG * AKEYS + 2 * PHD + 32 + 16) * 4;
-  const size_t exch = (size_t)kXStageBytes + (size_t)kPWarps * 4 * 128 * 4;    // staged activations + 16 warps x NT(4) x 128 fp32 (>= the unstaged NT = 8 exchange)
+  const size_t exch = (size_t)kXStageBytes + (size_t)kPWarps * 2 * 4 * 128 * 4;    // staged activations + 16 warps x NT(4) x 128 fp32 (>= the unstaged NT = 8 exchange)
   return attn > exch ? attn : exch;
 }
 
