@@ -481,7 +481,7 @@ struct Engine {
   static int decode_step(sonic_ctx* h, int B) {
     T* x = reinterpret_cast<T*>(h->dx);
     TAG(PC_DEC_OTHER);
-    if (h->use_persist && std::is_same<T, bf16>::value) {
+    if (h->use_persist && B <= 64 && std::is_same<T, bf16>::value) {            // the persistent kernel tiles at most 64 tokens
       DecodePersistArgs p;
       memset(&p, 0, sizeof(p));
       p.layers = h->dev_layers; p.n_layers = h->cfg.dec_layers;
@@ -817,7 +817,7 @@ int do_generate(sonic_ctx* h, const int32_t* ids, const int32_t* id_offsets, int
   // greedy steps 2..max_new: one CUDA graph per (batch, max_new) replayed; no per-token host sync.
   h->decode_chunks = (max_q + max_new + 63) / 64;
   if (h->decode_chunks > h->dattn_max_chunks) h->decode_chunks = h->dattn_max_chunks;
-  if (max_new > 1 && (h->prof_on || (h->use_persist && !h->is_f32))) {
+  if (max_new > 1 && (h->prof_on || (h->use_persist && batch <= 64 && !h->is_f32))) {
     int* flag = h->h_pinned + h->h_pinned_ints - 16;
     for (int step = 1; step < max_new; ++step) {
       rc = dispatch(h, [&] { return Engine<float>::decode_step(h, batch); }, [&] { return Engine<bf16>::decode_step(h, batch); });
@@ -917,7 +917,7 @@ int sonic_create(const sonic_config* cfg, sonic_handle* out) {
   *out = nullptr;
   if (cfg->mode != SONIC_MODE_BF16 && cfg->mode != SONIC_MODE_FP32 && cfg->mode != SONIC_MODE_INT8) return fail(nullptr, "sonic_create: unsupported mode");
   if (cfg->enc_layers < 1 || cfg->enc_layers > 64 || cfg->dec_layers < 1 || cfg->dec_layers > 64 || cfg->max_batch < 1 ||
-      cfg->max_batch > 256 || cfg->max_prompt < 8 || cfg->max_new < 1)
+      cfg->max_batch > 1024 || cfg->max_prompt < 8 || cfg->max_new < 1)
     return fail(nullptr, "sonic_create: bad configuration");
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);

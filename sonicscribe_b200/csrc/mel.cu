@@ -114,7 +114,7 @@ __device__ __forceinline__ float fetch_sample(const float* __restrict__ x, int n
 
 __global__ void __launch_bounds__(kMelThreads, 2)
 mel_frames_kernel(const float* __restrict__ pcm, const long long* __restrict__ offs, const int* __restrict__ lens,
-                  const unsigned* __restrict__ peak_bits, const MelTables* __restrict__ tab, int flags,
+                  const unsigned* __restrict__ peak_bits, const MelTables* __restrict__ tab, int flags, int batch, int tiles_per_seg,
                   float* __restrict__ raw /*[B][128][3000]*/, unsigned* __restrict__ gmax_bits /*[B]*/) {
   extern __shared__ float smem[];
   float* s_samp = smem;                              // kSpan
@@ -127,26 +127,45 @@ mel_frames_kernel(const float* __restrict__ pcm, const long long* __restrict__ o
   int* s_tcount = s_tstart + kMels;
   __shared__ float red[32];
 
-  const int b = blockIdx.y, tid = threadIdx.x;
-  const int n = min(lens[b], kWin);
-  const int n_active = min(kFrames, (n + 200 + kHop - 1) / kHop);
-  const int n_tiles = (n_active + kTileFrames - 1) / kTileFrames;
-  if ((int)blockIdx.x >= n_tiles) return;
-
+  const int tid = threadIdx.x;
   for (int i = tid; i < kNfft; i += kMelThreads) { s_win[i] = tab->window[i]; s_w400[i] = tab->w400[i]; }
   for (int i = tid; i < kMels * kMaxTaps; i += kMelThreads) s_tapw[i] = tab->tapw[i];
   for (int i = tid; i < kMels; i += kMelThreads) { s_tstart[i] = tab->tap_start[i]; s_tcount[i] = tab->tap_count[i]; }
 
-  const float* x = pcm + offs[b];
-  const float peak = __uint_as_float(peak_bits[b]);
-  const float gate = (peak > 1e-6f) ? 1.f : 0.f;
-  float lmax = -10.0f;
-
-  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+  // persistent CTAs: work item = (segment, tile of 32 frames); the tables above are loaded once per CTA
+  for (int work = blockIdx.x; work < batch * tiles_per_seg; work += gridDim.x) {
+    const int b = work / tiles_per_seg, tile = work - b * tiles_per_seg;
+    const int n = min(lens[b], kWin);
+    const int n_active = min(kFrames, (n + 200 + kHop - 1) / kHop);
+    if (tile * kTileFrames >= n_active) continue;               // CTA-uniform
+    const float* x = pcm + offs[b];
+    const float peak = __uint_as_float(peak_bits[b]);
+    const float gate = (peak > 1e-6f) ? 1.f : 0.f;
+    float lmax = -10.0f;
     const int t0 = tile * kTileFrames;
-    __syncthreads();                                  // previous tile's readers are done with smem
+    __syncthreads();                                  // previous item's readers are done with smem
     const int j0 = t0 * kHop - 200;
-    for (int i = tid; i < kSpan; i += kMelThreads) s_samp[i] = fetch_sample(x, n, j0 + i, gate, peak, flags);
+    {
+      // all of a thread's loads are issued before the first value is transformed (kSpan / 256 = 21 independent loads)
+      constexpr int kPer = (kSpan + kMelThreads - 1) / kMelThreads;
+      float rawv[kPer];
+#pragma unroll
+      for (int q = 0; q < kPer; ++q) {
+        const int i = tid + q * kMelThreads;
+        int j = j0 + i;
+        if (j < 0) j = -j;
+        if (j >= kWin) j = 2 * (kWin - 1) - j;
+        rawv[q] = (i < kSpan && j < n) ? __ldg(x + j) : 0.f;
+      }
+#pragma unroll
+      for (int q = 0; q < kPer; ++q) {
+        const int i = tid + q * kMelThreads;
+        float v = rawv[q];
+        if ((flags & SONIC_MEL_PEAK_NORM) && gate > 0.f) v = v / peak;              // asr.py:266-267 (true division)
+        if (flags & SONIC_MEL_PCM16) v = rintf(v * 32767.0f) * (1.0f / 32768.0f);   // soundfile PCM_16 write + float read
+        if (i < kSpan) s_samp[i] = v;
+      }
+    }
     __syncthreads();
 
     // ---- step 1: for each (pair, n2): 16-point DFT over n1 of z[25*n1+n2], z = wA*fA + i*wB*fB; twiddle W400^{n2*k1}
@@ -214,16 +233,17 @@ mel_frames_kernel(const float* __restrict__ pcm, const long long* __restrict__ o
           const int k = ks + j;
           acc = fmaf(s_tapw[m * kMaxTaps + j], P[(k & 15) * 25 + (k >> 4)], acc);
         }
-        const float l = log10f(fmaxf(acc, 1e-10f));
+        // log10 via MUFU lg2 (relative error 2^-22: < 2e-7 in the log, far below the 1e-4 parity bar)
+        const float l = __log2f(fmaxf(acc, 1e-10f)) * 0.30102999566398120f;
         if (t < n_active) {
           raw[((size_t)b * kMels + m) * kFrames + t] = l;
           lmax = fmaxf(lmax, l);
         }
       }
     }
+    lmax = block_max(lmax, red);
+    if (tid == 0) atomicMax(gmax_bits + b, f32_to_ordered(lmax));
   }
-  lmax = block_max(lmax, red);
-  if (tid == 0) atomicMax(gmax_bits + b, f32_to_ordered(lmax));
 }
 
 template <typename T>
@@ -307,8 +327,13 @@ cudaError_t launch_mel(const float* pcm, const long long* offs, const int* lens,
   const int n_eff = min(max_len, kWin);
   const int max_active = min(kFrames, (n_eff + 200 + kHop - 1) / kHop);
   const int tiles = cdiv(max_active, kTileFrames);
-  mel_frames_kernel<<<dim3(tiles, batch), kMelThreads, mel_smem_bytes(), st>>>(
-      pcm, offs, lens, peak_bits, reinterpret_cast<const MelTables*>(tables), flags, raw, gmax_bits);
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const long long total = (long long)tiles * batch;
+  const int grid = (int)(total < 2LL * sms ? total : 2LL * sms);      // two resident CTAs per SM, persistent
+  mel_frames_kernel<<<grid, kMelThreads, mel_smem_bytes(), st>>>(
+      pcm, offs, lens, peak_bits, reinterpret_cast<const MelTables*>(tables), flags, batch, tiles, raw, gmax_bits);
   SONIC_LAUNCH_CHECK();
   mel_finalize_kernel<T><<<dim3(cdiv(kFrames, 32), batch), dim3(32, 8), 0, st>>>(raw, gmax_bits, lens, feat, feat_tm);
   SONIC_LAUNCH_CHECK();
