@@ -495,6 +495,7 @@ struct Engine {
       p.gs = h->gs; p.bar = h->persist_bar; p.timestamps = h->cfg.debug ? h->persist_ts : nullptr;
       { const char* pf = getenv("SONIC_PERSIST_PREFETCH"); p.prefetch = (pf && pf[0] == '1') ? 1 : 0; }
       p.w8 = h->is_int8 ? 1 : 0;
+      { const char* am = getenv("SONIC_ATTN"); p.attn_mode = (am && std::string(am) == "simt") ? 1 : 0; }
       p.B = B; p.Bpad = (B + 7) / 8 * 8; p.max_ctx = h->max_ctx; p.eps = kRmsEps; p.scale = 0.08838834764831845f;
       TAG(PC_DEC_PERSIST);
       if (h->prof_on) { cudaEventRecord(prof_event(h), h->stream); h->prof_tags.push_back(h->prof_cls); }
@@ -659,7 +660,7 @@ int alloc_all(sonic_ctx* h) {
   DA(h->emlp, (size_t)B * kEncT * kEncInter * E);
   DA(h->a1, (size_t)B * kMerged * 2 * kDecH * E); DA(h->audio, (size_t)B * kMerged * kDecH * E);
   // decoder
-  const size_t rows = (size_t)B * c.max_prompt;
+  const size_t rows = std::max<size_t>((size_t)B * c.max_prompt, 64);   // the decode kernel reads whole 8-token tiles
   DA(h->dx, rows * kDecH * E); DA(h->du, rows * kDecH * E); DA(h->dqkv, rows * kQkvDec * E); DA(h->dattn, rows * kDecH * E);
   DA(h->dact, rows * kDecInter * E);
   const size_t kv = (size_t)c.dec_layers * B * kDecKv * h->max_ctx * kDecHd * E;

@@ -164,13 +164,10 @@ __device__ __forceinline__ void gemm_phase(const void* __restrict__ Wv, const fl
             x0 = *reinterpret_cast<const uint4*>(px);
             x1 = *reinterpret_cast<const uint4*>(px + 16);
           } else {
-            const int tok = tok0 + nt * 8 + g;
-            x0 = make_uint4(0, 0, 0, 0); x1 = x0;
-            if (tok < B) {
-              const bf16* px = X + (size_t)tok * K + (size_t)gs * 2048 + warp * 128 + 64 * v + 16 * t;
-              x0 = *reinterpret_cast<const uint4*>(px);
-              x1 = *reinterpret_cast<const uint4*>(px + 8);
-            }
+            // rows >= B of the activation buffers are allocated (prefill sizes them) and their columns are never stored
+            const bf16* px = X + (size_t)(tok0 + nt * 8 + g) * K + (size_t)gs * 2048 + warp * 128 + 64 * v + 16 * t;
+            x0 = *reinterpret_cast<const uint4*>(px);
+            x1 = *reinterpret_cast<const uint4*>(px + 8);
           }
 #pragma unroll
           for (int rbl = 0; rbl < RBW; ++rbl) {
@@ -190,9 +187,7 @@ __device__ __forceinline__ void gemm_phase(const void* __restrict__ Wv, const fl
           if (STAGE) {
             xv = *reinterpret_cast<const uint4*>(sX + (size_t)(nt * 8 + g) * kXRowBytes + (warp * 128 + 32 * u + 8 * t) * 2);
           } else {
-            const int tok = tok0 + nt * 8 + g;
-            xv = make_uint4(0, 0, 0, 0);
-            if (tok < B) xv = *reinterpret_cast<const uint4*>(X + (size_t)tok * K + (size_t)gs * 2048 + warp * 128 + 32 * u + 8 * t);
+            xv = *reinterpret_cast<const uint4*>(X + (size_t)(tok0 + nt * 8 + g) * K + (size_t)gs * 2048 + warp * 128 + 32 * u + 8 * t);
           }
           mma16816(acc[0][nt], wa[u].x, wb[u].x, wa[u].y, wb[u].y, xv.x, xv.y);
           mma16816(acc[0][nt], wa[u].z, wb[u].z, wa[u].w, wb[u].w, xv.z, xv.w);
@@ -230,13 +225,14 @@ __device__ __forceinline__ void gemm_phase(const void* __restrict__ Wv, const fl
   }
 }
 
-template <int EPI, bool W8>
+// NT (8-token tiles) is a template parameter of the whole kernel: one instantiation per batch class keeps a single copy of
+// the GEMM phase per epilogue in the kernel, which matters for register allocation (measured)
+template <int EPI, bool W8, int NT>
 __device__ __forceinline__ void gemm_dispatch(const void* W, const float* wscale, int N, int K, const bf16* X, int B, int Bpad, float* out32,
                                               bf16* xres, bf16* act, uint8_t* smem) {
-  if (B <= 8) gemm_phase<1, EPI, false, W8>(W, wscale, N, K, X, B, Bpad, 0, out32, xres, act, smem);
-  else if (B <= 16) gemm_phase<2, EPI, true, W8>(W, wscale, N, K, X, B, Bpad, 0, out32, xres, act, smem);
-  else if (B <= 32) gemm_phase<4, EPI, true, W8>(W, wscale, N, K, X, B, Bpad, 0, out32, xres, act, smem);
-  else gemm_phase<8, EPI, false, W8>(W, wscale, N, K, X, B, Bpad, 0, out32, xres, act, smem);   // measured: two staged 32-token passes are slower
+  // activations staged in shared memory for 9..32 tokens; <= 8 read them directly (tiny), > 32 too (two staged 32-token
+  // passes measured slower)
+  gemm_phase<NT, EPI, (NT == 2 || NT == 4), W8>(W, wscale, N, K, X, B, Bpad, 0, out32, xres, act, smem);
 }
 
 // fixed-order sum of the KS split-K partials of one element; fully unrolled so the KS L2 loads are in flight together
@@ -416,48 +412,72 @@ __device__ __forceinline__ void attention_phase(const DecodePersistArgs& a, cons
   }
 }
 
-// ---- attention phase, large-batch variant: item = (segment, kv head), chunks walked in-CTA with an online softmax: finish q/k/v from the partials, RoPE, append to the cache, attend ---------
-__device__ __forceinline__ void attention_phase_serial(const DecodePersistArgs& a, const DecLayerDev& L, uint8_t* smem) {
-  uint8_t* sK = smem;                                          // AKEYS * kAKRow
-  bf16* sV = reinterpret_cast<bf16*>(smem + AKEYS * kAKRow);   // AKEYS * 128
-  float* sQ = reinterpret_cast<float*>(smem + AKEYS * kAKRow + AKEYS * PHD * 2);   // [4][128]
-  float* sP = sQ + PG * PHD;                                   // [4][AKEYS]
-  float* sKV = sP + PG * AKEYS;                                // new k (128) | new v (128)
-  float* sRed = sKV + 2 * PHD;                                 // [4 heads][4 key groups] max, then sums
-  float* sState = sRed + 32;                                   // m[4], l[4], corr[4]
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+// ---- attention phase on mma.sync (used when every CTA has at least one (segment, kv head) group to itself) -----------------
+// Per 128-key chunk: S[4 heads(16) x 128 keys] = Q.K^T with warp w owning keys 8w..8w+7 (8 k-steps over head_dim), online
+// softmax state per head kept by the lanes that own that head's fragment rows, P (bf16) through shared memory, then
+// O[4(16) x 128 dims] += P.V with warp w owning dims 8w..8w+7 (V fragments via ldmatrix.trans).  Rows 4..15 of the 16-row MMA
+// tile are zero padding.
+static constexpr int kARow = PHD * 2 + 16;               // padded bf16 row (272 B): conflict-free 32-bit fragment loads
+
+__device__ __forceinline__ void ldmatrix_x2_trans(uint32_t& r0, uint32_t& r1, const void* smem_row) {
+  const uint32_t addr = (uint32_t)__cvta_generic_to_shared(smem_row);
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0, %1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(addr));
+}
+
+__device__ __forceinline__ void attention_phase_mma(const DecodePersistArgs& a, const DecLayerDev& L, uint8_t* smem) {
+  uint8_t* sK = smem;                                     // [128 keys][272 B]
+  uint8_t* sV = sK + AKEYS * kARow;                       // [128 keys][272 B]
+  uint8_t* sQ = sV + AKEYS * kARow;                       // [16][272 B]   rows 0..3 = rotated query heads (bf16), rest zero
+  uint8_t* sP = sQ + 16 * kARow;                          // [16][272 B]   rows 0..3 = probabilities of the chunk (bf16)
+  float* sKV = reinterpret_cast<float*>(sP + 16 * kARow); // new k (128) | new v (128)
+  float* sMax = sKV + 2 * PHD;                            // [4 heads][16 warps]
+  float* sSum = sMax + 4 * kPWarps;                       // [4 heads][16 warps]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+  // zero the padding rows once per phase (rows 4..15 of sQ and sP)
+  for (int i = tid; i < 12 * (kARow / 4); i += kPThreads) {
+    reinterpret_cast<uint32_t*>(sQ + 4 * kARow)[i] = 0u;
+    reinterpret_cast<uint32_t*>(sP + 4 * kARow)[i] = 0u;
+  }
   for (int item = blockIdx.x; item < a.B * PKVH; item += gridDim.x) {
     const int seg = item / PKVH, kvh = item - seg * PKVH;
     const int pos = a.gs.ctx_len[seg], kv_len = pos + 1;
     bf16* kc = L.kc + ((size_t)seg * PKVH + kvh) * a.max_ctx * PHD;
     bf16* vc = L.vc + ((size_t)seg * PKVH + kvh) * a.max_ctx * PHD;
-    // q (4 heads), k, v of the new token: sum the split-K partials, round to bf16 like the unfused path, rotate
+    __syncthreads();                                       // previous item's fragments are consumed
     for (int i = tid; i < (PG + 2) * (PHD / 2); i += kPThreads) {
       const int hh = i / (PHD / 2), j = i - hh * (PHD / 2);     // hh < 4: query head; 4: key; 5: value (pair j, j+64)
       const int col = (hh < PG) ? (kvh * PG + hh) * PHD : (hh == PG ? (16 + kvh) * PHD : (16 + PKVH + kvh) * PHD);
       const float x = bf16r(__ldcg(a.part + (size_t)seg * PQKV + col + j));
       const float y = bf16r(__ldcg(a.part + (size_t)seg * PQKV + col + j + PHD / 2));
       if (hh <= PG) {
-        const float c = bf16r(a.cos_t[(size_t)pos * (PHD / 2) + j]), s = bf16r(a.sin_t[(size_t)pos * (PHD / 2) + j]);
-        const float rx = bf16r(x * c - y * s), ry = bf16r(y * c + x * s);
-        if (hh < PG) { sQ[hh * PHD + j] = rx * a.scale; sQ[hh * PHD + j + PHD / 2] = ry * a.scale; }
-        else { sKV[j] = rx; sKV[j + PHD / 2] = ry; }
+        const float c = bf16r(a.cos_t[(size_t)pos * (PHD / 2) + j]), sn = bf16r(a.sin_t[(size_t)pos * (PHD / 2) + j]);
+        const float rx = bf16r(x * c - y * sn), ry = bf16r(y * c + x * sn);
+        if (hh < PG) {
+          reinterpret_cast<bf16*>(sQ + hh * kARow)[j] = __float2bfloat16_rn(rx);
+          reinterpret_cast<bf16*>(sQ + hh * kARow)[j + PHD / 2] = __float2bfloat16_rn(ry);
+        } else { sKV[j] = rx; sKV[j + PHD / 2] = ry; }
       } else { sKV[PHD + j] = x; sKV[PHD + j + PHD / 2] = y; }
     }
-    if (tid < PG) { sState[tid] = -INFINITY; sState[4 + tid] = 0.f; }
     __syncthreads();
     if (tid < PHD) kc[(size_t)pos * PHD + tid] = __float2bfloat16_rn(sKV[tid]);
     else if (tid < 2 * PHD) vc[(size_t)pos * PHD + tid - PHD] = __float2bfloat16_rn(sKV[tid]);
-    const int head = warp & 3, kgrp = warp >> 2;                 // scores: 4 heads x 4 groups of 32 keys
-    float o_acc = 0.f;                                           // PV: thread = (head = tid / 128, dim = tid % 128)
+    // Q fragments of this lane (rows g, k-steps 0..7); rows >= 4 are zero
+    uint32_t qa0[8], qa2[8];
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks) {
+      qa0[ks] = *reinterpret_cast<const uint32_t*>(sQ + g * kARow + (16 * ks + 2 * t) * 2);
+      qa2[ks] = *reinterpret_cast<const uint32_t*>(sQ + g * kARow + (16 * ks + 8 + 2 * t) * 2);
+    }
+    float m_run = -INFINITY, l_run = 0.f;                  // online-softmax state of head g (lanes with g < 4)
+    float o0 = 0.f, o1 = 0.f;                              // O[head g][dims 8*warp + 2t, +1]
     for (int k0 = 0; k0 < kv_len; k0 += AKEYS) {
       const int nk = min(AKEYS, kv_len - k0);
-      __syncthreads();                                           // previous chunk fully consumed; new k/v row written
+      __syncthreads();                                     // previous chunk fully consumed
       for (int i = tid; i < AKEYS * (PHD / 8); i += kPThreads) {
         const int r = i / (PHD / 8), c8 = i - r * (PHD / 8);
         uint4 kk = make_uint4(0, 0, 0, 0), vv = make_uint4(0, 0, 0, 0);
         if (r < nk) {
-          if (k0 + r == pos) {                                   // the row appended above by this CTA: take it from smem
+          if (k0 + r == pos) {                             // the row appended above: take it from shared memory
             uint32_t wk[4], wv[4];
 #pragma unroll
             for (int e2 = 0; e2 < 4; ++e2) {
@@ -471,64 +491,71 @@ __device__ __forceinline__ void attention_phase_serial(const DecodePersistArgs& 
             vv = __ldcg(reinterpret_cast<const uint4*>(vc + (size_t)(k0 + r) * PHD + c8 * 8));
           }
         }
-        *reinterpret_cast<uint4*>(sK + r * kAKRow + c8 * 16) = kk;
-        *reinterpret_cast<uint4*>(sV + r * PHD + c8 * 8) = vv;
+        *reinterpret_cast<uint4*>(sK + r * kARow + c8 * 16) = kk;
+        *reinterpret_cast<uint4*>(sV + r * kARow + c8 * 16) = vv;
       }
       __syncthreads();
-      // scores for (head, key = kgrp*32 + lane)
-      const int r = kgrp * 32 + lane;
-      float sc = -INFINITY;
-      if (r < nk) {
-        float acc = 0.f;
-#pragma unroll 4
-        for (int c8 = 0; c8 < PHD / 8; ++c8) {
-          const uint4 kv = *reinterpret_cast<const uint4*>(sK + r * kAKRow + c8 * 16);
-          const float4 q0 = *reinterpret_cast<const float4*>(sQ + head * PHD + c8 * 8);
-          const float4 q1 = *reinterpret_cast<const float4*>(sQ + head * PHD + c8 * 8 + 4);
-          acc = fmaf(__uint_as_float(kv.x << 16), q0.x, acc); acc = fmaf(__uint_as_float(kv.x & 0xffff0000u), q0.y, acc);
-          acc = fmaf(__uint_as_float(kv.y << 16), q0.z, acc); acc = fmaf(__uint_as_float(kv.y & 0xffff0000u), q0.w, acc);
-          acc = fmaf(__uint_as_float(kv.z << 16), q1.x, acc); acc = fmaf(__uint_as_float(kv.z & 0xffff0000u), q1.y, acc);
-          acc = fmaf(__uint_as_float(kv.w << 16), q1.z, acc); acc = fmaf(__uint_as_float(kv.w & 0xffff0000u), q1.w, acc);
-        }
-        sc = acc;
+      // S tile of this warp: keys 8*warp + {2t, 2t+1} for head g
+      float sc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int ks = 0; ks < 8; ++ks) {
+        const uint32_t b0 = *reinterpret_cast<const uint32_t*>(sK + (8 * warp + g) * kARow + (16 * ks + 2 * t) * 2);
+        const uint32_t b1 = *reinterpret_cast<const uint32_t*>(sK + (8 * warp + g) * kARow + (16 * ks + 8 + 2 * t) * 2);
+        mma16816(sc, qa0[ks], 0u, qa2[ks], 0u, b0, b1);
       }
-      const float wmax = warp_max(sc);
-      if (lane == 0) sRed[head * 4 + kgrp] = wmax;
+      const int key0 = 8 * warp + 2 * t;
+      const float s0 = (key0 < nk) ? sc[0] * a.scale : -INFINITY;
+      const float s1 = (key0 + 1 < nk) ? sc[1] * a.scale : -INFINITY;
+      float wmax = fmaxf(s0, s1);
+      wmax = fmaxf(wmax, __shfl_xor_sync(0xffffffffu, wmax, 1));
+      wmax = fmaxf(wmax, __shfl_xor_sync(0xffffffffu, wmax, 2));
+      if (g < PG && t == 0) sMax[g * kPWarps + warp] = wmax;
       __syncthreads();
-      const float cmax = fmaxf(fmaxf(sRed[head * 4], sRed[head * 4 + 1]), fmaxf(sRed[head * 4 + 2], sRed[head * 4 + 3]));
-      const float m_old = sState[head];
-      const float m_new = fmaxf(m_old, cmax);
-      const float p = (sc == -INFINITY) ? 0.f : expf(sc - m_new);
-      sP[head * AKEYS + r] = p;
-      const float wsum = warp_sum(p);
-      __syncthreads();                                           // every thread has read the maxima and the running state
-      if (lane == 0) sRed[head * 4 + kgrp] = wsum;
-      __syncthreads();
-      if (kgrp == 0 && lane == 0) {                              // one thread per head advances the online-softmax state
-        const float corr = (m_old == -INFINITY) ? 0.f : expf(m_old - m_new);
-        const float lsum = sRed[head * 4] + sRed[head * 4 + 1] + sRed[head * 4 + 2] + sRed[head * 4 + 3];
-        sState[8 + head] = corr;
-        sState[head] = m_new;
-        sState[4 + head] = sState[4 + head] * corr + lsum;
+      float corr = 1.f;
+      if (g < PG) {
+        float cmax = sMax[g * kPWarps];
+#pragma unroll
+        for (int w = 1; w < kPWarps; ++w) cmax = fmaxf(cmax, sMax[g * kPWarps + w]);
+        const float m_new = fmaxf(m_run, cmax);
+        corr = (m_run == -INFINITY) ? 0.f : expf(m_run - m_new);
+        m_run = m_new;
+        const float p0 = (s0 == -INFINITY) ? 0.f : expf(s0 - m_new);
+        const float p1 = (s1 == -INFINITY) ? 0.f : expf(s1 - m_new);
+        __nv_bfloat162 pb = __floats2bfloat162_rn(p0, p1);
+        *reinterpret_cast<uint32_t*>(sP + g * kARow + key0 * 2) = *reinterpret_cast<uint32_t*>(&pb);
+        float ws = __low2float(pb) + __high2float(pb);      // the denominator sums what the tensor core multiplies
+        ws += __shfl_xor_sync(0x0000ffffu, ws, 1);
+        ws += __shfl_xor_sync(0x0000ffffu, ws, 2);
+        if (t == 0) sSum[g * kPWarps + warp] = ws;
       }
       __syncthreads();
-      {
-        const int ph = tid >> 7, d = tid & 127;
-        float acc = o_acc * sState[8 + ph];
-        const float* pp = sP + ph * AKEYS;
-        for (int j = 0; j < nk; ++j) acc = fmaf(pp[j], __bfloat162float(sV[j * PHD + d]), acc);
-        o_acc = acc;
+      if (g < PG) {
+        float ls = 0.f;
+#pragma unroll
+        for (int w = 0; w < kPWarps; ++w) ls += sSum[g * kPWarps + w];
+        l_run = l_run * corr + ls;
       }
+      // O tile of this warp: dims 8*warp + {2t, 2t+1} for head g
+      float oc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int ks = 0; ks < 8; ++ks) {
+        const uint32_t pa0 = *reinterpret_cast<const uint32_t*>(sP + g * kARow + (16 * ks + 2 * t) * 2);
+        const uint32_t pa2 = *reinterpret_cast<const uint32_t*>(sP + g * kARow + (16 * ks + 8 + 2 * t) * 2);
+        uint32_t vb0, vb1;
+        ldmatrix_x2_trans(vb0, vb1, sV + (16 * ks + (lane & 15)) * kARow + 16 * warp);
+        mma16816(oc, pa0, 0u, pa2, 0u, vb0, vb1);
+      }
+      o0 = o0 * corr + oc[0];
+      o1 = o1 * corr + oc[1];
     }
-    __syncthreads();
-    {
-      const int ph = tid >> 7, d = tid & 127;
-      a.attn[(size_t)seg * PH + (size_t)(kvh * PG + ph) * PHD + d] = __float2bfloat16_rn(o_acc / sState[4 + ph]);
+    if (g < PG) {
+      const float inv = 1.f / l_run;
+      __nv_bfloat162 ob = __floats2bfloat162_rn(o0 * inv, o1 * inv);
+      *reinterpret_cast<uint32_t*>(a.attn + (size_t)seg * PH + (size_t)(kvh * PG + g) * PHD + 8 * warp + 2 * t) = *reinterpret_cast<uint32_t*>(&ob);
     }
-    __syncthreads();
   }
+  __syncthreads();
 }
-
 
 __device__ __forceinline__ unsigned long long gtimer() {
   unsigned long long t;
@@ -540,7 +567,7 @@ __device__ __forceinline__ unsigned long long gtimer() {
     if (a.timestamps && blockIdx.x == 0 && threadIdx.x == 0) a.timestamps[n_stamp++] = gtimer(); \
   } while (0)
 
-template <bool W8>
+template <bool W8, int NT>
 __global__ void __launch_bounds__(kPThreads, 1) decode_persist_kernel(DecodePersistArgs a) {
   extern __shared__ __align__(16) uint8_t smem[];
   __shared__ float red[32];
@@ -569,25 +596,25 @@ __global__ void __launch_bounds__(kPThreads, 1) decode_persist_kernel(DecodePers
 
   for (int l = 0; l < a.n_layers; ++l) {
     const DecLayerDev L = a.layers[l];
-    gemm_dispatch<EPI_F32, W8>(L.wqkv, L.sqkv, PQKV, PH, a.u, B, Bpad, a.part, nullptr, nullptr, smem);
+    gemm_dispatch<EPI_F32, W8, NT>(L.wqkv, L.sqkv, PQKV, PH, a.u, B, Bpad, a.part, nullptr, nullptr, smem);
     grid_barrier(a.bar, epoch); STAMP();
     if (a.attn_chunks > 1) attention_phase(a, L, smem);          // few segments: split the keys over CTAs
-    else attention_phase_serial(a, L, smem);
+    else attention_phase_mma(a, L, smem);
     grid_barrier(a.bar, epoch); STAMP();
-    gemm_dispatch<EPI_RESID, W8>(L.wo, L.so, PH, PH, a.attn, B, Bpad, nullptr, a.x, nullptr, smem);
+    gemm_dispatch<EPI_RESID, W8, NT>(L.wo, L.so, PH, PH, a.attn, B, Bpad, nullptr, a.x, nullptr, smem);
     grid_barrier(a.bar, epoch); STAMP();
     residual_norm_phase<0>(nullptr, B, Bpad, a.x, a.u, L.rms2, a.eps, red);
     grid_barrier(a.bar, epoch); STAMP();
-    gemm_dispatch<EPI_SWIGLU, W8>(L.wgu, L.sgu, 2 * PI, PH, a.u, B, Bpad, nullptr, nullptr, a.act, smem);
+    gemm_dispatch<EPI_SWIGLU, W8, NT>(L.wgu, L.sgu, 2 * PI, PH, a.u, B, Bpad, nullptr, nullptr, a.act, smem);
     grid_barrier(a.bar, epoch); STAMP();
-    gemm_dispatch<EPI_F32, W8>(L.wdown, L.sdown, PH, PI, a.act, B, Bpad, a.part, nullptr, nullptr, smem);
+    gemm_dispatch<EPI_F32, W8, NT>(L.wdown, L.sdown, PH, PI, a.act, B, Bpad, a.part, nullptr, nullptr, smem);
     grid_barrier(a.bar, epoch); STAMP();
     residual_norm_phase<3>(a.part, B, Bpad, a.x, a.u, (l + 1 < a.n_layers) ? a.layers[l + 1].rms1 : a.final_norm, a.eps, red);
     grid_barrier(a.bar, epoch); STAMP();
   }
 
   // ---- lm_head + greedy pick: every CTA scans its slice of the vocabulary for all tokens, CTA b merges token b
-  gemm_dispatch<EPI_F32, false>(a.lm_head, nullptr, PV_, PH, a.u, B, Bpad, a.part, nullptr, nullptr, smem);
+  gemm_dispatch<EPI_F32, false, NT>(a.lm_head, nullptr, PV_, PH, a.u, B, Bpad, a.part, nullptr, nullptr, smem);
   grid_barrier(a.bar, epoch); STAMP();
   {
     const int per = (PV_ + gridDim.x - 1) / gridDim.x;
@@ -662,34 +689,47 @@ size_t decode_persist_smem_bytes() {
 size_t decode_persist_part_floats(int Bpad) { return (size_t)PV_ * Bpad; }     // >= qkv (3072) and 3 down sections (6144)
 size_t decode_persist_pick_floats(int max_batch, int num_sms) { return (size_t)max_batch * num_sms * 4; }
 
-cudaError_t decode_persist_configure() {
-  SONIC_CUDA_TRY(cudaFuncSetAttribute(decode_persist_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)decode_persist_smem_bytes()));
-  return cudaFuncSetAttribute(decode_persist_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)decode_persist_smem_bytes());
+typedef void (*PersistKernel)(DecodePersistArgs);
+static PersistKernel persist_kernel_for(bool w8, int B) {
+  const int cls = B <= 8 ? 0 : (B <= 16 ? 1 : (B <= 32 ? 2 : 3));
+  static const PersistKernel tab[2][4] = {
+      {decode_persist_kernel<false, 1>, decode_persist_kernel<false, 2>, decode_persist_kernel<false, 4>, decode_persist_kernel<false, 8>},
+      {decode_persist_kernel<true, 1>, decode_persist_kernel<true, 2>, decode_persist_kernel<true, 4>, decode_persist_kernel<true, 8>}};
+  return tab[w8 ? 1 : 0][cls];
 }
+static const int kBatchOfClass[4] = {8, 16, 32, 64};
 
 int decode_persist_occupancy() {
-  int per_sm = -1;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, decode_persist_kernel<false>, kPThreads, decode_persist_smem_bytes());
-  return per_sm;
+  int worst = 1 << 30;
+  for (int w8 = 0; w8 < 2; ++w8)
+    for (int c = 0; c < 4; ++c) {
+      int per_sm = -1;
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, persist_kernel_for(w8 != 0, kBatchOfClass[c]), kPThreads, decode_persist_smem_bytes());
+      if (per_sm < worst) worst = per_sm;
+    }
+  return worst;
 }
 // largest cooperative grid (<= one CTA per SM) the device can hold for this kernel right now; 0 if it cannot be launched
 int decode_persist_max_grid(int num_sms) {
-  int per_sm = 0, coop = 0, dev = 0;
+  int coop = 0, dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return 0;
   cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
   if (!coop) return 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, decode_persist_kernel<false>, kPThreads, decode_persist_smem_bytes()) != cudaSuccess) return 0;
-  int per_sm8 = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm8, decode_persist_kernel<true>, kPThreads, decode_persist_smem_bytes()) != cudaSuccess) return 0;
-  if (per_sm8 < per_sm) per_sm = per_sm8;
-  if (per_sm < 1) return 0;
-  return num_sms;
+  return decode_persist_occupancy() >= 1 ? num_sms : 0;
+}
+
+cudaError_t decode_persist_configure() {
+  for (int w8 = 0; w8 < 2; ++w8)
+    for (int c = 0; c < 4; ++c)
+      SONIC_CUDA_TRY(cudaFuncSetAttribute(persist_kernel_for(w8 != 0, kBatchOfClass[c]), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)decode_persist_smem_bytes()));
+  return cudaSuccess;
 }
 
 cudaError_t launch_decode_persist(const DecodePersistArgs& a, int grid, cudaStream_t st) {
-  if (grid < 1) return cudaErrorInvalidConfiguration;
+  if (grid < 1 || a.B < 1 || a.B > 64) return cudaErrorInvalidConfiguration;
   const int num_sms = grid;
-
+  PersistKernel kern = persist_kernel_for(a.w8 != 0, a.B);
   {
     cudaError_t me = cudaMemsetAsync(a.bar, 0, sizeof(unsigned), st);
     if (me != cudaSuccess) { fprintf(stderr, "[sonicscribe_b200] barrier memset failed: %s\n", cudaGetErrorName(me)); return me; }
@@ -706,17 +746,15 @@ cudaError_t launch_decode_persist(const DecodePersistArgs& a, int grid, cudaStre
       attr[0].id = cudaLaunchAttributeCooperative;
       attr[0].val.cooperative = 1;
       cfg.attrs = attr; cfg.numAttrs = 1;
-      e = a.w8 ? cudaLaunchKernelEx(&cfg, decode_persist_kernel<true>, a) : cudaLaunchKernelEx(&cfg, decode_persist_kernel<false>, a);
+      e = cudaLaunchKernelEx(&cfg, kern, a);
     } else if (mode == 1) {
       DecodePersistArgs copy = a;
       void* args[1] = {&copy};
-      e = cudaLaunchCooperativeKernel(a.w8 ? reinterpret_cast<const void*>(decode_persist_kernel<true>) : reinterpret_cast<const void*>(decode_persist_kernel<false>), dim3(num_sms), dim3(kPThreads), args,
-                                      decode_persist_smem_bytes(), st);
+      e = cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(kern), dim3(num_sms), dim3(kPThreads), args, decode_persist_smem_bytes(), st);
     } else {
       // grid <= SM count with one CTA per SM: co-resident on an otherwise idle device (stream order guarantees our own
       // earlier kernels have drained); without the cooperative attribute this is not guaranteed by the programming model
-      if (a.w8) decode_persist_kernel<true><<<dim3(num_sms), dim3(kPThreads), decode_persist_smem_bytes(), st>>>(a);
-      else decode_persist_kernel<false><<<dim3(num_sms), dim3(kPThreads), decode_persist_smem_bytes(), st>>>(a);
+      kern<<<dim3(num_sms), dim3(kPThreads), decode_persist_smem_bytes(), st>>>(a);
       e = cudaGetLastError();
     }
     if (e == cudaSuccess) return e;

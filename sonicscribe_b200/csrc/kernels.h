@@ -137,6 +137,7 @@ struct DecodePersistArgs {
   unsigned long long* timestamps; // optional: %globaltimer after every grid barrier (CTA 0), 1 + 8*layers + 3 entries
   int B, Bpad, max_ctx;
   int w8;                         // 1: decoder linears are int8 weight-only (lm_head / embedding stay bf16)
+  int attn_mode;                  // 0: mma.sync attention phase, 1: CUDA-core attention phase (A/B switch)
   int prefetch;                   // 1: L2-prefetch the next GEMM's weights at the start of every GEMM phase
   float eps, scale;
 };

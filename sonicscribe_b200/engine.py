@@ -30,7 +30,8 @@ class SonicConfig(C.Structure):
 
 
 def lib_path() -> str:
-    return os.path.join(os.path.dirname(os.path.abspath(__file__)), _LIB_NAME)
+    # SONIC_LIB points at an alternative build of the same library (A/B measurements); default is the in-tree build
+    return os.environ.get("SONIC_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), _LIB_NAME)
 
 
 def load_library():
