@@ -157,8 +157,10 @@ struct sonic_ctx {
   GreedyState gs{};
   int* h_pinned = nullptr;              // pinned scratch for metadata upload / flags
   size_t h_pinned_ints = 0;
+  bool persist_tc = false;             // batch class 33..64 of the persistent kernel runs its GEMM phases on tcgen05
   bool use_persist = false;            // one cooperative kernel per greedy step (bf16 mode; SONIC_DECODE=graph disables)
   DecLayerDev* dev_layers = nullptr;
+  void* persist_tmaps = nullptr;       // device CUtensorMap array of the tcgen05 decode phases (kernels.h DecodePersistArgs::tmaps)
   float* persist_part = nullptr;
   unsigned* persist_bar = nullptr;
   unsigned long long* persist_ts = nullptr;
@@ -495,6 +497,7 @@ struct Engine {
       p.gs = h->gs; p.bar = h->persist_bar; p.timestamps = h->cfg.debug ? h->persist_ts : nullptr;
       { const char* pf = getenv("SONIC_PERSIST_PREFETCH"); p.prefetch = (pf && pf[0] == '1') ? 1 : 0; }
       p.w8 = h->is_int8 ? 1 : 0;
+      p.tmaps = h->persist_tc ? h->persist_tmaps : nullptr;
       { const char* am = getenv("SONIC_ATTN"); p.attn_mode = (am && std::string(am) == "simt") ? 1 : 0; }
       p.B = B; p.Bpad = (B + 7) / 8 * 8; p.max_ctx = h->max_ctx; p.eps = kRmsEps; p.scale = 0.08838834764831845f;
       TAG(PC_DEC_PERSIST);
@@ -673,6 +676,7 @@ int alloc_all(sonic_ctx* h) {
     DAZ(h->persist_ts, 2048 * 8);
     DA(h->persist_pick, decode_persist_pick_floats(B, h->num_sms) * 4);
     DA(h->dev_layers, (size_t)c.dec_layers * sizeof(DecLayerDev));
+    DA(h->persist_tmaps, (size_t)(4 * c.dec_layers + 4) * sizeof(CUtensorMap));
   }
   h->dattn_max_chunks = (h->max_ctx + 63) / 64;
   DA(h->dattn_ws, (size_t)B * kDecKv * h->dattn_max_chunks * 4 * 130 * 4);
@@ -1018,6 +1022,25 @@ int sonic_finalize_weights(sonic_handle h) {
       tab[l].vc = reinterpret_cast<bf16*>(h->vcache) + (size_t)l * layer_kv;
     }
     CK(cudaMemcpy(h->dev_layers, tab.data(), tab.size() * sizeof(DecLayerDev), cudaMemcpyHostToDevice));
+    const char* ptc = getenv("SONIC_PERSIST_TC");
+    h->persist_tc = !h->is_int8 && h->cfg.max_batch > 32 && !(ptc && ptc[0] == '0');
+    if (h->persist_tc) {
+      // weight maps: {K, rows} with a 64 x 128 box; activation maps: {K, 64 token rows} with a 64 x 64 box (128B swizzle)
+      const int L = h->cfg.dec_layers;
+      std::vector<CUtensorMap> maps(4 * L + 4);
+      for (int l = 0; l < L; ++l) {
+        const DecLayerW& w = h->dec[l];
+        CK(make_tensor_map_2d(&maps[4 * l + 0], w.wqkv, kDecH, kQkvDec, kDecH, 64, 128));
+        CK(make_tensor_map_2d(&maps[4 * l + 1], w.wo, kDecH, kDecH, kDecH, 64, 128));
+        CK(make_tensor_map_2d(&maps[4 * l + 2], w.wgu, kDecH, 2 * kDecInter, kDecH, 64, 128));
+        CK(make_tensor_map_2d(&maps[4 * l + 3], w.wdown, kDecInter, kDecH, kDecInter, 64, 128));
+      }
+      CK(make_tensor_map_2d(&maps[4 * L], h->lm_head, kDecH, kVocab, kDecH, 64, 128));
+      CK(make_tensor_map_2d(&maps[4 * L + 1], h->du, kDecH, kPersistTcTokens, kDecH, 64, kPersistTcTokens));
+      CK(make_tensor_map_2d(&maps[4 * L + 2], h->dattn, kDecH, kPersistTcTokens, kDecH, 64, kPersistTcTokens));
+      CK(make_tensor_map_2d(&maps[4 * L + 3], h->dact, kDecInter, kPersistTcTokens, kDecInter, 64, kPersistTcTokens));
+      CK(cudaMemcpy(h->persist_tmaps, maps.data(), maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice));
+    }
   }
   h->finalized = true;
   return 0;

@@ -15,6 +15,7 @@
 #include <cooperative_groups.h>
 #include "common.cuh"
 #include "kernels.h"
+#include "tc_ptx.cuh"
 
 namespace sonic {
 
@@ -38,7 +39,11 @@ __device__ __forceinline__ float bf16r(float v) { return __bfloat162float(__floa
 
 // grid-wide barrier: monotonically increasing arrival counter (zeroed by the host before the launch).  The gpu-scope fences
 // order every thread's global writes before the arrival and invalidate L1 after the wait, so plain loads see fresh data.
+template <bool PROXY = false>
 __device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& epoch) {
+  // PROXY: the next phase may read this phase's global writes, or overwrite shared memory it used, through the async proxy
+  // (TMA); order the generic-proxy accesses of every thread before that
+  if (PROXY) asm volatile("fence.proxy.async;" ::: "memory");
   __syncthreads();
   if (threadIdx.x == 0) {
     epoch += gridDim.x;
@@ -51,6 +56,7 @@ __device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& epoch)
     __threadfence();
   }
   __syncthreads();
+  if (PROXY) asm volatile("fence.proxy.async;" ::: "memory");
 }
 
 // ---- GEMM phase: part[s][tok][n] = sum_{k in slice s} W[n][k] * X[tok][k] ------------------------------------------------
@@ -235,6 +241,134 @@ __device__ __forceinline__ void gemm_dispatch(const void* W, const float* wscale
   gemm_phase<NT, EPI, (NT == 2 || NT == 4), W8>(W, wscale, N, K, X, B, Bpad, 0, out32, xres, act, smem);
 }
 
+// ---- GEMM phase on tcgen05 (batch class 33..64, bf16 weights) ---------------------------------------------------------------
+// D[128 weight rows x 64 tokens] (fp32, TMEM) += W tile . X tile^T per 64-wide k block; both operands arrive by TMA
+// (SWIZZLE_128B) in a 6-stage shared-memory ring, so the weight stream does not pass through registers and each weight byte
+// meets only half a byte of activation traffic (the mma.sync phase re-reads 4 B of activations per weight byte at 64 tokens).
+// item = (128-row tile, K split); `splits` is chosen per matrix so that items ~ grid.  Warp 0 lane 0 produces, warp 1 lane 0
+// issues the MMAs, warps 4..11 drain the two alternating TMEM accumulators (lane quadrant = warp % 4, 32 tokens each).
+// The ring / accumulator barriers live for the whole kernel; their phase is derived from running counters that every thread
+// advances identically.
+static constexpr int kTcStages = 6;
+static constexpr int kTcStageA = 128 * 64 * 2, kTcStageB = kPersistTcTokens * 64 * 2;
+static constexpr int kTcRingBytes = kTcStages * (kTcStageA + kTcStageB) + 1024;     // + alignment slack
+struct TcCtx {
+  uint32_t ringA, ringB, bars, tmem;
+  uint32_t kb_count, item_count;
+  uint32_t pre;                  // k blocks of the coming phase whose weight tile is already in flight (tc_prefetch_weights)
+};
+__device__ __forceinline__ uint32_t tc_full(const TcCtx& c, uint32_t s) { return c.bars + 8u * s; }
+__device__ __forceinline__ uint32_t tc_empty(const TcCtx& c, uint32_t s) { return c.bars + 8u * (kTcStages + s); }
+__device__ __forceinline__ uint32_t tc_acc_full(const TcCtx& c, uint32_t a) { return c.bars + 8u * (2 * kTcStages + a); }
+__device__ __forceinline__ uint32_t tc_acc_empty(const TcCtx& c, uint32_t a) { return c.bars + 8u * (2 * kTcStages + 2 + a); }
+
+// Weights do not depend on the previous phase: thread 0 (the producer) puts the weight tiles of this CTA's first k blocks of
+// the NEXT tcgen05 phase in flight (arming the stage for weight + activation bytes) before the grid barrier / while a
+// non-GEMM phase runs; the producer of that phase then only adds the activation tiles.  Every thread computes `pre`.
+__device__ __forceinline__ void tc_prefetch_weights(const CUtensorMap* wmap, int N, int K, int splits, TcCtx& tc) {
+  const int tiles = N >> 7, nkb = K >> 6, n_items = tiles * splits;
+  uint32_t n = 0;
+  for (int item = blockIdx.x; item < n_items && n < (uint32_t)kTcStages; item += gridDim.x) {
+    const int tile = item / splits, ks = item - tile * splits;
+    const int kb0 = (ks * nkb) / splits, kb1 = ((ks + 1) * nkb) / splits;
+    for (int kb = kb0; kb < kb1 && n < (uint32_t)kTcStages; ++kb, ++n) {
+      if (threadIdx.x == 0) {
+        const uint32_t cnt = tc.kb_count + n, st = cnt % kTcStages, par = (cnt / kTcStages) & 1u;
+        mbar_wait(tc_empty(tc, st), par ^ 1u);
+        mbar_expect_tx(tc_full(tc, st), kTcStageA + kTcStageB);
+        tma_load_2d(tc.ringA + st * kTcStageA, wmap, tc_full(tc, st), kb * 64, tile * 128);
+      }
+    }
+  }
+  tc.pre = n;
+}
+
+template <int EPI>
+__device__ __forceinline__ void gemm_phase_tc(const CUtensorMap* wmap, const CUtensorMap* xmap, int N, int K, int splits, int B, int Bpad,
+                                              float* __restrict__ out32, bf16* __restrict__ act, TcCtx& tc) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles = N >> 7, nkb = K >> 6, n_items = tiles * splits;
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t cnt = tc.kb_count, idx = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int tile = item / splits, ks = item - tile * splits;
+        const int kb0 = (ks * nkb) / splits, kb1 = ((ks + 1) * nkb) / splits;
+        for (int kb = kb0; kb < kb1; ++kb, ++cnt, ++idx) {
+          const uint32_t st = cnt % kTcStages, par = (cnt / kTcStages) & 1u;
+          if (idx >= tc.pre) {
+            mbar_wait(tc_empty(tc, st), par ^ 1u);
+            mbar_expect_tx(tc_full(tc, st), kTcStageA + kTcStageB);
+            tma_load_2d(tc.ringA + st * kTcStageA, wmap, tc_full(tc, st), kb * 64, tile * 128);
+          }
+          tma_load_2d(tc.ringB + st * kTcStageB, xmap, tc_full(tc, st), kb * 64, 0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(128, kPersistTcTokens);
+      uint32_t cnt = tc.kb_count, ic = tc.item_count;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++ic) {
+        const int tile = item / splits, ks = item - tile * splits;
+        const int kb0 = (ks * nkb) / splits, kb1 = ((ks + 1) * nkb) / splits;
+        const uint32_t acc = ic & 1u, apar = (ic >> 1) & 1u;
+        mbar_wait(tc_acc_empty(tc, acc), apar ^ 1u);
+        tc_fence_after();
+        for (int kb = kb0; kb < kb1; ++kb, ++cnt) {
+          const uint32_t st = cnt % kTcStages, par = (cnt / kTcStages) & 1u;
+          mbar_wait(tc_full(tc, st), par);
+          tc_fence_after();
+          const uint64_t da = make_sw128_desc(tc.ringA + st * kTcStageA), db = make_sw128_desc(tc.ringB + st * kTcStageB);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            tc_mma_bf16(tc.tmem + acc * kPersistTcTokens, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb > kb0 || k != 0) ? 1u : 0u);
+          tc_commit(tc_empty(tc, st));
+        }
+        tc_commit(tc_acc_full(tc, acc));
+      }
+    }
+  } else if (warp >= 4 && warp < 12) {
+    const int q = warp & 3, half = (warp - 4) >> 2;
+    uint32_t ic = tc.item_count;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++ic) {
+      const int tile = item / splits, ks = item - tile * splits;
+      const uint32_t acc = ic & 1u, apar = (ic >> 1) & 1u;
+      mbar_wait(tc_acc_full(tc, acc), apar);
+      tc_fence_after();
+      uint32_t v[32];
+      tmem_ld32(tc.tmem + ((uint32_t)(q * 32) << 16) + acc * kPersistTcTokens + half * 32, v);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tc_acc_empty(tc, acc));           // the accumulator is in registers: the next item may start
+      const int row = tile * 128 + q * 32 + lane;
+      if (EPI == EPI_SWIGLU) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float x = __uint_as_float(v[j]);
+          const float up = __shfl_xor_sync(0xffffffffu, x, 1);       // rows are interleaved (gate, up)
+          const int tok = half * 32 + j;
+          if ((lane & 1) == 0 && tok < B) act[(size_t)tok * (N >> 1) + (row >> 1)] = __float2bfloat16_rn(silu(x) * up);
+        }
+      } else {
+        float* o = out32 + (size_t)ks * Bpad * N + row;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int tok = half * 32 + j;
+          if (tok < B) o[(size_t)tok * N] = __uint_as_float(v[j]);
+        }
+      }
+    }
+  }
+  for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    const int tile = item / splits, ks = item - tile * splits;
+    tc.kb_count += (uint32_t)(((ks + 1) * nkb) / splits - (ks * nkb) / splits);
+    tc.item_count += 1u;
+  }
+  tc.pre = 0;
+}
+
 // fixed-order sum of the KS split-K partials of one element; fully unrolled so the KS L2 loads are in flight together
 template <int KS>
 __device__ __forceinline__ float sum_partials(const float* part, size_t stride, size_t idx) {
@@ -260,9 +394,14 @@ __device__ __forceinline__ void residual_norm_phase(const float* part, int B, in
     v[2] = __uint_as_float(xr.y << 16); v[3] = __uint_as_float(xr.y & 0xffff0000u);
     float ss = 0.f;
     if (KS > 0) {
-      float add[4];
+      float add[4] = {0.f, 0.f, 0.f, 0.f};
+      {
+        float4 pv[KS > 0 ? KS : 1];                                  // all split-K partials in flight, summed in split order
 #pragma unroll
-      for (int i = 0; i < 4; ++i) add[i] = sum_partials<(KS > 0 ? KS : 1)>(part, (size_t)Bpad * PH, (size_t)b * PH + c0 + i);
+        for (int s2 = 0; s2 < KS; ++s2) pv[s2] = __ldcg(reinterpret_cast<const float4*>(part + (size_t)s2 * Bpad * PH + (size_t)b * PH + c0));
+#pragma unroll
+        for (int s2 = 0; s2 < KS; ++s2) { add[0] += pv[s2].x; add[1] += pv[s2].y; add[2] += pv[s2].z; add[3] += pv[s2].w; }
+      }
 #pragma unroll
       for (int i = 0; i < 4; ++i) v[i] = bf16r(v[i] + add[i]);
       __nv_bfloat162 o0 = __floats2bfloat162_rn(v[0], v[1]), o1 = __floats2bfloat162_rn(v[2], v[3]);
@@ -282,6 +421,7 @@ __device__ __forceinline__ void residual_norm_phase(const float* part, int B, in
 // ---- attention phase: item = (segment, kv head, chunk of 128 keys).  Every item finishes q (4 heads) from the fp32 qkv
 // section and rotates it; the item owning the newest position also rotates k and appends k, v to the cache.  Each item writes
 // an (m, l, o) partial; the item arriving last at the (segment, kv head) counter merges the partials in chunk order.
+template <int KSQ>
 __device__ __forceinline__ void attention_phase(const DecodePersistArgs& a, const DecLayerDev& L, uint8_t* smem) {
   uint8_t* sK = smem;                                          // AKEYS * kAKRow
   bf16* sV = reinterpret_cast<bf16*>(smem + AKEYS * kAKRow);   // AKEYS * 128
@@ -308,8 +448,8 @@ __device__ __forceinline__ void attention_phase(const DecodePersistArgs& a, cons
       for (int i = tid; i < n_pairs; i += kPThreads) {
         const int hh = i / (PHD / 2), j = i - hh * (PHD / 2);     // hh < 4: query head; 4: key; 5: value (pair j, j+64)
         const int col = (hh < PG) ? (kvh * PG + hh) * PHD : (hh == PG ? (16 + kvh) * PHD : (16 + PKVH + kvh) * PHD);
-        const float x = bf16r(__ldcg(a.part + (size_t)seg * PQKV + col + j));
-        const float y = bf16r(__ldcg(a.part + (size_t)seg * PQKV + col + j + PHD / 2));
+        const float x = bf16r(sum_partials<KSQ>(a.part, (size_t)a.Bpad * PQKV, (size_t)seg * PQKV + col + j));
+        const float y = bf16r(sum_partials<KSQ>(a.part, (size_t)a.Bpad * PQKV, (size_t)seg * PQKV + col + j + PHD / 2));
         if (hh <= PG) {
           const float c = bf16r(a.cos_t[(size_t)pos * (PHD / 2) + j]), sn = bf16r(a.sin_t[(size_t)pos * (PHD / 2) + j]);
           const float rx = bf16r(x * c - y * sn), ry = bf16r(y * c + x * sn);
@@ -424,6 +564,7 @@ __device__ __forceinline__ void ldmatrix_x2_trans(uint32_t& r0, uint32_t& r1, co
   asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0, %1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(addr));
 }
 
+template <int KSQ>
 __device__ __forceinline__ void attention_phase_mma(const DecodePersistArgs& a, const DecLayerDev& L, uint8_t* smem) {
   uint8_t* sK = smem;                                     // [128 keys][272 B]
   uint8_t* sV = sK + AKEYS * kARow;                       // [128 keys][272 B]
@@ -447,8 +588,8 @@ __device__ __forceinline__ void attention_phase_mma(const DecodePersistArgs& a, 
     for (int i = tid; i < (PG + 2) * (PHD / 2); i += kPThreads) {
       const int hh = i / (PHD / 2), j = i - hh * (PHD / 2);     // hh < 4: query head; 4: key; 5: value (pair j, j+64)
       const int col = (hh < PG) ? (kvh * PG + hh) * PHD : (hh == PG ? (16 + kvh) * PHD : (16 + PKVH + kvh) * PHD);
-      const float x = bf16r(__ldcg(a.part + (size_t)seg * PQKV + col + j));
-      const float y = bf16r(__ldcg(a.part + (size_t)seg * PQKV + col + j + PHD / 2));
+      const float x = bf16r(sum_partials<KSQ>(a.part, (size_t)a.Bpad * PQKV, (size_t)seg * PQKV + col + j));
+      const float y = bf16r(sum_partials<KSQ>(a.part, (size_t)a.Bpad * PQKV, (size_t)seg * PQKV + col + j + PHD / 2));
       if (hh <= PG) {
         const float c = bf16r(a.cos_t[(size_t)pos * (PHD / 2) + j]), sn = bf16r(a.sin_t[(size_t)pos * (PHD / 2) + j]);
         const float rx = bf16r(x * c - y * sn), ry = bf16r(y * c + x * sn);
@@ -567,15 +708,45 @@ __device__ __forceinline__ unsigned long long gtimer() {
     if (a.timestamps && blockIdx.x == 0 && threadIdx.x == 0) a.timestamps[n_stamp++] = gtimer(); \
   } while (0)
 
-template <bool W8, int NT>
+// K splits of the tcgen05 phases (items = tiles x splits ~ one per CTA of a 148-SM grid): qkv 24 tiles x 6, o 16 x 9,
+// gate/up 96 x 1 (the SwiGLU epilogue needs whole sums), down 16 x 9, lm_head 463 x 1
+static constexpr int kTcSplitQkv = 6, kTcSplitO = 9, kTcSplitDown = 9;
+
+template <bool W8, int NT, bool TC>
 __global__ void __launch_bounds__(kPThreads, 1) decode_persist_kernel(DecodePersistArgs a) {
+  static_assert(!TC || (!W8 && NT == 8), "tcgen05 phases: bf16 weights, 64-token class");
   extern __shared__ __align__(16) uint8_t smem[];
   __shared__ float red[32];
+  __shared__ __align__(8) uint64_t tc_bars[2 * kTcStages + 4];
+  __shared__ uint32_t tc_tmem_slot;
   unsigned epoch = 0;
   int n_stamp = 0;
   STAMP();
   const int tid = threadIdx.x;
   const int B = a.B, Bpad = a.Bpad;
+  TcCtx tc;
+  const CUtensorMap* tmaps = reinterpret_cast<const CUtensorMap*>(a.tmaps);
+  const CUtensorMap* xmaps = tmaps + 4 * a.n_layers + 1;                    // u, attn, act
+  if (TC) {
+    const uint32_t raw = smem_u32(smem);
+    tc.ringA = (raw + 1023u) & ~1023u;
+    tc.ringB = tc.ringA + kTcStages * kTcStageA;
+    tc.bars = smem_u32(tc_bars);
+    tc.kb_count = 0; tc.item_count = 0; tc.pre = 0;
+    if (tid == 32) {
+      for (int s = 0; s < kTcStages; ++s) { mbar_init(tc_full(tc, s), 1); mbar_init(tc_empty(tc, s), 1); }
+      for (int i = 0; i < 2; ++i) { mbar_init(tc_acc_full(tc, i), 1); mbar_init(tc_acc_empty(tc, i), 8); }
+      fence_barrier_init();
+    }
+    if ((tid >> 5) == 2) tmem_alloc<2 * kPersistTcTokens>(smem_u32(&tc_tmem_slot));
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    tc.tmem = tc_tmem_slot;
+    tc_prefetch_weights(tmaps, PQKV, PH, kTcSplitQkv, tc);
+  }
+  // the attention phase of the tcgen05 variant works beside the TMA ring (weight tiles are in flight while it runs)
+  uint8_t* smem_attn = TC ? smem + ((((smem_u32(smem) + 1023u) & ~1023u) - smem_u32(smem)) + kTcStages * (kTcStageA + kTcStageB)) : smem;
 
   // ---- phase 0: x = E[cur_tok]; u = rmsnorm(x) * g(layer 0 input norm)
   for (int b = blockIdx.x; b < B; b += gridDim.x) {
@@ -592,30 +763,53 @@ __global__ void __launch_bounds__(kPThreads, 1) decode_persist_kernel(DecodePers
     *reinterpret_cast<uint2*>(a.u + (size_t)b * PH + c0) = make_uint2(*reinterpret_cast<uint32_t*>(&u0), *reinterpret_cast<uint32_t*>(&u1));
     __syncthreads();
   }
-  grid_barrier(a.bar, epoch); STAMP();
+  grid_barrier<TC>(a.bar, epoch); STAMP();
 
   for (int l = 0; l < a.n_layers; ++l) {
     const DecLayerDev L = a.layers[l];
-    gemm_dispatch<EPI_F32, W8, NT>(L.wqkv, L.sqkv, PQKV, PH, a.u, B, Bpad, a.part, nullptr, nullptr, smem);
-    grid_barrier(a.bar, epoch); STAMP();
-    if (a.attn_chunks > 1) attention_phase(a, L, smem);          // few segments: split the keys over CTAs
-    else attention_phase_mma(a, L, smem);
-    grid_barrier(a.bar, epoch); STAMP();
-    gemm_dispatch<EPI_RESID, W8, NT>(L.wo, L.so, PH, PH, a.attn, B, Bpad, nullptr, a.x, nullptr, smem);
-    grid_barrier(a.bar, epoch); STAMP();
-    residual_norm_phase<0>(nullptr, B, Bpad, a.x, a.u, L.rms2, a.eps, red);
-    grid_barrier(a.bar, epoch); STAMP();
-    gemm_dispatch<EPI_SWIGLU, W8, NT>(L.wgu, L.sgu, 2 * PI, PH, a.u, B, Bpad, nullptr, nullptr, a.act, smem);
-    grid_barrier(a.bar, epoch); STAMP();
-    gemm_dispatch<EPI_F32, W8, NT>(L.wdown, L.sdown, PH, PI, a.act, B, Bpad, a.part, nullptr, nullptr, smem);
-    grid_barrier(a.bar, epoch); STAMP();
-    residual_norm_phase<3>(a.part, B, Bpad, a.x, a.u, (l + 1 < a.n_layers) ? a.layers[l + 1].rms1 : a.final_norm, a.eps, red);
-    grid_barrier(a.bar, epoch); STAMP();
+    if (TC) {
+      gemm_phase_tc<EPI_F32>(tmaps + 4 * l, xmaps, PQKV, PH, kTcSplitQkv, B, Bpad, a.part, nullptr, tc);
+      tc_prefetch_weights(tmaps + 4 * l + 1, PH, PH, kTcSplitO, tc);
+    } else gemm_dispatch<EPI_F32, W8, NT>(L.wqkv, L.sqkv, PQKV, PH, a.u, B, Bpad, a.part, nullptr, nullptr, smem);
+    grid_barrier<TC>(a.bar, epoch); STAMP();
+    if (!TC && a.attn_chunks > 1) attention_phase<1>(a, L, smem);          // few segments: split the keys over CTAs
+    else attention_phase_mma<TC ? kTcSplitQkv : 1>(a, L, smem_attn);
+    grid_barrier<TC>(a.bar, epoch); STAMP();
+    if (TC) {
+      gemm_phase_tc<EPI_F32>(tmaps + 4 * l + 1, xmaps + 1, PH, PH, kTcSplitO, B, Bpad, a.part, nullptr, tc);
+      tc_prefetch_weights(tmaps + 4 * l + 2, 2 * PI, PH, 1, tc);
+      grid_barrier<TC>(a.bar, epoch); STAMP();
+      residual_norm_phase<kTcSplitO>(a.part, B, Bpad, a.x, a.u, L.rms2, a.eps, red);
+    } else {
+      gemm_dispatch<EPI_RESID, W8, NT>(L.wo, L.so, PH, PH, a.attn, B, Bpad, nullptr, a.x, nullptr, smem);
+      grid_barrier<TC>(a.bar, epoch); STAMP();
+      residual_norm_phase<0>(nullptr, B, Bpad, a.x, a.u, L.rms2, a.eps, red);
+    }
+    grid_barrier<TC>(a.bar, epoch); STAMP();
+    if (TC) {
+      gemm_phase_tc<EPI_SWIGLU>(tmaps + 4 * l + 2, xmaps, 2 * PI, PH, 1, B, Bpad, nullptr, a.act, tc);
+      tc_prefetch_weights(tmaps + 4 * l + 3, PH, PI, kTcSplitDown, tc);
+    } else gemm_dispatch<EPI_SWIGLU, W8, NT>(L.wgu, L.sgu, 2 * PI, PH, a.u, B, Bpad, nullptr, nullptr, a.act, smem);
+    grid_barrier<TC>(a.bar, epoch); STAMP();
+    const float* next_gamma = (l + 1 < a.n_layers) ? a.layers[l + 1].rms1 : a.final_norm;
+    if (TC) {
+      gemm_phase_tc<EPI_F32>(tmaps + 4 * l + 3, xmaps + 2, PH, PI, kTcSplitDown, B, Bpad, a.part, nullptr, tc);
+      if (l + 1 < a.n_layers) tc_prefetch_weights(tmaps + 4 * (l + 1), PQKV, PH, kTcSplitQkv, tc);
+      else tc_prefetch_weights(tmaps + 4 * a.n_layers, PV_, PH, 1, tc);
+      grid_barrier<TC>(a.bar, epoch); STAMP();
+      residual_norm_phase<kTcSplitDown>(a.part, B, Bpad, a.x, a.u, next_gamma, a.eps, red);
+    } else {
+      gemm_dispatch<EPI_F32, W8, NT>(L.wdown, L.sdown, PH, PI, a.act, B, Bpad, a.part, nullptr, nullptr, smem);
+      grid_barrier<TC>(a.bar, epoch); STAMP();
+      residual_norm_phase<3>(a.part, B, Bpad, a.x, a.u, next_gamma, a.eps, red);
+    }
+    grid_barrier<TC>(a.bar, epoch); STAMP();
   }
 
   // ---- lm_head + greedy pick: every CTA scans its slice of the vocabulary for all tokens, CTA b merges token b
-  gemm_dispatch<EPI_F32, false, NT>(a.lm_head, nullptr, PV_, PH, a.u, B, Bpad, a.part, nullptr, nullptr, smem);
-  grid_barrier(a.bar, epoch); STAMP();
+  if (TC) gemm_phase_tc<EPI_F32>(tmaps + 4 * a.n_layers, xmaps, PV_, PH, 1, B, Bpad, a.part, nullptr, tc);
+  else gemm_dispatch<EPI_F32, false, NT>(a.lm_head, nullptr, PV_, PH, a.u, B, Bpad, a.part, nullptr, nullptr, smem);
+  grid_barrier<TC>(a.bar, epoch); STAMP();
   {
     const int per = (PV_ + gridDim.x - 1) / gridDim.x;
     const int lo = blockIdx.x * per, hi = min(PV_, lo + per);
@@ -623,11 +817,19 @@ __global__ void __launch_bounds__(kPThreads, 1) decode_persist_kernel(DecodePers
     for (int b = warp; b < B; b += kPWarps) {                       // one warp per token over this CTA's slice
       float best = -INFINITY, second = -INFINITY;
       int bi = 0x7fffffff;
-      for (int i = lo + lane; i < hi; i += 32) {
-        const float v = __ldcg(a.part + (size_t)b * PV_ + i);
-        if (a.logits_out) a.logits_out[(size_t)b * PV_ + i] = v;
-        if (v > best) { second = best; best = v; bi = i; }
-        else if (v > second) second = v;
+      for (int i0 = lo + lane; i0 < hi; i0 += 32 * 16) {             // 16 independent L2 loads in flight per lane
+        float v[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) v[u] = (i0 + 32 * u < hi) ? __ldcg(a.part + (size_t)b * PV_ + i0 + 32 * u) : -INFINITY;
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+          const int i = i0 + 32 * u;
+          if (i < hi) {
+            if (a.logits_out) a.logits_out[(size_t)b * PV_ + i] = v[u];
+            if (v[u] > best) { second = best; best = v[u]; bi = i; }
+            else if (v[u] > second) second = v[u];
+          }
+        }
       }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
@@ -642,7 +844,7 @@ __global__ void __launch_bounds__(kPThreads, 1) decode_persist_kernel(DecodePers
       }
     }
   }
-  grid_barrier(a.bar, epoch); STAMP();
+  grid_barrier<false>(a.bar, epoch); STAMP();
   for (int b = blockIdx.x; b < B; b += gridDim.x) {
     if (tid < 32) {
       float best = -INFINITY, second = -INFINITY;
@@ -676,37 +878,51 @@ __global__ void __launch_bounds__(kPThreads, 1) decode_persist_kernel(DecodePers
       }
     }
   }
-  grid_barrier(a.bar, epoch); STAMP();
+  grid_barrier<false>(a.bar, epoch); STAMP();
   if (blockIdx.x == 0 && tid == 0) *a.gs.step += 1;
+  if (TC) {
+    tc_fence_before();
+    __syncthreads();
+    if ((tid >> 5) == 2) tmem_dealloc<2 * kPersistTcTokens>(tc.tmem);
+  }
 }
 
-size_t decode_persist_smem_bytes() {
+static size_t persist_smem_for(bool tc) {
   const size_t attn = (size_t)AKEYS * kAKRow + (size_t)AKEYS * PHD * 2 + (PG * PHD + PG * AKEYS + 2 * PHD + 32 + 16) * 4;
   const size_t exch = (size_t)kXStageBytes + (size_t)kPWarps * 2 * 4 * 128 * 4;    // staged activations + 16 warps x NT(4) x 128 fp32 (>= the unstaged NT = 8 exchange)
-  return attn > exch ? attn : exch;
+  const size_t attn_mma = 2 * (size_t)AKEYS * kARow + 2 * 16 * (size_t)kARow + (2 * PHD + 8 * kPWarps) * 4;
+  size_t m = attn > exch ? attn : exch;
+  if (attn_mma > m) m = attn_mma;
+  if (tc) m = kTcRingBytes + attn_mma;            // TMA ring of the tcgen05 phases + the attention phase beside it
+  return m;
 }
+size_t decode_persist_smem_bytes() { return persist_smem_for(true); }
 
 size_t decode_persist_part_floats(int Bpad) { return (size_t)PV_ * Bpad; }     // >= qkv (3072) and 3 down sections (6144)
 size_t decode_persist_pick_floats(int max_batch, int num_sms) { return (size_t)max_batch * num_sms * 4; }
 
 typedef void (*PersistKernel)(DecodePersistArgs);
-static PersistKernel persist_kernel_for(bool w8, int B) {
-  const int cls = B <= 8 ? 0 : (B <= 16 ? 1 : (B <= 32 ? 2 : 3));
-  static const PersistKernel tab[2][4] = {
-      {decode_persist_kernel<false, 1>, decode_persist_kernel<false, 2>, decode_persist_kernel<false, 4>, decode_persist_kernel<false, 8>},
-      {decode_persist_kernel<true, 1>, decode_persist_kernel<true, 2>, decode_persist_kernel<true, 4>, decode_persist_kernel<true, 8>}};
-  return tab[w8 ? 1 : 0][cls];
+static constexpr int kPersistVariants = 9;
+static PersistKernel persist_variant(int i) {
+  static const PersistKernel tab[kPersistVariants] = {
+      decode_persist_kernel<false, 1, false>, decode_persist_kernel<false, 2, false>, decode_persist_kernel<false, 4, false>,
+      decode_persist_kernel<false, 8, false>, decode_persist_kernel<true, 1, false>,  decode_persist_kernel<true, 2, false>,
+      decode_persist_kernel<true, 4, false>,  decode_persist_kernel<true, 8, false>,  decode_persist_kernel<false, 8, true>};
+  return tab[i];
 }
-static const int kBatchOfClass[4] = {8, 16, 32, 64};
+static PersistKernel persist_kernel_for(bool w8, int B, bool tc) {
+  const int cls = B <= 8 ? 0 : (B <= 16 ? 1 : (B <= 32 ? 2 : 3));
+  if (tc && !w8 && cls == 3) return persist_variant(8);
+  return persist_variant((w8 ? 4 : 0) + cls);
+}
 
 int decode_persist_occupancy() {
   int worst = 1 << 30;
-  for (int w8 = 0; w8 < 2; ++w8)
-    for (int c = 0; c < 4; ++c) {
-      int per_sm = -1;
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, persist_kernel_for(w8 != 0, kBatchOfClass[c]), kPThreads, decode_persist_smem_bytes());
-      if (per_sm < worst) worst = per_sm;
-    }
+  for (int i = 0; i < kPersistVariants; ++i) {
+    int per_sm = -1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, persist_variant(i), kPThreads, persist_smem_for(i == 8));
+    if (per_sm < worst) worst = per_sm;
+  }
   return worst;
 }
 // largest cooperative grid (<= one CTA per SM) the device can hold for this kernel right now; 0 if it cannot be launched
@@ -719,17 +935,16 @@ int decode_persist_max_grid(int num_sms) {
 }
 
 cudaError_t decode_persist_configure() {
-  for (int w8 = 0; w8 < 2; ++w8)
-    for (int c = 0; c < 4; ++c)
-      SONIC_CUDA_TRY(cudaFuncSetAttribute(persist_kernel_for(w8 != 0, kBatchOfClass[c]), cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          (int)decode_persist_smem_bytes()));
+  for (int i = 0; i < kPersistVariants; ++i)
+    SONIC_CUDA_TRY(cudaFuncSetAttribute(persist_variant(i), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)persist_smem_for(i == 8)));
   return cudaSuccess;
 }
 
 cudaError_t launch_decode_persist(const DecodePersistArgs& a, int grid, cudaStream_t st) {
   if (grid < 1 || a.B < 1 || a.B > 64) return cudaErrorInvalidConfiguration;
   const int num_sms = grid;
-  PersistKernel kern = persist_kernel_for(a.w8 != 0, a.B);
+  PersistKernel kern = persist_kernel_for(a.w8 != 0, a.B, a.tmaps != nullptr);
+  const size_t smem_bytes = persist_smem_for(kern == persist_variant(8));
   {
     cudaError_t me = cudaMemsetAsync(a.bar, 0, sizeof(unsigned), st);
     if (me != cudaSuccess) { fprintf(stderr, "[sonicscribe_b200] barrier memset failed: %s\n", cudaGetErrorName(me)); return me; }
@@ -740,7 +955,7 @@ cudaError_t launch_decode_persist(const DecodePersistArgs& a, int grid, cudaStre
     if (mode == 0) {
       cudaLaunchConfig_t cfg;
       memset(&cfg, 0, sizeof(cfg));
-      cfg.gridDim = dim3(num_sms); cfg.blockDim = dim3(kPThreads); cfg.dynamicSmemBytes = decode_persist_smem_bytes(); cfg.stream = st;
+      cfg.gridDim = dim3(num_sms); cfg.blockDim = dim3(kPThreads); cfg.dynamicSmemBytes = smem_bytes; cfg.stream = st;
       cudaLaunchAttribute attr[1];
       memset(attr, 0, sizeof(attr));
       attr[0].id = cudaLaunchAttributeCooperative;
@@ -750,11 +965,11 @@ cudaError_t launch_decode_persist(const DecodePersistArgs& a, int grid, cudaStre
     } else if (mode == 1) {
       DecodePersistArgs copy = a;
       void* args[1] = {&copy};
-      e = cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(kern), dim3(num_sms), dim3(kPThreads), args, decode_persist_smem_bytes(), st);
+      e = cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(kern), dim3(num_sms), dim3(kPThreads), args, smem_bytes, st);
     } else {
       // grid <= SM count with one CTA per SM: co-resident on an otherwise idle device (stream order guarantees our own
       // earlier kernels have drained); without the cooperative attribute this is not guaranteed by the programming model
-      kern<<<dim3(num_sms), dim3(kPThreads), decode_persist_smem_bytes(), st>>>(a);
+      kern<<<dim3(num_sms), dim3(kPThreads), smem_bytes, st>>>(a);
       e = cudaGetLastError();
     }
     if (e == cudaSuccess) return e;

@@ -139,6 +139,10 @@ struct DecodePersistArgs {
   int w8;                         // 1: decoder linears are int8 weight-only (lm_head / embedding stay bf16)
   int attn_mode;                  // 0: mma.sync attention phase, 1: CUDA-core attention phase (A/B switch)
   int prefetch;                   // 1: L2-prefetch the next GEMM's weights at the start of every GEMM phase
+  // batch class 33..64, bf16 weights: the GEMM phases run on tcgen05 fed by TMA.  Device array of CUtensorMap (128 B each):
+  // [4*l + {0: qkv, 1: o, 2: gate/up, 3: down}] weight maps (box 64 k x 128 rows), [4*n_layers] lm_head,
+  // [4*n_layers + 1 + {0: u, 1: attn, 2: act}] activation maps (box 64 k x 64 token rows).  nullptr: mma.sync phases.
+  const void* tmaps;
   float eps, scale;
 };
 size_t decode_persist_smem_bytes();
@@ -148,5 +152,6 @@ cudaError_t decode_persist_configure();
 int decode_persist_max_grid(int num_sms);
 int decode_persist_occupancy();
 cudaError_t launch_decode_persist(const DecodePersistArgs& a, int grid, cudaStream_t st);
+static constexpr int kPersistTcTokens = 64;   // token rows of the activation tensor maps
 
 }  // namespace sonic

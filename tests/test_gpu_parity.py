@@ -401,6 +401,45 @@ def test_persistent_decode_kernel_vs_graph_path(tiny_sd, eng_bf16):
         assert np.abs(np.array(ma[s][:n]) - np.array(mb[s][:n])).max() < 0.15
 
 
+@pytest.mark.parametrize("B", [36, 64])
+def test_persistent_decode_tcgen05_phases_vs_mma_phases(tiny_sd, B):
+    """Batch class 33..64 of the persistent decode kernel streams its weights through TMA + tcgen05 (split-K partials summed
+    by the consumer phase); SONIC_PERSIST_TC=0 keeps the mma.sync phases.  Same bf16 arithmetic up to summation order:
+    ids agree until a step whose top-2 margin is inside bf16 noise, margins agree before that; ragged lengths and a
+    segment shorter than one key chunk included."""
+    lens = [320000 - 4000 * (i % 7) for i in range(B)]
+    lens[3] = 20480
+    segs = [mo.synth_audio("speech" if i % 3 else "noise", lens[i], seed=i) for i in range(B)]
+    prompts = [synthetic_prompt_ids(num_audio_tokens(n)) for n in lens]
+    out = {}
+    for tc in ("0", "1"):
+        os.environ["SONIC_PERSIST_TC"] = tc
+        try:
+            eng = Engine(2, 2, mode="bf16", device=0, max_batch=B, max_prompt=300, max_new=24, debug=True)
+            eng.load_state_dict(tiny_sd)
+        finally:
+            del os.environ["SONIC_PERSIST_TC"]
+        out[tc] = eng.transcribe_ids(segs, prompts, 20, want_margins=True)
+        if tc == "1":
+            again = eng.transcribe_ids(segs, prompts, 20)
+            assert again == out[tc][0]                               # fixed reduction order: bit-reproducible
+        eng.close()
+    (a, ma), (b, mb) = out["0"], out["1"]
+    agree = 0
+    for s in range(B):
+        assert len(a[s]) == len(b[s]) == 20
+        n = 20
+        for t, (x, y) in enumerate(zip(a[s], b[s])):
+            if x != y:
+                assert min(ma[s][t], mb[s][t]) < 0.2, (s, t, ma[s][t], mb[s][t])
+                n = t
+                break
+        agree += int(n == 20)
+        if n:
+            assert np.abs(np.array(ma[s][:n]) - np.array(mb[s][:n])).max() < 0.15
+    assert agree >= B // 2
+
+
 def test_single_segment_long_generation_reaches_max_ctx(eng_bf16):
     """max_new_tokens up to the handle's limit with a 20 s prompt: context 270 + 40 crosses the 64/128-key chunk borders."""
     x = mo.synth_audio("speech", 320000, 1)
