@@ -579,12 +579,39 @@ __device__ __forceinline__ void attention_phase_mma(const DecodePersistArgs& a, 
     reinterpret_cast<uint32_t*>(sQ + 4 * kARow)[i] = 0u;
     reinterpret_cast<uint32_t*>(sP + 4 * kARow)[i] = 0u;
   }
-  for (int item = blockIdx.x; item < a.B * PKVH; item += gridDim.x) {
-    const int seg = item / PKVH, kvh = item - seg * PKVH;
-    const int pos = a.gs.ctx_len[seg], kv_len = pos + 1;
-    bf16* kc = L.kc + ((size_t)seg * PKVH + kvh) * a.max_ctx * PHD;
-    bf16* vc = L.vc + ((size_t)seg * PKVH + kvh) * a.max_ctx * PHD;
-    __syncthreads();                                       // previous item's fragments are consumed
+  const int n_items = a.B * PKVH;
+  // The next 128-key chunk (of this group, or the first chunk of this CTA's next group) is loaded into registers while the
+  // current one is being multiplied: thread -> 4 x (16 B of K, 16 B of V), piece i = tid + 512 u = key (i >> 4), column (i & 15).
+  // The row being appended this step is never read from global memory (it is taken from sKV when the chunk is stored).
+  uint4 pk[4], pv[4];
+  auto issue_loads = [&](const bf16* kc, const bf16* vc, int k0, int nk, int pos) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = tid + kPThreads * u, r = i >> 4, c8 = i & 15;
+      pk[u] = make_uint4(0, 0, 0, 0); pv[u] = make_uint4(0, 0, 0, 0);
+      if (r < nk && k0 + r != pos) {
+        pk[u] = __ldcg(reinterpret_cast<const uint4*>(kc + (size_t)(k0 + r) * PHD + c8 * 8));
+        pv[u] = __ldcg(reinterpret_cast<const uint4*>(vc + (size_t)(k0 + r) * PHD + c8 * 8));
+      }
+    }
+  };
+  auto group_of = [&](int item, int& seg, int& kvh, int& pos, const bf16*& kc, const bf16*& vc) {
+    seg = item / PKVH; kvh = item - seg * PKVH;
+    pos = a.gs.ctx_len[seg];
+    kc = L.kc + ((size_t)seg * PKVH + kvh) * a.max_ctx * PHD;
+    vc = L.vc + ((size_t)seg * PKVH + kvh) * a.max_ctx * PHD;
+  };
+  int item = blockIdx.x;
+  if (item < n_items) {
+    int seg, kvh, pos; const bf16 *kc, *vc;
+    group_of(item, seg, kvh, pos, kc, vc);
+    issue_loads(kc, vc, 0, min(AKEYS, pos + 1), pos);
+  }
+  for (; item < n_items; item += gridDim.x) {
+    int seg, kvh, pos; const bf16 *kc, *vc;
+    group_of(item, seg, kvh, pos, kc, vc);
+    const int kv_len = pos + 1;
+    __syncthreads();                                       // previous group's fragments are consumed
     for (int i = tid; i < (PG + 2) * (PHD / 2); i += kPThreads) {
       const int hh = i / (PHD / 2), j = i - hh * (PHD / 2);     // hh < 4: query head; 4: key; 5: value (pair j, j+64)
       const int col = (hh < PG) ? (kvh * PG + hh) * PHD : (hh == PG ? (16 + kvh) * PHD : (16 + PKVH + kvh) * PHD);
@@ -600,49 +627,51 @@ __device__ __forceinline__ void attention_phase_mma(const DecodePersistArgs& a, 
       } else { sKV[PHD + j] = x; sKV[PHD + j + PHD / 2] = y; }
     }
     __syncthreads();
-    if (tid < PHD) kc[(size_t)pos * PHD + tid] = __float2bfloat16_rn(sKV[tid]);
-    else if (tid < 2 * PHD) vc[(size_t)pos * PHD + tid - PHD] = __float2bfloat16_rn(sKV[tid]);
-    // Q fragments of this lane (rows g, k-steps 0..7); rows >= 4 are zero
-    uint32_t qa0[8], qa2[8];
-#pragma unroll
-    for (int ks = 0; ks < 8; ++ks) {
-      qa0[ks] = *reinterpret_cast<const uint32_t*>(sQ + g * kARow + (16 * ks + 2 * t) * 2);
-      qa2[ks] = *reinterpret_cast<const uint32_t*>(sQ + g * kARow + (16 * ks + 8 + 2 * t) * 2);
+    {
+      bf16* kcw = const_cast<bf16*>(kc); bf16* vcw = const_cast<bf16*>(vc);
+      if (tid < PHD) kcw[(size_t)pos * PHD + tid] = __float2bfloat16_rn(sKV[tid]);
+      else if (tid < 2 * PHD) vcw[(size_t)pos * PHD + tid - PHD] = __float2bfloat16_rn(sKV[tid]);
     }
-    float m_run = -INFINITY, l_run = 0.f;                  // online-softmax state of head g (lanes with g < 4)
+    float m_run = -INFINITY, l_part = 0.f;                 // online-softmax state of head g (lanes with g < 4); l_part: this lane's keys only
     float o0 = 0.f, o1 = 0.f;                              // O[head g][dims 8*warp + 2t, +1]
     for (int k0 = 0; k0 < kv_len; k0 += AKEYS) {
       const int nk = min(AKEYS, kv_len - k0);
-      __syncthreads();                                     // previous chunk fully consumed
-      for (int i = tid; i < AKEYS * (PHD / 8); i += kPThreads) {
-        const int r = i / (PHD / 8), c8 = i - r * (PHD / 8);
-        uint4 kk = make_uint4(0, 0, 0, 0), vv = make_uint4(0, 0, 0, 0);
-        if (r < nk) {
-          if (k0 + r == pos) {                             // the row appended above: take it from shared memory
-            uint32_t wk[4], wv[4];
+      if (k0 > 0) __syncthreads();                         // previous chunk fully consumed
 #pragma unroll
-            for (int e2 = 0; e2 < 4; ++e2) {
-              __nv_bfloat162 pk = __floats2bfloat162_rn(sKV[c8 * 8 + 2 * e2], sKV[c8 * 8 + 2 * e2 + 1]);
-              __nv_bfloat162 pv = __floats2bfloat162_rn(sKV[PHD + c8 * 8 + 2 * e2], sKV[PHD + c8 * 8 + 2 * e2 + 1]);
-              wk[e2] = *reinterpret_cast<uint32_t*>(&pk); wv[e2] = *reinterpret_cast<uint32_t*>(&pv);
-            }
-            kk = make_uint4(wk[0], wk[1], wk[2], wk[3]); vv = make_uint4(wv[0], wv[1], wv[2], wv[3]);
-          } else {
-            kk = __ldcg(reinterpret_cast<const uint4*>(kc + (size_t)(k0 + r) * PHD + c8 * 8));
-            vv = __ldcg(reinterpret_cast<const uint4*>(vc + (size_t)(k0 + r) * PHD + c8 * 8));
+      for (int u = 0; u < 4; ++u) {
+        const int i = tid + kPThreads * u, r = i >> 4, c8 = i & 15;
+        uint4 kk = pk[u], vv = pv[u];
+        if (r < nk && k0 + r == pos) {                     // the row appended above: take it from shared memory
+          uint32_t wk[4], wv[4];
+#pragma unroll
+          for (int e2 = 0; e2 < 4; ++e2) {
+            __nv_bfloat162 qk = __floats2bfloat162_rn(sKV[c8 * 8 + 2 * e2], sKV[c8 * 8 + 2 * e2 + 1]);
+            __nv_bfloat162 qv = __floats2bfloat162_rn(sKV[PHD + c8 * 8 + 2 * e2], sKV[PHD + c8 * 8 + 2 * e2 + 1]);
+            wk[e2] = *reinterpret_cast<uint32_t*>(&qk); wv[e2] = *reinterpret_cast<uint32_t*>(&qv);
           }
+          kk = make_uint4(wk[0], wk[1], wk[2], wk[3]); vv = make_uint4(wv[0], wv[1], wv[2], wv[3]);
         }
         *reinterpret_cast<uint4*>(sK + r * kARow + c8 * 16) = kk;
         *reinterpret_cast<uint4*>(sV + r * kARow + c8 * 16) = vv;
       }
       __syncthreads();
+      if (k0 + AKEYS < kv_len) {
+        issue_loads(kc, vc, k0 + AKEYS, min(AKEYS, kv_len - k0 - AKEYS), pos);
+      } else if (item + (int)gridDim.x < n_items) {
+        int nseg, nkvh, npos; const bf16 *nkc, *nvc;
+        group_of(item + gridDim.x, nseg, nkvh, npos, nkc, nvc);
+        issue_loads(nkc, nvc, 0, min(AKEYS, npos + 1), npos);
+      }
       // S tile of this warp: keys 8*warp + {2t, 2t+1} for head g
       float sc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int ks = 0; ks < 8; ++ks) {
+        // Q fragment (rows g of the 16-row tile; rows >= 4 are zero) is re-read from shared memory: registers hold the prefetch
+        const uint32_t qa0 = *reinterpret_cast<const uint32_t*>(sQ + g * kARow + (16 * ks + 2 * t) * 2);
+        const uint32_t qa2 = *reinterpret_cast<const uint32_t*>(sQ + g * kARow + (16 * ks + 8 + 2 * t) * 2);
         const uint32_t b0 = *reinterpret_cast<const uint32_t*>(sK + (8 * warp + g) * kARow + (16 * ks + 2 * t) * 2);
         const uint32_t b1 = *reinterpret_cast<const uint32_t*>(sK + (8 * warp + g) * kARow + (16 * ks + 8 + 2 * t) * 2);
-        mma16816(sc, qa0[ks], 0u, qa2[ks], 0u, b0, b1);
+        mma16816(sc, qa0, 0u, qa2, 0u, b0, b1);
       }
       const int key0 = 8 * warp + 2 * t;
       const float s0 = (key0 < nk) ? sc[0] * a.scale : -INFINITY;
@@ -664,18 +693,9 @@ __device__ __forceinline__ void attention_phase_mma(const DecodePersistArgs& a, 
         const float p1 = (s1 == -INFINITY) ? 0.f : expf(s1 - m_new);
         __nv_bfloat162 pb = __floats2bfloat162_rn(p0, p1);
         *reinterpret_cast<uint32_t*>(sP + g * kARow + key0 * 2) = *reinterpret_cast<uint32_t*>(&pb);
-        float ws = __low2float(pb) + __high2float(pb);      // the denominator sums what the tensor core multiplies
-        ws += __shfl_xor_sync(0x0000ffffu, ws, 1);
-        ws += __shfl_xor_sync(0x0000ffffu, ws, 2);
-        if (t == 0) sSum[g * kPWarps + warp] = ws;
+        l_part = l_part * corr + (__low2float(pb) + __high2float(pb));   // the denominator sums what the tensor core multiplies
       }
       __syncthreads();
-      if (g < PG) {
-        float ls = 0.f;
-#pragma unroll
-        for (int w = 0; w < kPWarps; ++w) ls += sSum[g * kPWarps + w];
-        l_run = l_run * corr + ls;
-      }
       // O tile of this warp: dims 8*warp + {2t, 2t+1} for head g
       float oc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -689,8 +709,19 @@ __device__ __forceinline__ void attention_phase_mma(const DecodePersistArgs& a, 
       o0 = o0 * corr + oc[0];
       o1 = o1 * corr + oc[1];
     }
+    // denominator: this lane's keys -> the 4 lanes of the head row -> the 16 warps (fixed order)
     if (g < PG) {
-      const float inv = 1.f / l_run;
+      float ws = l_part;
+      ws += __shfl_xor_sync(0x0000ffffu, ws, 1);
+      ws += __shfl_xor_sync(0x0000ffffu, ws, 2);
+      if (t == 0) sSum[g * kPWarps + warp] = ws;
+    }
+    __syncthreads();
+    if (g < PG) {
+      float ls = 0.f;
+#pragma unroll
+      for (int w = 0; w < kPWarps; ++w) ls += sSum[g * kPWarps + w];
+      const float inv = 1.f / ls;
       __nv_bfloat162 ob = __floats2bfloat162_rn(o0 * inv, o1 * inv);
       *reinterpret_cast<uint32_t*>(a.attn + (size_t)seg * PH + (size_t)(kvh * PG + g) * PHD + 8 * warp + 2 * t) = *reinterpret_cast<uint32_t*>(&ob);
     }
