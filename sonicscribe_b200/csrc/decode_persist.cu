@@ -564,30 +564,42 @@ __device__ __forceinline__ void ldmatrix_x2_trans(uint32_t& r0, uint32_t& r1, co
   asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0, %1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(addr));
 }
 
-template <int KSQ>
-__device__ __forceinline__ void attention_phase_mma(const DecodePersistArgs& a, const DecLayerDev& L, uint8_t* smem) {
-  uint8_t* sK = smem;                                     // [128 keys][272 B]
-  uint8_t* sV = sK + AKEYS * kARow;                       // [128 keys][272 B]
-  uint8_t* sQ = sV + AKEYS * kARow;                       // [16][272 B]   rows 0..3 = rotated query heads (bf16), rest zero
-  uint8_t* sP = sQ + 16 * kARow;                          // [16][272 B]   rows 0..3 = probabilities of the chunk (bf16)
-  float* sKV = reinterpret_cast<float*>(sP + 16 * kARow); // new k (128) | new v (128)
-  float* sMax = sKV + 2 * PHD;                            // [4 heads][16 warps]
-  float* sSum = sMax + 4 * kPWarps;                       // [4 heads][16 warps]
+// TW warps form a team that owns one (segment, kv head) group at a time: 16 (one team, 128-key chunks) or 8 (two teams per
+// CTA, 64-key chunks; used by the 33..64-token class, where there are more groups than CTAs and the per-chunk latency chain,
+// not bandwidth, sets the time).  Teams synchronise on their own named barrier.
+template <int TW>
+__device__ __forceinline__ void team_sync(int team) {
+  asm volatile("bar.sync %0, %1;" ::"r"(team + 1), "n"(TW * 32) : "memory");
+}
+template <int TW>
+static constexpr size_t attn_team_smem() { return 2 * (size_t)(8 * TW) * kARow + 2 * 4 * (size_t)kARow + (2 * PHD + 8 * TW) * 4; }
+
+template <int KSQ, int TW>
+__device__ __forceinline__ void attention_phase_mma(const DecodePersistArgs& a, const DecLayerDev& L, uint8_t* smem_all) {
+  constexpr int CK = 8 * TW;                              // keys per chunk
+  constexpr int TT = 32 * TW;                             // threads per team
+  constexpr int NTEAM = kPWarps / TW;
+  constexpr int NTD = 16 / TW;                            // 8-dim output tiles per warp
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
-  // zero the padding rows once per phase (rows 4..15 of sQ and sP)
-  for (int i = tid; i < 12 * (kARow / 4); i += kPThreads) {
-    reinterpret_cast<uint32_t*>(sQ + 4 * kARow)[i] = 0u;
-    reinterpret_cast<uint32_t*>(sP + 4 * kARow)[i] = 0u;
-  }
+  const int team = warp / TW, wt = warp - team * TW, tt = tid - team * TT;
+  uint8_t* smem = smem_all + (size_t)team * attn_team_smem<TW>();
+  uint8_t* sK = smem;                                     // [CK keys][272 B]
+  uint8_t* sV = sK + CK * kARow;                          // [CK keys][272 B]
+  uint8_t* sQ = sV + CK * kARow;                          // [4][272 B]   rotated query heads (bf16); MMA rows 4..15 are zero registers
+  uint8_t* sP = sQ + 4 * kARow;                           // [4][272 B]   probabilities of the chunk (bf16)
+  float* sKV = reinterpret_cast<float*>(sP + 4 * kARow);  // new k (128) | new v (128)
+  float* sMax = sKV + 2 * PHD;                            // [4 heads][TW warps]
+  float* sSum = sMax + 4 * TW;                            // [4 heads][TW warps]
   const int n_items = a.B * PKVH;
-  // The next 128-key chunk (of this group, or the first chunk of this CTA's next group) is loaded into registers while the
-  // current one is being multiplied: thread -> 4 x (16 B of K, 16 B of V), piece i = tid + 512 u = key (i >> 4), column (i & 15).
+  const int item_stride = gridDim.x * NTEAM;
+  // The next chunk (of this group, or the first chunk of this team's next group) is loaded into registers while the
+  // current one is being multiplied: thread -> 4 x (16 B of K, 16 B of V), piece i = tt + TT u = key (i >> 4), column (i & 15).
   // The row being appended this step is never read from global memory (it is taken from sKV when the chunk is stored).
   uint4 pk[4], pv[4];
   auto issue_loads = [&](const bf16* kc, const bf16* vc, int k0, int nk, int pos) {
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      const int i = tid + kPThreads * u, r = i >> 4, c8 = i & 15;
+      const int i = tt + TT * u, r = i >> 4, c8 = i & 15;
       pk[u] = make_uint4(0, 0, 0, 0); pv[u] = make_uint4(0, 0, 0, 0);
       if (r < nk && k0 + r != pos) {
         pk[u] = __ldcg(reinterpret_cast<const uint4*>(kc + (size_t)(k0 + r) * PHD + c8 * 8));
@@ -601,18 +613,18 @@ __device__ __forceinline__ void attention_phase_mma(const DecodePersistArgs& a, 
     kc = L.kc + ((size_t)seg * PKVH + kvh) * a.max_ctx * PHD;
     vc = L.vc + ((size_t)seg * PKVH + kvh) * a.max_ctx * PHD;
   };
-  int item = blockIdx.x;
+  int item = blockIdx.x * NTEAM + team;
   if (item < n_items) {
     int seg, kvh, pos; const bf16 *kc, *vc;
     group_of(item, seg, kvh, pos, kc, vc);
-    issue_loads(kc, vc, 0, min(AKEYS, pos + 1), pos);
+    issue_loads(kc, vc, 0, min(CK, pos + 1), pos);
   }
-  for (; item < n_items; item += gridDim.x) {
+  for (; item < n_items; item += item_stride) {
     int seg, kvh, pos; const bf16 *kc, *vc;
     group_of(item, seg, kvh, pos, kc, vc);
     const int kv_len = pos + 1;
-    __syncthreads();                                       // previous group's fragments are consumed
-    for (int i = tid; i < (PG + 2) * (PHD / 2); i += kPThreads) {
+    team_sync<TW>(team);                                   // previous group's fragments are consumed
+    for (int i = tt; i < (PG + 2) * (PHD / 2); i += TT) {
       const int hh = i / (PHD / 2), j = i - hh * (PHD / 2);     // hh < 4: query head; 4: key; 5: value (pair j, j+64)
       const int col = (hh < PG) ? (kvh * PG + hh) * PHD : (hh == PG ? (16 + kvh) * PHD : (16 + PKVH + kvh) * PHD);
       const float x = bf16r(sum_partials<KSQ>(a.part, (size_t)a.Bpad * PQKV, (size_t)seg * PQKV + col + j));
@@ -626,20 +638,22 @@ __device__ __forceinline__ void attention_phase_mma(const DecodePersistArgs& a, 
         } else { sKV[j] = rx; sKV[j + PHD / 2] = ry; }
       } else { sKV[PHD + j] = x; sKV[PHD + j + PHD / 2] = y; }
     }
-    __syncthreads();
+    team_sync<TW>(team);
     {
       bf16* kcw = const_cast<bf16*>(kc); bf16* vcw = const_cast<bf16*>(vc);
-      if (tid < PHD) kcw[(size_t)pos * PHD + tid] = __float2bfloat16_rn(sKV[tid]);
-      else if (tid < 2 * PHD) vcw[(size_t)pos * PHD + tid - PHD] = __float2bfloat16_rn(sKV[tid]);
+      if (tt < PHD) kcw[(size_t)pos * PHD + tt] = __float2bfloat16_rn(sKV[tt]);
+      else if (tt < 2 * PHD) vcw[(size_t)pos * PHD + tt - PHD] = __float2bfloat16_rn(sKV[tt]);
     }
     float m_run = -INFINITY, l_part = 0.f;                 // online-softmax state of head g (lanes with g < 4); l_part: this lane's keys only
-    float o0 = 0.f, o1 = 0.f;                              // O[head g][dims 8*warp + 2t, +1]
-    for (int k0 = 0; k0 < kv_len; k0 += AKEYS) {
-      const int nk = min(AKEYS, kv_len - k0);
-      if (k0 > 0) __syncthreads();                         // previous chunk fully consumed
+    float o[NTD][2];                                       // O[head g][dims 8*(NTD*wt + nt) + 2t, +1]
+#pragma unroll
+    for (int nt = 0; nt < NTD; ++nt) { o[nt][0] = 0.f; o[nt][1] = 0.f; }
+    for (int k0 = 0; k0 < kv_len; k0 += CK) {
+      const int nk = min(CK, kv_len - k0);
+      if (k0 > 0) team_sync<TW>(team);                     // previous chunk fully consumed
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        const int i = tid + kPThreads * u, r = i >> 4, c8 = i & 15;
+        const int i = tt + TT * u, r = i >> 4, c8 = i & 15;
         uint4 kk = pk[u], vv = pv[u];
         if (r < nk && k0 + r == pos) {                     // the row appended above: take it from shared memory
           uint32_t wk[4], wv[4];
@@ -654,38 +668,41 @@ __device__ __forceinline__ void attention_phase_mma(const DecodePersistArgs& a, 
         *reinterpret_cast<uint4*>(sK + r * kARow + c8 * 16) = kk;
         *reinterpret_cast<uint4*>(sV + r * kARow + c8 * 16) = vv;
       }
-      __syncthreads();
-      if (k0 + AKEYS < kv_len) {
-        issue_loads(kc, vc, k0 + AKEYS, min(AKEYS, kv_len - k0 - AKEYS), pos);
-      } else if (item + (int)gridDim.x < n_items) {
+      team_sync<TW>(team);
+      if (k0 + CK < kv_len) {
+        issue_loads(kc, vc, k0 + CK, min(CK, kv_len - k0 - CK), pos);
+      } else if (item + item_stride < n_items) {
         int nseg, nkvh, npos; const bf16 *nkc, *nvc;
-        group_of(item + gridDim.x, nseg, nkvh, npos, nkc, nvc);
-        issue_loads(nkc, nvc, 0, min(AKEYS, npos + 1), npos);
+        group_of(item + item_stride, nseg, nkvh, npos, nkc, nvc);
+        issue_loads(nkc, nvc, 0, min(CK, npos + 1), npos);
       }
-      // S tile of this warp: keys 8*warp + {2t, 2t+1} for head g
+      // S tile of this warp: keys 8*wt + {2t, 2t+1} for head g
       float sc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int ks = 0; ks < 8; ++ks) {
-        // Q fragment (rows g of the 16-row tile; rows >= 4 are zero) is re-read from shared memory: registers hold the prefetch
-        const uint32_t qa0 = *reinterpret_cast<const uint32_t*>(sQ + g * kARow + (16 * ks + 2 * t) * 2);
-        const uint32_t qa2 = *reinterpret_cast<const uint32_t*>(sQ + g * kARow + (16 * ks + 8 + 2 * t) * 2);
-        const uint32_t b0 = *reinterpret_cast<const uint32_t*>(sK + (8 * warp + g) * kARow + (16 * ks + 2 * t) * 2);
-        const uint32_t b1 = *reinterpret_cast<const uint32_t*>(sK + (8 * warp + g) * kARow + (16 * ks + 8 + 2 * t) * 2);
+        // Q fragment (row g of the 16-row tile, zero for g >= 4) is re-read from shared memory: registers hold the prefetch
+        uint32_t qa0 = 0u, qa2 = 0u;
+        if (g < PG) {
+          qa0 = *reinterpret_cast<const uint32_t*>(sQ + g * kARow + (16 * ks + 2 * t) * 2);
+          qa2 = *reinterpret_cast<const uint32_t*>(sQ + g * kARow + (16 * ks + 8 + 2 * t) * 2);
+        }
+        const uint32_t b0 = *reinterpret_cast<const uint32_t*>(sK + (8 * wt + g) * kARow + (16 * ks + 2 * t) * 2);
+        const uint32_t b1 = *reinterpret_cast<const uint32_t*>(sK + (8 * wt + g) * kARow + (16 * ks + 8 + 2 * t) * 2);
         mma16816(sc, qa0, 0u, qa2, 0u, b0, b1);
       }
-      const int key0 = 8 * warp + 2 * t;
+      const int key0 = 8 * wt + 2 * t;
       const float s0 = (key0 < nk) ? sc[0] * a.scale : -INFINITY;
       const float s1 = (key0 + 1 < nk) ? sc[1] * a.scale : -INFINITY;
       float wmax = fmaxf(s0, s1);
       wmax = fmaxf(wmax, __shfl_xor_sync(0xffffffffu, wmax, 1));
       wmax = fmaxf(wmax, __shfl_xor_sync(0xffffffffu, wmax, 2));
-      if (g < PG && t == 0) sMax[g * kPWarps + warp] = wmax;
-      __syncthreads();
+      if (g < PG && t == 0) sMax[g * TW + wt] = wmax;
+      team_sync<TW>(team);
       float corr = 1.f;
       if (g < PG) {
-        float cmax = sMax[g * kPWarps];
+        float cmax = sMax[g * TW];
 #pragma unroll
-        for (int w = 1; w < kPWarps; ++w) cmax = fmaxf(cmax, sMax[g * kPWarps + w]);
+        for (int w = 1; w < TW; ++w) cmax = fmaxf(cmax, sMax[g * TW + w]);
         const float m_new = fmaxf(m_run, cmax);
         corr = (m_run == -INFINITY) ? 0.f : expf(m_run - m_new);
         m_run = m_new;
@@ -695,35 +712,46 @@ __device__ __forceinline__ void attention_phase_mma(const DecodePersistArgs& a, 
         *reinterpret_cast<uint32_t*>(sP + g * kARow + key0 * 2) = *reinterpret_cast<uint32_t*>(&pb);
         l_part = l_part * corr + (__low2float(pb) + __high2float(pb));   // the denominator sums what the tensor core multiplies
       }
-      __syncthreads();
-      // O tile of this warp: dims 8*warp + {2t, 2t+1} for head g
-      float oc[4] = {0.f, 0.f, 0.f, 0.f};
+      team_sync<TW>(team);
+      // O tiles of this warp: dims 8*(NTD*wt + nt) + {2t, 2t+1} for head g
+      float oc[NTD][4];
 #pragma unroll
-      for (int ks = 0; ks < 8; ++ks) {
-        const uint32_t pa0 = *reinterpret_cast<const uint32_t*>(sP + g * kARow + (16 * ks + 2 * t) * 2);
-        const uint32_t pa2 = *reinterpret_cast<const uint32_t*>(sP + g * kARow + (16 * ks + 8 + 2 * t) * 2);
-        uint32_t vb0, vb1;
-        ldmatrix_x2_trans(vb0, vb1, sV + (16 * ks + (lane & 15)) * kARow + 16 * warp);
-        mma16816(oc, pa0, 0u, pa2, 0u, vb0, vb1);
+      for (int nt = 0; nt < NTD; ++nt) { oc[nt][0] = oc[nt][1] = oc[nt][2] = oc[nt][3] = 0.f; }
+#pragma unroll
+      for (int ks = 0; ks < CK / 16; ++ks) {
+        uint32_t pa0 = 0u, pa2 = 0u;
+        if (g < PG) {
+          pa0 = *reinterpret_cast<const uint32_t*>(sP + g * kARow + (16 * ks + 2 * t) * 2);
+          pa2 = *reinterpret_cast<const uint32_t*>(sP + g * kARow + (16 * ks + 8 + 2 * t) * 2);
+        }
+#pragma unroll
+        for (int nt = 0; nt < NTD; ++nt) {
+          uint32_t vb0, vb1;
+          ldmatrix_x2_trans(vb0, vb1, sV + (16 * ks + (lane & 15)) * kARow + 16 * (NTD * wt + nt));
+          mma16816(oc[nt], pa0, 0u, pa2, 0u, vb0, vb1);
+        }
       }
-      o0 = o0 * corr + oc[0];
-      o1 = o1 * corr + oc[1];
+#pragma unroll
+      for (int nt = 0; nt < NTD; ++nt) { o[nt][0] = o[nt][0] * corr + oc[nt][0]; o[nt][1] = o[nt][1] * corr + oc[nt][1]; }
     }
-    // denominator: this lane's keys -> the 4 lanes of the head row -> the 16 warps (fixed order)
+    // denominator: this lane's keys -> the 4 lanes of the head row -> the team's warps (fixed order)
     if (g < PG) {
       float ws = l_part;
       ws += __shfl_xor_sync(0x0000ffffu, ws, 1);
       ws += __shfl_xor_sync(0x0000ffffu, ws, 2);
-      if (t == 0) sSum[g * kPWarps + warp] = ws;
+      if (t == 0) sSum[g * TW + wt] = ws;
     }
-    __syncthreads();
+    team_sync<TW>(team);
     if (g < PG) {
       float ls = 0.f;
 #pragma unroll
-      for (int w = 0; w < kPWarps; ++w) ls += sSum[g * kPWarps + w];
+      for (int w = 0; w < TW; ++w) ls += sSum[g * TW + w];
       const float inv = 1.f / ls;
-      __nv_bfloat162 ob = __floats2bfloat162_rn(o0 * inv, o1 * inv);
-      *reinterpret_cast<uint32_t*>(a.attn + (size_t)seg * PH + (size_t)(kvh * PG + g) * PHD + 8 * warp + 2 * t) = *reinterpret_cast<uint32_t*>(&ob);
+#pragma unroll
+      for (int nt = 0; nt < NTD; ++nt) {
+        __nv_bfloat162 ob = __floats2bfloat162_rn(o[nt][0] * inv, o[nt][1] * inv);
+        *reinterpret_cast<uint32_t*>(a.attn + (size_t)seg * PH + (size_t)(kvh * PG + g) * PHD + 8 * (NTD * wt + nt) + 2 * t) = *reinterpret_cast<uint32_t*>(&ob);
+      }
     }
   }
   __syncthreads();
@@ -804,7 +832,7 @@ __global__ void __launch_bounds__(kPThreads, 1) decode_persist_kernel(DecodePers
     } else gemm_dispatch<EPI_F32, W8, NT>(L.wqkv, L.sqkv, PQKV, PH, a.u, B, Bpad, a.part, nullptr, nullptr, smem);
     grid_barrier<TC>(a.bar, epoch); STAMP();
     if (!TC && a.attn_chunks > 1) attention_phase<1>(a, L, smem);          // few segments: split the keys over CTAs
-    else attention_phase_mma<TC ? kTcSplitQkv : 1>(a, L, smem_attn);
+    else attention_phase_mma<TC ? kTcSplitQkv : 1, (NT == 8) ? 8 : 16>(a, L, smem_attn);
     grid_barrier<TC>(a.bar, epoch); STAMP();
     if (TC) {
       gemm_phase_tc<EPI_F32>(tmaps + 4 * l + 1, xmaps + 1, PH, PH, kTcSplitO, B, Bpad, a.part, nullptr, tc);
@@ -921,7 +949,7 @@ __global__ void __launch_bounds__(kPThreads, 1) decode_persist_kernel(DecodePers
 static size_t persist_smem_for(bool tc) {
   const size_t attn = (size_t)AKEYS * kAKRow + (size_t)AKEYS * PHD * 2 + (PG * PHD + PG * AKEYS + 2 * PHD + 32 + 16) * 4;
   const size_t exch = (size_t)kXStageBytes + (size_t)kPWarps * 2 * 4 * 128 * 4;    // staged activations + 16 warps x NT(4) x 128 fp32 (>= the unstaged NT = 8 exchange)
-  const size_t attn_mma = 2 * (size_t)AKEYS * kARow + 2 * 16 * (size_t)kARow + (2 * PHD + 8 * kPWarps) * 4;
+  const size_t attn_mma = attn_team_smem<16>() > 2 * attn_team_smem<8>() ? attn_team_smem<16>() : 2 * attn_team_smem<8>();
   size_t m = attn > exch ? attn : exch;
   if (attn_mma > m) m = attn_mma;
   if (tc) m = kTcRingBytes + attn_mma;            // TMA ring of the tcgen05 phases + the attention phase beside it
