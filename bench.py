@@ -266,8 +266,9 @@ def run_ours(args):
             kv_bytes = B * 57344.0 * (S + G / 2.0)                          # K and V of 28 layers over the mean context
             bytes_per_launch = w_bytes + kv_bytes
             c = pc
-            kname = ("decode_persist_kernel: cooperative per-token kernel (28 layers + lm_head + greedy pick; mma.sync weight "
-                     "streaming, CTA-level split-K, fused RoPE/KV-append/attention/RMSNorm/SwiGLU)")
+            kname = ("decode_persist_kernel: cooperative per-token kernel (28 layers + lm_head + greedy pick; weight streaming by "
+                     + ("TMA + tcgen05 with split-K partials" if 32 < B <= 64 and args.mode != "int8" else "mma.sync with CTA-level split-K")
+                     + ", fused RoPE/KV-append/attention/RMSNorm/SwiGLU)")
         else:
             esz = 2
             bytes_per_launch = 2 * 6144 * 2048 * esz + B * 2048 * esz + B * 6144 * esz      # weights + activations in/out

@@ -3,12 +3,15 @@
 //
 // One CTA = one (segment, head, 128-query tile).  Per 128-key tile:
 //   S = Q.K^T   tcgen05.mma 128x128x64 (Q, K tiles K-major, TMA 128B swizzle)            -> TMEM cols [0,128)
-//   softmax     4 warps, one query row per thread: tcgen05.ld S, running max / sum in registers (exp2),
-//               P written as bf16 into shared memory in the K-major SW128 operand layout
+//   softmax     8 warps, TWO threads per query row (64 keys each): tcgen05.ld S, row max exchanged between the two halves
+//               through shared memory, running max / partial sum in registers (ex2.approx), P written as bf16 into
+//               shared memory in the K-major SW128 operand layout
 //   O_t = P.V   tcgen05.mma 128x64x128, V tile used as an MN-major SW128 B operand (no transpose)  -> TMEM cols [128,192)
-//   O = O*corr + O_t accumulated in registers (exact online softmax, fp32)
-// Two CTAs fit per SM (112 KB smem, 256 TMEM columns each) so one CTA's softmax overlaps the other's MMAs.
-// Warp roles (192 threads): w0 TMA producer, w1 MMA issuer + TMEM owner, w2..5 softmax (TMEM lane quadrant = warp % 4).
+//   O = O*corr + O_t accumulated in registers (exact online softmax, fp32), 32 of the 64 output columns per thread
+// Two CTAs fit per SM (97 KB smem, 256 TMEM columns each) so one CTA's softmax overlaps the other's MMAs; the softmax is
+// the MUFU/ALU-bound part, which is why it gets 16 of the SM's 20 resident warps.
+// Warp roles (320 threads): w0 TMA producer, w1 MMA issuer + TMEM owner, w2..9 softmax (TMEM lane quadrant = warp % 4,
+// key / output-column half = (warp - 2) / 4).
 #include "common.cuh"
 #include "kernels.h"
 #include "gemm_tc.h"
@@ -21,8 +24,10 @@ static constexpr int kTileBytes = AQ * AD * 2;          // 16 KB: a [128 x 64] b
 static constexpr int kKvStages = 2;                     // K tiles are double-buffered; V needs one buffer (it is consumed a
                                                         // whole softmax later than it is requested)
 static constexpr int kPBytes = AQ * AK * 2;             // 32 KB: P as two K-major SW128 atoms of 64 keys
-static constexpr int kAttnSmem = kTileBytes * (1 + kKvStages + 1) + kPBytes + 1024 + 256;   // ~97 KB -> 2 CTAs / SM
+static constexpr int kXchgBytes = 2 * 2 * AQ * 4;       // row-max exchange between the two halves, double-buffered by tile parity
+static constexpr int kAttnSmem = kTileBytes * (1 + kKvStages + 1) + kPBytes + 1024 + 256 + kXchgBytes;   // ~99 KB -> 2 CTAs / SM
 static constexpr int kAttnTmemCols = 256;
+static constexpr int kAttnThreads = 320;
 
 struct AttnTcArgs {
   bf16* out; long long out_stride;    // out[(seg*T + q) * out_stride + h*64 + d]
@@ -31,7 +36,13 @@ struct AttnTcArgs {
   float scale_log2;                   // softmax scale * log2(e)
 };
 
-__global__ void __launch_bounds__(192, 2)
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__global__ void __launch_bounds__(kAttnThreads, 2)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tm, AttnTcArgs a) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -42,6 +53,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm, AttnTcArgs a) {
   // barriers: 0 q_full | 1,2 k_full | 3,4 k_empty | 5 v_full | 7 v_empty | 9 s_full | 10 p_full | 11 o_full
   auto bar = [&](int i) { return bars + 8u * i; };
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sgen + (bars - base) + 8 * 12);
+  float* sX = reinterpret_cast<float*>(sgen + (bars - base) + 256);          // [parity][half][row]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * AQ, h = blockIdx.y, seg = blockIdx.z;
@@ -50,7 +62,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm, AttnTcArgs a) {
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm);
-    for (int i = 0; i < 12; ++i) mbar_init(bar(i), i == 10 ? 128 : 1);
+    for (int i = 0; i < 12; ++i) mbar_init(bar(i), i == 10 ? 256 : 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<kAttnTmemCols>(smem_u32(tmem_slot));
@@ -108,57 +120,67 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm, AttnTcArgs a) {
     }
   } else {
     const int quad = warp & 3;                       // TMEM lanes [32*quad, 32*quad+32)
+    const int half = (warp - 2) >> 2;                // keys [64*half, +64) of the tile, output columns [32*half, +32)
     const int r = quad * 32 + lane;                  // query row inside the tile
     const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
-    float o[AD];
+    float o[AD / 2];
 #pragma unroll
-    for (int d = 0; d < AD; ++d) o[d] = 0.f;
-    float m = -INFINITY, l = 0.f;
-    uint8_t* pP = sgen + (sP - base);
+    for (int d = 0; d < AD / 2; ++d) o[d] = 0.f;
+    float m = -INFINITY, l = 0.f;                    // l: this thread's 64 keys per tile only
+    uint8_t* pP = sgen + (sP - base) + half * (kPBytes / 2);           // this half's 64-key atom
     for (int j = 0; j < n_kt; ++j) {
       mbar_wait(bar(9), (uint32_t)(j & 1));
       tc_fence_after();
-      // pass 1: row max of this tile
-      const int kv_left = a.T - j * AK;              // keys >= kv_left are outside the segment
+      const int kv_left = a.T - j * AK - half * 64;  // keys >= kv_left (in this half's numbering) are outside the segment
+      const bool full = kv_left >= 64;
+      // pass 1: row max over this thread's 64 keys, then over both halves
       float tmax = -INFINITY;
 #pragma unroll 1
-      for (int c = 0; c < AK / 32; ++c) {
+      for (int c = 0; c < 2; ++c) {
         uint32_t v[32];
-        tmem_ld32(tS + lane_off + c * 32, v);
+        tmem_ld32(tS + lane_off + half * 64 + c * 32, v);
         tmem_ld_wait();
+        if (full) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float s = (c * 32 + i < kv_left) ? __uint_as_float(v[i]) : -INFINITY;
-          tmax = fmaxf(tmax, s);
+          for (int i = 0; i < 32; ++i) tmax = fmaxf(tmax, __uint_as_float(v[i]));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) tmax = fmaxf(tmax, (c * 32 + i < kv_left) ? __uint_as_float(v[i]) : -INFINITY);
         }
       }
-      const float m_new = fmaxf(m, tmax);
-      const float corr = exp2f((m - m_new) * a.scale_log2);          // m = -inf on the first tile -> 0
+      float* xb = sX + (j & 1) * 2 * AQ;
+      xb[half * AQ + r] = tmax;
+      asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");      // the two warps that share this lane quadrant
+      const float m_new = fmaxf(m, fmaxf(tmax, xb[(half ^ 1) * AQ + r]));
+      const float corr = ex2_approx((m - m_new) * a.scale_log2);     // m = -inf on the first tile -> 0
       const float mb = m_new * a.scale_log2;
       float psum = 0.f;
       // pass 2: p = exp2(s*scale - m*scale) -> bf16 -> shared memory (K-major SW128: 16 B chunk c8 of row r at (c8 ^ (r & 7)))
 #pragma unroll 1
-      for (int c = 0; c < AK / 32; ++c) {
+      for (int c = 0; c < 2; ++c) {
         uint32_t v[32];
-        tmem_ld32(tS + lane_off + c * 32, v);
+        tmem_ld32(tS + lane_off + half * 64 + c * 32, v);
         tmem_ld_wait();
         uint32_t pk[16];
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
-          float p0 = (c * 32 + i < kv_left) ? exp2f(fmaf(__uint_as_float(v[i]), a.scale_log2, -mb)) : 0.f;
-          float p1 = (c * 32 + i + 1 < kv_left) ? exp2f(fmaf(__uint_as_float(v[i + 1]), a.scale_log2, -mb)) : 0.f;
+          float p0 = ex2_approx(fmaf(__uint_as_float(v[i]), a.scale_log2, -mb));
+          float p1 = ex2_approx(fmaf(__uint_as_float(v[i + 1]), a.scale_log2, -mb));
+          if (!full) {
+            if (c * 32 + i >= kv_left) p0 = 0.f;
+            if (c * 32 + i + 1 >= kv_left) p1 = 0.f;
+          }
           __nv_bfloat162 pb = __floats2bfloat162_rn(p0, p1);
           // the denominator sums what the tensor core will actually multiply (bf16-rounded P), like the reference's
           // softmax-then-cast only up to rounding; keeps rows normalised exactly
           psum += __low2float(pb) + __high2float(pb);
           pk[i >> 1] = *reinterpret_cast<uint32_t*>(&pb);
         }
-        const int atom = c >> 1;                                       // 64 keys per atom
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          const int chunk = (c & 1) * 4 + q;                           // 16 B chunk index inside the 128 B row
+          const int chunk = c * 4 + q;                                 // 16 B chunk index inside the 128 B row
           uint4 val = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
-          *reinterpret_cast<uint4*>(pP + atom * (kPBytes / 2) + r * 128 + ((chunk ^ (r & 7)) << 4)) = val;
+          *reinterpret_cast<uint4*>(pP + r * 128 + ((chunk ^ (r & 7)) << 4)) = val;
         }
       }
       l = l * corr + psum;
@@ -166,25 +188,29 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm, AttnTcArgs a) {
       fence_proxy_async_smem();          // generic-proxy writes of P -> visible to the tensor core (async proxy)
       tc_fence_before();
       mbar_arrive(bar(10));
-      // O accumulate
+      // O accumulate (this thread's 32 output columns)
       mbar_wait(bar(11), (uint32_t)(j & 1));
       tc_fence_after();
-#pragma unroll
-      for (int c = 0; c < AD / 32; ++c) {
+      {
         uint32_t v[32];
-        tmem_ld32(tO + lane_off + c * 32, v);
+        tmem_ld32(tO + lane_off + half * 32, v);
         tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) o[c * 32 + i] = fmaf(o[c * 32 + i], corr, __uint_as_float(v[i]));
+        for (int i = 0; i < 32; ++i) o[i] = fmaf(o[i], corr, __uint_as_float(v[i]));
       }
       tc_fence_before();
     }
+    // denominator of the row = both halves' partial sums (same running max, so they add directly)
+    float* xb = sX + (n_kt & 1) * 2 * AQ;
+    xb[half * AQ + r] = l;
+    asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");
+    const float l_row = (half == 0) ? l + xb[AQ + r] : xb[r] + l;     // same order in both threads
     const int q = q0 + r;
     if (q < a.T) {
-      const float inv = 1.0f / l;
-      bf16* dst = a.out + (size_t)(row0 + q) * a.out_stride + h * AD;
+      const float inv = 1.0f / l_row;
+      bf16* dst = a.out + (size_t)(row0 + q) * a.out_stride + h * AD + half * 32;
 #pragma unroll
-      for (int c = 0; c < AD / 8; ++c) {
+      for (int c = 0; c < AD / 16; ++c) {
         uint4 val;
         __nv_bfloat162 p0 = __floats2bfloat162_rn(o[8 * c] * inv, o[8 * c + 1] * inv);
         __nv_bfloat162 p1 = __floats2bfloat162_rn(o[8 * c + 2] * inv, o[8 * c + 3] * inv);
@@ -216,7 +242,7 @@ cudaError_t launch_attention_tc(const bf16* qkv, int row_width, int q_col, int k
   a.out = out; a.out_stride = out_stride; a.T = T; a.q_col = q_col; a.k_col = k_col; a.v_col = v_col;
   a.scale_log2 = scale * 1.4426950408889634f;
   dim3 grid(cdiv(T, AQ), heads, segments);
-  attention_tc_kernel<<<grid, 192, kAttnSmem, st>>>(tm, a);
+  attention_tc_kernel<<<grid, kAttnThreads, kAttnSmem, st>>>(tm, a);
   return cudaGetLastError();
 }
 

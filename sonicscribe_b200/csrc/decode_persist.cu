@@ -62,19 +62,6 @@ __device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& epoch)
 // ---- GEMM phase: part[s][tok][n] = sum_{k in slice s} W[n][k] * X[tok][k] ------------------------------------------------
 // item = (K-slice s, 16-row block rb); the warps of one CTA take consecutive row blocks of the same slice so that the
 // activation slice they all read stays in L1.
-// L2 prefetch of a weight matrix that a LATER phase will stream: every warp asks for its 1/(grid*16) share with one bulk
-// prefetch, so HBM keeps streaming the next matrix while the current phase computes and while the grid sits in barriers.
-__device__ __forceinline__ void prefetch_weights_l2(const void* W, size_t bytes, int enable = 1) {
-  if (!enable || (threadIdx.x & 31) != 0) return;
-  const size_t nw = (size_t)gridDim.x * kPWarps, gw = (size_t)blockIdx.x * kPWarps + (threadIdx.x >> 5);
-  size_t chunk = ((bytes + nw - 1) / nw + 127) & ~(size_t)127;
-  const size_t off = gw * chunk;
-  if (off >= bytes) return;
-  if (off + chunk > bytes) chunk = (bytes - off) & ~(size_t)15;
-  if (chunk == 0) return;
-  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<const uint8_t*>(W) + off), "r"((uint32_t)chunk) : "memory");
-}
-
 // ---- GEMM phase ---------------------------------------------------------------------------------------------------------
 // item = (16-row block rb, 2048-wide K section gs).  The 16 warps of the CTA split the section (128 k each: one group of
 // 8 weight loads per lane), exchange their fp32 fragments through shared memory and sum them in warp order (deterministic),
@@ -669,7 +656,7 @@ __device__ __forceinline__ void attention_phase_mma(const DecodePersistArgs& a, 
         *reinterpret_cast<uint4*>(sV + r * kARow + c8 * 16) = vv;
       }
       team_sync<TW>(team);
-      if (k0 + CK < kv_len) {
+        if (k0 + CK < kv_len) {
         issue_loads(kc, vc, k0 + CK, min(CK, kv_len - k0 - CK), pos);
       } else if (item + item_stride < n_items) {
         int nseg, nkvh, npos; const bf16 *nkc, *nvc;
@@ -698,7 +685,7 @@ __device__ __forceinline__ void attention_phase_mma(const DecodePersistArgs& a, 
       wmax = fmaxf(wmax, __shfl_xor_sync(0xffffffffu, wmax, 2));
       if (g < PG && t == 0) sMax[g * TW + wt] = wmax;
       team_sync<TW>(team);
-      float corr = 1.f;
+        float corr = 1.f;
       if (g < PG) {
         float cmax = sMax[g * TW];
 #pragma unroll
@@ -713,7 +700,7 @@ __device__ __forceinline__ void attention_phase_mma(const DecodePersistArgs& a, 
         l_part = l_part * corr + (__low2float(pb) + __high2float(pb));   // the denominator sums what the tensor core multiplies
       }
       team_sync<TW>(team);
-      // O tiles of this warp: dims 8*(NTD*wt + nt) + {2t, 2t+1} for head g
+        // O tiles of this warp: dims 8*(NTD*wt + nt) + {2t, 2t+1} for head g
       float oc[NTD][4];
 #pragma unroll
       for (int nt = 0; nt < NTD; ++nt) { oc[nt][0] = oc[nt][1] = oc[nt][2] = oc[nt][3] = 0.f; }
@@ -733,7 +720,7 @@ __device__ __forceinline__ void attention_phase_mma(const DecodePersistArgs& a, 
       }
 #pragma unroll
       for (int nt = 0; nt < NTD; ++nt) { o[nt][0] = o[nt][0] * corr + oc[nt][0]; o[nt][1] = o[nt][1] * corr + oc[nt][1]; }
-    }
+      }
     // denominator: this lane's keys -> the 4 lanes of the head row -> the team's warps (fixed order)
     if (g < PG) {
       float ws = l_part;
@@ -755,6 +742,23 @@ __device__ __forceinline__ void attention_phase_mma(const DecodePersistArgs& a, 
     }
   }
   __syncthreads();
+}
+
+// The KV cache of a layer does not depend on the current step (the appended row is handled in shared memory), so the team
+// that will own a (segment, kv head) group asks for its keys and values to be brought into L2 one to two phases earlier; the
+// attention phase is a latency chain per 64/128-key chunk and then reads at L2 instead of DRAM latency.
+template <int TW>
+__device__ __forceinline__ void attention_prefetch_l2(const DecodePersistArgs& a, const DecLayerDev& L) {
+  constexpr int NTEAM = kPWarps / TW;
+  const int tid = threadIdx.x, team = tid / (32 * TW), tt = tid - team * 32 * TW;
+  if (tt >= 2) return;
+  const int n_items = a.B * PKVH;
+  for (int item = blockIdx.x * NTEAM + team; item < n_items; item += gridDim.x * NTEAM) {
+    const int seg = item / PKVH, kvh = item - seg * PKVH;
+    const uint32_t bytes = (uint32_t)a.gs.ctx_len[seg] * PHD * 2;
+    const bf16* p = (tt == 0 ? L.kc : L.vc) + ((size_t)seg * PKVH + kvh) * a.max_ctx * PHD;
+    if (bytes) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+  }
 }
 
 __device__ __forceinline__ unsigned long long gtimer() {
@@ -822,6 +826,8 @@ __global__ void __launch_bounds__(kPThreads, 1) decode_persist_kernel(DecodePers
     *reinterpret_cast<uint2*>(a.u + (size_t)b * PH + c0) = make_uint2(*reinterpret_cast<uint32_t*>(&u0), *reinterpret_cast<uint32_t*>(&u1));
     __syncthreads();
   }
+  constexpr int ATW = (NT == 8) ? 8 : 16;                 // attention team width of this batch class
+  if (a.attn_chunks <= 1 && (a.prefetch & 1)) attention_prefetch_l2<ATW>(a, a.layers[0]);
   grid_barrier<TC>(a.bar, epoch); STAMP();
 
   for (int l = 0; l < a.n_layers; ++l) {
@@ -832,7 +838,7 @@ __global__ void __launch_bounds__(kPThreads, 1) decode_persist_kernel(DecodePers
     } else gemm_dispatch<EPI_F32, W8, NT>(L.wqkv, L.sqkv, PQKV, PH, a.u, B, Bpad, a.part, nullptr, nullptr, smem);
     grid_barrier<TC>(a.bar, epoch); STAMP();
     if (!TC && a.attn_chunks > 1) attention_phase<1>(a, L, smem);          // few segments: split the keys over CTAs
-    else attention_phase_mma<TC ? kTcSplitQkv : 1, (NT == 8) ? 8 : 16>(a, L, smem_attn);
+    else attention_phase_mma<TC ? kTcSplitQkv : 1, ATW>(a, L, smem_attn);
     grid_barrier<TC>(a.bar, epoch); STAMP();
     if (TC) {
       gemm_phase_tc<EPI_F32>(tmaps + 4 * l + 1, xmaps + 1, PH, PH, kTcSplitO, B, Bpad, a.part, nullptr, tc);
@@ -856,10 +862,12 @@ __global__ void __launch_bounds__(kPThreads, 1) decode_persist_kernel(DecodePers
       if (l + 1 < a.n_layers) tc_prefetch_weights(tmaps + 4 * (l + 1), PQKV, PH, kTcSplitQkv, tc);
       else tc_prefetch_weights(tmaps + 4 * a.n_layers, PV_, PH, 1, tc);
       grid_barrier<TC>(a.bar, epoch); STAMP();
+      if (l + 1 < a.n_layers && a.attn_chunks <= 1 && (a.prefetch & 1)) attention_prefetch_l2<ATW>(a, a.layers[l + 1]);
       residual_norm_phase<kTcSplitDown>(a.part, B, Bpad, a.x, a.u, next_gamma, a.eps, red);
     } else {
       gemm_dispatch<EPI_F32, W8, NT>(L.wdown, L.sdown, PH, PI, a.act, B, Bpad, a.part, nullptr, nullptr, smem);
       grid_barrier<TC>(a.bar, epoch); STAMP();
+      if (l + 1 < a.n_layers && a.attn_chunks <= 1 && (a.prefetch & 1)) attention_prefetch_l2<ATW>(a, a.layers[l + 1]);
       residual_norm_phase<3>(a.part, B, Bpad, a.x, a.u, next_gamma, a.eps, red);
     }
     grid_barrier<TC>(a.bar, epoch); STAMP();
