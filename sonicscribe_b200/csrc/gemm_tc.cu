@@ -415,6 +415,199 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
 }
 
+// ---- persistent 128 x 256 tile kernel for the token-major (non-swap) bf16 GEMMs of the encoder and the prefill ----------------
+// A 128 x 128 tile makes tcgen05.mma read 8 KB of shared memory per 64 clocks, which is the SM's whole shared-memory
+// bandwidth; with N = 256 it is 12 KB per 128 clocks.  One CTA per SM walks tiles (n fastest, so the A rows of a tile row
+// stay in L2), the 4-stage TMA ring runs across tile boundaries, and the two 256-column TMEM accumulators alternate so the
+// 8 epilogue warps drain tile i while the tensor core is already working on tile i + 1.
+// Warp roles (384 threads): w0 TMA producer, w1 MMA issuer, w2 TMEM owner, w4..11 epilogue (lane quadrant = warp % 4, column
+// half = (warp - 4) / 4).
+static constexpr int PBN = 256;
+static constexpr int kPStages = 4;
+static constexpr int kPStageA = BM * BK * 2, kPStageB = PBN * BK * 2;
+static constexpr int kPersistGemmSmem = kPStages * (kPStageA + kPStageB) + 1024 + 256;
+static constexpr int kPersistGemmThreads = 384;
+
+template <typename TC>
+__device__ __forceinline__ void epilogue_chunk32(const TcEpi& e, float (&x)[32], int m, int n, TC* Cb, const TC* Rb) {
+  if (e.bias) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      const float4 bv = __ldg(reinterpret_cast<const float4*>(e.bias + n + j));
+      x[j] += bv.x; x[j + 1] += bv.y; x[j + 2] += bv.z; x[j + 3] += bv.w;
+    }
+  }
+  if (e.act == ACT_GELU) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) x[j] = gelu_erf(x[j]);
+  }
+  if (e.rope_cos != nullptr && n < e.rope_ncols && (n & 63) == 0) {
+    const int pos = m % e.rope_T;
+    const float4* cp = reinterpret_cast<const float4*>(e.rope_cos + (size_t)pos * 16);
+    const float4* sp = reinterpret_cast<const float4*>(e.rope_sin + (size_t)pos * 16);
+#pragma unroll
+    for (int q4 = 0; q4 < 4; ++q4) {
+      const float4 c4 = __ldg(cp + q4), s4 = __ldg(sp + q4);
+      const float cc[4] = {c4.x, c4.y, c4.z, c4.w}, ss[4] = {s4.x, s4.y, s4.z, s4.w};
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const int j = 4 * q4 + t;
+        const float c = __bfloat162float(__float2bfloat16_rn(cc[t])), sn = __bfloat162float(__float2bfloat16_rn(ss[t]));
+        const float av = x[j], bv = x[j + 16];
+        x[j] = av * c - bv * sn;
+        x[j + 16] = bv * c + av * sn;
+      }
+    }
+  }
+  if (e.act == ACT_SWIGLU) {
+    float y[32];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) y[j] = silu(x[2 * j]) * x[2 * j + 1];
+    TC* dst = Cb + (size_t)m * e.ldc + (n >> 1);
+    if constexpr (sizeof(TC) == 2) {
+      uint4* d = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        __nv_bfloat162 p0 = __floats2bfloat162_rn(y[8 * i + 0], y[8 * i + 1]);
+        __nv_bfloat162 p1 = __floats2bfloat162_rn(y[8 * i + 2], y[8 * i + 3]);
+        __nv_bfloat162 p2 = __floats2bfloat162_rn(y[8 * i + 4], y[8 * i + 5]);
+        __nv_bfloat162 p3 = __floats2bfloat162_rn(y[8 * i + 6], y[8 * i + 7]);
+        uint4 o;
+        o.x = *reinterpret_cast<uint32_t*>(&p0); o.y = *reinterpret_cast<uint32_t*>(&p1);
+        o.z = *reinterpret_cast<uint32_t*>(&p2); o.w = *reinterpret_cast<uint32_t*>(&p3);
+        d[i] = o;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) dst[j] = from_f32<TC>(y[j]);
+    }
+  } else {
+    if (Rb) {
+      const TC* r = Rb + (size_t)m * e.ldr + n;
+      if constexpr (sizeof(TC) == 2) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const uint4 rv = *reinterpret_cast<const uint4*>(r + 8 * i);
+          const uint32_t w[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            x[8 * i + 2 * t] += __uint_as_float(w[t] << 16);
+            x[8 * i + 2 * t + 1] += __uint_as_float(w[t] & 0xffff0000u);
+          }
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) x[j] += to_f32(r[j]);
+      }
+    }
+    store_chunk32<TC>(Cb + (size_t)m * e.ldc + n, x);
+  }
+}
+
+template <typename TC>
+__global__ void __launch_bounds__(kPersistGemmThreads, 1)
+gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TcEpi e, int tiles_m, int tiles_n,
+                       int batches) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* sgen = smem_raw + (base - raw);
+  const uint32_t sA = base, sB = base + kPStages * kPStageA;
+  const uint32_t bars = sB + kPStages * kPStageB;            // full[4], empty[4], acc_full[2], acc_empty[2], tmem slot
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sgen + (bars - base) + 8 * (2 * kPStages + 4));
+  auto full_bar = [&](uint32_t s) { return bars + 8u * s; };
+  auto empty_bar = [&](uint32_t s) { return bars + 8u * (kPStages + s); };
+  auto acc_full = [&](uint32_t a) { return bars + 8u * (2 * kPStages + a); };
+  auto acc_empty = [&](uint32_t a) { return bars + 8u * (2 * kPStages + 2 + a); };
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int total_kb = e.K / BK;
+  const int n_tiles = tiles_m * tiles_n * batches;
+
+  if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kPStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(acc_full(a), 1); mbar_init(acc_empty(a), 8); }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<512>(smem_u32(tmem_slot));
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t cnt = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int batch = tile / (tiles_m * tiles_n), r = tile - batch * tiles_m * tiles_n;
+        const int a0 = (r / tiles_n) * BM, b0 = (r % tiles_n) * PBN;
+        for (int kb = 0; kb < total_kb; ++kb, ++cnt) {
+          const uint32_t s = cnt % kPStages, ph = (cnt / kPStages) & 1u;
+          mbar_wait(empty_bar(s), ph ^ 1u);
+          mbar_expect_tx(full_bar(s), kPStageA + kPStageB);
+          const int tap = kb / e.kb_per_tap, kc = kb - tap * e.kb_per_tap;
+          tma_load_3d(sA + s * kPStageA, &tmA, full_bar(s), kc * BK + e.tap_col[tap], a0 + e.tap_row[tap], batch);
+          tma_load_3d(sB + s * kPStageB, &tmB, full_bar(s), kb * BK, b0, 0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(BM, PBN);
+      uint32_t cnt = 0, it = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+        const uint32_t acc = it & 1u, aph = (it >> 1) & 1u;
+        mbar_wait(acc_empty(acc), aph ^ 1u);
+        tc_fence_after();
+        for (int kb = 0; kb < total_kb; ++kb, ++cnt) {
+          const uint32_t s = cnt % kPStages, ph = (cnt / kPStages) & 1u;
+          mbar_wait(full_bar(s), ph);
+          tc_fence_after();
+          const uint64_t da = make_sw128_desc(sA + s * kPStageA), db = make_sw128_desc(sB + s * kPStageB);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k)
+            tc_mma_bf16(tmem_base + acc * PBN, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb != 0 || k != 0) ? 1u : 0u);
+          tc_commit(empty_bar(s));
+        }
+        tc_commit(acc_full(acc));
+      }
+    }
+  } else if (warp >= 4) {
+    const int q = warp & 3, half = (warp - 4) >> 2;
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      const int batch = tile / (tiles_m * tiles_n), r = tile - batch * tiles_m * tiles_n;
+      const int a0 = (r / tiles_n) * BM, b0 = (r % tiles_n) * PBN;
+      const uint32_t acc = it & 1u, aph = (it >> 1) & 1u;
+      mbar_wait(acc_full(acc), aph);
+      tc_fence_after();
+      const int m = a0 + q * 32 + lane;
+      TC* Cb = reinterpret_cast<TC*>(e.C) + (size_t)batch * e.c_bstride + (size_t)e.c_row0 * e.ldc;
+      const TC* Rb = e.resid ? reinterpret_cast<const TC*>(e.resid) + (size_t)batch * e.r_bstride : nullptr;
+#pragma unroll 1
+      for (int c = 0; c < PBN / 64; ++c) {
+        const int col = half * (PBN / 2) + c * 32;
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * PBN + col, v);
+        tmem_ld_wait();
+        const int n = b0 + col;
+        if (m < e.M && n < e.N) {
+          float x[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]);
+          epilogue_chunk32<TC>(e, x, m, n, Cb, Rb);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_empty(acc));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc<512>(tmem_base);
+}
+
 // ---- host side --------------------------------------------------------------------------------------------------------
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -489,6 +682,8 @@ static cudaError_t configure_one() {
 }
 // opt every instantiation into its dynamic shared memory up front (must not happen lazily inside a stream capture)
 cudaError_t gemm_tc_configure() {
+  SONIC_CUDA_TRY(cudaFuncSetAttribute(gemm_tc_persist_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPersistGemmSmem));
+  SONIC_CUDA_TRY(cudaFuncSetAttribute(gemm_tc_persist_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPersistGemmSmem));
   SONIC_CUDA_TRY((configure_one<128, false, bf16>()));
   SONIC_CUDA_TRY((configure_one<128, false, float>()));
   SONIC_CUDA_TRY((configure_one<16, true, bf16>()));
@@ -505,6 +700,20 @@ cudaError_t gemm_tc_configure() {
 }
 
 static constexpr int kMaxTiles = 2048;
+
+static bool persist_gemm_enabled() {
+  static const bool on = [] { const char* v = getenv("SONIC_GEMM_PERSIST"); return !(v && v[0] == '0'); }();
+  return on;
+}
+static int persist_gemm_sms() {
+  static const int n = [] {
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return sms > 0 ? sms : 148;
+  }();
+  return n;
+}
 
 int gemm_tc_pick_bn(const GemmArgs& g, bool swap) {
   if (swap) return g.M <= 16 ? 16 : (g.M <= 32 ? 32 : 64);
@@ -545,6 +754,17 @@ cudaError_t launch_gemm_tc(const GemmArgs& g, bool swap, cudaStream_t st) {
     SONIC_CUDA_TRY(make_map(&mb, g.W, g.K, g.N, g.ldw, 1, 0, bn));
     dim3 grid(cdiv(g.N, bn), cdiv(g.M, BM), g.batch);
     return g.out_f32 ? launch_one<128, false, float>(ma, mb, e, grid, st) : launch_one<128, false, bf16>(ma, mb, e, grid, st);
+  }
+  if (!swap && !w8 && g.N % 128 == 0 && persist_gemm_enabled()) {
+    // token-major bf16 GEMM: persistent 128 x 256 tiles, one CTA per SM
+    SONIC_CUDA_TRY(make_map(&ma, g.A, g.K, g.M, g.lda, g.batch, g.a_bstride, BM));
+    SONIC_CUDA_TRY(make_map(&mb, g.W, g.K, g.N, g.ldw, 1, 0, PBN));
+    const int tiles_m = cdiv(g.M, BM), tiles_n = cdiv(g.N, PBN);
+    const long long total = (long long)tiles_m * tiles_n * g.batch;
+    const int grid = (int)(total < persist_gemm_sms() ? total : persist_gemm_sms());
+    if (g.out_f32) gemm_tc_persist_kernel<float><<<grid, kPersistGemmThreads, kPersistGemmSmem, st>>>(ma, mb, e, tiles_m, tiles_n, g.batch);
+    else gemm_tc_persist_kernel<bf16><<<grid, kPersistGemmThreads, kPersistGemmSmem, st>>>(ma, mb, e, tiles_m, tiles_n, g.batch);
+    return cudaGetLastError();
   }
   if (!swap) {
     SONIC_CUDA_TRY(make_map(&ma, g.A, g.K, g.M, g.lda, g.batch, g.a_bstride, BM));
