@@ -276,9 +276,18 @@ def run_ours(args):
             kname = "gemm_tc_kernel<swap> gate/up projection of the greedy decode step (weight streaming, SwiGLU epilogue)"
         avg_ms = c["ms"] / max(c["launches"], 1)
         achieved = bytes_per_launch / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else 0.0
+        # DRAM bytes per launch of this kernel from the committed `ncu --set full` capture (profiles/r01_traffic.json, written
+        # by scripts/ncu_traffic.py from dram__bytes_read.sum + dram__bytes_write.sum); only quoted for the batch it was taken at
+        traffic = None
+        try:
+            tj = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_traffic.json")))
+            if pc["launches"] > 0 and tj.get("kernel") == "decode_persist_kernel" and tj.get("batch") == B and tj.get("mode") == args.mode:
+                traffic = tj.get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
         roofline = {
             "kernel": kname, "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-            "traffic": None, "peak_source": peak_src, "bytes_per_launch": bytes_per_launch, "avg_launch_ms": avg_ms,
+            "traffic": traffic, "peak_source": peak_src, "bytes_per_launch": bytes_per_launch, "avg_launch_ms": avg_ms,
             "launches_timed": c["launches"], "share_of_step": c["ms"] / total_prof if total_prof > 0 else None,
         }
         cpu_base = None
