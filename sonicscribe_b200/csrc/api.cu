@@ -495,10 +495,8 @@ struct Engine {
       // 128-key chunks over separate CTAs while that still leaves CTAs idle; otherwise one CTA walks all chunks of a group
       p.attn_chunks = (B * kDecKv * ((h->decode_chunks + 1) / 2) <= h->persist_grid) ? (h->decode_chunks + 1) / 2 : 1;
       p.gs = h->gs; p.bar = h->persist_bar; p.timestamps = h->cfg.debug ? h->persist_ts : nullptr;
-      { const char* pf = getenv("SONIC_PERSIST_PREFETCH"); p.prefetch = pf ? atoi(pf) : 0; }   // 1: ask for the next layer's KV in L2 one phase early (measured: no net gain, off)
       p.w8 = h->is_int8 ? 1 : 0;
       p.tmaps = h->persist_tc ? h->persist_tmaps : nullptr;
-      { const char* am = getenv("SONIC_ATTN"); p.attn_mode = (am && std::string(am) == "simt") ? 1 : 0; }
       p.B = B; p.Bpad = (B + 7) / 8 * 8; p.max_ctx = h->max_ctx; p.eps = kRmsEps; p.scale = 0.08838834764831845f;
       TAG(PC_DEC_PERSIST);
       if (h->prof_on) { cudaEventRecord(prof_event(h), h->stream); h->prof_tags.push_back(h->prof_cls); }

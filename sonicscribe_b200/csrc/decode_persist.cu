@@ -236,7 +236,7 @@ __device__ __forceinline__ void gemm_dispatch(const void* W, const float* wscale
 // issues the MMAs, warps 4..11 drain the two alternating TMEM accumulators (lane quadrant = warp % 4, 32 tokens each).
 // The ring / accumulator barriers live for the whole kernel; their phase is derived from running counters that every thread
 // advances identically.
-static constexpr int kTcStages = 6;
+static constexpr int kTcStages = 6;                   // 8 measured no faster
 static constexpr int kTcStageA = 128 * 64 * 2, kTcStageB = kPersistTcTokens * 64 * 2;
 static constexpr int kTcRingBytes = kTcStages * (kTcStageA + kTcStageB) + 1024;     // + alignment slack
 struct TcCtx {
@@ -554,44 +554,51 @@ __device__ __forceinline__ void ldmatrix_x2_trans(uint32_t& r0, uint32_t& r1, co
 // TW warps form a team that owns one (segment, kv head) group at a time: 16 (one team, 128-key chunks) or 8 (two teams per
 // CTA, 64-key chunks; used by the 33..64-token class, where there are more groups than CTAs and the per-chunk latency chain,
 // not bandwidth, sets the time).  Teams synchronise on their own named barrier.
+// K and V chunks arrive by bulk-async row copies (cp.async.bulk, 256 B per key row into 272 B padded rows) into two
+// alternating buffers per team, completion on an mbarrier: the next chunk (of this group, or the first chunk of the team's
+// next group) is in flight while the current one is multiplied, without passing through registers or the LSU queue
+// (register-staged 16 B loads stalled ~1 us per chunk at issue: 64 KB per SM of outstanding LDG is the limit, measured).
 template <int TW>
 __device__ __forceinline__ void team_sync(int team) {
   asm volatile("bar.sync %0, %1;" ::"r"(team + 1), "n"(TW * 32) : "memory");
 }
 template <int TW>
-static constexpr size_t attn_team_smem() { return 2 * (size_t)(8 * TW) * kARow + 2 * 4 * (size_t)kARow + (2 * PHD + 8 * TW) * 4; }
+static constexpr size_t attn_kv_smem() { return (size_t)(kPWarps / TW) * 2 * 2 * (8 * TW) * kARow; }      // teams x 2 buffers x (K + V)
+template <int TW>
+static constexpr size_t attn_small_smem() { return 2 * 4 * (size_t)kARow + (2 * PHD + 8 * TW) * 4; }       // per team
+__device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
 
 template <int KSQ, int TW>
-__device__ __forceinline__ void attention_phase_mma(const DecodePersistArgs& a, const DecLayerDev& L, uint8_t* smem_all) {
+__device__ __forceinline__ void attention_phase_mma(const DecodePersistArgs& a, const DecLayerDev& L, uint8_t* smem_kv, uint8_t* smem_small,
+                                                    uint32_t bars, uint32_t& n_chunk) {
   constexpr int CK = 8 * TW;                              // keys per chunk
   constexpr int TT = 32 * TW;                             // threads per team
   constexpr int NTEAM = kPWarps / TW;
   constexpr int NTD = 16 / TW;                            // 8-dim output tiles per warp
+  constexpr int kHalf = CK * kARow;                       // bytes of the K (or V) part of a buffer
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
   const int team = warp / TW, wt = warp - team * TW, tt = tid - team * TT;
-  uint8_t* smem = smem_all + (size_t)team * attn_team_smem<TW>();
-  uint8_t* sK = smem;                                     // [CK keys][272 B]
-  uint8_t* sV = sK + CK * kARow;                          // [CK keys][272 B]
-  uint8_t* sQ = sV + CK * kARow;                          // [4][272 B]   rotated query heads (bf16); MMA rows 4..15 are zero registers
+  uint8_t* kv = smem_kv + (size_t)team * 4 * kHalf;        // buffer b: K at b*2*kHalf, V at b*2*kHalf + kHalf
+  uint8_t* small = smem_small + (size_t)team * attn_small_smem<TW>();
+  uint8_t* sQ = small;                                    // [4][272 B]   rotated query heads (bf16); MMA rows 4..15 are zero registers
   uint8_t* sP = sQ + 4 * kARow;                           // [4][272 B]   probabilities of the chunk (bf16)
   float* sKV = reinterpret_cast<float*>(sP + 4 * kARow);  // new k (128) | new v (128)
   float* sMax = sKV + 2 * PHD;                            // [4 heads][TW warps]
   float* sSum = sMax + 4 * TW;                            // [4 heads][TW warps]
   const int n_items = a.B * PKVH;
   const int item_stride = gridDim.x * NTEAM;
-  // The next chunk (of this group, or the first chunk of this team's next group) is loaded into registers while the
-  // current one is being multiplied: thread -> 4 x (16 B of K, 16 B of V), piece i = tt + TT u = key (i >> 4), column (i & 15).
-  // The row being appended this step is never read from global memory (it is taken from sKV when the chunk is stored).
-  uint4 pk[4], pv[4];
-  auto issue_loads = [&](const bf16* kc, const bf16* vc, int k0, int nk, int pos) {
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int i = tt + TT * u, r = i >> 4, c8 = i & 15;
-      pk[u] = make_uint4(0, 0, 0, 0); pv[u] = make_uint4(0, 0, 0, 0);
-      if (r < nk && k0 + r != pos) {
-        pk[u] = __ldcg(reinterpret_cast<const uint4*>(kc + (size_t)(k0 + r) * PHD + c8 * 8));
-        pv[u] = __ldcg(reinterpret_cast<const uint4*>(vc + (size_t)(k0 + r) * PHD + c8 * 8));
-      }
+  auto bar_of = [&](uint32_t b) { return bars + 8u * (team * 2 + b); };
+  // rows [0, nk) of the chunk starting at key k0, except the row appended this step (written from sKV when the chunk is used)
+  auto issue_chunk = [&](const bf16* kc, const bf16* vc, int k0, int nk, int pos, uint32_t b) {
+    if (tt == 0) mbar_expect_tx(bar_of(b), (uint32_t)(nk - ((pos >= k0 && pos < k0 + nk) ? 1 : 0)) * 2u * (PHD * 2));
+    for (int i = tt; i < 2 * CK; i += TT) {
+      const int isv = i >= CK ? 1 : 0, r = i - isv * CK;
+      if (r < nk && k0 + r != pos)
+        bulk_copy_g2s(smem_u32(kv + (size_t)b * 2 * kHalf + (size_t)isv * kHalf + (size_t)r * kARow), (isv ? vc : kc) + (size_t)(k0 + r) * PHD,
+                      PHD * 2, bar_of(b));
     }
   };
   auto group_of = [&](int item, int& seg, int& kvh, int& pos, const bf16*& kc, const bf16*& vc) {
@@ -604,7 +611,7 @@ __device__ __forceinline__ void attention_phase_mma(const DecodePersistArgs& a, 
   if (item < n_items) {
     int seg, kvh, pos; const bf16 *kc, *vc;
     group_of(item, seg, kvh, pos, kc, vc);
-    issue_loads(kc, vc, 0, min(CK, pos + 1), pos);
+    issue_chunk(kc, vc, 0, min(CK, pos + 1), pos, n_chunk & 1u);
   }
   for (; item < n_items; item += item_stride) {
     int seg, kvh, pos; const bf16 *kc, *vc;
@@ -635,40 +642,41 @@ __device__ __forceinline__ void attention_phase_mma(const DecodePersistArgs& a, 
     float o[NTD][2];                                       // O[head g][dims 8*(NTD*wt + nt) + 2t, +1]
 #pragma unroll
     for (int nt = 0; nt < NTD; ++nt) { o[nt][0] = 0.f; o[nt][1] = 0.f; }
-    for (int k0 = 0; k0 < kv_len; k0 += CK) {
+    for (int k0 = 0; k0 < kv_len; k0 += CK, ++n_chunk) {
       const int nk = min(CK, kv_len - k0);
-      if (k0 > 0) team_sync<TW>(team);                     // previous chunk fully consumed
+      const uint32_t b = n_chunk & 1u;
+      uint8_t* sK = kv + (size_t)b * 2 * kHalf;
+      uint8_t* sV = sK + kHalf;
+      // rows that do not come from the cache: the appended row (from sKV) and, in a ragged last chunk, zero V rows
+      if (pos >= k0 && pos < k0 + CK && tt < 32) {
+        const int r = pos - k0, c8 = tt & 15, isv = tt >> 4;
+        uint32_t w[4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int i = tt + TT * u, r = i >> 4, c8 = i & 15;
-        uint4 kk = pk[u], vv = pv[u];
-        if (r < nk && k0 + r == pos) {                     // the row appended above: take it from shared memory
-          uint32_t wk[4], wv[4];
-#pragma unroll
-          for (int e2 = 0; e2 < 4; ++e2) {
-            __nv_bfloat162 qk = __floats2bfloat162_rn(sKV[c8 * 8 + 2 * e2], sKV[c8 * 8 + 2 * e2 + 1]);
-            __nv_bfloat162 qv = __floats2bfloat162_rn(sKV[PHD + c8 * 8 + 2 * e2], sKV[PHD + c8 * 8 + 2 * e2 + 1]);
-            wk[e2] = *reinterpret_cast<uint32_t*>(&qk); wv[e2] = *reinterpret_cast<uint32_t*>(&qv);
-          }
-          kk = make_uint4(wk[0], wk[1], wk[2], wk[3]); vv = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+        for (int e2 = 0; e2 < 4; ++e2) {
+          __nv_bfloat162 q2 = __floats2bfloat162_rn(sKV[isv * PHD + c8 * 8 + 2 * e2], sKV[isv * PHD + c8 * 8 + 2 * e2 + 1]);
+          w[e2] = *reinterpret_cast<uint32_t*>(&q2);
         }
-        *reinterpret_cast<uint4*>(sK + r * kARow + c8 * 16) = kk;
-        *reinterpret_cast<uint4*>(sV + r * kARow + c8 * 16) = vv;
+        *reinterpret_cast<uint4*>((isv ? sV : sK) + r * kARow + c8 * 16) = make_uint4(w[0], w[1], w[2], w[3]);
       }
-      team_sync<TW>(team);
-        if (k0 + CK < kv_len) {
-        issue_loads(kc, vc, k0 + CK, min(CK, kv_len - k0 - CK), pos);
+      if (nk < CK) {
+        for (int i = tt; i < (CK - nk) * 16; i += TT)
+          *reinterpret_cast<uint4*>(sV + (nk + (i >> 4)) * kARow + (i & 15) * 16) = make_uint4(0, 0, 0, 0);
+      }
+      mbar_wait(bar_of(b), (n_chunk >> 1) & 1u);           // this chunk's rows have landed
+      team_sync<TW>(team);                                 // fix-up rows visible; the other buffer is fully consumed
+      fence_proxy_async_smem();                            // ... by generic-proxy reads, before the async proxy overwrites it
+      if (k0 + CK < kv_len) {
+        issue_chunk(kc, vc, k0 + CK, min(CK, kv_len - k0 - CK), pos, b ^ 1u);
       } else if (item + item_stride < n_items) {
         int nseg, nkvh, npos; const bf16 *nkc, *nvc;
         group_of(item + item_stride, nseg, nkvh, npos, nkc, nvc);
-        issue_loads(nkc, nvc, 0, min(CK, npos + 1), npos);
+        issue_chunk(nkc, nvc, 0, min(CK, npos + 1), npos, b ^ 1u);
       }
       // S tile of this warp: keys 8*wt + {2t, 2t+1} for head g
       float sc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int ks = 0; ks < 8; ++ks) {
-        // Q fragment (row g of the 16-row tile, zero for g >= 4) is re-read from shared memory: registers hold the prefetch
-        uint32_t qa0 = 0u, qa2 = 0u;
+        uint32_t qa0 = 0u, qa2 = 0u;                       // Q fragment: row g of the 16-row tile, zero for g >= 4
         if (g < PG) {
           qa0 = *reinterpret_cast<const uint32_t*>(sQ + g * kARow + (16 * ks + 2 * t) * 2);
           qa2 = *reinterpret_cast<const uint32_t*>(sQ + g * kARow + (16 * ks + 8 + 2 * t) * 2);
@@ -685,7 +693,7 @@ __device__ __forceinline__ void attention_phase_mma(const DecodePersistArgs& a, 
       wmax = fmaxf(wmax, __shfl_xor_sync(0xffffffffu, wmax, 2));
       if (g < PG && t == 0) sMax[g * TW + wt] = wmax;
       team_sync<TW>(team);
-        float corr = 1.f;
+      float corr = 1.f;
       if (g < PG) {
         float cmax = sMax[g * TW];
 #pragma unroll
@@ -700,7 +708,7 @@ __device__ __forceinline__ void attention_phase_mma(const DecodePersistArgs& a, 
         l_part = l_part * corr + (__low2float(pb) + __high2float(pb));   // the denominator sums what the tensor core multiplies
       }
       team_sync<TW>(team);
-        // O tiles of this warp: dims 8*(NTD*wt + nt) + {2t, 2t+1} for head g
+      // O tiles of this warp: dims 8*(NTD*wt + nt) + {2t, 2t+1} for head g
       float oc[NTD][4];
 #pragma unroll
       for (int nt = 0; nt < NTD; ++nt) { oc[nt][0] = oc[nt][1] = oc[nt][2] = oc[nt][3] = 0.f; }
@@ -720,7 +728,7 @@ __device__ __forceinline__ void attention_phase_mma(const DecodePersistArgs& a, 
       }
 #pragma unroll
       for (int nt = 0; nt < NTD; ++nt) { o[nt][0] = o[nt][0] * corr + oc[nt][0]; o[nt][1] = o[nt][1] * corr + oc[nt][1]; }
-      }
+    }
     // denominator: this lane's keys -> the 4 lanes of the head row -> the team's warps (fixed order)
     if (g < PG) {
       float ws = l_part;
@@ -744,23 +752,6 @@ __device__ __forceinline__ void attention_phase_mma(const DecodePersistArgs& a, 
   __syncthreads();
 }
 
-// The KV cache of a layer does not depend on the current step (the appended row is handled in shared memory), so the team
-// that will own a (segment, kv head) group asks for its keys and values to be brought into L2 one to two phases earlier; the
-// attention phase is a latency chain per 64/128-key chunk and then reads at L2 instead of DRAM latency.
-template <int TW>
-__device__ __forceinline__ void attention_prefetch_l2(const DecodePersistArgs& a, const DecLayerDev& L) {
-  constexpr int NTEAM = kPWarps / TW;
-  const int tid = threadIdx.x, team = tid / (32 * TW), tt = tid - team * 32 * TW;
-  if (tt >= 2) return;
-  const int n_items = a.B * PKVH;
-  for (int item = blockIdx.x * NTEAM + team; item < n_items; item += gridDim.x * NTEAM) {
-    const int seg = item / PKVH, kvh = item - seg * PKVH;
-    const uint32_t bytes = (uint32_t)a.gs.ctx_len[seg] * PHD * 2;
-    const bf16* p = (tt == 0 ? L.kc : L.vc) + ((size_t)seg * PKVH + kvh) * a.max_ctx * PHD;
-    if (bytes) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
-  }
-}
-
 __device__ __forceinline__ unsigned long long gtimer() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
@@ -782,12 +773,19 @@ __global__ void __launch_bounds__(kPThreads, 1) decode_persist_kernel(DecodePers
   __shared__ float red[32];
   __shared__ __align__(8) uint64_t tc_bars[2 * kTcStages + 4];
   __shared__ uint32_t tc_tmem_slot;
+  __shared__ __align__(8) uint64_t attn_bars[4];                  // [team][buffer] K/V chunk arrival
   unsigned epoch = 0;
   int n_stamp = 0;
   STAMP();
   const int tid = threadIdx.x;
   const int B = a.B, Bpad = a.Bpad;
   TcCtx tc;
+  uint32_t attn_chunks_done = 0;                                   // this team's running chunk count (buffer / barrier phase)
+  if (tid == 0) {
+    for (int i = 0; i < 4; ++i) mbar_init(smem_u32(&attn_bars[i]), 1);
+    fence_barrier_init();
+  }
+  if (!TC) __syncthreads();
   const CUtensorMap* tmaps = reinterpret_cast<const CUtensorMap*>(a.tmaps);
   const CUtensorMap* xmaps = tmaps + 4 * a.n_layers + 1;                    // u, attn, act
   if (TC) {
@@ -808,8 +806,11 @@ __global__ void __launch_bounds__(kPThreads, 1) decode_persist_kernel(DecodePers
     tc.tmem = tc_tmem_slot;
     tc_prefetch_weights(tmaps, PQKV, PH, kTcSplitQkv, tc);
   }
-  // the attention phase of the tcgen05 variant works beside the TMA ring (weight tiles are in flight while it runs)
-  uint8_t* smem_attn = TC ? smem + ((((smem_u32(smem) + 1023u) & ~1023u) - smem_u32(smem)) + kTcStages * (kTcStageA + kTcStageB)) : smem;
+  // attention: K/V chunk buffers overlay the (then idle) TMA ring / GEMM staging area, the small per-team arrays sit after it
+  constexpr int ATW = (NT == 8) ? 8 : 16;                 // attention team width of this batch class
+  const uint32_t ring_off = ((smem_u32(smem) + 1023u) & ~1023u) - smem_u32(smem);
+  uint8_t* smem_kv = TC ? smem + ring_off : smem;
+  uint8_t* smem_small = TC ? smem + ring_off + kTcStages * (kTcStageA + kTcStageB) : smem + attn_kv_smem<ATW>();
 
   // ---- phase 0: x = E[cur_tok]; u = rmsnorm(x) * g(layer 0 input norm)
   for (int b = blockIdx.x; b < B; b += gridDim.x) {
@@ -826,19 +827,17 @@ __global__ void __launch_bounds__(kPThreads, 1) decode_persist_kernel(DecodePers
     *reinterpret_cast<uint2*>(a.u + (size_t)b * PH + c0) = make_uint2(*reinterpret_cast<uint32_t*>(&u0), *reinterpret_cast<uint32_t*>(&u1));
     __syncthreads();
   }
-  constexpr int ATW = (NT == 8) ? 8 : 16;                 // attention team width of this batch class
-  if (a.attn_chunks <= 1 && (a.prefetch & 1)) attention_prefetch_l2<ATW>(a, a.layers[0]);
   grid_barrier<TC>(a.bar, epoch); STAMP();
 
   for (int l = 0; l < a.n_layers; ++l) {
     const DecLayerDev L = a.layers[l];
     if (TC) {
       gemm_phase_tc<EPI_F32>(tmaps + 4 * l, xmaps, PQKV, PH, kTcSplitQkv, B, Bpad, a.part, nullptr, tc);
-      tc_prefetch_weights(tmaps + 4 * l + 1, PH, PH, kTcSplitO, tc);
     } else gemm_dispatch<EPI_F32, W8, NT>(L.wqkv, L.sqkv, PQKV, PH, a.u, B, Bpad, a.part, nullptr, nullptr, smem);
     grid_barrier<TC>(a.bar, epoch); STAMP();
     if (!TC && a.attn_chunks > 1) attention_phase<1>(a, L, smem);          // few segments: split the keys over CTAs
-    else attention_phase_mma<TC ? kTcSplitQkv : 1, ATW>(a, L, smem_attn);
+    else attention_phase_mma<TC ? kTcSplitQkv : 1, ATW>(a, L, smem_kv, smem_small, smem_u32(attn_bars), attn_chunks_done);
+    if (TC) tc_prefetch_weights(tmaps + 4 * l + 1, PH, PH, kTcSplitO, tc);      // the ring is free again
     grid_barrier<TC>(a.bar, epoch); STAMP();
     if (TC) {
       gemm_phase_tc<EPI_F32>(tmaps + 4 * l + 1, xmaps + 1, PH, PH, kTcSplitO, B, Bpad, a.part, nullptr, tc);
@@ -862,12 +861,10 @@ __global__ void __launch_bounds__(kPThreads, 1) decode_persist_kernel(DecodePers
       if (l + 1 < a.n_layers) tc_prefetch_weights(tmaps + 4 * (l + 1), PQKV, PH, kTcSplitQkv, tc);
       else tc_prefetch_weights(tmaps + 4 * a.n_layers, PV_, PH, 1, tc);
       grid_barrier<TC>(a.bar, epoch); STAMP();
-      if (l + 1 < a.n_layers && a.attn_chunks <= 1 && (a.prefetch & 1)) attention_prefetch_l2<ATW>(a, a.layers[l + 1]);
       residual_norm_phase<kTcSplitDown>(a.part, B, Bpad, a.x, a.u, next_gamma, a.eps, red);
     } else {
       gemm_dispatch<EPI_F32, W8, NT>(L.wdown, L.sdown, PH, PI, a.act, B, Bpad, a.part, nullptr, nullptr, smem);
       grid_barrier<TC>(a.bar, epoch); STAMP();
-      if (l + 1 < a.n_layers && a.attn_chunks <= 1 && (a.prefetch & 1)) attention_prefetch_l2<ATW>(a, a.layers[l + 1]);
       residual_norm_phase<3>(a.part, B, Bpad, a.x, a.u, next_gamma, a.eps, red);
     }
     grid_barrier<TC>(a.bar, epoch); STAMP();
@@ -957,10 +954,12 @@ __global__ void __launch_bounds__(kPThreads, 1) decode_persist_kernel(DecodePers
 static size_t persist_smem_for(bool tc) {
   const size_t attn = (size_t)AKEYS * kAKRow + (size_t)AKEYS * PHD * 2 + (PG * PHD + PG * AKEYS + 2 * PHD + 32 + 16) * 4;
   const size_t exch = (size_t)kXStageBytes + (size_t)kPWarps * 2 * 4 * 128 * 4;    // staged activations + 16 warps x NT(4) x 128 fp32 (>= the unstaged NT = 8 exchange)
-  const size_t attn_mma = attn_team_smem<16>() > 2 * attn_team_smem<8>() ? attn_team_smem<16>() : 2 * attn_team_smem<8>();
+  const size_t attn_mma16 = attn_kv_smem<16>() + attn_small_smem<16>(), attn_mma8 = attn_kv_smem<8>() + 2 * attn_small_smem<8>();
   size_t m = attn > exch ? attn : exch;
-  if (attn_mma > m) m = attn_mma;
-  if (tc) m = kTcRingBytes + attn_mma;            // TMA ring of the tcgen05 phases + the attention phase beside it
+  if (attn_mma16 > m) m = attn_mma16;
+  if (attn_mma8 > m) m = attn_mma8;
+  // tcgen05 class: TMA ring (the attention K/V buffers overlay it) + the per-team attention arrays after it
+  if (tc) m = kTcRingBytes + 2 * attn_small_smem<8>();
   return m;
 }
 size_t decode_persist_smem_bytes() { return persist_smem_for(true); }

@@ -137,8 +137,6 @@ struct DecodePersistArgs {
   unsigned long long* timestamps; // optional: %globaltimer after every grid barrier (CTA 0), 1 + 8*layers + 3 entries
   int B, Bpad, max_ctx;
   int w8;                         // 1: decoder linears are int8 weight-only (lm_head / embedding stay bf16)
-  int attn_mode;                  // 0: mma.sync attention phase, 1: CUDA-core attention phase (A/B switch)
-  int prefetch;                   // 1: L2-prefetch the next GEMM's weights at the start of every GEMM phase
   // batch class 33..64, bf16 weights: the GEMM phases run on tcgen05 fed by TMA.  Device array of CUtensorMap (128 B each):
   // [4*l + {0: qkv, 1: o, 2: gate/up, 3: down}] weight maps (box 64 k x 128 rows), [4*n_layers] lm_head,
   // [4*n_layers + 1 + {0: u, 1: attn, 2: act}] activation maps (box 64 k x 64 token rows).  nullptr: mma.sync phases.
