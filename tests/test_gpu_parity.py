@@ -88,7 +88,8 @@ def test_mel_time_major_copy(eng_fp32, eng_bf16):
 # tcgen05 GEMM against a float64 product of the bf16-rounded operands
 # ---------------------------------------------------------------------------------------------------------------------
 GEMM_SHAPES = [(128, 128, 64), (256, 384, 128), (300, 256, 1280), (1500, 1280, 1280), (77, 3840, 1280), (1, 128, 64),
-               (270, 3072, 2048), (375, 4096, 5120)]
+               (270, 3072, 2048), (375, 4096, 5120),
+               (40000, 768, 64)]        # 939 tiles of 128 x 256: every CTA of the persistent kernel walks 6+ tiles
 
 
 @pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
