@@ -41,6 +41,31 @@ __device__ __forceinline__ float ex2_approx(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// The softmax warps are issue-bound (ncu: issue-active 67 %, ALU 50 %, XU 41 %, tensor pipe 20 %), so the per-element
+// arithmetic uses Blackwell's packed fp32 pairs and the three-input max: half the FMA / ADD / MNMX instructions.
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+  float2 d;
+  asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\t"
+      "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
+      "fma.rn.f32x2 rd, ra, rb, rc;\n\t"
+      "mov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+  return d;
+}
+__device__ __forceinline__ float2 add2(float2 a, float2 b) {
+  float2 d;
+  asm("{\n\t.reg .b64 ra, rb, rd;\n\t"
+      "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
+      "add.rn.f32x2 rd, ra, rb;\n\t"
+      "mov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return d;
+}
+__device__ __forceinline__ float max3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
 
 __global__ void __launch_bounds__(kAttnThreads, 2)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tm, AttnTcArgs a) {
@@ -142,7 +167,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm, AttnTcArgs a) {
         tmem_ld_wait();
         if (full) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) tmax = fmaxf(tmax, __uint_as_float(v[i]));
+          for (int i = 0; i < 32; i += 2) tmax = max3(tmax, __uint_as_float(v[i]), __uint_as_float(v[i + 1]));
         } else {
 #pragma unroll
           for (int i = 0; i < 32; ++i) tmax = fmaxf(tmax, (c * 32 + i < kv_left) ? __uint_as_float(v[i]) : -INFINITY);
@@ -154,7 +179,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm, AttnTcArgs a) {
       const float m_new = fmaxf(m, fmaxf(tmax, xb[(half ^ 1) * AQ + r]));
       const float corr = ex2_approx((m - m_new) * a.scale_log2);     // m = -inf on the first tile -> 0
       const float mb = m_new * a.scale_log2;
-      float psum = 0.f;
+      float2 psum2 = make_float2(0.f, 0.f);
+      const float2 sc2 = make_float2(a.scale_log2, a.scale_log2), nmb2 = make_float2(-mb, -mb);
       // pass 2: p = exp2(s*scale - m*scale) -> bf16 -> shared memory (K-major SW128: 16 B chunk c8 of row r at (c8 ^ (r & 7)))
 #pragma unroll 1
       for (int c = 0; c < 2; ++c) {
@@ -164,16 +190,15 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm, AttnTcArgs a) {
         uint32_t pk[16];
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
-          float p0 = ex2_approx(fmaf(__uint_as_float(v[i]), a.scale_log2, -mb));
-          float p1 = ex2_approx(fmaf(__uint_as_float(v[i + 1]), a.scale_log2, -mb));
+          const float2 e = fma2(make_float2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])), sc2, nmb2);
+          float p0 = ex2_approx(e.x), p1 = ex2_approx(e.y);
           if (!full) {
             if (c * 32 + i >= kv_left) p0 = 0.f;
             if (c * 32 + i + 1 >= kv_left) p1 = 0.f;
           }
+          // the denominator is the fp32 sum, the numerator uses P cast to bf16: the reference's softmax (fp32) then cast
+          psum2 = add2(psum2, make_float2(p0, p1));
           __nv_bfloat162 pb = __floats2bfloat162_rn(p0, p1);
-          // the denominator sums what the tensor core will actually multiply (bf16-rounded P), like the reference's
-          // softmax-then-cast only up to rounding; keeps rows normalised exactly
-          psum += __low2float(pb) + __high2float(pb);
           pk[i >> 1] = *reinterpret_cast<uint32_t*>(&pb);
         }
 #pragma unroll
@@ -183,7 +208,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm, AttnTcArgs a) {
           *reinterpret_cast<uint4*>(pP + r * 128 + ((chunk ^ (r & 7)) << 4)) = val;
         }
       }
-      l = l * corr + psum;
+      l = l * corr + (psum2.x + psum2.y);
       m = m_new;
       fence_proxy_async_smem();          // generic-proxy writes of P -> visible to the tensor core (async proxy)
       tc_fence_before();
@@ -195,8 +220,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm, AttnTcArgs a) {
         uint32_t v[32];
         tmem_ld32(tO + lane_off + half * 32, v);
         tmem_ld_wait();
+        const float2 corr2 = make_float2(corr, corr);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) o[i] = fmaf(o[i], corr, __uint_as_float(v[i]));
+        for (int i = 0; i < 32; i += 2) {
+          const float2 r2 = fma2(make_float2(o[i], o[i + 1]), corr2, make_float2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])));
+          o[i] = r2.x; o[i + 1] = r2.y;
+        }
       }
       tc_fence_before();
     }
