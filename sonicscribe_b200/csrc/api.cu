@@ -160,6 +160,7 @@ struct sonic_ctx {
   bool persist_tc = false;             // batch class 33..64 of the persistent kernel runs its GEMM phases on tcgen05
   bool use_persist = false;            // one cooperative kernel per greedy step (bf16 mode; SONIC_DECODE=graph disables)
   DecLayerDev* dev_layers = nullptr;
+  void* persist_kv_maps = nullptr;     // device CUtensorMap[2]: K cache, V cache (decode attention phase)
   void* persist_tmaps = nullptr;       // device CUtensorMap array of the tcgen05 decode phases (kernels.h DecodePersistArgs::tmaps)
   float* persist_part = nullptr;
   unsigned* persist_bar = nullptr;
@@ -497,6 +498,7 @@ struct Engine {
       p.gs = h->gs; p.bar = h->persist_bar; p.timestamps = h->cfg.debug ? h->persist_ts : nullptr;
       p.w8 = h->is_int8 ? 1 : 0;
       p.tmaps = h->persist_tc ? h->persist_tmaps : nullptr;
+      p.kv_maps = h->persist_kv_maps; p.kc_base = reinterpret_cast<const bf16*>(h->kcache);
       p.B = B; p.Bpad = (B + 7) / 8 * 8; p.max_ctx = h->max_ctx; p.eps = kRmsEps; p.scale = 0.08838834764831845f;
       TAG(PC_DEC_PERSIST);
       if (h->prof_on) { cudaEventRecord(prof_event(h), h->stream); h->prof_tags.push_back(h->prof_cls); }
@@ -675,6 +677,7 @@ int alloc_all(sonic_ctx* h) {
     DA(h->persist_pick, decode_persist_pick_floats(B, h->num_sms) * 4);
     DA(h->dev_layers, (size_t)c.dec_layers * sizeof(DecLayerDev));
     DA(h->persist_tmaps, (size_t)(4 * c.dec_layers + 4) * sizeof(CUtensorMap));
+    DA(h->persist_kv_maps, 2 * sizeof(CUtensorMap));
   }
   h->dattn_max_chunks = (h->max_ctx + 63) / 64;
   DA(h->dattn_ws, (size_t)B * kDecKv * h->dattn_max_chunks * 4 * 130 * 4);
@@ -1020,6 +1023,14 @@ int sonic_finalize_weights(sonic_handle h) {
       tab[l].vc = reinterpret_cast<bf16*>(h->vcache) + (size_t)l * layer_kv;
     }
     CK(cudaMemcpy(h->dev_layers, tab.data(), tab.size() * sizeof(DecLayerDev), cudaMemcpyHostToDevice));
+    {
+      // K / V caches as 2-D tensors {128 dims, every key row of every layer / segment / kv head}, 64 x 64 boxes
+      CUtensorMap kvm[2];
+      const long long kv_rows = (long long)h->cfg.dec_layers * h->cfg.max_batch * kDecKv * h->max_ctx;
+      CK(make_tensor_map_2d(&kvm[0], h->kcache, kDecHd, kv_rows, kDecHd, 64, 64));
+      CK(make_tensor_map_2d(&kvm[1], h->vcache, kDecHd, kv_rows, kDecHd, 64, 64));
+      CK(cudaMemcpy(h->persist_kv_maps, kvm, sizeof(kvm), cudaMemcpyHostToDevice));
+    }
     const char* ptc = getenv("SONIC_PERSIST_TC");
     h->persist_tc = !h->is_int8 && h->cfg.max_batch > 32 && !(ptc && ptc[0] == '0');
     if (h->persist_tc) {

@@ -563,12 +563,13 @@ __device__ __forceinline__ void team_sync(int team) {
   asm volatile("bar.sync %0, %1;" ::"r"(team + 1), "n"(TW * 32) : "memory");
 }
 template <int TW>
-static constexpr size_t attn_kv_smem() { return (size_t)(kPWarps / TW) * 2 * 2 * (8 * TW) * kARow; }      // teams x 2 buffers x (K + V)
+static constexpr size_t attn_kv_smem() { return (size_t)(kPWarps / TW) * 2 * (8 * TW) * 512; }   // teams x 2 buffers x (K lo|hi, V lo|hi) x 128 B rows
 template <int TW>
 static constexpr size_t attn_small_smem() { return 2 * 4 * (size_t)kARow + (2 * PHD + 8 * TW) * 4; }       // per team
-__device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+// byte offset of the 16 B piece `c16` (0..15 over the 256 B of a key row) of row r inside a chunk part laid out by TMA as
+// two [rows x 128 B] SWIZZLE_128B halves (dims 0..63 | 64..127), `half_bytes` = rows * 128
+__device__ __forceinline__ uint32_t kv_sw(int r, int c16, int half_bytes) {
+  return (uint32_t)((c16 >> 3) * half_bytes + r * 128 + ((((c16 & 7) ^ (r & 7))) << 4));
 }
 
 template <int KSQ, int TW>
@@ -578,45 +579,56 @@ __device__ __forceinline__ void attention_phase_mma(const DecodePersistArgs& a, 
   constexpr int TT = 32 * TW;                             // threads per team
   constexpr int NTEAM = kPWarps / TW;
   constexpr int NTD = 16 / TW;                            // 8-dim output tiles per warp
-  constexpr int kHalf = CK * kARow;                       // bytes of the K (or V) part of a buffer
+  constexpr int kHalfB = CK * 128;                        // one [CK rows x 128 B] swizzled half of K or V
+  constexpr int kBuf = 4 * kHalfB;                        // K lo | K hi | V lo | V hi
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
   const int team = warp / TW, wt = warp - team * TW, tt = tid - team * TT;
-  uint8_t* kv = smem_kv + (size_t)team * 4 * kHalf;        // buffer b: K at b*2*kHalf, V at b*2*kHalf + kHalf
+  uint8_t* kv = smem_kv + (size_t)team * 2 * kBuf;         // two buffers
   uint8_t* small = smem_small + (size_t)team * attn_small_smem<TW>();
   uint8_t* sQ = small;                                    // [4][272 B]   rotated query heads (bf16); MMA rows 4..15 are zero registers
   uint8_t* sP = sQ + 4 * kARow;                           // [4][272 B]   probabilities of the chunk (bf16)
   float* sKV = reinterpret_cast<float*>(sP + 4 * kARow);  // new k (128) | new v (128)
   float* sMax = sKV + 2 * PHD;                            // [4 heads][TW warps]
   float* sSum = sMax + 4 * TW;                            // [4 heads][TW warps]
+  const CUtensorMap* kmap = reinterpret_cast<const CUtensorMap*>(a.kv_maps);
+  const CUtensorMap* vmap = kmap + 1;
   const int n_items = a.B * PKVH;
   const int item_stride = gridDim.x * NTEAM;
   auto bar_of = [&](uint32_t b) { return bars + 8u * (team * 2 + b); };
-  // rows [0, nk) of the chunk starting at key k0, except the row appended this step (written from sKV when the chunk is used)
-  auto issue_chunk = [&](const bf16* kc, const bf16* vc, int k0, int nk, int pos, uint32_t b) {
-    if (tt == 0) mbar_expect_tx(bar_of(b), (uint32_t)(nk - ((pos >= k0 && pos < k0 + nk) ? 1 : 0)) * 2u * (PHD * 2));
-    for (int i = tt; i < 2 * CK; i += TT) {
-      const int isv = i >= CK ? 1 : 0, r = i - isv * CK;
-      if (r < nk && k0 + r != pos)
-        bulk_copy_g2s(smem_u32(kv + (size_t)b * 2 * kHalf + (size_t)isv * kHalf + (size_t)r * kARow), (isv ? vc : kc) + (size_t)(k0 + r) * PHD,
-                      PHD * 2, bar_of(b));
+  // one thread asks TMA for the whole chunk: [64 keys x 64 dims] boxes of the K and V caches (one 2-D map per cache over all
+  // layers, segments and kv heads; row = key), landing as SWIZZLE_128B halves.  Rows past the context are finite cache
+  // contents (masked below); the row appended this step is overwritten from sKV after the chunk has landed.
+  auto issue_chunk = [&](int row0, int k0, uint32_t b) {
+    if (tt == 0) {
+      mbar_expect_tx(bar_of(b), (uint32_t)kBuf);
+      const uint32_t dst = smem_u32(kv + (size_t)b * kBuf);
+#pragma unroll
+      for (int s2 = 0; s2 < CK / 64; ++s2) {
+#pragma unroll
+        for (int h2 = 0; h2 < 2; ++h2) {
+          tma_load_2d(dst + h2 * kHalfB + s2 * 8192, kmap, bar_of(b), 64 * h2, row0 + k0 + 64 * s2);
+          tma_load_2d(dst + 2 * kHalfB + h2 * kHalfB + s2 * 8192, vmap, bar_of(b), 64 * h2, row0 + k0 + 64 * s2);
+        }
+      }
     }
   };
-  auto group_of = [&](int item, int& seg, int& kvh, int& pos, const bf16*& kc, const bf16*& vc) {
+  auto group_of = [&](int item, int& seg, int& kvh, int& pos, int& row0) {
     seg = item / PKVH; kvh = item - seg * PKVH;
     pos = a.gs.ctx_len[seg];
-    kc = L.kc + ((size_t)seg * PKVH + kvh) * a.max_ctx * PHD;
-    vc = L.vc + ((size_t)seg * PKVH + kvh) * a.max_ctx * PHD;
+    row0 = (int)((L.kc - a.kc_base) / PHD) + (seg * PKVH + kvh) * a.max_ctx;
   };
   int item = blockIdx.x * NTEAM + team;
   if (item < n_items) {
-    int seg, kvh, pos; const bf16 *kc, *vc;
-    group_of(item, seg, kvh, pos, kc, vc);
-    issue_chunk(kc, vc, 0, min(CK, pos + 1), pos, n_chunk & 1u);
+    int seg, kvh, pos, row0;
+    group_of(item, seg, kvh, pos, row0);
+    issue_chunk(row0, 0, n_chunk & 1u);
   }
   for (; item < n_items; item += item_stride) {
-    int seg, kvh, pos; const bf16 *kc, *vc;
-    group_of(item, seg, kvh, pos, kc, vc);
+    int seg, kvh, pos, row0;
+    group_of(item, seg, kvh, pos, row0);
     const int kv_len = pos + 1;
+    bf16* kcw = L.kc + ((size_t)seg * PKVH + kvh) * a.max_ctx * PHD;
+    bf16* vcw = L.vc + ((size_t)seg * PKVH + kvh) * a.max_ctx * PHD;
     team_sync<TW>(team);                                   // previous group's fragments are consumed
     for (int i = tt; i < (PG + 2) * (PHD / 2); i += TT) {
       const int hh = i / (PHD / 2), j = i - hh * (PHD / 2);     // hh < 4: query head; 4: key; 5: value (pair j, j+64)
@@ -633,11 +645,8 @@ __device__ __forceinline__ void attention_phase_mma(const DecodePersistArgs& a, 
       } else { sKV[PHD + j] = x; sKV[PHD + j + PHD / 2] = y; }
     }
     team_sync<TW>(team);
-    {
-      bf16* kcw = const_cast<bf16*>(kc); bf16* vcw = const_cast<bf16*>(vc);
-      if (tt < PHD) kcw[(size_t)pos * PHD + tt] = __float2bfloat16_rn(sKV[tt]);
-      else if (tt < 2 * PHD) vcw[(size_t)pos * PHD + tt - PHD] = __float2bfloat16_rn(sKV[tt]);
-    }
+    if (tt < PHD) kcw[(size_t)pos * PHD + tt] = __float2bfloat16_rn(sKV[tt]);
+    else if (tt < 2 * PHD) vcw[(size_t)pos * PHD + tt - PHD] = __float2bfloat16_rn(sKV[tt]);
     float m_run = -INFINITY, l_part = 0.f;                 // online-softmax state of head g (lanes with g < 4); l_part: this lane's keys only
     float o[NTD][2];                                       // O[head g][dims 8*(NTD*wt + nt) + 2t, +1]
 #pragma unroll
@@ -645,35 +654,31 @@ __device__ __forceinline__ void attention_phase_mma(const DecodePersistArgs& a, 
     for (int k0 = 0; k0 < kv_len; k0 += CK, ++n_chunk) {
       const int nk = min(CK, kv_len - k0);
       const uint32_t b = n_chunk & 1u;
-      uint8_t* sK = kv + (size_t)b * 2 * kHalf;
-      uint8_t* sV = sK + kHalf;
-      // rows that do not come from the cache: the appended row (from sKV) and, in a ragged last chunk, zero V rows
-      if (pos >= k0 && pos < k0 + CK && tt < 32) {
-        const int r = pos - k0, c8 = tt & 15, isv = tt >> 4;
+      uint8_t* sK = kv + (size_t)b * kBuf;
+      uint8_t* sV = sK + 2 * kHalfB;
+      mbar_wait(bar_of(b), (n_chunk >> 1) & 1u);           // this chunk has landed
+      if (pos >= k0 && pos < k0 + CK && tt < 32) {         // the appended row comes from sKV, not from the cache
+        const int r = pos - k0, c16 = tt & 15, isv = tt >> 4;
         uint32_t w[4];
 #pragma unroll
         for (int e2 = 0; e2 < 4; ++e2) {
-          __nv_bfloat162 q2 = __floats2bfloat162_rn(sKV[isv * PHD + c8 * 8 + 2 * e2], sKV[isv * PHD + c8 * 8 + 2 * e2 + 1]);
+          __nv_bfloat162 q2 = __floats2bfloat162_rn(sKV[isv * PHD + c16 * 8 + 2 * e2], sKV[isv * PHD + c16 * 8 + 2 * e2 + 1]);
           w[e2] = *reinterpret_cast<uint32_t*>(&q2);
         }
-        *reinterpret_cast<uint4*>((isv ? sV : sK) + r * kARow + c8 * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+        *reinterpret_cast<uint4*>((isv ? sV : sK) + kv_sw(r, c16, kHalfB)) = make_uint4(w[0], w[1], w[2], w[3]);
       }
-      if (nk < CK) {
-        for (int i = tt; i < (CK - nk) * 16; i += TT)
-          *reinterpret_cast<uint4*>(sV + (nk + (i >> 4)) * kARow + (i & 15) * 16) = make_uint4(0, 0, 0, 0);
-      }
-      mbar_wait(bar_of(b), (n_chunk >> 1) & 1u);           // this chunk's rows have landed
-      team_sync<TW>(team);                                 // fix-up rows visible; the other buffer is fully consumed
+      team_sync<TW>(team);                                 // fix-up row visible; the other buffer is fully consumed
       fence_proxy_async_smem();                            // ... by generic-proxy reads, before the async proxy overwrites it
       if (k0 + CK < kv_len) {
-        issue_chunk(kc, vc, k0 + CK, min(CK, kv_len - k0 - CK), pos, b ^ 1u);
+        issue_chunk(row0, k0 + CK, b ^ 1u);
       } else if (item + item_stride < n_items) {
-        int nseg, nkvh, npos; const bf16 *nkc, *nvc;
-        group_of(item + item_stride, nseg, nkvh, npos, nkc, nvc);
-        issue_chunk(nkc, nvc, 0, min(CK, npos + 1), npos, b ^ 1u);
+        int nseg, nkvh, npos, nrow0;
+        group_of(item + item_stride, nseg, nkvh, npos, nrow0);
+        issue_chunk(nrow0, 0, b ^ 1u);
       }
       // S tile of this warp: keys 8*wt + {2t, 2t+1} for head g
       float sc[4] = {0.f, 0.f, 0.f, 0.f};
+      const int kr = 8 * wt + g;                           // key row of this lane's B fragment
 #pragma unroll
       for (int ks = 0; ks < 8; ++ks) {
         uint32_t qa0 = 0u, qa2 = 0u;                       // Q fragment: row g of the 16-row tile, zero for g >= 4
@@ -681,8 +686,8 @@ __device__ __forceinline__ void attention_phase_mma(const DecodePersistArgs& a, 
           qa0 = *reinterpret_cast<const uint32_t*>(sQ + g * kARow + (16 * ks + 2 * t) * 2);
           qa2 = *reinterpret_cast<const uint32_t*>(sQ + g * kARow + (16 * ks + 8 + 2 * t) * 2);
         }
-        const uint32_t b0 = *reinterpret_cast<const uint32_t*>(sK + (8 * wt + g) * kARow + (16 * ks + 2 * t) * 2);
-        const uint32_t b1 = *reinterpret_cast<const uint32_t*>(sK + (8 * wt + g) * kARow + (16 * ks + 8 + 2 * t) * 2);
+        const uint32_t b0 = *reinterpret_cast<const uint32_t*>(sK + kv_sw(kr, 2 * ks, kHalfB) + 4 * t);
+        const uint32_t b1 = *reinterpret_cast<const uint32_t*>(sK + kv_sw(kr, 2 * ks + 1, kHalfB) + 4 * t);
         mma16816(sc, qa0, 0u, qa2, 0u, b0, b1);
       }
       const int key0 = 8 * wt + 2 * t;
@@ -722,7 +727,7 @@ __device__ __forceinline__ void attention_phase_mma(const DecodePersistArgs& a, 
 #pragma unroll
         for (int nt = 0; nt < NTD; ++nt) {
           uint32_t vb0, vb1;
-          ldmatrix_x2_trans(vb0, vb1, sV + (16 * ks + (lane & 15)) * kARow + 16 * (NTD * wt + nt));
+          ldmatrix_x2_trans(vb0, vb1, sV + kv_sw(16 * ks + (lane & 15), NTD * wt + nt, kHalfB));
           mma16816(oc[nt], pa0, 0u, pa2, 0u, vb0, vb1);
         }
       }
@@ -809,8 +814,8 @@ __global__ void __launch_bounds__(kPThreads, 1) decode_persist_kernel(DecodePers
   // attention: K/V chunk buffers overlay the (then idle) TMA ring / GEMM staging area, the small per-team arrays sit after it
   constexpr int ATW = (NT == 8) ? 8 : 16;                 // attention team width of this batch class
   const uint32_t ring_off = ((smem_u32(smem) + 1023u) & ~1023u) - smem_u32(smem);
-  uint8_t* smem_kv = TC ? smem + ring_off : smem;
-  uint8_t* smem_small = TC ? smem + ring_off + kTcStages * (kTcStageA + kTcStageB) : smem + attn_kv_smem<ATW>();
+  uint8_t* smem_kv = smem + ring_off;                     // 1024 B aligned (TMA swizzle atoms)
+  uint8_t* smem_small = smem + ring_off + (TC ? (size_t)kTcStages * (kTcStageA + kTcStageB) : attn_kv_smem<ATW>());
 
   // ---- phase 0: x = E[cur_tok]; u = rmsnorm(x) * g(layer 0 input norm)
   for (int b = blockIdx.x; b < B; b += gridDim.x) {
@@ -954,7 +959,7 @@ __global__ void __launch_bounds__(kPThreads, 1) decode_persist_kernel(DecodePers
 static size_t persist_smem_for(bool tc) {
   const size_t attn = (size_t)AKEYS * kAKRow + (size_t)AKEYS * PHD * 2 + (PG * PHD + PG * AKEYS + 2 * PHD + 32 + 16) * 4;
   const size_t exch = (size_t)kXStageBytes + (size_t)kPWarps * 2 * 4 * 128 * 4;    // staged activations + 16 warps x NT(4) x 128 fp32 (>= the unstaged NT = 8 exchange)
-  const size_t attn_mma16 = attn_kv_smem<16>() + attn_small_smem<16>(), attn_mma8 = attn_kv_smem<8>() + 2 * attn_small_smem<8>();
+  const size_t attn_mma16 = 1024 + attn_kv_smem<16>() + attn_small_smem<16>(), attn_mma8 = 1024 + attn_kv_smem<8>() + 2 * attn_small_smem<8>();
   size_t m = attn > exch ? attn : exch;
   if (attn_mma16 > m) m = attn_mma16;
   if (attn_mma8 > m) m = attn_mma8;

@@ -141,6 +141,9 @@ struct DecodePersistArgs {
   // [4*l + {0: qkv, 1: o, 2: gate/up, 3: down}] weight maps (box 64 k x 128 rows), [4*n_layers] lm_head,
   // [4*n_layers + 1 + {0: u, 1: attn, 2: act}] activation maps (box 64 k x 64 token rows).  nullptr: mma.sync phases.
   const void* tmaps;
+  // attention phase: device array of two CUtensorMap over the whole K and V caches ({128 dims, layers*batch*4*max_ctx key rows},
+  // box 64 dims x 64 keys, 128B swizzle); kc_base = first element of the K cache (row 0 of the maps)
+  const void* kv_maps; const bf16* kc_base;
   float eps, scale;
 };
 size_t decode_persist_smem_bytes();
