@@ -177,14 +177,16 @@ def run_ours(args):
 
     from sonicscribe_b200.engine import FLAG_PCM_DEVICE, FLAG_REFERENCE_PRESTEP, Engine, num_audio_tokens
     from sonicscribe_b200.prompt import synthetic_prompt_ids
-    from sonicscribe_b200.weights import ModelDims, synthetic_state_dict
+    from sonicscribe_b200.weights import ModelDims, iter_synthetic_tensors, synthetic_state_dict
 
     B, G = args.batch, args.max_new
     dims = ModelDims(enc_layers=args.enc_layers, dec_layers=args.dec_layers)
     t0 = time.time()
-    sd = synthetic_state_dict(dims, seed=0)
     eng = Engine(dims.enc_layers, dims.dec_layers, mode=args.mode, device=local, max_batch=B, max_prompt=320, max_new=G)
-    eng.load_state_dict(sd)
+    # only the rank that times the CPU baseline keeps the 9 GB fp32 checkpoint on the host; everyone else streams it
+    need_sd = rank == 0 and world == 1 and not args.no_cpu_baseline
+    sd = synthetic_state_dict(dims, seed=0) if need_sd else None
+    eng.load_state_dict(sd if need_sd else iter_synthetic_tensors(dims, seed=0))
     if rank == 0:
         log(f"[bench] weights ready in {time.time() - t0:.1f}s; device bytes {eng.device_bytes() / 2**30:.2f} GiB")
 
@@ -291,7 +293,7 @@ def run_ours(args):
             "launches_timed": c["launches"], "share_of_step": c["ms"] / total_prof if total_prof > 0 else None,
         }
         cpu_base = None
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:          # the CPU baseline is timed on rank 0 of the 1-GPU run only
             t1 = time.time()
             v, detail = cpu_reference_sample(sd, dims, args.ref_sample_tokens, G, os.cpu_count() or 1)
             cpu_base = {"value": v, "unit": "audio-seconds/second", "cores": os.cpu_count() or 1, "kind": "port",

@@ -134,10 +134,11 @@ class Engine:
 
     # -- weights ------------------------------------------------------------------------------------------------------
     def load_state_dict(self, sd: dict):
-        """sd: HF-named tensors (torch CPU tensors or numpy arrays), fp32 or bf16."""
+        """sd: HF-named tensors (torch CPU tensors or numpy arrays), fp32 or bf16 — a dict, or any iterable of
+        (name, tensor) pairs (tensors are consumed one at a time, so a generator keeps the host footprint at one tensor)."""
         import torch  # plumbing only: reading checkpoint tensors
 
-        for name, t in sd.items():
+        for name, t in (sd.items() if hasattr(sd, "items") else sd):
             if isinstance(t, np.ndarray):
                 t = torch.from_numpy(t)
             t = t.detach().cpu().contiguous()

@@ -102,6 +102,13 @@ def synthetic_state_dict(dims: ModelDims = ModelDims(), seed: int = 0, dtype=tor
     return {n: synthetic_tensor(n, s, k, seed).to(dtype) for n, s, k in tensor_specs(dims)}
 
 
+def iter_synthetic_tensors(dims: ModelDims = ModelDims(), seed: int = 0, dtype=torch.float32):
+    """The same tensors as ``synthetic_state_dict``, one (name, tensor) at a time: the full-size checkpoint is 9 GB in fp32,
+    which eight benchmark ranks on one host should not each hold while their engine only needs one tensor at a time."""
+    for n, s, k in tensor_specs(dims):
+        yield n, synthetic_tensor(n, s, k, seed).to(dtype)
+
+
 def load_checkpoint_dir(path: str) -> dict:
     """Flat state dict from a HF checkpoint directory (``model*.safetensors``)."""
     from safetensors.torch import load_file  # local import: only needed with a real checkpoint

@@ -96,3 +96,17 @@ def test_model_oracle_vs_hf_golden_tiny(golden_dir):
 def test_model_oracle_vs_hf_golden_full_short(golden_dir):
     # full-size model, the 1.28 s / 15-token interim case (~40 s on 8 cores)
     _check_model(golden_dir, "full", ModelDims(), [1])
+
+
+def test_streamed_synthetic_checkpoint_equals_dict():
+    """bench.py streams the synthetic checkpoint tensor by tensor; same names, order and values as the dict form."""
+    import torch
+    from sonicscribe_b200.weights import ModelDims, iter_synthetic_tensors, synthetic_state_dict
+    dims = ModelDims(enc_layers=1, dec_layers=1)
+    sd = synthetic_state_dict(dims, seed=3)
+    names = []
+    for name, t in iter_synthetic_tensors(dims, seed=3):
+        names.append(name)
+        if t.numel() < 4_000_000:
+            assert torch.equal(t, sd[name]), name
+    assert names == list(sd.keys())
