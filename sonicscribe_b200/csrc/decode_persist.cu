@@ -4,11 +4,18 @@
 //
 // Why: a decode step moves 2.9 GB of weights (0.45 ms at HBM speed) through ~200 tiny dependent operations; as separate
 // kernels each one costs ~9-20 us of launch/setup/drain latency (measured).  Here every SM keeps 16 warps
-// resident for the whole step; each warp streams 16 weight rows x a K-slice straight from global memory into mma.sync
-// fragments (16 B loads, 8 in flight per lane => ~64 KB in flight per SM, which is what saturates HBM; the tensor pipe is
-// irrelevant at <= 64 tokens), multiplies them with the (L1-resident) activation slice and writes an fp32 partial.  The
-// consumer phase sums the partials in split order (deterministic, batch-invariant) while applying residual / RMSNorm /
-// RoPE / SwiGLU, so those never exist as separate passes.
+// resident for the whole step, one kernel instantiation per batch class:
+//   * 33..64 tokens, bf16: every GEMM phase is TMA (6-stage ring) -> tcgen05.mma (128 weight rows x 64 tokens, two TMEM
+//     accumulators) -> tcgen05.ld epilogue; split-K partials are summed by the consumer phase; the next phase's weight tiles
+//     are put in flight before the grid barrier (gemm_phase_tc).
+//   * <= 32 tokens, and int8 weights: each warp streams 16 weight rows x a K-slice straight from global memory into
+//     mma.sync fragments (16 B loads, 8 in flight per lane), the 16 warps of a CTA split K and reduce through shared memory
+//     (gemm_phase).
+//   * attention: a team of warps per (segment, kv head); K/V chunks by TMA tile loads into two alternating buffers,
+//     QK^T / online softmax / PV on mma.sync (attention_phase_mma); with few segments the keys are split over CTAs with a
+//     last-arriver merge (attention_phase).
+// Every reduction has a fixed order (deterministic); residual / RMSNorm / RoPE / SwiGLU / KV append / argmax are phases or
+// epilogues of the same kernel and never exist as separate passes.
 //
 // Replaces, for one new token per segment: LlamaDecoderLayer x28 + final norm + lm_head + argmax/EOS bookkeeping
 // (transformers/models/llama/modeling_llama.py:53-499, transformers/generation/utils.py:2743-2809).
