@@ -35,10 +35,14 @@ typedef struct sonic_ctx* sonic_handle;
 
 enum { SONIC_MODE_BF16 = 0, SONIC_MODE_FP32 = 1, SONIC_MODE_INT8 = 2 };
 enum { SONIC_DTYPE_F32 = 0, SONIC_DTYPE_BF16 = 1 };
+/* return codes: 0 ok, -1 failure (message in sonic_last_error), -2 sonic_load_tensor was given a name the model does not have */
+#define SONIC_ERR_UNKNOWN_TENSOR (-2)
 
 /* flags of sonic_mel / sonic_transcribe_batch */
 #define SONIC_FLAG_PEAK_NORM   0x01  /* asr.py:265-267  wav / max|wav| when max > 1e-6                         */
 #define SONIC_FLAG_PCM16       0x02  /* asr.py:276      soundfile PCM_16 write + float re-load                  */
+#define SONIC_FLAG_PCM_S16     0x04  /* pcm holds int16 LE samples (the WebSocket wire format, pcm-processor.js:59-75): widened to
+                                        float32 / 32768 on the device, as transcription_manager.py:45-51 does on the host        */
 #define SONIC_FLAG_PCM_DEVICE  0x10  /* pcm pointer is device memory (bench: inputs resident in HBM)            */
 #define SONIC_FLAG_OUT_DEVICE  0x20  /* features pointer of sonic_mel is device memory                          */
 #define SONIC_FLAG_REFERENCE_PRESTEP (SONIC_FLAG_PEAK_NORM | SONIC_FLAG_PCM16)
@@ -68,11 +72,12 @@ SONIC_API int sonic_load_tensor(sonic_handle h, const char* name, const void* da
 SONIC_API int sonic_finalize_weights(sonic_handle h);
 
 /* Pre-step + log-mel for `batch` segments.  Segment b is pcm[offsets[b] .. offsets[b]+lengths[b]) (float32, 16 kHz mono).
+ * With SONIC_FLAG_PCM_S16 `pcm` points at int16 samples instead (offsets still count samples).
  * Writes input_features [batch,128,3000] float32 to `features` (may be NULL) and the valid-frame count
  * (input_features_mask.sum(), ceil(min(n,480000)/160)) to n_frames[b].  The time-major copy the encoder consumes stays
  * in the handle.  Replaces asr.py:230-278 + WhisperFeatureExtractor.__call__
  * (transformers/models/whisper/feature_extraction_whisper.py:135-164,296-337). */
-SONIC_API int sonic_mel(sonic_handle h, const float* pcm, const int64_t* offsets, const int32_t* lengths, int32_t batch,
+SONIC_API int sonic_mel(sonic_handle h, const void* pcm, const int64_t* offsets, const int32_t* lengths, int32_t batch,
               int32_t flags, float* features, int32_t* n_frames);
 
 /* Encoder + adapter on the features left in the handle by sonic_mel.  audio_embeds (may be NULL) receives
@@ -89,7 +94,7 @@ SONIC_API int sonic_generate(sonic_handle h, const int32_t* ids, const int32_t* 
                    int32_t* out_ids, int32_t* n_out, float* margins);
 
 /* The whole of ASRModel.transcribe up to (not including) tokenizer decode, for a batch of segments. */
-SONIC_API int sonic_transcribe_batch(sonic_handle h, const float* pcm, const int64_t* offsets, const int32_t* lengths, int32_t batch,
+SONIC_API int sonic_transcribe_batch(sonic_handle h, const void* pcm, const int64_t* offsets, const int32_t* lengths, int32_t batch,
                            int32_t flags, const int32_t* ids, const int32_t* id_offsets, int32_t max_new_tokens,
                            int32_t* out_ids, int32_t* n_out, float* margins);
 
@@ -111,6 +116,9 @@ SONIC_API int32_t sonic_profile_num_classes(void);
 SONIC_API const char* sonic_profile_class_name(int32_t c);
 /* Copy an intermediate tensor as float32 (handle created with debug=1):
  * "mel_tm", "conv_out", "enc_layer0", "enc_out", "audio_embeds", "first_logits", "dec_layer0", "rope_enc_cos", ... */
+/* debug handles: keep the full fp32 logit rows of these greedy steps (step 0 = prefill); read them back as
+ * "step_logits@<step>" [batch, 59264].  At most 8 steps; n = 0 clears.  Such handles run the decode loop eagerly. */
+SONIC_API int sonic_debug_set_logit_steps(sonic_handle h, const int32_t* steps, int32_t n);
 SONIC_API int sonic_debug_read(sonic_handle h, const char* name, float* out, size_t max_elems, size_t* n_elems);
 
 /* Stand-alone kernel entry points for the unit tests and the roofline bench (device pointers, handle's stream).

@@ -195,8 +195,9 @@ def embed_merge(w: dict, ids: torch.Tensor, audio_embeds: torch.Tensor) -> torch
 
 @torch.no_grad()
 def generate_greedy(w: dict, cfg: OracleConfig, mel: torch.Tensor, n_audio: int, ids, max_new_tokens: int,
-                    eos_ids=EOS_IDS, probes: dict | None = None):
-    """Full path: mel [128,3000] + prompt ids -> (new token ids list, top-2 margins list, first-step logits)."""
+                    eos_ids=EOS_IDS, probes: dict | None = None, logit_steps=()):
+    """Full path: mel [128,3000] + prompt ids -> (new token ids list, top-2 margins list, first-step logits).
+    ``logit_steps``: greedy steps (0 = prefill) whose fp32 logit rows are stored in ``probes["step_logits"][step]``."""
     ids = torch.as_tensor(ids, dtype=torch.long)
     enc = encoder_forward(w, cfg, mel, probes)
     ae = adapter_forward(w, cfg, enc, n_audio)
@@ -210,6 +211,8 @@ def generate_greedy(w: dict, cfg: OracleConfig, mel: torch.Tensor, n_audio: int,
     pos = ids.shape[0]
     for _ in range(max_new_tokens):
         lf = logits.float()
+        if probes is not None and len(out) in logit_steps:
+            probes.setdefault("step_logits", {})[len(out)] = lf.clone()
         top2 = torch.topk(lf, 2)
         tok = int(torch.argmax(lf))                                      # first max index on ties
         out.append(tok)

@@ -8,24 +8,32 @@ Differences from the reference, on purpose:
 * ``mode`` additionally accepts "fp32" (the parity arithmetic); "int8" is weight-only int8 (no bitsandbytes);
 * ``checkpoint_dir`` may be ``"synthetic[:seed=S,enc=E,dec=D]"`` to instantiate the seeded random checkpoint used by
   the tests and the benchmark (there is no network access to fetch GLM-ASR-Nano-2512);
-* ``transcribe_batch`` processes several independent segments in one device pass (weights are streamed once per
-  decode step for the whole batch).
+* concurrent ``transcribe`` calls (the reference's three executor threads + the event loop, main.py:429-445,
+  transcription_manager.py:58) are coalesced by ``batcher.DynamicBatcher`` into one device pass — weights are streamed
+  once per decode step for the whole batch; ``transcribe_batch`` hands a list of segments to the same queue;
+* ``transcribe_pcm16`` takes the int16 wire format directly (no float detour on the host).
 """
 from __future__ import annotations
 
+import os
 import time
+import weakref
 from pathlib import Path
 from typing import Any, Dict, List, Optional, Sequence, Union
 
 import numpy as np
 import torch
 
-from .engine import FLAG_REFERENCE_PRESTEP, Engine, num_audio_tokens
+from .batcher import DynamicBatcher, Request
+from .engine import FLAG_PCM_S16, FLAG_REFERENCE_PRESTEP, Engine, num_audio_tokens
 from .prompt import PromptBuilder
 from .weights import ModelDims, dims_from_state_dict, load_checkpoint_dir, synthetic_state_dict
 
 EOS_IDS = (59246, 59253, 59255)
 MAX_SAMPLES = 480000
+# worst-case prompt: 375 audio tokens (30 s) + chat template (~20) + base instruction (~10) + ten quoted hotwords of
+# several tokens each (CJK / product names): ~500-600.  The engine's buffers are sized from this at construction.
+DEFAULT_MAX_PROMPT = 640
 
 
 def _parse_synthetic(spec: str):
@@ -44,10 +52,27 @@ def _parse_synthetic(spec: str):
     return seed, ModelDims(enc_layers=enc, dec_layers=dec)
 
 
+def _run_batch(ref: "weakref.ReferenceType[ASRModel]", reqs: List[Request]):
+    """Worker-thread body of the batcher: one sonic_transcribe_batch call for the whole group."""
+    self = ref()
+    eng = getattr(self, "model", None) if self is not None else None
+    if eng is None or eng.h is None:
+        raise RuntimeError("ASR model has been released")
+    flags = FLAG_REFERENCE_PRESTEP | (FLAG_PCM_S16 if reqs[0].s16 else 0)
+    g = max(r.max_new for r in reqs)
+    t0 = time.perf_counter()
+    out = eng.transcribe_ids([r.wav for r in reqs], [r.prompt for r in reqs], g, flags)
+    info = eng.stage_times()
+    info["batch_size"] = len(reqs)
+    info["batch_wall_s"] = time.perf_counter() - t0
+    return out, info
+
+
 class ASRModel:
     def __init__(self, checkpoint_dir: str, device: str = "cuda", mode: str = "native", cpu_threads: Optional[int] = None,
-                 cpu_interop_threads: Optional[int] = None, *, max_batch: int = 8, max_prompt: int = 448, max_new_tokens: int = 256,
-                 state_dict: Optional[dict] = None, debug: bool = False):
+                 cpu_interop_threads: Optional[int] = None, *, max_batch: Optional[int] = None, max_prompt: int = DEFAULT_MAX_PROMPT,
+                 max_new_tokens: int = 256, state_dict: Optional[dict] = None, debug: bool = False,
+                 batch_window_ms: Optional[float] = None, engine: Optional[Engine] = None):
         if mode not in ("native", "int8", "fp32"):
             raise ValueError("mode must be either 'native' or 'int8'")       # message of asr.py:47
         dev = torch.device(device)
@@ -60,8 +85,16 @@ class ASRModel:
         self.target_sr = 16000
         self.is_glm_asr = True
         self.processor = None
+        if max_batch is None:
+            max_batch = int(os.environ.get("SONIC_MAX_BATCH", "16"))
+        if batch_window_ms is None:
+            batch_window_ms = float(os.environ.get("SONIC_BATCH_WINDOW_MS", "3"))
 
-        if state_dict is not None:
+        if engine is not None:
+            # wrap an already loaded replica (bench.py measures the class and the raw C ABI on the same weights)
+            sd, dims = None, ModelDims(enc_layers=engine.cfg.enc_layers, dec_layers=engine.cfg.dec_layers)
+            max_batch, max_prompt, max_new_tokens = engine.max_batch, engine.max_prompt, engine.max_new
+        elif state_dict is not None:
             sd, dims = state_dict, dims_from_state_dict(state_dict)
         elif str(checkpoint_dir).startswith("synthetic"):
             seed, dims = _parse_synthetic(str(checkpoint_dir))
@@ -73,22 +106,40 @@ class ASRModel:
                 from transformers import AutoProcessor
 
                 self.processor = AutoProcessor.from_pretrained(str(self.checkpoint_dir))
-            except Exception as e:  # pragma: no cover - needs a real checkpoint
+            except Exception as e:
                 raise RuntimeError(f"could not load the processor from {checkpoint_dir}: {e}")
         self.config = dims
-        self.model = Engine(dims.enc_layers, dims.dec_layers, mode={"native": "bf16"}.get(mode, mode), device=dev.index or 0,
-                            max_batch=max_batch, max_prompt=max_prompt, max_new=max_new_tokens, debug=debug)
-        self.model.load_state_dict(sd)
-        self._prompts = PromptBuilder(self.processor)
+        self._owns_engine = engine is None
+        if engine is not None:
+            self.model = engine
+        else:
+            self.model = Engine(dims.enc_layers, dims.dec_layers, mode={"native": "bf16"}.get(mode, mode), device=dev.index or 0,
+                                max_batch=max_batch, max_prompt=max_prompt, max_new=max_new_tokens, debug=debug)
+            self.model.load_state_dict(sd)
+        self._prompts = PromptBuilder(self.processor, max_prompt=max_prompt)
         self._max_batch = max_batch
+        self._max_new = max_new_tokens
+        ref = weakref.ref(self)
+        self._batcher = DynamicBatcher(lambda reqs: _run_batch(ref, reqs), max_batch, batch_window_ms / 1000.0)
 
     # -- helpers ------------------------------------------------------------------------------------------------------
     def close(self):
-        if getattr(self, "model", None) is not None:
+        b = self.__dict__.get("_batcher")
+        if b is not None:
+            b.close()
+        if self.__dict__.get("model") is not None and self.__dict__.get("_owns_engine", True):
             self.model.close()
 
+    def __del__(self):
+        try:
+            b = self.__dict__.get("_batcher")
+            if b is not None:
+                b.close()
+        except Exception:
+            pass
+
     def _engine(self) -> Engine:
-        eng = getattr(self, "model", None)
+        eng = getattr(self, "model", None)          # main.py:84-88 deletes the attribute at shutdown
         if eng is None or eng.h is None:
             raise RuntimeError("ASR model has been released")
         return eng
@@ -107,48 +158,65 @@ class ASRModel:
                 raise RuntimeError(f"resampling from {sampling_rate} Hz needs torchaudio: {e}")
             wav = torchaudio.transforms.Resample(orig_freq=sampling_rate, new_freq=self.target_sr)(wav)
         wav = wav.squeeze(0).contiguous().numpy()
-        n = wav.shape[0]
+        self._check_length(wav.shape[0])
+        return wav
+
+    @staticmethod
+    def _check_length(n: int):
         if n > MAX_SAMPLES:
             raise ValueError(f"segment of {n} samples exceeds the 30 s window; callers cut segments first "
                              "(backend/main.py:527-567, connection_manager.py:204-236)")
         if num_audio_tokens(n) <= 0:
             raise ValueError(f"segment of {n} samples is too short to produce an audio token")
-        return wav
 
     def _decode(self, ids: List[int]) -> str:
         if self.processor is not None:
-            return self.processor.batch_decode([ids], skip_special_tokens=True)[0].strip()
+            return self.processor.batch_decode([ids], skip_special_tokens=True)[0].strip()     # asr.py:425-429
         return " ".join(f"<{t}>" for t in ids if t not in EOS_IDS).strip()
+
+    def _submit(self, wavs: Sequence[np.ndarray], s16: bool, max_new_tokens: int, hotwords) -> List[Request]:
+        self._engine()
+        if max_new_tokens < 1 or max_new_tokens > self._max_new:
+            raise ValueError(f"max_new_tokens={max_new_tokens} outside 1..{self._max_new} (the engine's decode buffers)")
+        reqs = [Request(w, s16, self._prompts.build(num_audio_tokens(w.shape[0]), hotwords), max_new_tokens) for w in wavs]
+        self._batcher.submit_many(reqs)
+        self._batcher.wait(reqs)
+        return reqs
 
     # -- public API ---------------------------------------------------------------------------------------------------
     def transcribe_ids(self, audios: Sequence, sampling_rate: int = 16000, max_new_tokens: int = 128,
                        hotwords: Optional[List[str]] = None) -> List[List[int]]:
-        eng = self._engine()
+        """Generated token ids of several independent segments (results in input order)."""
         wavs = [self._to_mono_16k(a, sampling_rate) for a in audios]
-        out: List[List[int]] = []
-        for i in range(0, len(wavs), self._max_batch):
-            chunk = wavs[i:i + self._max_batch]
-            prompts = [self._prompts.build(num_audio_tokens(w.shape[0]), hotwords) for w in chunk]
-            out += eng.transcribe_ids(chunk, prompts, max_new_tokens, FLAG_REFERENCE_PRESTEP)
-        return out
+        return [r.ids for r in self._submit(wavs, False, max_new_tokens, hotwords)]
 
     def transcribe_batch(self, audios: Sequence, sampling_rate: int = 16000, max_new_tokens: int = 128,
                          hotwords: Optional[List[str]] = None) -> List[str]:
         return [self._decode(ids) for ids in self.transcribe_ids(audios, sampling_rate, max_new_tokens, hotwords)]
+
+    def transcribe_pcm16(self, pcm: Union[bytes, bytearray, memoryview, np.ndarray], max_new_tokens: int = 128,
+                         hotwords: Optional[List[str]] = None) -> str:
+        """int16 LE 16 kHz mono samples (the WebSocket wire format, frontend pcm-processor.js:59-75) -> text.  Equivalent to
+        ``transcribe(torch.from_numpy(int16).float() / 32768.0)`` (transcription_manager.py:45-62) with the widening done on
+        the device: 2 bytes per sample cross PCIe and no float copy is made on the host."""
+        a = np.frombuffer(pcm, dtype=np.int16) if not isinstance(pcm, np.ndarray) else np.ascontiguousarray(pcm, dtype=np.int16).reshape(-1)
+        self._check_length(a.shape[0])
+        return self._decode(self._submit([a], True, max_new_tokens, hotwords)[0].ids)
 
     def transcribe(self, audio_tensor: torch.Tensor, sampling_rate: int = 16000, max_new_tokens: int = 128,
                    hotwords: Optional[List[str]] = None, return_debug_info: bool = False) -> Union[str, Dict[str, Any]]:
         t0 = time.time()
         try:
             eng = self._engine()
-            ids = self.transcribe_ids([audio_tensor], sampling_rate, max_new_tokens, hotwords)[0]
+            req = self._submit([self._to_mono_16k(audio_tensor, sampling_rate)], False, max_new_tokens, hotwords)[0]
+            ids = req.ids
             transcript = self._decode(ids)
         except Exception as e:
             print(f"transcription failed: {e}")          # the reference prints and re-raises (asr.py:469-481)
             raise
         if not return_debug_info:
             return transcript
-        st = eng.stage_times()
+        st = {k: v for k, v in req.info.items() if k.endswith("_ms")}
         n = audio_tensor.shape[-1]
         info = {
             "transcript": transcript,
@@ -160,9 +228,13 @@ class ASRModel:
             "gpu_memory_allocated_mb": eng.device_bytes() / 1024 ** 2,
             "gpu_memory_reserved_mb": eng.device_bytes() / 1024 ** 2,
             "token_ids": ids,
+            "batch_size": req.info.get("batch_size", 1),
         }
         info.update(st)
         return info
+
+    def batcher_stats(self) -> Dict[str, Any]:
+        return self._batcher.stats()
 
     def get_model_info(self) -> Dict[str, Any]:
         info = {

@@ -21,4 +21,5 @@ class AppConfig:
     MAX_SPEECH_SEGMENTS = 3
     # additions of this implementation: never rename the reference's keys above
     SONIC_MODE = os.getenv("SONIC_MODE", "native")          # native | int8 | fp32
-    SONIC_MAX_BATCH = int(os.getenv("SONIC_MAX_BATCH", "8"))
+    SONIC_MAX_BATCH = int(os.getenv("SONIC_MAX_BATCH", "16"))   # segments the dynamic batcher may coalesce into one device pass
+    SONIC_BATCH_WINDOW_MS = float(os.getenv("SONIC_BATCH_WINDOW_MS", "3"))

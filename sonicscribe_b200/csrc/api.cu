@@ -157,6 +157,11 @@ struct sonic_ctx {
   GreedyState gs{};
   int* h_pinned = nullptr;              // pinned scratch for metadata upload / flags
   size_t h_pinned_ints = 0;
+  int persist_launch_mode = 0;         // cooperative launch API state of this handle (decode_persist.cu launch_decode_persist)
+  std::vector<int> probe_steps;        // debug: greedy steps whose full logit rows are kept (sonic_debug_set_logit_steps)
+  float* probe_logits = nullptr;       // [probe_steps][max_batch][vocab]
+  int cur_step = 0;                    // index of the token the next decode step produces (host-side mirror of gs.step)
+  int probe_batch = 0;
   bool persist_tc = false;             // batch class 33..64 of the persistent kernel runs its GEMM phases on tcgen05
   bool use_persist = false;            // one cooperative kernel per greedy step (bf16 mode; SONIC_DECODE=graph disables)
   DecLayerDev* dev_layers = nullptr;
@@ -208,6 +213,11 @@ int fail_cuda(sonic_ctx* h, cudaError_t e, const char* what) {
     cudaError_t _e = (expr);                                       \
     if (_e != cudaSuccess) return fail_cuda(h, _e, #expr);         \
   } while (0)
+float* probe_target(sonic_ctx* h, int step) {
+  for (size_t i = 0; i < h->probe_steps.size(); ++i)
+    if (h->probe_steps[i] == step && h->probe_logits) return h->probe_logits + i * (size_t)h->cfg.max_batch * 59264;
+  return nullptr;
+}
 enum ProfClass { PC_MEL = 0, PC_ENC_GEMM, PC_ENC_ATTN, PC_ENC_OTHER, PC_PRE_GEMM, PC_PRE_ATTN, PC_PRE_OTHER, PC_DEC_QKV, PC_DEC_O,
                  PC_DEC_GU, PC_DEC_DOWN, PC_DEC_LMHEAD, PC_DEC_ATTN, PC_DEC_OTHER, PC_DEC_PERSIST, PC_COUNT };
 const char* const kProfNames[PC_COUNT] = {"mel", "enc_gemm", "enc_attn", "enc_other", "prefill_gemm", "prefill_attn", "prefill_other",
@@ -322,7 +332,7 @@ struct Engine {
 
   static int mel(sonic_ctx* h, const float* pcm_dev, int batch, int max_len, int flags, float* feat_dev) {
     TAG(PC_MEL);
-    CKL(launch_mel<T>(pcm_dev, h->offs_dev, h->lens_dev, batch, max_len, flags & 3, h->mel_tables, h->peak_bits, h->gmax_bits,
+    CKL(launch_mel<T>(pcm_dev, h->offs_dev, h->lens_dev, batch, max_len, flags & 7, h->mel_tables, h->peak_bits, h->gmax_bits,
                       h->mel_raw, feat_dev, reinterpret_cast<T*>(h->mel_tm), h->stream),
         (flags & SONIC_FLAG_PEAK_NORM) ? 4 : 3);
     return 0;
@@ -457,6 +467,8 @@ struct Engine {
     GemmArgs g = lin(u, kDecH, h->lm_head, kDecH, h->logits, kVocab, nullptr, B, kVocab);
     g.out_f32 = 1;
     if (gemm(h, g, true, PC_DEC_LMHEAD)) return -1;
+    if (float* pt = probe_target(h, h->cur_step))            // debug handles only; such handles never capture the step into a graph
+      CK(cudaMemcpyAsync(pt, h->logits, (size_t)B * kVocab * 4, cudaMemcpyDeviceToDevice, h->stream));
     TAG(PC_DEC_OTHER);
     CKL(launch_greedy_pick(h->logits, B, kVocab, h->gs, advance, h->stream, h->pdl_now), 1);
     return 0;
@@ -491,7 +503,7 @@ struct Engine {
       p.embed = reinterpret_cast<const bf16*>(h->embed); p.lm_head = reinterpret_cast<const bf16*>(h->lm_head); p.final_norm = h->final_norm;
       p.cos_t = h->rope_dec_cos; p.sin_t = h->rope_dec_sin;
       p.x = reinterpret_cast<bf16*>(h->dx); p.u = reinterpret_cast<bf16*>(h->du); p.attn = reinterpret_cast<bf16*>(h->dattn);
-      p.act = reinterpret_cast<bf16*>(h->dact); p.part = h->persist_part; p.logits_out = nullptr; p.pick_scratch = h->persist_pick;
+      p.act = reinterpret_cast<bf16*>(h->dact); p.part = h->persist_part; p.logits_out = probe_target(h, h->cur_step); p.pick_scratch = h->persist_pick;
       p.attn_ws = h->dattn_ws; p.attn_counters = h->dattn_counters;
       // 128-key chunks over separate CTAs while that still leaves CTAs idle; otherwise one CTA walks all chunks of a group
       p.attn_chunks = (B * kDecKv * ((h->decode_chunks + 1) / 2) <= h->persist_grid) ? (h->decode_chunks + 1) / 2 : 1;
@@ -502,7 +514,7 @@ struct Engine {
       p.B = B; p.Bpad = (B + 7) / 8 * 8; p.max_ctx = h->max_ctx; p.eps = kRmsEps; p.scale = 0.08838834764831845f;
       TAG(PC_DEC_PERSIST);
       if (h->prof_on) { cudaEventRecord(prof_event(h), h->stream); h->prof_tags.push_back(h->prof_cls); }
-      cudaError_t pe = launch_decode_persist(p, h->persist_grid, h->stream);
+      cudaError_t pe = launch_decode_persist(p, h->persist_grid, h->stream, &h->persist_launch_mode);
       if (h->prof_on) cudaEventRecord(prof_event(h), h->stream);
       if (pe == cudaSuccess) { h->launches += 1; return 0; }
       // a cooperative launch can be refused (co-residency not available on this device/driver state): fall back, for the
@@ -700,31 +712,40 @@ int alloc_all(sonic_ctx* h) {
   return 0;
 }
 
-int do_mel(sonic_ctx* h, const float* pcm, const int64_t* offsets, const int32_t* lengths, int batch, int flags, float* features,
+int do_mel(sonic_ctx* h, const void* pcm_any, const int64_t* offsets, const int32_t* lengths, int batch, int flags, float* features,
            int32_t* n_frames) {
   if (batch <= 0 || batch > h->cfg.max_batch) return fail(h, "sonic_mel: batch out of range");
+  // validate every length before anything is copied or staged
+  for (int b = 0; b < batch; ++b) {
+    if (lengths[b] <= 0) return fail(h, "sonic_mel: empty segment");
+    // only the first 30 s window is consumed; the peak of the reference pre-step is over the whole segment, so longer
+    // inputs are rejected rather than silently changing semantics (callers cap segments at 30 s, config.py:41)
+    if (!(flags & SONIC_FLAG_PCM_DEVICE) && lengths[b] > kWinSamples) return fail(h, "sonic_mel: segment longer than 30 s (480000 samples)");
+    if (offsets[b] < 0) return fail(h, "sonic_mel: negative offset");
+  }
   // stage metadata (and PCM, when it lives on the host) on the device
   long long* h_offs = reinterpret_cast<long long*>(h->h_pinned);          // mel metadata region: 3*max_batch ints
   int* h_lens = h->h_pinned + 2 * h->cfg.max_batch;
   int max_len = 0;
   h->last_lens.assign(batch, 0);
+  const float* pcm = reinterpret_cast<const float*>(pcm_any);    // int16 when SONIC_FLAG_PCM_S16 (the kernels re-cast)
   const float* pcm_dev = nullptr;
+  const bool s16 = (flags & SONIC_FLAG_PCM_S16) != 0;
   if (flags & SONIC_FLAG_PCM_DEVICE) {
     for (int b = 0; b < batch; ++b) { h_offs[b] = offsets[b]; h_lens[b] = lengths[b]; }
     pcm_dev = pcm;
   } else {
+    // int16 input is staged as int16 (2 B per sample over PCIe) and widened by the kernel's load
+    const size_t esz = s16 ? 2 : 4;
     for (int b = 0; b < batch; ++b) {
-      // only the first 30 s window is consumed; the peak of the reference pre-step is over the whole segment, so
-      // longer inputs are rejected rather than silently changing semantics (callers cap segments at 30 s, config.py:41)
-      if (lengths[b] > kWinSamples) return fail(h, "sonic_mel: segment longer than 30 s (480000 samples)");
       h_offs[b] = (long long)b * kWinSamples;
       h_lens[b] = lengths[b];
-      CK(cudaMemcpyAsync(h->pcm_dev + (size_t)b * kWinSamples, pcm + offsets[b], (size_t)lengths[b] * 4, cudaMemcpyHostToDevice, h->stream));
+      CK(cudaMemcpyAsync(reinterpret_cast<char*>(h->pcm_dev) + (size_t)b * kWinSamples * esz,
+                         reinterpret_cast<const char*>(pcm) + (size_t)offsets[b] * esz, (size_t)lengths[b] * esz, cudaMemcpyHostToDevice, h->stream));
     }
     pcm_dev = h->pcm_dev;
   }
   for (int b = 0; b < batch; ++b) {
-    if (lengths[b] <= 0) return fail(h, "sonic_mel: empty segment");
     if (lengths[b] > max_len) max_len = lengths[b];
     h->last_lens[b] = lengths[b];
     if (n_frames) n_frames[b] = n_valid_frames(lengths[b]);
@@ -816,6 +837,8 @@ int do_generate(sonic_ctx* h, const int32_t* ids, const int32_t* id_offsets, int
   h->gs.max_new = max_new;
 
   CK(cudaEventRecord(h->ev[2], st));
+  h->cur_step = 0;
+  h->probe_batch = batch;
   int rc = dispatch(h, [&] { return Engine<float>::prefill(h, batch, total, max_q); }, [&] { return Engine<bf16>::prefill(h, batch, total, max_q); });
   if (rc) return rc;
   CK(cudaEventRecord(h->ev[3], st));
@@ -823,9 +846,10 @@ int do_generate(sonic_ctx* h, const int32_t* ids, const int32_t* id_offsets, int
   // greedy steps 2..max_new: one CUDA graph per (batch, max_new) replayed; no per-token host sync.
   h->decode_chunks = (max_q + max_new + 63) / 64;
   if (h->decode_chunks > h->dattn_max_chunks) h->decode_chunks = h->dattn_max_chunks;
-  if (max_new > 1 && (h->prof_on || (h->use_persist && batch <= 64 && !h->is_f32))) {
+  if (max_new > 1 && (h->prof_on || !h->probe_steps.empty() || (h->use_persist && batch <= 64 && !h->is_f32))) {
     int* flag = h->h_pinned + h->h_pinned_ints - 16;
     for (int step = 1; step < max_new; ++step) {
+      h->cur_step = step;
       rc = dispatch(h, [&] { return Engine<float>::decode_step(h, batch); }, [&] { return Engine<bf16>::decode_step(h, batch); });
       if (rc) return rc;
       if (!h->prof_on && (step % 16) == 0 && step + 1 < max_new) {       // early exit once every segment hit EOS
@@ -992,7 +1016,7 @@ int sonic_load_tensor(sonic_handle h, const char* name, const void* data, int32_
   ENTER();
   if (!name || !data || !shape) return fail(h, "sonic_load_tensor: null argument");
   Dest d;
-  if (!route(h, name, &d)) return fail(h, std::string("sonic_load_tensor: unknown tensor ") + name);
+  if (!route(h, name, &d)) { fail(h, std::string("sonic_load_tensor: unknown tensor ") + name); return SONIC_ERR_UNKNOWN_TENSOR; }
   size_t n = 1;
   for (int i = 0; i < ndim; ++i) n *= (size_t)shape[i];
   bool ok = false;
@@ -1055,7 +1079,7 @@ int sonic_finalize_weights(sonic_handle h) {
   return 0;
 }
 
-int sonic_mel(sonic_handle h, const float* pcm, const int64_t* offsets, const int32_t* lengths, int32_t batch, int32_t flags,
+int sonic_mel(sonic_handle h, const void* pcm, const int64_t* offsets, const int32_t* lengths, int32_t batch, int32_t flags,
               float* features, int32_t* n_frames) {
   ENTER();
   if (!pcm || !offsets || !lengths) return fail(h, "sonic_mel: null argument");
@@ -1078,7 +1102,7 @@ int sonic_generate(sonic_handle h, const int32_t* ids, const int32_t* id_offsets
   return do_generate(h, ids, id_offsets, batch, max_new_tokens, out_ids, n_out, margins);
 }
 
-int sonic_transcribe_batch(sonic_handle h, const float* pcm, const int64_t* offsets, const int32_t* lengths, int32_t batch,
+int sonic_transcribe_batch(sonic_handle h, const void* pcm, const int64_t* offsets, const int32_t* lengths, int32_t batch,
                            int32_t flags, const int32_t* ids, const int32_t* id_offsets, int32_t max_new_tokens, int32_t* out_ids,
                            int32_t* n_out, float* margins) {
   ENTER();
@@ -1145,6 +1169,15 @@ int sonic_profile_end(sonic_handle h, float* ms_per_class, int64_t* launches_per
 int32_t sonic_profile_num_classes(void) { return PC_COUNT; }
 const char* sonic_profile_class_name(int32_t c) { return (c >= 0 && c < PC_COUNT) ? kProfNames[c] : ""; }
 
+int sonic_debug_set_logit_steps(sonic_handle h, const int32_t* steps, int32_t n) {
+  ENTER();
+  if (!h->cfg.debug) return fail(h, "sonic_debug_set_logit_steps: the handle was not created with debug=1");
+  if (n < 0 || n > 8 || (n > 0 && !steps)) return fail(h, "sonic_debug_set_logit_steps: 0..8 steps");
+  h->probe_steps.assign(steps, steps + n);
+  if (n > 0 && !h->probe_logits) { DA(h->probe_logits, (size_t)8 * h->cfg.max_batch * kVocab * 4); }
+  return 0;
+}
+
 int sonic_debug_read(sonic_handle h, const char* name, float* out, size_t max_elems, size_t* n_elems) {
   ENTER();
   if (!name || !out) return fail(h, "sonic_debug_read: null argument");
@@ -1164,6 +1197,11 @@ int sonic_debug_read(sonic_handle h, const char* name, float* out, size_t max_el
     for (int i = 0; i < n; ++i) out[i] = (float)((double)(ts[i] - ts[0]) * 1e-3);
     if (n_elems) *n_elems = n;
     return 0;
+  }
+  else if (nm.rfind("step_logits@", 0) == 0) {
+    float* pt = probe_target(h, atoi(nm.c_str() + 12));
+    if (!pt) return fail(h, "sonic_debug_read: that step was not registered with sonic_debug_set_logit_steps");
+    src_f32 = pt; n = (size_t)h->probe_batch * kVocab;
   }
   else if (nm == "mel_raw") { src_f32 = h->mel_raw; n = (size_t)h->last_batch * kMels * kFrames; }
   else if (h->probes_f32.count(nm)) { src_f32 = h->probes_f32[nm].first; n = h->probes_f32[nm].second; }

@@ -941,6 +941,7 @@ __global__ void __launch_bounds__(kPThreads, 1) decode_persist_kernel(DecodePers
       }
       if (tid == 0) {
         const int step = *a.gs.step;
+        if (bi < 0 || bi >= PV_) bi = a.gs.eos[0];         // all-NaN logits: emit EOS rather than an out-of-range id
         a.gs.ctx_len[b] += 1;
         if (!a.gs.finished[b]) {
           a.gs.out_ids[(size_t)b * a.gs.max_new + step] = bi;
@@ -1018,7 +1019,7 @@ cudaError_t decode_persist_configure() {
   return cudaSuccess;
 }
 
-cudaError_t launch_decode_persist(const DecodePersistArgs& a, int grid, cudaStream_t st) {
+cudaError_t launch_decode_persist(const DecodePersistArgs& a, int grid, cudaStream_t st, int* mode) {
   if (grid < 1 || a.B < 1 || a.B > 64) return cudaErrorInvalidConfiguration;
   const int num_sms = grid;
   PersistKernel kern = persist_kernel_for(a.w8 != 0, a.B, a.tmaps != nullptr);
@@ -1027,10 +1028,12 @@ cudaError_t launch_decode_persist(const DecodePersistArgs& a, int grid, cudaStre
     cudaError_t me = cudaMemsetAsync(a.bar, 0, sizeof(unsigned), st);
     if (me != cudaSuccess) { fprintf(stderr, "[sonicscribe_b200] barrier memset failed: %s\n", cudaGetErrorName(me)); return me; }
   }
-  static int mode = 0;          // 0: cudaLaunchKernelEx + cooperative attribute, 1: cudaLaunchCooperativeKernel, 2: plain launch
+  // *mode (per handle): 0: cudaLaunchKernelEx + cooperative attribute, 1: cudaLaunchCooperativeKernel.  Both guarantee
+  // co-residency of the grid (the software grid barrier spins); there is no plain-launch variant — when both are refused
+  // the caller falls back to the CUDA-graph decode path.
   cudaError_t e = cudaErrorUnknown;
-  for (; mode < 3; ++mode) {
-    if (mode == 0) {
+  for (; *mode < 2; ++*mode) {
+    if (*mode == 0) {
       cudaLaunchConfig_t cfg;
       memset(&cfg, 0, sizeof(cfg));
       cfg.gridDim = dim3(num_sms); cfg.blockDim = dim3(kPThreads); cfg.dynamicSmemBytes = smem_bytes; cfg.stream = st;
@@ -1040,18 +1043,13 @@ cudaError_t launch_decode_persist(const DecodePersistArgs& a, int grid, cudaStre
       attr[0].val.cooperative = 1;
       cfg.attrs = attr; cfg.numAttrs = 1;
       e = cudaLaunchKernelEx(&cfg, kern, a);
-    } else if (mode == 1) {
+    } else {
       DecodePersistArgs copy = a;
       void* args[1] = {&copy};
       e = cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(kern), dim3(num_sms), dim3(kPThreads), args, smem_bytes, st);
-    } else {
-      // grid <= SM count with one CTA per SM: co-resident on an otherwise idle device (stream order guarantees our own
-      // earlier kernels have drained); without the cooperative attribute this is not guaranteed by the programming model
-      kern<<<dim3(num_sms), dim3(kPThreads), smem_bytes, st>>>(a);
-      e = cudaGetLastError();
     }
     if (e == cudaSuccess) return e;
-    fprintf(stderr, "[sonicscribe_b200] decode_persist launch mode %d failed: %s (%s)\n", mode, cudaGetErrorName(e), cudaGetErrorString(e));
+    fprintf(stderr, "[sonicscribe_b200] decode_persist launch mode %d failed: %s (%s)\n", *mode, cudaGetErrorName(e), cudaGetErrorString(e));
     cudaGetLastError();
   }
   return e;

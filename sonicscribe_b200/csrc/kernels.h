@@ -7,6 +7,7 @@
 
 #define SONIC_MEL_PEAK_NORM 1
 #define SONIC_MEL_PCM16 2
+#define SONIC_MEL_S16 4      // PCM buffer holds int16 samples (scaled by 1/32768 on load)
 
 namespace sonic {
 
@@ -152,7 +153,8 @@ size_t decode_persist_pick_floats(int max_batch, int num_sms);
 cudaError_t decode_persist_configure();
 int decode_persist_max_grid(int num_sms);
 int decode_persist_occupancy();
-cudaError_t launch_decode_persist(const DecodePersistArgs& a, int grid, cudaStream_t st);
+// *mode: per-handle launch API state (0 on first use); advanced when a launch API is refused
+cudaError_t launch_decode_persist(const DecodePersistArgs& a, int grid, cudaStream_t st, int* mode);
 static constexpr int kPersistTcTokens = 64;   // token rows of the activation tensor maps
 
 }  // namespace sonic

@@ -88,28 +88,24 @@ __device__ __forceinline__ void dft25(float2 (&x)[25]) {
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// sample j of a segment whose first sample is element `base` of the PCM buffer: float32, or int16 scaled by 1/32768 (the
+// wire format of the realtime path; backend/transcription_manager.py:45-51 does the same division on the host)
+__device__ __forceinline__ float load_pcm(const float* __restrict__ pcm, long long base, int j, int flags) {
+  if (flags & SONIC_MEL_S16) return (float)__ldg(reinterpret_cast<const short*>(pcm) + base + j) * (1.0f / 32768.0f);
+  return __ldg(pcm + base + j);
+}
+
 __global__ void mel_peak_kernel(const float* __restrict__ pcm, const long long* __restrict__ offs,
-                                const int* __restrict__ lens, unsigned* __restrict__ peak_bits) {
+                                const int* __restrict__ lens, unsigned* __restrict__ peak_bits, int flags) {
   const int b = blockIdx.y;
   const int n = min(lens[b], INT_MAX);
-  const float* x = pcm + offs[b];
+  const long long base = offs[b];
   float m = 0.f;
   // the reference normalises by the peak of the WHOLE input segment (asr.py:265), before the 30 s truncation
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) m = fmaxf(m, fabsf(x[i]));
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) m = fmaxf(m, fabsf(load_pcm(pcm, base, i, flags)));
   __shared__ float red[32];
   m = block_max(m, red);
   if (threadIdx.x == 0 && m > 0.f) atomicMax(peak_bits + b, __float_as_uint(m));   // non-negative floats order as uints
-}
-
-__device__ __forceinline__ float fetch_sample(const float* __restrict__ x, int n, int j, float inv_gate, float peak, int flags) {
-  // j: index into the zero-padded 480000-sample window, reflect-extended by 200 on both sides (torch.stft center=True)
-  if (j < 0) j = -j;
-  if (j >= kWin) j = 2 * (kWin - 1) - j;
-  if (j >= n) return 0.f;
-  float v = __ldg(x + j);
-  if ((flags & SONIC_MEL_PEAK_NORM) && inv_gate > 0.f) v = v / peak;              // asr.py:266-267 (true division)
-  if (flags & SONIC_MEL_PCM16) v = rintf(v * 32767.0f) * (1.0f / 32768.0f);       // soundfile PCM_16 write + float read
-  return v;
 }
 
 __global__ void __launch_bounds__(kMelThreads, 2)
@@ -138,7 +134,7 @@ mel_frames_kernel(const float* __restrict__ pcm, const long long* __restrict__ o
     const int n = min(lens[b], kWin);
     const int n_active = min(kFrames, (n + 200 + kHop - 1) / kHop);
     if (tile * kTileFrames >= n_active) continue;               // CTA-uniform
-    const float* x = pcm + offs[b];
+    const long long base = offs[b];
     const float peak = __uint_as_float(peak_bits[b]);
     const float gate = (peak > 1e-6f) ? 1.f : 0.f;
     float lmax = -10.0f;
@@ -155,7 +151,7 @@ mel_frames_kernel(const float* __restrict__ pcm, const long long* __restrict__ o
         int j = j0 + i;
         if (j < 0) j = -j;
         if (j >= kWin) j = 2 * (kWin - 1) - j;
-        rawv[q] = (i < kSpan && j < n) ? __ldg(x + j) : 0.f;
+        rawv[q] = (i < kSpan && j < n) ? load_pcm(pcm, base, j, flags) : 0.f;
       }
 #pragma unroll
       for (int q = 0; q < kPer; ++q) {
@@ -321,7 +317,7 @@ cudaError_t launch_mel(const float* pcm, const long long* offs, const int* lens,
   SONIC_LAUNCH_CHECK();
   if (flags & SONIC_MEL_PEAK_NORM) {
     int gx = max(1, min(cdiv(max_len, 256 * 8), 64));
-    mel_peak_kernel<<<dim3(gx, batch), 256, 0, st>>>(pcm, offs, lens, peak_bits);
+    mel_peak_kernel<<<dim3(gx, batch), 256, 0, st>>>(pcm, offs, lens, peak_bits, flags);
     SONIC_LAUNCH_CHECK();
   }
   const int n_eff = min(max_len, kWin);

@@ -310,7 +310,9 @@ __global__ void __launch_bounds__(256) greedy_pick_kernel(const float* __restric
     const volatile PickPartial* p = partials + b * kPickSlices + s;
     pick_merge(mb, ms, mi, p->best, p->second, p->idx);
   }
-  const int tok = mi;
+  // a row of NaN logits (NaN PCM, poisoned cache) never updates the running maximum: emit EOS instead of an out-of-range id
+  const bool bad = (mi < 0 || mi >= V);
+  const int tok = bad ? gs.eos[0] : mi;
   const int step = *gs.step;
   if (advance_ctx) gs.ctx_len[b] += 1;                 // the token just consumed is now in the cache
   if (!gs.finished[b]) {

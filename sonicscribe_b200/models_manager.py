@@ -16,6 +16,7 @@ def asr_model_init(**kwargs) -> None:
     if _asr_model is not None:
         logger.warning("ASR model already initialized. Skipping re-initialization.")
         return
+    kwargs.setdefault("max_batch", AppConfig.SONIC_MAX_BATCH)
     _asr_model = ASRModel(AppConfig.CHECKPOINT_PATH, device=AppConfig.DEVICE, mode=AppConfig.SONIC_MODE, **kwargs)
 
 

@@ -36,9 +36,14 @@ class TranscriptionManager:
         audio_array = np.frombuffer(audio_data, dtype=np.int16)
         if len(audio_array) == 0:
             return ""
+        asr_model = asr_model_get()
+        if hasattr(asr_model, "transcribe_pcm16"):
+            # same numbers as the reference's int16 -> float32 / 32768 -> [1, N] detour (transcription_manager.py:45-54), with the
+            # widening done on the device: the int16 bytes go to the GPU as they arrived from the WebSocket
+            result = asr_model.transcribe_pcm16(audio_array, max_new_tokens=max_new_tokens)
+            return result.strip()
         audio_tensor = torch.from_numpy(audio_array.copy()).float() / 32768.0
         if audio_tensor.dim() == 1:
             audio_tensor = audio_tensor.unsqueeze(0)
-        asr_model = asr_model_get()
         result = asr_model.transcribe(audio_tensor, sampling_rate=16000, max_new_tokens=max_new_tokens)
         return result.strip()

@@ -447,3 +447,98 @@ def test_single_segment_long_generation_reaches_max_ctx(eng_bf16):
     ids = synthetic_prompt_ids(num_audio_tokens(x.shape[0]))
     out = eng_bf16.transcribe_ids([x], [ids], 40)
     assert len(out[0]) == 40 and all(0 <= t < 59264 for t in out[0])
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The benchmarked configurations pinned to the oracle: bf16 at 36 / 64 segments (tcgen05 decode class, ragged tcgen05
+# prefill), int8 at 64, and the small-batch classes.  Full fp32 logit rows of greedy steps 0 (prefill), 1, 8 and 20 are read
+# back and compared with the CPU oracle's logits of the same step (rel-L2 <= 5e-2, the stated bf16 tolerance) for eight
+# sampled segments, as long as the generated prefix is the oracle's; ids must equal the oracle's wherever its top-2 margin
+# exceeds 0.25.
+# ---------------------------------------------------------------------------------------------------------------------
+PIN_STEPS = (0, 1, 8, 20)
+PIN_G = 21
+_pin_cache = {}
+
+
+def _pin_case(B):
+    lens = [320000 - 4000 * (i % 7) for i in range(B)]
+    if B > 3:
+        lens[3] = 20480
+    segs = [mo.synth_audio("speech" if i % 3 else "noise", lens[i], seed=i) for i in range(B)]
+    prompts = [synthetic_prompt_ids(num_audio_tokens(n)) for n in lens]
+    return lens, segs, prompts
+
+
+def _pin_oracle(sd, tag, i, x, ids):
+    key = (tag, i, x.shape[0])
+    if key not in _pin_cache:
+        mel, _ = mo.log_mel(mo.prestep(x))
+        probes = {}
+        new, margins, _ = ora.generate_greedy(sd, ora.OracleConfig(enc_layers=2, dec_layers=2), torch.from_numpy(mel),
+                                              num_audio_tokens(x.shape[0]), ids, PIN_G, probes=probes, logit_steps=PIN_STEPS)
+        _pin_cache[key] = (new, margins, {s: v.numpy() for s, v in probes["step_logits"].items()})
+    return _pin_cache[key]
+
+
+@pytest.mark.parametrize("mode,B", [("bf16", 64), ("bf16", 36), ("int8", 64), ("bf16", 16), ("bf16", 24), ("int8", 8), ("bf16", 1)])
+def test_decode_step_logits_pinned_to_oracle(tiny_sd, mode, B):
+    lens, segs, prompts = _pin_case(B)
+    eng = Engine(2, 2, mode=mode, device=0, max_batch=B, max_prompt=300, max_new=24, debug=True)
+    eng.load_state_dict(tiny_sd)
+    eng.debug_set_logit_steps(PIN_STEPS)
+    got, mar = eng.transcribe_ids(segs, prompts, PIN_G, want_margins=True)
+    logits = {s: eng.debug_read(f"step_logits@{s}", B * 59264).reshape(B, 59264) for s in PIN_STEPS}
+    eng.close()
+    sd = ora.int8_weight_only_state(tiny_sd) if mode == "int8" else tiny_sd
+    sample = sorted(set([0, 3, 5, 7, B // 2, B - 3, B - 2, B - 1]) & set(range(B)))
+    compared = 0
+    for b in sample:
+        ref_new, margins, ref_logits = _pin_oracle(sd, mode == "int8", b, segs[b], prompts[b])
+        assert len(got[b]) == PIN_G
+        for t, (a, r) in enumerate(zip(got[b], ref_new)):
+            if a != r:
+                assert margins[t] < 0.25, (mode, B, b, t, margins[t])       # ids equal wherever the oracle margin is healthy
+                break
+        for s in PIN_STEPS:
+            if got[b][:s] == ref_new[:s]:                                    # same prefix => same inputs to this step
+                err = rel_l2(logits[s][b], ref_logits[s])
+                assert err < 5e-2, (mode, B, b, s, err)
+                compared += 1
+        assert got[b][0] == ref_new[0]
+    assert compared >= 2 * len(sample), compared
+
+
+def test_server_sized_handle_serves_small_batches(tiny_sd):
+    """A max_batch=64 handle (which owns the tcgen05 decode maps) must give a lone segment and a 20-segment batch the same
+    ids as right-sized handles do: the decode class follows the live batch, never the handle's capacity."""
+    lens, segs, prompts = _pin_case(20)
+    big = Engine(2, 2, mode="bf16", device=0, max_batch=64, max_prompt=300, max_new=24)
+    big.load_state_dict(tiny_sd)
+    small = Engine(2, 2, mode="bf16", device=0, max_batch=20, max_prompt=300, max_new=24)
+    small.load_state_dict(tiny_sd)
+    for n in (1, 20):
+        assert big.transcribe_ids(segs[:n], prompts[:n], 16) == small.transcribe_ids(segs[:n], prompts[:n], 16)
+    big.close(); small.close()
+
+
+def test_int16_wire_format_equals_float_path(eng_fp32):
+    """SONIC_FLAG_PCM_S16: int16 samples widened on the device == the host-side int16/32768 float tensor the reference builds
+    (transcription_manager.py:45-51): bit-identical features and ids."""
+    from sonicscribe_b200.engine import FLAG_PCM_S16, FLAG_REFERENCE_PRESTEP
+    x = mo.synth_audio("speech", 48000, 9)
+    s16 = np.clip(np.rint(x * 32767.0), -32768, 32767).astype(np.int16)
+    xf = s16.astype(np.float32) / 32768.0
+    f_float, n1 = eng_fp32.mel([xf])
+    f_s16, n2 = eng_fp32.mel([s16], flags=FLAG_REFERENCE_PRESTEP | FLAG_PCM_S16)
+    assert np.array_equal(f_float, f_s16) and n1[0] == n2[0]
+    ids = synthetic_prompt_ids(num_audio_tokens(x.shape[0]))
+    assert eng_fp32.transcribe_ids([xf], [ids], 8) == eng_fp32.transcribe_ids([s16], [ids], 8, FLAG_REFERENCE_PRESTEP | FLAG_PCM_S16)
+
+
+def test_nan_audio_does_not_emit_out_of_range_ids(eng_bf16):
+    x = mo.synth_audio("speech", 32000, 2)
+    x[100] = np.nan
+    ids = synthetic_prompt_ids(num_audio_tokens(x.shape[0]))
+    out = eng_bf16.transcribe_ids([x], [ids], 6)
+    assert all(0 <= t < 59264 for t in out[0])

@@ -45,13 +45,3 @@ def test_no_cpu_fallback():
         ASRModel("synthetic:enc=2,dec=2", device="cpu")
     with pytest.raises(ValueError):
         ASRModel("synthetic", mode="fp16")
-
-
-def test_prompt_builder_and_hotwords():
-    from sonicscribe_b200.prompt import format_hotwords_prompt, synthetic_prompt_ids
-    assert format_hotwords_prompt(None) == ""
-    assert format_hotwords_prompt([" Foo ", "foo", "", "Bar"]) == '. Pay special attention to these important terms: "foo", "bar"'
-    assert len(format_hotwords_prompt([f"w{i}" for i in range(20)]).split('", "')) == 10
-    ids = synthetic_prompt_ids(250)
-    assert len(ids) == 270 and ids.count(59260) == 250
-    assert synthetic_prompt_ids(16, ["x"]) != synthetic_prompt_ids(16)
