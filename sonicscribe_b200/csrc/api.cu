@@ -157,6 +157,17 @@ struct sonic_ctx {
   GreedyState gs{};
   int* h_pinned = nullptr;              // pinned scratch for metadata upload / flags
   size_t h_pinned_ints = 0;
+  // row-sliced decode class (decode_rs.cu): <= 32 segments bf16, <= 16 segments int8
+  bool use_rs = false;
+  int rs_launch_mode = 0;
+  int rs_grid = 0;
+  std::vector<void*> wqkv_il;          // per layer: fused qkv weights with the q / k head rows interleaved for the RoPE epilogue
+  std::vector<float*> s_qkv_il;        // int8: the row scales in the same order
+  RsLayer* rs_layers = nullptr;        // device table
+  void* rs_wmaps = nullptr;            // device CUtensorMap[4 * layers + 2]
+  void* rs_amaps = nullptr;            // device CUtensorMap[4]: {attn, act} x {16, 32 token rows}
+  float* rs_pick = nullptr;
+  int cur_max_q = 0;                   // longest prompt of the current generate call
   int persist_launch_mode = 0;         // cooperative launch API state of this handle (decode_persist.cu launch_decode_persist)
   std::vector<int> probe_steps;        // debug: greedy steps whose full logit rows are kept (sonic_debug_set_logit_steps)
   float* probe_logits = nullptr;       // [probe_steps][max_batch][vocab]
@@ -496,6 +507,31 @@ struct Engine {
   static int decode_step(sonic_ctx* h, int B) {
     T* x = reinterpret_cast<T*>(h->dx);
     TAG(PC_DEC_OTHER);
+    if (h->use_rs && std::is_same<T, bf16>::value && decode_rs_supports(h->is_int8, B)) {
+      DecodeRsArgs p;
+      memset(&p, 0, sizeof(p));
+      p.layers = h->rs_layers; p.n_layers = h->cfg.dec_layers;
+      p.embed = reinterpret_cast<const bf16*>(h->embed); p.final_norm = h->final_norm;
+      p.cos_t = h->rope_dec_cos; p.sin_t = h->rope_dec_sin;
+      p.x = reinterpret_cast<bf16*>(h->dx); p.q = reinterpret_cast<bf16*>(h->dqkv); p.attn = reinterpret_cast<bf16*>(h->dattn);
+      p.act = reinterpret_cast<bf16*>(h->dact);
+      p.wmaps = h->rs_wmaps;
+      p.amaps = reinterpret_cast<const CUtensorMap*>(h->rs_amaps) + (decode_rs_tokens(h->is_int8, B) == 16 ? 0 : 2);
+      p.pick_scratch = h->rs_pick; p.logits_out = probe_target(h, h->cur_step);
+      p.attn_ws = h->dattn_ws; p.attn_counters = h->dattn_counters;
+      p.attn_chunks = std::min((h->cur_max_q + h->cur_step + 63) / 64, h->dattn_max_chunks);
+      p.gs = h->gs; p.bar = h->persist_bar; p.timestamps = h->cfg.debug ? h->persist_ts : nullptr;
+      p.B = B; p.max_ctx = h->max_ctx; p.step = h->cur_step; p.eps = kRmsEps; p.scale = 0.08838834764831845f;
+      TAG(PC_DEC_PERSIST);
+      if (h->prof_on) { cudaEventRecord(prof_event(h), h->stream); h->prof_tags.push_back(h->prof_cls); }
+      cudaError_t pe = launch_decode_rs(p, h->is_int8, h->rs_grid, h->stream, &h->rs_launch_mode);
+      if (h->prof_on) cudaEventRecord(prof_event(h), h->stream);
+      if (pe == cudaSuccess) { h->launches += 1; return 0; }
+      cudaGetLastError();
+      fprintf(stderr, "[sonicscribe_b200] row-sliced decode kernel refused (%s, grid %d, B %d); using the split-K persistent kernel\n",
+              cudaGetErrorName(pe), h->rs_grid, B);
+      h->use_rs = false;
+    }
     if (h->use_persist && B <= 64 && std::is_same<T, bf16>::value) {            // the persistent kernel tiles at most 64 tokens
       DecodePersistArgs p;
       memset(&p, 0, sizeof(p));
@@ -691,6 +727,19 @@ int alloc_all(sonic_ctx* h) {
     DA(h->persist_tmaps, (size_t)(4 * c.dec_layers + 4) * sizeof(CUtensorMap));
     DA(h->persist_kv_maps, 2 * sizeof(CUtensorMap));
   }
+  if (h->use_rs) {
+    const size_t Qe = h->is_int8 ? 1 : 2;
+    h->wqkv_il.assign(c.dec_layers, nullptr);
+    h->s_qkv_il.assign(c.dec_layers, nullptr);
+    for (int l = 0; l < c.dec_layers; ++l) {
+      DA(h->wqkv_il[l], (size_t)kQkvDec * kDecH * Qe);
+      if (h->is_int8) DA(h->s_qkv_il[l], kQkvDec * 4);
+    }
+    DA(h->rs_layers, (size_t)c.dec_layers * sizeof(RsLayer));
+    DA(h->rs_wmaps, (size_t)(4 * c.dec_layers + 2) * sizeof(CUtensorMap));
+    DA(h->rs_amaps, 4 * sizeof(CUtensorMap));
+    DA(h->rs_pick, (size_t)B * h->num_sms * 4 * 4);
+  }
   h->dattn_max_chunks = (h->max_ctx + 63) / 64;
   DA(h->dattn_ws, (size_t)B * kDecKv * h->dattn_max_chunks * 4 * 130 * 4);
   DAZ(h->dattn_counters, (size_t)B * kDecKv * 4);
@@ -838,6 +887,7 @@ int do_generate(sonic_ctx* h, const int32_t* ids, const int32_t* id_offsets, int
 
   CK(cudaEventRecord(h->ev[2], st));
   h->cur_step = 0;
+  h->cur_max_q = max_q;
   h->probe_batch = batch;
   int rc = dispatch(h, [&] { return Engine<float>::prefill(h, batch, total, max_q); }, [&] { return Engine<bf16>::prefill(h, batch, total, max_q); });
   if (rc) return rc;
@@ -984,6 +1034,16 @@ int sonic_create(const sonic_config* cfg, sonic_handle* out) {
       h->use_persist = false;
     }
   }
+  {
+    const char* rs = getenv("SONIC_DECODE_RS");
+    h->use_rs = h->use_persist && !(rs && rs[0] == '0');
+    if (h->use_rs && (decode_rs_configure() != cudaSuccess || decode_rs_occupancy() < 1)) {
+      cudaGetLastError();
+      fprintf(stderr, "[sonicscribe_b200] row-sliced decode kernel unavailable on this device; using the split-K persistent kernel\n");
+      h->use_rs = false;
+    }
+    h->rs_grid = h->persist_grid;
+  }
   if (!h->is_f32 && attention_prefill_tc_configure() != cudaSuccess) { h->err = "attention_prefill_tc_configure failed"; return bail(0); }
   if (!h->is_f32 && attention_tc_configure() != cudaSuccess) { h->err = "attention_tc_configure failed"; return bail(0); }
   if (alloc_all(h)) return bail(0);
@@ -1074,6 +1134,39 @@ int sonic_finalize_weights(sonic_handle h) {
       CK(make_tensor_map_2d(&maps[4 * L + 3], h->dact, kDecInter, kPersistTcTokens, kDecInter, 64, kPersistTcTokens));
       CK(cudaMemcpy(h->persist_tmaps, maps.data(), maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice));
     }
+  }
+  if (h->use_rs) {
+    const int L = h->cfg.dec_layers;
+    const size_t layer_kv = (size_t)h->cfg.max_batch * kDecKv * h->max_ctx * kDecHd;
+    const int row_bytes = kDecH * (h->is_int8 ? 1 : 2);
+    std::vector<RsLayer> tab(L);
+    std::vector<CUtensorMap> maps(4 * L + 2);
+    for (int l = 0; l < L; ++l) {
+      const DecLayerW& w = h->dec[l];
+      CK(decode_rs_permute_qkv(w.wqkv, h->wqkv_il[l], row_bytes, w.s_qkv, h->s_qkv_il[l], h->stream));
+      tab[l].rms1 = w.rms1; tab[l].rms2 = w.rms2;
+      tab[l].s_qkv = h->s_qkv_il[l]; tab[l].s_o = w.s_o; tab[l].s_gu = w.s_gu; tab[l].s_down = w.s_down;
+      tab[l].kc = reinterpret_cast<bf16*>(h->kcache) + (size_t)l * layer_kv;
+      tab[l].vc = reinterpret_cast<bf16*>(h->vcache) + (size_t)l * layer_kv;
+      const void* mats[4] = {h->wqkv_il[l], w.wo, w.wgu, w.wdown};
+      const long long rows[4] = {kQkvDec, kDecH, 2 * kDecInter, kDecH}, ks[4] = {kDecH, kDecH, kDecH, kDecInter};
+      for (int k = 0; k < 4; ++k) {
+        if (h->is_int8) CK(make_tensor_map_2d_u8(&maps[4 * l + k], mats[k], ks[k], rows[k], ks[k], 64, decode_rs_box_rows(k)));
+        else CK(make_tensor_map_2d(&maps[4 * l + k], mats[k], ks[k], rows[k], ks[k], 64, decode_rs_box_rows(k)));
+      }
+    }
+    CK(make_tensor_map_2d(&maps[4 * L], h->lm_head, kDecH, kVocab, kDecH, 64, decode_rs_box_rows(4)));
+    CK(make_tensor_map_2d(&maps[4 * L + 1], h->lm_head, kDecH, kVocab, kDecH, 64, decode_rs_box_rows(5)));
+    CUtensorMap am[4];
+    for (int i = 0; i < 2; ++i) {
+      const int ntok = i == 0 ? 16 : 32;
+      CK(make_tensor_map_2d(&am[2 * i], h->dattn, kDecH, kPersistTcTokens, kDecH, 64, ntok));
+      CK(make_tensor_map_2d(&am[2 * i + 1], h->dact, kDecInter, kPersistTcTokens, kDecInter, 64, ntok));
+    }
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaMemcpy(h->rs_layers, tab.data(), tab.size() * sizeof(RsLayer), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(h->rs_wmaps, maps.data(), maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(h->rs_amaps, am, sizeof(am), cudaMemcpyHostToDevice));
   }
   h->finalized = true;
   return 0;
@@ -1187,6 +1280,17 @@ int sonic_debug_read(sonic_handle h, const char* name, float* out, size_t max_el
   size_t n = 0;
   if (nm == "rope_enc_cos") { src_f32 = h->rope_enc_cos; n = (size_t)kEncT * kEncRot / 2; }
   else if (nm == "rope_dec_cos") { src_f32 = h->rope_dec_cos; n = (size_t)h->max_ctx * kDecHd / 2; }
+  else if (nm == "rs_ts" && h->persist_ts) {
+    // phase timestamps of the last row-sliced decode step (microseconds relative to the first stamp): 5 per layer + 3
+    const int n = 5 * h->cfg.dec_layers + 3;
+    std::vector<unsigned long long> ts(n);
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaMemcpy(ts.data(), h->persist_ts, n * 8, cudaMemcpyDeviceToHost));
+    if ((size_t)n > max_elems) return fail(h, "sonic_debug_read: output buffer too small");
+    for (int i = 0; i < n; ++i) out[i] = (float)((double)(ts[i] - ts[0]) * 1e-3);
+    if (n_elems) *n_elems = n;
+    return 0;
+  }
   else if (nm == "persist_ts" && h->persist_ts) {
     // phase timestamps of the last persistent decode step, returned as float32 microseconds relative to the first stamp
     const int n = 2 + 7 * h->cfg.dec_layers + 3;

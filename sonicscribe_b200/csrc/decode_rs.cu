@@ -1,0 +1,798 @@
+// Row-sliced persistent greedy-decode step for up to 32 segments (bf16 or int8 weight-only linears): ONE cooperative kernel
+// per generated token; every weight matrix is cut into 148 contiguous ROW slices (one per CTA) that are streamed over the
+// FULL K dimension by TMA into a shared-memory ring and multiplied on tcgen05 (weights = the M operand, 64- or 128-row MMA;
+// the <= 32 token rows = the N operand), accumulators in TMEM.
+//
+// Why this shape:
+//   * a batch-1..32 decode step is a chain of ~140 dependent phases whose weight bytes (96 MB per layer) take 15 us at HBM
+//     speed while the dependency chain took 49 us with the split-K / mma.sync design of decode_persist.cu.  Here no phase
+//     produces split-K partials, so residual add, RoPE + KV append, SwiGLU and the argmax are epilogues of the GEMM that
+//     owns the rows, and RMSNorm is recomputed by every CTA while it builds its MMA operand in shared memory: 5 grid
+//     barriers per layer instead of 7, no fp32 partial traffic, no separate norm / embed / pick-scan phases;
+//   * weights do not depend on the token: a dedicated producer warp walks the CTA's whole weight schedule (all layers) and
+//     is throttled only by ring space, so the stream keeps flowing through grid barriers, attention and epilogues;
+//   * accumulation runs over K in one fixed order inside one accumulator: results do not depend on the batch size or on
+//     which other segments share the batch (bit-identical ids for a segment alone or in a batch).
+//
+// Phases per layer:  P1 [u = rmsnorm(x) g1 -> smem] qkv slice, epilogue RoPE + q store + K/V append | barrier |
+//                    P2 attention (split over key chunks and CTAs, last-arriver merge)              | barrier |
+//                    P3 o-proj slice (operand: attention output by TMA), epilogue x += o            | barrier |
+//                    P4 [u = rmsnorm(x) g2 -> smem] gate/up slice, epilogue SwiGLU -> act           | barrier |
+//                    P5 down slice (operand: act by TMA, 1024-k chunks), epilogue x += d            | barrier |
+// then lm_head slice with the argmax as epilogue | barrier | per-token merge + greedy bookkeeping.
+//
+// Warp roles (17 warps): w16 weight producer; w0 activation-chunk loader; w1 MMA issuer; w2 TMEM owner; w4-7 epilogue
+// (TMEM lane quadrants); w8-15 int8 -> bf16 converters (int8 mode); w0-15 build the normalised operand and run attention.
+//
+// Replaces, for one new token per segment: LlamaDecoderLayer x28 + final norm + lm_head + argmax/EOS bookkeeping
+// (transformers/models/llama/modeling_llama.py:53-499, transformers/generation/utils.py:2743-2809), with the reference's
+// bf16 rounding points (linear outputs, RoPE products, SiLU, residual sums are rounded to bf16 where HF materialises a
+// bf16 tensor).
+#include <cuda.h>
+#include "common.cuh"
+#include "kernels.h"
+#include "gemm_tc.h"
+#include "tc_ptx.cuh"
+
+namespace sonic {
+
+namespace {
+
+constexpr int RH = 2048, RQKV = 3072, RI = 6144, RV = 59264, RHD = 128, RKVH = 4, RG = 4;
+constexpr int kRsThreads = 544, kRsWork = 512;            // 16 worker warps + the producer warp
+constexpr int kStageBytes = 16384;
+constexpr int kAttnCK = 64;                               // keys per attention chunk
+constexpr int kAttnKRow = RHD * 2 + 16;                   // padded K row (bytes): conflict-free 16 B reads across keys
+
+// ---- bounded waits: a protocol bug must surface as a launch failure, not as a hung GPU -------------------------------
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __noinline__ void rs_timeout(int tag, unsigned v) {
+  printf("[sonicscribe_b200] decode_rs: wait %d timed out (block %d thread %d, value %u)\n", tag, blockIdx.x, threadIdx.x, v);
+  __trap();
+}
+__device__ __forceinline__ void mbar_wait_wd(uint32_t bar, uint32_t parity, int tag) {
+  uint32_t done;
+  unsigned long long t0 = 0;
+  for (unsigned it = 0;; ++it) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) return;
+    if ((it & 1023u) == 1023u) {
+      const unsigned long long t = gtime();
+      if (t0 == 0) t0 = t;
+      else if (t - t0 > 4000000000ull) rs_timeout(tag, parity);
+    }
+  }
+}
+__device__ __forceinline__ void sync_workers() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
+__device__ __forceinline__ void sync_epilogue() { asm volatile("bar.sync 2, 128;" ::: "memory"); }
+__device__ __forceinline__ void sync_converters() { asm volatile("bar.sync 3, 256;" ::: "memory"); }
+
+__device__ __forceinline__ void grid_barrier_rs(unsigned* counter, unsigned& epoch) {
+  asm volatile("fence.proxy.async;" ::: "memory");       // generic writes of this phase vs TMA reads of the next
+  sync_workers();
+  if (threadIdx.x == 0) {
+    epoch += gridDim.x;
+    __threadfence();
+    atomicAdd(counter, 1u);
+    unsigned v;
+    unsigned long long t0 = 0;
+    for (unsigned it = 0;; ++it) {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+      if (v >= epoch) break;
+      if ((it & 1023u) == 1023u) {
+        const unsigned long long t = gtime();
+        if (t0 == 0) t0 = t;
+        else if (t - t0 > 4000000000ull) rs_timeout(100, v);
+      }
+    }
+    __threadfence();
+  }
+  sync_workers();
+  asm volatile("fence.proxy.async;" ::: "memory");
+}
+
+__device__ __forceinline__ float bf16r(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
+__device__ __forceinline__ float bf_lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 p = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&p);
+}
+
+// ---- geometry of one weight matrix as seen by one CTA ----------------------------------------------------------------------
+enum { MAT_QKV = 0, MAT_O = 1, MAT_GU = 2, MAT_DOWN = 3, MAT_HEAD = 4, MAT_HEAD_TAIL = 5 };
+struct Geom {
+  const CUtensorMap* map;
+  int r0, r1;        // this CTA's rows [r0, r1)
+  int box;           // rows per TMA box == rows per sub-tile
+  int nkb;           // 64-wide k blocks
+  int kps;           // k blocks per ring stage
+  int sub;           // bytes between the bf16 images of consecutive k blocks (1024-aligned, >= box * 128)
+  int raw_sub;       // int8 items: bytes between the raw int8 tiles of consecutive k blocks inside a ring stage
+  int m;             // MMA M (64 or 128)
+  int i8;            // weights arrive as int8
+};
+// box rows per matrix kind (multiples of 8 that cover the largest slice of a 148-CTA grid; other grids walk sub-tiles)
+__host__ __device__ constexpr int rs_box(int kind) { return kind == MAT_QKV ? 24 : kind == MAT_O ? 16 : kind == MAT_GU ? 88 : kind == MAT_DOWN ? 16 : kind == MAT_HEAD ? 128 : 32; }
+
+template <bool W8>
+__device__ __forceinline__ Geom make_geom(const CUtensorMap* maps, int n_layers, int layer, int kind) {
+  Geom g;
+  const int G = gridDim.x, c = blockIdx.x;
+  g.box = rs_box(kind);
+  g.i8 = (W8 && kind <= MAT_DOWN) ? 1 : 0;
+  g.nkb = (kind == MAT_DOWN) ? RI / 64 : RH / 64;
+  if (kind == MAT_QKV) { g.r0 = 2 * (int)(((long long)c * (RQKV / 2)) / G); g.r1 = 2 * (int)(((long long)(c + 1) * (RQKV / 2)) / G); }
+  else if (kind == MAT_GU) { g.r0 = 2 * (int)(((long long)c * RI) / G); g.r1 = 2 * (int)(((long long)(c + 1) * RI) / G); }
+  else if (kind == MAT_O || kind == MAT_DOWN) { g.r0 = (int)(((long long)c * RH) / G); g.r1 = (int)(((long long)(c + 1) * RH) / G); }
+  else {
+    const int a0 = (int)(((long long)c * RV) / G), a1 = (int)(((long long)(c + 1) * RV) / G);
+    const int full = (a1 - a0) / 128 * 128;                           // 128-row tiles first, the remainder in 32-row boxes
+    if (kind == MAT_HEAD) { g.r0 = a0; g.r1 = a0 + full; } else { g.r0 = a0 + full; g.r1 = a1; }
+  }
+  g.map = maps + ((kind <= MAT_DOWN) ? 4 * layer + kind : 4 * n_layers + (kind - MAT_HEAD));
+  g.sub = (g.box * 128 + 1023) & ~1023;
+  g.m = g.box <= 64 ? 64 : 128;
+  int kps = kStageBytes / g.sub;                                       // bf16: the stage holds kps images
+  if (kps > 8) kps = 8;
+  while (g.nkb % kps) --kps;
+  if (g.i8) {                                                          // int8: twice the k blocks per stage, images go to a 32 KB converter buffer
+    g.raw_sub = (g.box * 64 + 127) & ~127;
+    kps = (2 * kStageBytes) / g.sub;
+    if (kps > 16) kps = 16;
+    while (g.nkb % kps || kps * g.raw_sub > kStageBytes) --kps;
+  } else g.raw_sub = 0;
+  g.kps = kps;
+  return g;
+}
+
+struct RsCtx {
+  uint32_t ring, region, conv, bars, tmem;
+  uint8_t* region_g;     // generic pointer to the operand region (also the attention scratch)
+  uint8_t* ring_g;
+  uint8_t* conv_g;
+  int n_stages;
+  uint32_t cnt;          // ring stages consumed so far (all matrices)
+  uint32_t ic;           // accumulator uses so far
+  uint32_t cc;           // converter buffer uses so far (int8)
+  uint32_t au[2];        // activation half-region loads so far
+};
+// barrier slots: full[NS] empty[NS] acc_full[2] acc_empty[2] act_full[2] act_empty[2] conv_full[2] conv_empty[2]
+__device__ __forceinline__ uint32_t b_full(const RsCtx& c, uint32_t s) { return c.bars + 8u * s; }
+__device__ __forceinline__ uint32_t b_empty(const RsCtx& c, uint32_t s) { return c.bars + 8u * (c.n_stages + s); }
+__device__ __forceinline__ uint32_t b_misc(const RsCtx& c, uint32_t i) { return c.bars + 8u * (2 * c.n_stages + i); }
+enum { ACC_FULL = 0, ACC_EMPTY = 2, ACT_FULL = 4, ACT_EMPTY = 6, CONV_FULL = 8, CONV_EMPTY = 10, N_MISC = 12 };
+
+// ---- the weight producer: one thread walks the CTA's whole schedule ----------------------------------------------------------
+template <bool W8>
+__device__ void produce_matrix(const RsCtx& c, const Geom& g, uint32_t& cnt) {
+  const uint32_t row_bytes = g.i8 ? 64u : 128u;
+  const uint32_t sub = g.i8 ? (uint32_t)g.raw_sub : (uint32_t)g.sub;
+  for (int r = g.r0; r < g.r1; r += g.box) {
+    for (int kb0 = 0; kb0 < g.nkb; kb0 += g.kps, ++cnt) {
+      const uint32_t s = cnt % c.n_stages, par = (cnt / c.n_stages) & 1u;
+      mbar_wait_wd(b_empty(c, s), par ^ 1u, 1);
+      mbar_expect_tx(b_full(c, s), (uint32_t)g.kps * g.box * row_bytes);
+      const uint32_t dst = c.ring + s * kStageBytes;
+#pragma unroll 1
+      for (int j = 0; j < g.kps; ++j) tma_load_2d(dst + j * sub, g.map, b_full(c, s), (kb0 + j) * 64, r);
+    }
+  }
+}
+
+template <bool W8>
+__device__ void producer_loop(const DecodeRsArgs& a, const RsCtx& c) {
+  const CUtensorMap* maps = reinterpret_cast<const CUtensorMap*>(a.wmaps);
+  uint32_t cnt = 0;
+  for (int l = 0; l < a.n_layers; ++l)
+    for (int k = MAT_QKV; k <= MAT_DOWN; ++k) produce_matrix<W8>(c, make_geom<W8>(maps, a.n_layers, l, k), cnt);
+  produce_matrix<W8>(c, make_geom<W8>(maps, a.n_layers, 0, MAT_HEAD), cnt);
+  produce_matrix<W8>(c, make_geom<W8>(maps, a.n_layers, 0, MAT_HEAD_TAIL), cnt);
+}
+
+// ---- operand builders ------------------------------------------------------------------------------------------------------
+// u[t] = gamma * bf16(x[t] * rsqrt(mean(x[t]^2) + eps)) for every token, written as the K-major SWIZZLE_128B operand the MMA
+// reads: k block kb is a [NTOK rows x 128 B] slab, 16 B chunk ch of row t sits at chunk (ch ^ (t & 7)).  One warp per token.
+// from_embed: x[t] is the embedding row of the token picked by the previous step (and is stored to x by one CTA).
+template <int NTOK>
+__device__ __forceinline__ void build_norm_operand(const DecodeRsArgs& a, const RsCtx& c, const float* __restrict__ gamma, bool from_embed) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int t = warp; t < a.B; t += 16) {
+    const bf16* row;
+    if (from_embed) {
+      int tok = a.gs.cur_tok[t];
+      tok = tok < 0 ? 0 : (tok >= RV ? RV - 1 : tok);
+      row = a.embed + (size_t)tok * RH;
+    } else row = a.x + (size_t)t * RH;
+    uint4 v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __ldcg(reinterpret_cast<const uint4*>(row) + lane + 32 * i);
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const uint32_t w[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { const float lo = bf_lo(w[e]), hi = bf_hi(w[e]); ss = fmaf(lo, lo, ss); ss = fmaf(hi, hi, ss); }
+    }
+    ss = warp_sum(ss);
+    const float rstd = rsqrtf(ss * (1.0f / RH) + a.eps);
+    if (from_embed && (int)blockIdx.x == t % (int)gridDim.x) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) *(reinterpret_cast<uint4*>(a.x + (size_t)t * RH) + lane + 32 * i) = v[i];
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int ch = lane + 32 * i;                       // 16 B chunk of the row: k = 8 * ch
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * ch), g1 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * ch + 1);
+      const uint32_t w[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+      uint4 o;
+      o.x = pack_bf16(g0.x * bf16r(bf_lo(w[0]) * rstd), g0.y * bf16r(bf_hi(w[0]) * rstd));
+      o.y = pack_bf16(g0.z * bf16r(bf_lo(w[1]) * rstd), g0.w * bf16r(bf_hi(w[1]) * rstd));
+      o.z = pack_bf16(g1.x * bf16r(bf_lo(w[2]) * rstd), g1.y * bf16r(bf_hi(w[2]) * rstd));
+      o.w = pack_bf16(g1.z * bf16r(bf_lo(w[3]) * rstd), g1.w * bf16r(bf_hi(w[3]) * rstd));
+      const int kb = ch >> 3, cc = ch & 7;
+      *reinterpret_cast<uint4*>(c.region_g + (size_t)kb * (NTOK * 128) + t * 128 + ((cc ^ (t & 7)) << 4)) = o;
+    }
+  }
+  fence_proxy_async_smem();
+  sync_workers();
+}
+
+// ---- epilogues -------------------------------------------------------------------------------------------------------------
+enum { EPI_QKV = 0, EPI_RESID = 1, EPI_SWIGLU = 2, EPI_HEAD = 3 };
+struct PickState { float best, second; int idx; };
+__device__ __forceinline__ void pick_merge2(float& mb, float& ms, int& mi, float ob, float os, int oi) {
+  if (ob > mb || (ob == mb && oi < mi)) { ms = fmaxf(fmaxf(ms, os), mb); mb = ob; mi = oi; }
+  else { ms = fmaxf(ms, ob); }
+}
+
+template <int NTOK, int EPI>
+__device__ __forceinline__ void epilogue_tile(const DecodeRsArgs& a, const RsLayer& L, const Geom& g, int r, const float* __restrict__ wscale,
+                                              uint32_t taddr, float* s_pick) {
+  const int lane = threadIdx.x & 31, q = (threadIdx.x >> 5) & 3;
+  uint32_t v[NTOK];
+  if constexpr (NTOK == 16) tmem_ld16(taddr + ((uint32_t)(q * 32) << 16), v);
+  else tmem_ld32(taddr + ((uint32_t)(q * 32) << 16), v);
+  tmem_ld_wait();
+  const int rl = (g.m == 64) ? (lane < 16 ? q * 16 + lane : -1) : q * 32 + lane;     // row of the tile held by this lane
+  const int nrows = min(g.box, g.r1 - r);
+  const bool valid = rl >= 0 && rl < nrows;
+  const int gr = r + (rl < 0 ? 0 : rl);
+  const float sc = (g.i8 && valid) ? __ldg(wscale + gr) : 1.0f;
+  if constexpr (EPI == EPI_QKV) {
+    // rows of q and k heads are interleaved (2j, 2j+1) = natural dims (j, j+64): the RoPE partner sits in the neighbouring lane
+    const bool is_qk = gr < (RQKV - RKVH * RHD);
+    const int hb = gr >> 7, i = gr & 127, j = i >> 1, second = i & 1;
+#pragma unroll
+    for (int t = 0; t < NTOK; ++t) {
+      const float own = bf16r(__uint_as_float(v[t]) * sc);
+      const float other = __shfl_xor_sync(0xffffffffu, own, 1);
+      if (t < a.B && valid) {
+        const int pos = a.gs.ctx_len[t];
+        if (is_qk) {
+          const float cs = bf16r(__ldg(a.cos_t + (size_t)pos * (RHD / 2) + j)), sn = bf16r(__ldg(a.sin_t + (size_t)pos * (RHD / 2) + j));
+          const float p0 = bf16r(own * cs), p1 = bf16r(other * sn);
+          const bf16 res = __float2bfloat16_rn(second ? p0 + p1 : p0 - p1);
+          const int d = j + 64 * second;
+          if (hb < 16) a.q[(size_t)t * RH + hb * RHD + d] = res;
+          else L.kc[((size_t)(t * RKVH + (hb - 16)) * a.max_ctx + pos) * RHD + d] = res;
+        } else {
+          const int vr = gr - (RQKV - RKVH * RHD);
+          L.vc[((size_t)(t * RKVH + (vr >> 7)) * a.max_ctx + pos) * RHD + (vr & 127)] = __float2bfloat16_rn(own);
+        }
+      }
+    }
+  } else if constexpr (EPI == EPI_RESID) {
+#pragma unroll
+    for (int t = 0; t < NTOK; ++t) {
+      if (t < a.B && valid) {
+        bf16* px = a.x + (size_t)t * RH + gr;                          // this thread is the only writer of x[t][gr]
+        const float xo = __uint_as_float((uint32_t)__ldcg(reinterpret_cast<const unsigned short*>(px)) << 16);
+        *px = __float2bfloat16_rn(xo + bf16r(__uint_as_float(v[t]) * sc));
+      }
+    }
+  } else if constexpr (EPI == EPI_SWIGLU) {
+#pragma unroll
+    for (int t = 0; t < NTOK; ++t) {
+      const float own = bf16r(__uint_as_float(v[t]) * sc);
+      const float up = __shfl_xor_sync(0xffffffffu, own, 1);       // rows are interleaved (gate, up)
+      if (t < a.B && valid && (gr & 1) == 0) a.act[(size_t)t * RI + (gr >> 1)] = __float2bfloat16_rn(bf16r(silu_exact(own)) * up);
+    }
+  } else {
+    // lm_head: fp32 logits; running (best, second, argmax) of this warp per token lives in shared memory
+    const int warp4 = (threadIdx.x >> 5) & 3;
+#pragma unroll
+    for (int t = 0; t < NTOK; ++t) {
+      if (t < a.B) {                                                 // uniform
+        float x = valid ? __uint_as_float(v[t]) : -INFINITY;
+        if (!(x == x)) x = -INFINITY;                                 // NaN never wins
+        if (a.logits_out && valid) a.logits_out[(size_t)t * RV + gr] = x;
+        float best = x, second = -INFINITY;
+        int bi = valid ? gr : 0x7fffffff;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const float ob = __shfl_xor_sync(0xffffffffu, best, o), os = __shfl_xor_sync(0xffffffffu, second, o);
+          const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+          pick_merge2(best, second, bi, ob, os, oi);
+        }
+        if (lane == 0) {
+          float* sp = s_pick + (warp4 * NTOK + t) * 3;
+          float mb = sp[0], ms = sp[1];
+          int mi = __float_as_int(sp[2]);
+          pick_merge2(mb, ms, mi, best, second, bi);
+          sp[0] = mb; sp[1] = ms; sp[2] = __int_as_float(mi);
+        }
+      }
+    }
+  }
+}
+
+// ---- one GEMM phase: rows [g.r0, g.r1) of one matrix against the operand region ------------------------------------------
+// ACT: the operand is a global bf16 activation [tokens][K] loaded by TMA in 1024-k half-region chunks (act_map); otherwise the
+// region already holds the normalised operand for the whole K = 2048.
+template <int NTOK, bool W8, int EPI, bool ACT>
+__device__ __forceinline__ void gemm_phase_rs(const DecodeRsArgs& a, const RsLayer& L, RsCtx& c, const Geom& g, const CUtensorMap* act_map,
+                                              const float* __restrict__ wscale, float* s_pick) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_sub = (g.r1 - g.r0 + g.box - 1) / g.box;
+  const int n_groups = g.nkb / g.kps;
+  const int n_chunks = g.nkb / 16;                                    // activation chunks of 16 k blocks per sub-tile
+  constexpr uint32_t kHalf = NTOK * 128 * 16;                         // bytes of one activation chunk
+  if (ACT && warp == 0) {
+    if (lane == 0) {
+      uint32_t au[2] = {c.au[0], c.au[1]};
+      for (int st = 0; st < n_sub; ++st)
+        for (int ci = 0; ci < n_chunks; ++ci) {
+          const int h = ci & 1;
+          mbar_wait_wd(b_misc(c, ACT_EMPTY + h), (au[h] & 1u) ^ 1u, 2);
+          mbar_expect_tx(b_misc(c, ACT_FULL + h), kHalf);
+#pragma unroll 1
+          for (int kb = 0; kb < 16; ++kb)
+            tma_load_2d(c.region + h * kHalf + kb * (NTOK * 128), act_map, b_misc(c, ACT_FULL + h), (ci * 16 + kb) * 64, 0);
+          ++au[h];
+        }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(g.m, NTOK);
+      uint32_t cnt = c.cnt, ic = c.ic, cc = c.cc;
+      uint32_t au[2] = {c.au[0], c.au[1]};
+      for (int st = 0; st < n_sub; ++st, ++ic) {
+        const uint32_t acc = ic & 1u;
+        mbar_wait_wd(b_misc(c, ACC_EMPTY + acc), ((ic >> 1) & 1u) ^ 1u, 3);
+        tc_fence_after();
+        for (int grp = 0; grp < n_groups; ++grp, ++cnt) {
+          const uint32_t s = cnt % c.n_stages, par = (cnt / c.n_stages) & 1u;
+          uint32_t abase;
+          if (W8 && g.i8) {
+            const uint32_t cb = cc & 1u;
+            mbar_wait_wd(b_misc(c, CONV_FULL + cb), (cc >> 1) & 1u, 4);
+            abase = c.conv + cb * (2 * kStageBytes);
+          } else {
+            mbar_wait_wd(b_full(c, s), par, 5);
+            abase = c.ring + s * kStageBytes;
+          }
+          tc_fence_after();
+          for (int j = 0; j < g.kps; ++j) {
+            const int kb = grp * g.kps + j;
+            if (ACT && (kb & 15) == 0) {
+              const int h = (kb >> 4) & 1;
+              mbar_wait_wd(b_misc(c, ACT_FULL + h), au[h] & 1u, 6);
+              tc_fence_after();
+            }
+            const uint64_t da = make_sw128_desc(abase + j * g.sub), db = make_sw128_desc(c.region + (uint32_t)(kb & 31) * (NTOK * 128));
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              tc_mma_bf16(c.tmem + acc * NTOK, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb != 0 || k != 0) ? 1u : 0u);
+            if (ACT && (kb & 15) == 15) {
+              const int h = (kb >> 4) & 1;
+              tc_commit(b_misc(c, ACT_EMPTY + h));
+              ++au[h];
+            }
+          }
+          if (W8 && g.i8) { tc_commit(b_misc(c, CONV_EMPTY + (cc & 1u))); ++cc; }
+          else tc_commit(b_empty(c, s));
+        }
+        tc_commit(b_misc(c, ACC_FULL + acc));
+      }
+    }
+  } else if (warp >= 4 && warp < 8) {
+    uint32_t ic = c.ic;
+    int r = g.r0;
+    for (int st = 0; st < n_sub; ++st, ++ic, r += g.box) {
+      const uint32_t acc = ic & 1u;
+      mbar_wait_wd(b_misc(c, ACC_FULL + acc), (ic >> 1) & 1u, 7);
+      tc_fence_after();
+      epilogue_tile<NTOK, EPI>(a, L, g, r, wscale, c.tmem + acc * NTOK, s_pick);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(b_misc(c, ACC_EMPTY + acc));
+    }
+  } else if (W8 && g.i8 && warp >= 8) {
+    // int8 -> bf16: ring stage (kps raw tiles of [box rows x 64 B]) -> converter buffer (kps SWIZZLE_128B images)
+    const int tid = threadIdx.x - 256;
+    uint32_t cnt = c.cnt, cc = c.cc;
+    const int per_kb = g.box * 4;                                     // 16 B pieces per k block
+    for (int st = 0; st < n_sub; ++st)
+      for (int grp = 0; grp < n_groups; ++grp, ++cnt, ++cc) {
+        const uint32_t s = cnt % c.n_stages, par = (cnt / c.n_stages) & 1u, cb = cc & 1u;
+        mbar_wait_wd(b_full(c, s), par, 8);
+        mbar_wait_wd(b_misc(c, CONV_EMPTY + cb), ((cc >> 1) & 1u) ^ 1u, 9);
+        const uint8_t* src = c.ring_g + (size_t)s * kStageBytes;
+        uint8_t* dst = c.conv_g + (size_t)cb * (2 * kStageBytes);
+        for (int it = tid; it < g.kps * per_kb; it += 256) {
+          const int j = it / per_kb, rem = it - j * per_kb, row = rem >> 2, piece = rem & 3;
+          const uint4 w = *reinterpret_cast<const uint4*>(src + (size_t)j * g.raw_sub + row * 64 + piece * 16);
+          const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+          uint32_t o[8];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            // two's complement byte b = low7 - 128 * bit7: bf16(0x4300 | low7) = 128 + low7, bf16(0x4300 | bit7 << 7) = 128 or 256
+            const uint32_t lo2 = __byte_perm(ww[e], 0x43434343u, 0x4140), hi2 = __byte_perm(ww[e], 0x43434343u, 0x4342);
+            const uint32_t one = 0xbf80bf80u;                         // -1.0 in both bf16 halves
+            __nv_bfloat162 alo, blo, ahi, bhi;
+            *reinterpret_cast<uint32_t*>(&alo) = lo2 & 0xff7fff7fu; *reinterpret_cast<uint32_t*>(&blo) = lo2 & 0xff80ff80u;
+            *reinterpret_cast<uint32_t*>(&ahi) = hi2 & 0xff7fff7fu; *reinterpret_cast<uint32_t*>(&bhi) = hi2 & 0xff80ff80u;
+            const __nv_bfloat162 m1 = *reinterpret_cast<const __nv_bfloat162*>(&one);
+            const __nv_bfloat162 rlo = __hfma2(blo, m1, alo), rhi = __hfma2(bhi, m1, ahi);
+            o[2 * e] = *reinterpret_cast<const uint32_t*>(&rlo);
+            o[2 * e + 1] = *reinterpret_cast<const uint32_t*>(&rhi);
+          }
+          uint8_t* drow = dst + (size_t)j * g.sub + row * 128;
+          *reinterpret_cast<uint4*>(drow + (((2 * piece) ^ (row & 7)) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
+          *reinterpret_cast<uint4*>(drow + (((2 * piece + 1) ^ (row & 7)) << 4)) = make_uint4(o[4], o[5], o[6], o[7]);
+        }
+        fence_proxy_async_smem();
+        sync_converters();                                               // all 8 converter warps are done with this stage
+        if (tid == 0) { mbar_arrive(b_misc(c, CONV_FULL + cb)); mbar_arrive(b_empty(c, s)); }
+      }
+  }
+  // mirrored counters (every worker thread advances them identically)
+  c.cnt += (uint32_t)(n_sub * n_groups);
+  c.ic += (uint32_t)n_sub;
+  if (W8 && g.i8) c.cc += (uint32_t)(n_sub * n_groups);
+  if (ACT) { c.au[0] += (uint32_t)(n_sub * ((n_chunks + 1) / 2)); c.au[1] += (uint32_t)(n_sub * (n_chunks / 2)); }
+}
+
+// ---- attention: item = (segment, kv head, chunk of 64 keys); partial (m, l, o) per item, merged by the item that arrives last
+// at the (segment, kv head) counter, in chunk order (deterministic, independent of how many chunks the launch was given) ------
+__device__ __forceinline__ void attention_phase_rs(const DecodeRsArgs& a, const RsLayer& L, uint8_t* scratch) {
+  uint8_t* sK = scratch;                                                // kAttnCK x 272 B
+  uint8_t* sV = scratch + kAttnCK * kAttnKRow;                          // kAttnCK x 256 B
+  float* sQ = reinterpret_cast<float*>(sV + kAttnCK * RHD * 2);        // [4][128], pre-scaled
+  float* sP = sQ + RG * RHD;                                            // [4][64]
+  float* sM = sP + RG * kAttnCK;                                        // [16] per-warp maxima
+  float* sL = sM + 16;                                                  // [16] per-warp sums
+  int* s_last = reinterpret_cast<int*>(sL + 16);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int C = a.attn_chunks;
+  const int n_items = a.B * RKVH * C;
+  for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    const int chunk = item % C, grp = item / C;
+    const int seg = grp / RKVH, kvh = grp - seg * RKVH;
+    const int pos = a.gs.ctx_len[seg], kv_len = pos + 1;
+    const int n_chunks = (kv_len + kAttnCK - 1) / kAttnCK;
+    float* ws = a.attn_ws + ((size_t)grp * C + chunk) * RG * (RHD + 2);
+    if (chunk < n_chunks) {
+      const bf16* kc = L.kc + ((size_t)seg * RKVH + kvh) * a.max_ctx * RHD;
+      const bf16* vc = L.vc + ((size_t)seg * RKVH + kvh) * a.max_ctx * RHD;
+      const int k0 = chunk * kAttnCK, nk = min(kAttnCK, kv_len - k0);
+      if (tid < 64) {                                                   // q: 4 heads x 128 dims, 8 per thread
+        const uint4 qv = __ldcg(reinterpret_cast<const uint4*>(a.q + (size_t)seg * RH + kvh * RG * RHD) + tid);
+        const uint32_t w[4] = {qv.x, qv.y, qv.z, qv.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { sQ[tid * 8 + 2 * e] = bf_lo(w[e]) * a.scale; sQ[tid * 8 + 2 * e + 1] = bf_hi(w[e]) * a.scale; }
+      }
+      for (int i = tid; i < kAttnCK * 16; i += kRsWork) {
+        const int r = i >> 4, c16 = i & 15;
+        uint4 kk = make_uint4(0, 0, 0, 0), vv = make_uint4(0, 0, 0, 0);
+        if (r < nk) {
+          kk = __ldcg(reinterpret_cast<const uint4*>(kc + (size_t)(k0 + r) * RHD) + c16);
+          vv = __ldcg(reinterpret_cast<const uint4*>(vc + (size_t)(k0 + r) * RHD) + c16);
+        }
+        *reinterpret_cast<uint4*>(sK + r * kAttnKRow + c16 * 16) = kk;
+        *reinterpret_cast<uint4*>(sV + r * (RHD * 2) + c16 * 16) = vv;
+      }
+      sync_workers();
+      // scores: pair p = tid / 2 -> (head, key); the two threads of a pair take 64 dims each
+      const int p = tid >> 1, half = tid & 1, head = p >> 6, key = p & 63;
+      float acc = 0.f;
+      {
+        const uint8_t* kr = sK + key * kAttnKRow + half * 128;
+        const float* qh = sQ + head * RHD + half * 64;
+#pragma unroll
+        for (int c8 = 0; c8 < 8; ++c8) {
+          const uint4 kv = *reinterpret_cast<const uint4*>(kr + c8 * 16);
+          const float4 q0 = *reinterpret_cast<const float4*>(qh + c8 * 8), q1 = *reinterpret_cast<const float4*>(qh + c8 * 8 + 4);
+          acc = fmaf(bf_lo(kv.x), q0.x, acc); acc = fmaf(bf_hi(kv.x), q0.y, acc);
+          acc = fmaf(bf_lo(kv.y), q0.z, acc); acc = fmaf(bf_hi(kv.y), q0.w, acc);
+          acc = fmaf(bf_lo(kv.z), q1.x, acc); acc = fmaf(bf_hi(kv.z), q1.y, acc);
+          acc = fmaf(bf_lo(kv.w), q1.z, acc); acc = fmaf(bf_hi(kv.w), q1.w, acc);
+        }
+      }
+      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+      const float sc = (key < nk) ? acc : -INFINITY;
+      const float wmax = warp_max(sc);
+      if (lane == 0) sM[warp] = wmax;                                   // warps 4h .. 4h+3 hold head h
+      sync_workers();
+      const float cmax = fmaxf(fmaxf(sM[head * 4], sM[head * 4 + 1]), fmaxf(sM[head * 4 + 2], sM[head * 4 + 3]));
+      const float pr = (sc == -INFINITY) ? 0.f : expf(sc - cmax);
+      if (half == 0) sP[head * kAttnCK + key] = pr;
+      const float wsum = warp_sum(half == 0 ? pr : 0.f);
+      if (lane == 0) sL[warp] = wsum;
+      sync_workers();
+      {
+        const int ph = tid >> 7, d = tid & 127;                          // PV: thread = (head, dim)
+        float o = 0.f;
+        const float* pp = sP + ph * kAttnCK;
+        const bf16* vcol = reinterpret_cast<const bf16*>(sV) + d;
+        for (int j = 0; j < nk; ++j) o = fmaf(pp[j], __bfloat162float(vcol[j * RHD]), o);
+        ws[(size_t)ph * (RHD + 2) + d] = o;
+        if (d == 0) {
+          ws[(size_t)ph * (RHD + 2) + RHD] = fmaxf(fmaxf(sM[ph * 4], sM[ph * 4 + 1]), fmaxf(sM[ph * 4 + 2], sM[ph * 4 + 3]));
+          ws[(size_t)ph * (RHD + 2) + RHD + 1] = sL[ph * 4] + sL[ph * 4 + 1] + sL[ph * 4 + 2] + sL[ph * 4 + 3];
+        }
+      }
+    }
+    __threadfence();
+    sync_workers();
+    if (tid == 0) {
+      const int prev = atomicAdd(a.attn_counters + grp, 1);
+      *s_last = (prev == C - 1) ? 1 : 0;
+      if (prev == C - 1) a.attn_counters[grp] = 0;
+    }
+    sync_workers();
+    if (*s_last) {
+      __threadfence();
+      const int ph = tid >> 7, d = tid & 127;
+      const float* wg = a.attn_ws + (size_t)grp * C * RG * (RHD + 2);
+      float M = -INFINITY;
+      for (int cidx = 0; cidx < n_chunks; ++cidx) M = fmaxf(M, __ldcg(wg + ((size_t)cidx * RG + ph) * (RHD + 2) + RHD));
+      float Ls = 0.f, o = 0.f;
+      for (int cidx = 0; cidx < n_chunks; ++cidx) {
+        const float* pc = wg + ((size_t)cidx * RG + ph) * (RHD + 2);
+        const float w = expf(__ldcg(pc + RHD) - M);
+        Ls += __ldcg(pc + RHD + 1) * w;
+        o += __ldcg(pc + d) * w;
+      }
+      a.attn[(size_t)seg * RH + (size_t)(kvh * RG + ph) * RHD + d] = __float2bfloat16_rn(o / Ls);
+    }
+    sync_workers();
+  }
+}
+
+#define RS_STAMP()                                                                                  \
+  do {                                                                                              \
+    if (a.timestamps && blockIdx.x == 0 && threadIdx.x == 0) a.timestamps[n_stamp++] = gtime();     \
+  } while (0)
+
+template <int NTOK, bool W8>
+struct RsSmem {
+  static constexpr int kRegion = NTOK * RH * 2;                          // operand region: 64 KB / 128 KB
+  static constexpr int kConv = W8 ? 2 * 2 * kStageBytes : 0;             // two 32 KB converter buffers
+  static constexpr int kSmall = 2048;                                    // barriers, tmem slot, pick state
+  static constexpr int kStages = (227 * 1024 - 1024 - kRegion - kConv - kSmall) / kStageBytes;
+  static constexpr int kTotal = 1024 + kStages * kStageBytes + kConv + kRegion + kSmall;
+  static_assert(kStages >= 3, "ring too shallow");
+  static_assert(kRegion >= kAttnCK * kAttnKRow + kAttnCK * RHD * 2 + (RG * RHD + RG * kAttnCK + 40) * 4, "attention scratch does not fit the operand region");
+};
+
+template <int NTOK, bool W8>
+__global__ void __launch_bounds__(kRsThreads, 1) decode_rs_kernel(DecodeRsArgs a) {
+  using SM = RsSmem<NTOK, W8>;
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* sg = smem_raw + (base - raw);
+  RsCtx c;
+  c.n_stages = SM::kStages;
+  c.ring = base; c.ring_g = sg;
+  c.conv = base + SM::kStages * kStageBytes; c.conv_g = sg + SM::kStages * kStageBytes;
+  c.region = c.conv + SM::kConv; c.region_g = c.conv_g + SM::kConv;
+  uint8_t* small = c.region_g + SM::kRegion;
+  c.bars = c.region + SM::kRegion;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(small + 8 * (2 * SM::kStages + N_MISC));
+  float* s_pick = reinterpret_cast<float*>(small + 8 * (2 * SM::kStages + N_MISC) + 16);      // [4 warps][NTOK][3]
+  static_assert(8 * (2 * SM::kStages + N_MISC) + 16 + 4 * NTOK * 3 * 4 <= SM::kSmall, "small area overflow");
+  c.cnt = 0; c.ic = 0; c.cc = 0; c.au[0] = 0; c.au[1] = 0;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  constexpr int kTmemCols = 2 * NTOK < 32 ? 32 : 2 * NTOK;
+  if (tid == 0) {
+    for (int s = 0; s < SM::kStages; ++s) { mbar_init(b_full(c, s), 1); mbar_init(b_empty(c, s), 1); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(b_misc(c, ACC_FULL + i), 1); mbar_init(b_misc(c, ACC_EMPTY + i), 4);
+      mbar_init(b_misc(c, ACT_FULL + i), 1); mbar_init(b_misc(c, ACT_EMPTY + i), 1);
+      mbar_init(b_misc(c, CONV_FULL + i), 1); mbar_init(b_misc(c, CONV_EMPTY + i), 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<kTmemCols>(smem_u32(tmem_slot));
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  c.tmem = *tmem_slot;
+
+  if (warp == 16) {                                                     // the weight stream never waits for a grid barrier
+    if ((tid & 31) == 0) producer_loop<W8>(a, c);
+    return;
+  }
+  unsigned epoch = 0;
+  int n_stamp = 0;
+  RS_STAMP();
+  const CUtensorMap* wmaps = reinterpret_cast<const CUtensorMap*>(a.wmaps);
+  const CUtensorMap* amaps = reinterpret_cast<const CUtensorMap*>(a.amaps);       // [0] attention output, [1] SwiGLU output
+  for (int l = 0; l < a.n_layers; ++l) {
+    const RsLayer L = a.layers[l];
+    build_norm_operand<NTOK>(a, c, L.rms1, l == 0);
+    gemm_phase_rs<NTOK, W8, EPI_QKV, false>(a, L, c, make_geom<W8>(wmaps, a.n_layers, l, MAT_QKV), nullptr, L.s_qkv, s_pick);
+    grid_barrier_rs(a.bar, epoch); RS_STAMP();
+    attention_phase_rs(a, L, c.region_g);
+    grid_barrier_rs(a.bar, epoch); RS_STAMP();
+    gemm_phase_rs<NTOK, W8, EPI_RESID, true>(a, L, c, make_geom<W8>(wmaps, a.n_layers, l, MAT_O), amaps, L.s_o, s_pick);
+    grid_barrier_rs(a.bar, epoch); RS_STAMP();
+    build_norm_operand<NTOK>(a, c, L.rms2, false);
+    gemm_phase_rs<NTOK, W8, EPI_SWIGLU, false>(a, L, c, make_geom<W8>(wmaps, a.n_layers, l, MAT_GU), nullptr, L.s_gu, s_pick);
+    grid_barrier_rs(a.bar, epoch); RS_STAMP();
+    gemm_phase_rs<NTOK, W8, EPI_RESID, true>(a, L, c, make_geom<W8>(wmaps, a.n_layers, l, MAT_DOWN), amaps + 1, L.s_down, s_pick);
+    grid_barrier_rs(a.bar, epoch); RS_STAMP();
+  }
+  // ---- lm_head with the argmax as epilogue
+  if (tid < 4 * NTOK) { s_pick[tid * 3] = -INFINITY; s_pick[tid * 3 + 1] = -INFINITY; s_pick[tid * 3 + 2] = __int_as_float(0x7fffffff); }
+  build_norm_operand<NTOK>(a, c, a.final_norm, false);
+  {
+    const RsLayer L0 = a.layers[0];
+    gemm_phase_rs<NTOK, W8, EPI_HEAD, false>(a, L0, c, make_geom<W8>(wmaps, a.n_layers, 0, MAT_HEAD), nullptr, nullptr, s_pick);
+    gemm_phase_rs<NTOK, W8, EPI_HEAD, false>(a, L0, c, make_geom<W8>(wmaps, a.n_layers, 0, MAT_HEAD_TAIL), nullptr, nullptr, s_pick);
+  }
+  if (warp >= 4 && warp < 8) {
+    sync_epilogue();
+    if (warp == 4) {
+      for (int t = tid & 31; t < a.B; t += 32) {
+        float mb = -INFINITY, ms = -INFINITY;
+        int mi = 0x7fffffff;
+        for (int w = 0; w < 4; ++w) {
+          const float* sp = s_pick + (w * NTOK + t) * 3;
+          pick_merge2(mb, ms, mi, sp[0], sp[1], __float_as_int(sp[2]));
+        }
+        float* pp = a.pick_scratch + ((size_t)t * gridDim.x + blockIdx.x) * 4;
+        pp[0] = mb; pp[1] = ms; pp[2] = __int_as_float(mi);
+      }
+    }
+  }
+  grid_barrier_rs(a.bar, epoch); RS_STAMP();
+  for (int b = blockIdx.x; b < a.B; b += gridDim.x) {
+    if (tid < 32) {
+      float best = -INFINITY, second = -INFINITY;
+      int bi = 0x7fffffff;
+      for (int cta = tid; cta < (int)gridDim.x; cta += 32) {
+        const float* pp = a.pick_scratch + ((size_t)b * gridDim.x + cta) * 4;
+        pick_merge2(best, second, bi, __ldcg(pp), __ldcg(pp + 1), __float_as_int(__ldcg(pp + 2)));
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ob = __shfl_xor_sync(0xffffffffu, best, o), os = __shfl_xor_sync(0xffffffffu, second, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        pick_merge2(best, second, bi, ob, os, oi);
+      }
+      if (tid == 0) {
+        const int step = a.step;
+        if (bi < 0 || bi >= RV) bi = a.gs.eos[0];             // all-NaN logits: emit EOS rather than an out-of-range id
+        a.gs.ctx_len[b] += 1;
+        if (!a.gs.finished[b]) {
+          a.gs.out_ids[(size_t)b * a.gs.max_new + step] = bi;
+          if (a.gs.margins) a.gs.margins[(size_t)b * a.gs.max_new + step] = best - second;
+          a.gs.n_out[b] = step + 1;
+          bool eos = false;
+          for (int e = 0; e < a.gs.n_eos; ++e) eos |= (bi == a.gs.eos[e]);
+          if (eos || step + 1 >= a.gs.max_new) { a.gs.finished[b] = 1; atomicSub(a.gs.n_unfinished, 1); }
+        }
+        a.gs.cur_tok[b] = bi;
+      }
+    }
+  }
+  if (blockIdx.x == 0 && tid == 0) *a.gs.step = a.step + 1;      // the other decode paths read the step from device memory
+  RS_STAMP();
+  tc_fence_before();
+  sync_workers();
+  if (warp == 2) tmem_dealloc<kTmemCols>(c.tmem);
+}
+
+typedef void (*RsKernel)(DecodeRsArgs);
+struct RsVariant { RsKernel fn; int smem; int ntok; bool w8; };
+const RsVariant kRsVariants[3] = {
+    {decode_rs_kernel<16, false>, RsSmem<16, false>::kTotal, 16, false},
+    {decode_rs_kernel<32, false>, RsSmem<32, false>::kTotal, 32, false},
+    {decode_rs_kernel<16, true>, RsSmem<16, true>::kTotal, 16, true},
+};
+const RsVariant* rs_variant_for(bool w8, int B) {
+  if (w8) return B <= 16 ? &kRsVariants[2] : nullptr;
+  return B <= 16 ? &kRsVariants[0] : (B <= 32 ? &kRsVariants[1] : nullptr);
+}
+
+// rows of the fused qkv matrix: the q and k heads are re-ordered so that the RoPE pair (j, j + 64) of a head sits in rows
+// (2j, 2j + 1); v rows keep their place.  dst row r <- src row decode_rs_qkv_src_row(r).
+__host__ __device__ inline int qkv_src_row(int r) {
+  if (r >= RQKV - RKVH * RHD) return r;
+  const int hb = r >> 7, i = r & 127;
+  return hb * RHD + (i >> 1) + 64 * (i & 1);
+}
+__global__ void permute_qkv_rows_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int row_bytes) {
+  const int r = blockIdx.x;
+  const uint4* s = reinterpret_cast<const uint4*>(src + (size_t)qkv_src_row(r) * row_bytes);
+  uint4* d = reinterpret_cast<uint4*>(dst + (size_t)r * row_bytes);
+  for (int i = threadIdx.x; i < row_bytes / 16; i += blockDim.x) d[i] = s[i];
+}
+__global__ void permute_qkv_scale_kernel(const float* __restrict__ src, float* __restrict__ dst) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < RQKV) dst[r] = src[qkv_src_row(r)];
+}
+
+}  // namespace
+
+bool decode_rs_supports(bool w8, int B) { return B >= 1 && rs_variant_for(w8, B) != nullptr; }
+int decode_rs_tokens(bool w8, int B) { const RsVariant* v = rs_variant_for(w8, B); return v ? v->ntok : 0; }
+int decode_rs_box_rows(int kind) { return rs_box(kind); }
+
+cudaError_t decode_rs_configure() {
+  for (const RsVariant& v : kRsVariants) SONIC_CUDA_TRY(cudaFuncSetAttribute(v.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, v.smem));
+  return cudaSuccess;
+}
+int decode_rs_occupancy() {
+  int worst = 1 << 30;
+  for (const RsVariant& v : kRsVariants) {
+    int per_sm = -1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, v.fn, kRsThreads, v.smem);
+    if (per_sm < worst) worst = per_sm;
+  }
+  return worst;
+}
+
+cudaError_t decode_rs_permute_qkv(const void* src, void* dst, int row_bytes, const float* scale_src, float* scale_dst, cudaStream_t st) {
+  permute_qkv_rows_kernel<<<RQKV, 128, 0, st>>>(reinterpret_cast<const uint8_t*>(src), reinterpret_cast<uint8_t*>(dst), row_bytes);
+  SONIC_LAUNCH_CHECK();
+  if (scale_src) {
+    permute_qkv_scale_kernel<<<(RQKV + 255) / 256, 256, 0, st>>>(scale_src, scale_dst);
+    SONIC_LAUNCH_CHECK();
+  }
+  return cudaSuccess;
+}
+
+cudaError_t launch_decode_rs(const DecodeRsArgs& a, bool w8, int grid, cudaStream_t st, int* mode) {
+  const RsVariant* v = rs_variant_for(w8, a.B);
+  if (!v || grid < 1) return cudaErrorInvalidConfiguration;
+  SONIC_CUDA_TRY(cudaMemsetAsync(a.bar, 0, sizeof(unsigned), st));
+  cudaError_t e = cudaErrorUnknown;
+  for (; *mode < 2; ++*mode) {
+    if (*mode == 0) {
+      cudaLaunchConfig_t cfg;
+      memset(&cfg, 0, sizeof(cfg));
+      cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kRsThreads); cfg.dynamicSmemBytes = v->smem; cfg.stream = st;
+      cudaLaunchAttribute attr[1];
+      memset(attr, 0, sizeof(attr));
+      attr[0].id = cudaLaunchAttributeCooperative;
+      attr[0].val.cooperative = 1;
+      cfg.attrs = attr; cfg.numAttrs = 1;
+      e = cudaLaunchKernelEx(&cfg, v->fn, a);
+    } else {
+      DecodeRsArgs copy = a;
+      void* args[1] = {&copy};
+      e = cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(v->fn), dim3(grid), dim3(kRsThreads), args, v->smem, st);
+    }
+    if (e == cudaSuccess) return e;
+    fprintf(stderr, "[sonicscribe_b200] decode_rs launch mode %d failed: %s (%s)\n", *mode, cudaGetErrorName(e), cudaGetErrorString(e));
+    cudaGetLastError();
+  }
+  return e;
+}
+
+}  // namespace sonic

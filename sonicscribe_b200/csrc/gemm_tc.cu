@@ -662,6 +662,18 @@ cudaError_t make_tensor_map_2d(CUtensorMap* map, const void* ptr, long long cols
   return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
 }
 
+cudaError_t make_tensor_map_2d_u8(CUtensorMap* map, const void* ptr, long long cols, long long rows, long long ld, int box_cols, int box_rows) {
+  SONIC_CUDA_TRY(gemm_tc_init());
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
+}
+
 template <int BN, bool SWAP, typename TC, bool W8 = false>
 static cudaError_t launch_one(const CUtensorMap& ma, const CUtensorMap& mb, const TcEpi& e, dim3 grid, cudaStream_t st, bool pdl = false) {
   using Cfg = TcCfg<BN, SWAP, W8>;

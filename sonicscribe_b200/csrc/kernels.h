@@ -157,4 +157,37 @@ int decode_persist_occupancy();
 cudaError_t launch_decode_persist(const DecodePersistArgs& a, int grid, cudaStream_t st, int* mode);
 static constexpr int kPersistTcTokens = 64;   // token rows of the activation tensor maps
 
+// ---- decode_rs.cu: row-sliced persistent decode step for <= 32 segments (bf16) / <= 16 segments (int8 weight-only) ---------
+struct RsLayer {
+  const float *rms1, *rms2;
+  const float *s_qkv, *s_o, *s_gu, *s_down;       // int8 mode: per-row scales (s_qkv in the interleaved row order of wqkv_il)
+  bf16 *kc, *vc;                                  // this layer's K / V cache [max_batch][4][max_ctx][128]
+};
+struct DecodeRsArgs {
+  const RsLayer* layers; int n_layers;
+  const bf16* embed; const float* final_norm;
+  const float* cos_t; const float* sin_t;
+  bf16 *x, *q, *attn, *act;       // residual stream [B][2048], rotated queries [B][2048], attention output [B][2048], SwiGLU output [B][6144]
+  // device array of CUtensorMap: [4*l + {0: qkv (q/k rows interleaved), 1: o, 2: gate/up, 3: down}] with box rows decode_rs_box_rows(kind),
+  // [4*n_layers] lm_head (128-row boxes), [4*n_layers + 1] lm_head (32-row boxes).  bf16 maps use 128B swizzle; int8 layer maps none.
+  const void* wmaps;
+  const void* amaps;              // CUtensorMap[2]: attn [64 rows][2048] and act [64 rows][6144], box 64 k x (16 | 32) token rows
+  float* pick_scratch;            // [max_batch][grid][4]
+  float* logits_out;              // optional [B][vocab]
+  float* attn_ws; int* attn_counters; int attn_chunks;   // split-KV partials [B*4][attn_chunks][4][130]; counters [B*4] (zeroed); chunks of 64 keys
+  GreedyState gs;
+  unsigned* bar;
+  unsigned long long* timestamps; // optional: %globaltimer of CTA 0 after every grid barrier (5 * layers + 3 entries)
+  int B, max_ctx, step;           // step: index of the token this launch produces
+  float eps, scale;
+};
+bool decode_rs_supports(bool w8, int B);
+int decode_rs_tokens(bool w8, int B);              // token rows of the activation boxes the class for this batch uses (16 | 32)
+int decode_rs_box_rows(int kind);                  // kind: 0 qkv, 1 o, 2 gate/up, 3 down, 4 lm_head, 5 lm_head tail
+cudaError_t decode_rs_configure();
+int decode_rs_occupancy();
+// dst <- fused qkv matrix with the q / k head rows interleaved for the RoPE epilogue (and the int8 row scales likewise)
+cudaError_t decode_rs_permute_qkv(const void* src, void* dst, int row_bytes, const float* scale_src, float* scale_dst, cudaStream_t st);
+cudaError_t launch_decode_rs(const DecodeRsArgs& a, bool w8, int grid, cudaStream_t st, int* mode);
+
 }  // namespace sonic

@@ -542,3 +542,66 @@ def test_nan_audio_does_not_emit_out_of_range_ids(eng_bf16):
     ids = synthetic_prompt_ids(num_audio_tokens(x.shape[0]))
     out = eng_bf16.transcribe_ids([x], [ids], 6)
     assert all(0 <= t < 59264 for t in out[0])
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# row-sliced decode class (decode_rs.cu: <= 32 segments bf16, <= 16 int8) against the split-K persistent classes
+# (SONIC_DECODE_RS=0) and its batch invariance
+# ---------------------------------------------------------------------------------------------------------------------
+def _engine_with_env(env, *args, **kw):
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)
+    try:
+        return Engine(*args, **kw)
+    finally:
+        for k, v in old.items():
+            if v is None:
+                del os.environ[k]
+            else:
+                os.environ[k] = v
+
+
+@pytest.mark.parametrize("mode,B", [("bf16", 1), ("bf16", 5), ("bf16", 16), ("bf16", 17), ("bf16", 32), ("int8", 1), ("int8", 16)])
+def test_row_sliced_decode_vs_splitk_decode(tiny_sd, mode, B):
+    lens, segs, prompts = _pin_case(B)
+    out = {}
+    for rs in ("0", "1"):
+        eng = _engine_with_env({"SONIC_DECODE_RS": rs}, 2, 2, mode=mode, device=0, max_batch=B, max_prompt=300, max_new=40, debug=True)
+        eng.load_state_dict(tiny_sd)
+        out[rs] = eng.transcribe_ids(segs, prompts, 32, want_margins=True)
+        if rs == "1":
+            assert eng.transcribe_ids(segs, prompts, 32) == out[rs][0]          # bit-reproducible
+            ts = eng.debug_read("rs_ts", 64)
+            assert len(ts) == 5 * 2 + 3 and np.all(np.diff(ts) >= 0) and ts[-1] > 0    # the row-sliced kernel is what ran
+        eng.close()
+    (a, ma), (b, mb) = out["0"], out["1"]
+    agree = 0
+    for s in range(B):
+        assert len(a[s]) == len(b[s]) == 32
+        n = 32
+        for t, (x, y) in enumerate(zip(a[s], b[s])):
+            if x != y:
+                assert min(ma[s][t], mb[s][t]) < 0.2, (s, t, ma[s][t], mb[s][t])
+                n = t
+                break
+        agree += int(n == 32)
+        assert a[s][:3] == b[s][:3]
+        m = min(n, 6)
+        if m:
+            assert np.abs(np.array(ma[s][:m]) - np.array(mb[s][:m])).max() < 0.15
+    assert agree >= (B + 1) // 2
+
+
+def test_row_sliced_decode_is_batch_invariant(tiny_sd):
+    """One accumulator, one K order, attention chunks at fixed 64-key boundaries: a segment decoded alone, in a ragged batch
+    of 4 and in a batch of 16 yields bit-identical ids and margins."""
+    lens, segs, prompts = _pin_case(16)
+    eng = Engine(2, 2, mode="bf16", device=0, max_batch=16, max_prompt=300, max_new=40)
+    eng.load_state_dict(tiny_sd)
+    full, mfull = eng.transcribe_ids(segs, prompts, 24, want_margins=True)
+    for idx in ([3], [0], [2, 3, 9, 15], [15]):
+        got, mg = eng.transcribe_ids([segs[i] for i in idx], [prompts[i] for i in idx], 24, want_margins=True)
+        for j, i in enumerate(idx):
+            assert got[j] == full[i]
+            assert np.array_equal(np.asarray(mg[j]), np.asarray(mfull[i]))
+    eng.close()
