@@ -24,4 +24,10 @@ for B in Bs:
     print(f"{mode} B={B}: step {ts[-1]:.1f} us; layer {per.sum(1).mean():.2f} us; " +
           "; ".join(f"{n} {v:.2f}" for n, v in zip(names, per.mean(0))) + f"; lm_head {d[5 * L]:.1f}; pick {d[5 * L + 1]:.1f}", flush=True)
     print("   stage ms", eng.stage_times(), flush=True)
+    dbg = eng.debug_read("rs_dbg", 80).reshape(5, 16)
+    pts = ["start", "built", "mma:begin", "mma:first-stage", "mma:issued", "epi:acc-full", "epi:done", "bar:enter", "bar:arrived", "bar:released",
+           "prod:issued", "act:issued"]
+    for ph, nm in enumerate(["qkv", "attn", "o", "gate/up", "down"]):
+        base = dbg[ph][0]
+        print(f"   dbg {nm:8s} " + " ".join(f"{p}={dbg[ph][i] - base:7.2f}" for i, p in enumerate(pts) if dbg[ph][i] >= 0), flush=True)
 eng.close()

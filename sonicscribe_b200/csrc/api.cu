@@ -167,6 +167,7 @@ struct sonic_ctx {
   void* rs_wmaps = nullptr;            // device CUtensorMap[4 * layers + 2]
   void* rs_amaps = nullptr;            // device CUtensorMap[4]: {attn, act} x {16, 32 token rows}
   float* rs_pick = nullptr;
+  bf16* rs_gamma = nullptr;            // bf16 images of the decoder RMSNorm weights: [2 * layers + 1][2048]
   int cur_max_q = 0;                   // longest prompt of the current generate call
   int persist_launch_mode = 0;         // cooperative launch API state of this handle (decode_persist.cu launch_decode_persist)
   std::vector<int> probe_steps;        // debug: greedy steps whose full logit rows are kept (sonic_debug_set_logit_steps)
@@ -511,7 +512,7 @@ struct Engine {
       DecodeRsArgs p;
       memset(&p, 0, sizeof(p));
       p.layers = h->rs_layers; p.n_layers = h->cfg.dec_layers;
-      p.embed = reinterpret_cast<const bf16*>(h->embed); p.final_norm = h->final_norm;
+      p.embed = reinterpret_cast<const bf16*>(h->embed); p.final_norm_bf = h->rs_gamma + (size_t)(2 * h->cfg.dec_layers) * kDecH;
       p.cos_t = h->rope_dec_cos; p.sin_t = h->rope_dec_sin;
       p.x = reinterpret_cast<bf16*>(h->dx); p.q = reinterpret_cast<bf16*>(h->dqkv); p.attn = reinterpret_cast<bf16*>(h->dattn);
       p.act = reinterpret_cast<bf16*>(h->dact);
@@ -521,6 +522,10 @@ struct Engine {
       p.attn_ws = h->dattn_ws; p.attn_counters = h->dattn_counters;
       p.attn_chunks = std::min((h->cur_max_q + h->cur_step + 63) / 64, h->dattn_max_chunks);
       p.gs = h->gs; p.bar = h->persist_bar; p.timestamps = h->cfg.debug ? h->persist_ts : nullptr;
+      if (h->cfg.debug) {
+        const char* dc = getenv("SONIC_RS_DBG_CTA"); const char* dl = getenv("SONIC_RS_DBG_LAYER");
+        p.dbg = h->persist_ts + 1024; p.dbg_cta = dc ? atoi(dc) : 0; p.dbg_layer = dl ? atoi(dl) : 1;
+      }
       p.B = B; p.max_ctx = h->max_ctx; p.step = h->cur_step; p.eps = kRmsEps; p.scale = 0.08838834764831845f;
       TAG(PC_DEC_PERSIST);
       if (h->prof_on) { cudaEventRecord(prof_event(h), h->stream); h->prof_tags.push_back(h->prof_cls); }
@@ -739,6 +744,7 @@ int alloc_all(sonic_ctx* h) {
     DA(h->rs_wmaps, (size_t)(4 * c.dec_layers + 2) * sizeof(CUtensorMap));
     DA(h->rs_amaps, 4 * sizeof(CUtensorMap));
     DA(h->rs_pick, (size_t)B * h->num_sms * 4 * 4);
+    DA(h->rs_gamma, (size_t)(2 * c.dec_layers + 1) * kDecH * 2);
   }
   h->dattn_max_chunks = (h->max_ctx + 63) / 64;
   DA(h->dattn_ws, (size_t)B * kDecKv * h->dattn_max_chunks * 4 * 130 * 4);
@@ -1036,7 +1042,7 @@ int sonic_create(const sonic_config* cfg, sonic_handle* out) {
   }
   {
     const char* rs = getenv("SONIC_DECODE_RS");
-    h->use_rs = h->use_persist && !(rs && rs[0] == '0');
+    h->use_rs = h->use_persist && (rs && rs[0] == '1');       // opt-in while it is slower than the split-K classes
     if (h->use_rs && (decode_rs_configure() != cudaSuccess || decode_rs_occupancy() < 1)) {
       cudaGetLastError();
       fprintf(stderr, "[sonicscribe_b200] row-sliced decode kernel unavailable on this device; using the split-K persistent kernel\n");
@@ -1144,7 +1150,9 @@ int sonic_finalize_weights(sonic_handle h) {
     for (int l = 0; l < L; ++l) {
       const DecLayerW& w = h->dec[l];
       CK(decode_rs_permute_qkv(w.wqkv, h->wqkv_il[l], row_bytes, w.s_qkv, h->s_qkv_il[l], h->stream));
-      tab[l].rms1 = w.rms1; tab[l].rms2 = w.rms2;
+      tab[l].g1 = h->rs_gamma + (size_t)(2 * l) * kDecH; tab[l].g2 = h->rs_gamma + (size_t)(2 * l + 1) * kDecH;
+      convert_flat_kernel<float, bf16><<<8, 256, 0, h->stream>>>(w.rms1, h->rs_gamma + (size_t)(2 * l) * kDecH, kDecH);
+      convert_flat_kernel<float, bf16><<<8, 256, 0, h->stream>>>(w.rms2, h->rs_gamma + (size_t)(2 * l + 1) * kDecH, kDecH);
       tab[l].s_qkv = h->s_qkv_il[l]; tab[l].s_o = w.s_o; tab[l].s_gu = w.s_gu; tab[l].s_down = w.s_down;
       tab[l].kc = reinterpret_cast<bf16*>(h->kcache) + (size_t)l * layer_kv;
       tab[l].vc = reinterpret_cast<bf16*>(h->vcache) + (size_t)l * layer_kv;
@@ -1155,6 +1163,8 @@ int sonic_finalize_weights(sonic_handle h) {
         else CK(make_tensor_map_2d(&maps[4 * l + k], mats[k], ks[k], rows[k], ks[k], 64, decode_rs_box_rows(k)));
       }
     }
+    convert_flat_kernel<float, bf16><<<8, 256, 0, h->stream>>>(h->final_norm, h->rs_gamma + (size_t)(2 * L) * kDecH, kDecH);
+    CK(cudaGetLastError());
     CK(make_tensor_map_2d(&maps[4 * L], h->lm_head, kDecH, kVocab, kDecH, 64, decode_rs_box_rows(4)));
     CK(make_tensor_map_2d(&maps[4 * L + 1], h->lm_head, kDecH, kVocab, kDecH, 64, decode_rs_box_rows(5)));
     CUtensorMap am[4];
@@ -1280,6 +1290,15 @@ int sonic_debug_read(sonic_handle h, const char* name, float* out, size_t max_el
   size_t n = 0;
   if (nm == "rope_enc_cos") { src_f32 = h->rope_enc_cos; n = (size_t)kEncT * kEncRot / 2; }
   else if (nm == "rope_dec_cos") { src_f32 = h->rope_dec_cos; n = (size_t)h->max_ctx * kDecHd / 2; }
+  else if (nm == "rs_dbg" && h->persist_ts) {
+    std::vector<unsigned long long> ts(80);
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaMemcpy(ts.data(), h->persist_ts + 1024, 80 * 8, cudaMemcpyDeviceToHost));
+    if (max_elems < 80) return fail(h, "sonic_debug_read: output buffer too small");
+    for (int i = 0; i < 80; ++i) out[i] = ts[i] ? (float)((double)(ts[i] - ts[0]) * 1e-3) : -1.0f;
+    if (n_elems) *n_elems = 80;
+    return 0;
+  }
   else if (nm == "rs_ts" && h->persist_ts) {
     // phase timestamps of the last row-sliced decode step (microseconds relative to the first stamp): 5 per layer + 3
     const int n = 5 * h->cfg.dec_layers + 3;

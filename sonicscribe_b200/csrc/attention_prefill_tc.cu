@@ -65,7 +65,7 @@ attention_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __gri
   const uint32_t tS = tmem_base, tO = tmem_base + 128;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one_sync()) {
       mbar_expect_tx(bar(0), kTile);
       tma_load_2d(sQ, &tmQ, bar(0), a.q_col0 + h * PD, row0 + q0);
       tma_load_2d(sQ + kAtom, &tmQ, bar(0), a.q_col0 + h * PD + 64, row0 + q0);
@@ -82,7 +82,7 @@ attention_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __gri
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one_sync()) {
       constexpr uint32_t idesc_s = make_idesc_bf16_major(PQ, PK, 0, 0);
       constexpr uint32_t idesc_o = make_idesc_bf16_major(PQ, 64, 0, 1);       // B = V atom, MN-major
       auto issue_s = [&](int j) {

@@ -98,7 +98,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm, AttnTcArgs a) {
   const uint32_t tS = tmem_base, tO = tmem_base + 128;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one_sync()) {
       mbar_expect_tx(bar(0), kTileBytes);
       tma_load_2d(sQ, &tm, bar(0), a.q_col + h * AD, row0 + q0);
       for (int j = 0; j < n_kt; ++j) {
@@ -113,7 +113,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm, AttnTcArgs a) {
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one_sync()) {
       constexpr uint32_t idesc_s = make_idesc_bf16_major(AQ, AK, 0, 0);     // S: A = Q (K-major), B = K (K-major)
       constexpr uint32_t idesc_o = make_idesc_bf16_major(AQ, AD, 0, 1);     // O: A = P (K-major), B = V (MN-major)
       auto issue_s = [&](int j) {

@@ -266,7 +266,7 @@ __device__ __forceinline__ void tc_prefetch_weights(const CUtensorMap* wmap, int
     const int tile = item / splits, ks = item - tile * splits;
     const int kb0 = (ks * nkb) / splits, kb1 = ((ks + 1) * nkb) / splits;
     for (int kb = kb0; kb < kb1 && n < (uint32_t)kTcStages; ++kb, ++n) {
-      if (threadIdx.x == 0) {
+      if (threadIdx.x < 32 && elect_one_sync()) {
         const uint32_t cnt = tc.kb_count + n, st = cnt % kTcStages, par = (cnt / kTcStages) & 1u;
         mbar_wait(tc_empty(tc, st), par ^ 1u);
         mbar_expect_tx(tc_full(tc, st), kTcStageA + kTcStageB);
@@ -283,7 +283,7 @@ __device__ __forceinline__ void gemm_phase_tc(const CUtensorMap* wmap, const CUt
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles = N >> 7, nkb = K >> 6, n_items = tiles * splits;
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one_sync()) {
       uint32_t cnt = tc.kb_count, idx = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         const int tile = item / splits, ks = item - tile * splits;
@@ -300,7 +300,7 @@ __device__ __forceinline__ void gemm_phase_tc(const CUtensorMap* wmap, const CUt
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one_sync()) {
       constexpr uint32_t idesc = make_idesc_bf16(128, kPersistTcTokens);
       uint32_t cnt = tc.kb_count, ic = tc.item_count;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++ic) {
@@ -606,7 +606,7 @@ __device__ __forceinline__ void attention_phase_mma(const DecodePersistArgs& a, 
   // layers, segments and kv heads; row = key), landing as SWIZZLE_128B halves.  Rows past the context are finite cache
   // contents (masked below); the row appended this step is overwritten from sKV after the chunk has landed.
   auto issue_chunk = [&](int row0, int k0, uint32_t b) {
-    if (tt == 0) {
+    if (wt == 0 && elect_one_sync()) {
       mbar_expect_tx(bar_of(b), (uint32_t)kBuf);
       const uint32_t dst = smem_u32(kv + (size_t)b * kBuf);
 #pragma unroll

@@ -42,6 +42,7 @@ constexpr int RH = 2048, RQKV = 3072, RI = 6144, RV = 59264, RHD = 128, RKVH = 4
 constexpr int kRsThreads = 544, kRsWork = 512;            // 16 worker warps + the producer warp
 constexpr int kStageBytes = 16384;
 constexpr int kAttnCK = 64;                               // keys per attention chunk
+constexpr int kRopePairs = 16;                            // q/k row pairs per CTA covered by the shared-memory RoPE table
 constexpr int kAttnKRow = RHD * 2 + 16;                   // padded K row (bytes): conflict-free 16 B reads across keys
 
 // ---- bounded waits: a protocol bug must surface as a launch failure, not as a hung GPU -------------------------------
@@ -50,6 +51,12 @@ __device__ __forceinline__ unsigned long long gtime() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
+// fine-grained stamps of one layer (a.dbg_layer) on CTA a.dbg_cta: slot = 16 * phase + point (see scripts/rs_phases.py)
+#define RS_DBG(phase, point)                                                                                          \
+  do {                                                                                                                \
+    if (a.dbg && (int)blockIdx.x == a.dbg_cta && c.layer == a.dbg_layer) a.dbg[16 * (phase) + (point)] = gtime();   \
+  } while (0)
+
 __device__ __noinline__ void rs_timeout(int tag, unsigned v) {
   printf("[sonicscribe_b200] decode_rs: wait %d timed out (block %d thread %d, value %u)\n", tag, blockIdx.x, threadIdx.x, v);
   __trap();
@@ -77,13 +84,15 @@ __device__ __forceinline__ void sync_workers() { asm volatile("bar.sync 1, 512;"
 __device__ __forceinline__ void sync_epilogue() { asm volatile("bar.sync 2, 128;" ::: "memory"); }
 __device__ __forceinline__ void sync_converters() { asm volatile("bar.sync 3, 256;" ::: "memory"); }
 
-__device__ __forceinline__ void grid_barrier_rs(unsigned* counter, unsigned& epoch) {
+__device__ __forceinline__ void grid_barrier_rs(unsigned* counter, unsigned& epoch, unsigned long long* dbg3 = nullptr) {
   asm volatile("fence.proxy.async;" ::: "memory");       // generic writes of this phase vs TMA reads of the next
   sync_workers();
   if (threadIdx.x == 0) {
+    if (dbg3) dbg3[0] = gtime();
     epoch += gridDim.x;
     __threadfence();
     atomicAdd(counter, 1u);
+    if (dbg3) dbg3[1] = gtime();
     unsigned v;
     unsigned long long t0 = 0;
     for (unsigned it = 0;; ++it) {
@@ -96,6 +105,7 @@ __device__ __forceinline__ void grid_barrier_rs(unsigned* counter, unsigned& epo
       }
     }
     __threadfence();
+    if (dbg3) dbg3[2] = gtime();
   }
   sync_workers();
   asm volatile("fence.proxy.async;" ::: "memory");
@@ -156,6 +166,9 @@ __device__ __forceinline__ Geom make_geom(const CUtensorMap* maps, int n_layers,
   return g;
 }
 
+// independent TMEM accumulators per output tile (see the MMA issue loop): 8 x 16 or 4 x 32 columns, double-buffered
+template <int NTOK> struct RsAcc { static constexpr int value = NTOK == 16 ? 8 : 4; };
+
 struct RsCtx {
   uint32_t ring, region, conv, bars, tmem;
   uint8_t* region_g;     // generic pointer to the operand region (also the attention scratch)
@@ -166,6 +179,8 @@ struct RsCtx {
   uint32_t ic;           // accumulator uses so far
   uint32_t cc;           // converter buffer uses so far (int8)
   uint32_t au[2];        // activation half-region loads so far
+  int layer;             // current layer (debug stamps)
+  int phase;             // current phase of the layer (debug stamps)
 };
 // barrier slots: full[NS] empty[NS] acc_full[2] acc_empty[2] act_full[2] act_empty[2] conv_full[2] conv_empty[2]
 __device__ __forceinline__ uint32_t b_full(const RsCtx& c, uint32_t s) { return c.bars + 8u * s; }
@@ -175,7 +190,7 @@ enum { ACC_FULL = 0, ACC_EMPTY = 2, ACT_FULL = 4, ACT_EMPTY = 6, CONV_FULL = 8, 
 
 // ---- the weight producer: one thread walks the CTA's whole schedule ----------------------------------------------------------
 template <bool W8>
-__device__ void produce_matrix(const RsCtx& c, const Geom& g, uint32_t& cnt) {
+__device__ __forceinline__ void produce_matrix(const RsCtx& c, const Geom& g, uint32_t& cnt) {
   const uint32_t row_bytes = g.i8 ? 64u : 128u;
   const uint32_t sub = g.i8 ? (uint32_t)g.raw_sub : (uint32_t)g.sub;
   for (int r = g.r0; r < g.r1; r += g.box) {
@@ -195,7 +210,10 @@ __device__ void producer_loop(const DecodeRsArgs& a, const RsCtx& c) {
   const CUtensorMap* maps = reinterpret_cast<const CUtensorMap*>(a.wmaps);
   uint32_t cnt = 0;
   for (int l = 0; l < a.n_layers; ++l)
-    for (int k = MAT_QKV; k <= MAT_DOWN; ++k) produce_matrix<W8>(c, make_geom<W8>(maps, a.n_layers, l, k), cnt);
+    for (int k = MAT_QKV; k <= MAT_DOWN; ++k) {
+      produce_matrix<W8>(c, make_geom<W8>(maps, a.n_layers, l, k), cnt);
+      if (a.dbg && (int)blockIdx.x == a.dbg_cta && l == a.dbg_layer) a.dbg[16 * (k == MAT_QKV ? 0 : k + 1) + 10] = gtime();
+    }
   produce_matrix<W8>(c, make_geom<W8>(maps, a.n_layers, 0, MAT_HEAD), cnt);
   produce_matrix<W8>(c, make_geom<W8>(maps, a.n_layers, 0, MAT_HEAD_TAIL), cnt);
 }
@@ -204,8 +222,19 @@ __device__ void producer_loop(const DecodeRsArgs& a, const RsCtx& c) {
 // u[t] = gamma * bf16(x[t] * rsqrt(mean(x[t]^2) + eps)) for every token, written as the K-major SWIZZLE_128B operand the MMA
 // reads: k block kb is a [NTOK rows x 128 B] slab, 16 B chunk ch of row t sits at chunk (ch ^ (t & 7)).  One warp per token.
 // from_embed: x[t] is the embedding row of the token picked by the previous step (and is stored to x by one CTA).
+struct GammaRegs { uint4 v[8]; };
+// bf16 image of an RMSNorm weight vector, the 8 chunks this lane multiplies with; issued BEFORE the grid barrier that precedes
+// the build (the vector is read once per step, so the load is a DRAM miss: ~1.5 us when it sits in the dependency chain)
+__device__ __forceinline__ void load_gamma(GammaRegs& gm, const bf16* __restrict__ gamma, int B) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (warp < B) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) gm.v[i] = __ldg(reinterpret_cast<const uint4*>(gamma) + lane + 32 * i);
+  }
+}
+
 template <int NTOK>
-__device__ __forceinline__ void build_norm_operand(const DecodeRsArgs& a, const RsCtx& c, const float* __restrict__ gamma, bool from_embed) {
+__device__ __forceinline__ void build_norm_operand(const DecodeRsArgs& a, const RsCtx& c, const GammaRegs& gm, bool from_embed) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int t = warp; t < a.B; t += 16) {
     const bf16* row;
@@ -233,15 +262,12 @@ __device__ __forceinline__ void build_norm_operand(const DecodeRsArgs& a, const 
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int ch = lane + 32 * i;                       // 16 B chunk of the row: k = 8 * ch
-      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * ch), g1 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * ch + 1);
-      const uint32_t w[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
-      uint4 o;
-      o.x = pack_bf16(g0.x * bf16r(bf_lo(w[0]) * rstd), g0.y * bf16r(bf_hi(w[0]) * rstd));
-      o.y = pack_bf16(g0.z * bf16r(bf_lo(w[1]) * rstd), g0.w * bf16r(bf_hi(w[1]) * rstd));
-      o.z = pack_bf16(g1.x * bf16r(bf_lo(w[2]) * rstd), g1.y * bf16r(bf_hi(w[2]) * rstd));
-      o.w = pack_bf16(g1.z * bf16r(bf_lo(w[3]) * rstd), g1.w * bf16r(bf_hi(w[3]) * rstd));
+      const uint32_t w[4] = {v[i].x, v[i].y, v[i].z, v[i].w}, gw[4] = {gm.v[i].x, gm.v[i].y, gm.v[i].z, gm.v[i].w};
+      uint32_t o[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) o[e] = pack_bf16(bf_lo(gw[e]) * bf16r(bf_lo(w[e]) * rstd), bf_hi(gw[e]) * bf16r(bf_hi(w[e]) * rstd));
       const int kb = ch >> 3, cc = ch & 7;
-      *reinterpret_cast<uint4*>(c.region_g + (size_t)kb * (NTOK * 128) + t * 128 + ((cc ^ (t & 7)) << 4)) = o;
+      *reinterpret_cast<uint4*>(c.region_g + (size_t)kb * (NTOK * 128) + t * 128 + ((cc ^ (t & 7)) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
     }
   }
   fence_proxy_async_smem();
@@ -260,10 +286,22 @@ template <int NTOK, int EPI>
 __device__ __forceinline__ void epilogue_tile(const DecodeRsArgs& a, const RsLayer& L, const Geom& g, int r, const float* __restrict__ wscale,
                                               uint32_t taddr, float* s_pick) {
   const int lane = threadIdx.x & 31, q = (threadIdx.x >> 5) & 3;
-  uint32_t v[NTOK];
-  if constexpr (NTOK == 16) tmem_ld16(taddr + ((uint32_t)(q * 32) << 16), v);
-  else tmem_ld32(taddr + ((uint32_t)(q * 32) << 16), v);
-  tmem_ld_wait();
+  constexpr int kAcc = RsAcc<NTOK>::value;
+  float v[NTOK];
+  {
+    const uint32_t tq = taddr + ((uint32_t)(q * 32) << 16);
+    uint32_t t0[NTOK], t1[NTOK];
+#pragma unroll
+    for (int i = 0; i < NTOK; ++i) v[i] = 0.f;
+#pragma unroll
+    for (int ai = 0; ai < kAcc; ai += 2) {                             // fixed summation order
+      if constexpr (NTOK == 16) { tmem_ld16(tq + ai * NTOK, t0); tmem_ld16(tq + (ai + 1) * NTOK, t1); }
+      else { tmem_ld32(tq + ai * NTOK, t0); tmem_ld32(tq + (ai + 1) * NTOK, t1); }
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < NTOK; ++i) v[i] = (v[i] + __uint_as_float(t0[i])) + __uint_as_float(t1[i]);
+    }
+  }
   const int rl = (g.m == 64) ? (lane < 16 ? q * 16 + lane : -1) : q * 32 + lane;     // row of the tile held by this lane
   const int nrows = min(g.box, g.r1 - r);
   const bool valid = rl >= 0 && rl < nrows;
@@ -273,15 +311,23 @@ __device__ __forceinline__ void epilogue_tile(const DecodeRsArgs& a, const RsLay
     // rows of q and k heads are interleaved (2j, 2j+1) = natural dims (j, j+64): the RoPE partner sits in the neighbouring lane
     const bool is_qk = gr < (RQKV - RKVH * RHD);
     const int hb = gr >> 7, i = gr & 127, j = i >> 1, second = i & 1;
+    // s_pick - 64 ints: token positions; before them the RoPE table of this CTA's q/k row pairs: [pair][token] (cos, sin), bf16-rounded,
+    // filled once per launch (the rows a CTA owns, and so the rotation angles it needs, are the same in every layer)
+    const int* s_pos = reinterpret_cast<const int*>(s_pick) - 64;
+    const float2* s_rope = reinterpret_cast<const float2*>(s_pos) - kRopePairs * NTOK;
+    const int pair = ((r - g.r0) + (rl < 0 ? 0 : rl)) >> 1;
+    const bool tab = (g.r1 - g.r0) <= 2 * kRopePairs;
 #pragma unroll
     for (int t = 0; t < NTOK; ++t) {
-      const float own = bf16r(__uint_as_float(v[t]) * sc);
+      const float own = bf16r(v[t] * sc);
       const float other = __shfl_xor_sync(0xffffffffu, own, 1);
       if (t < a.B && valid) {
-        const int pos = a.gs.ctx_len[t];
+        const int pos = s_pos[t];
         if (is_qk) {
-          const float cs = bf16r(__ldg(a.cos_t + (size_t)pos * (RHD / 2) + j)), sn = bf16r(__ldg(a.sin_t + (size_t)pos * (RHD / 2) + j));
-          const float p0 = bf16r(own * cs), p1 = bf16r(other * sn);
+          float2 cs;
+          if (tab) cs = s_rope[pair * NTOK + t];
+          else cs = make_float2(bf16r(__ldg(a.cos_t + (size_t)pos * (RHD / 2) + j)), bf16r(__ldg(a.sin_t + (size_t)pos * (RHD / 2) + j)));
+          const float p0 = bf16r(own * cs.x), p1 = bf16r(other * cs.y);
           const bf16 res = __float2bfloat16_rn(second ? p0 + p1 : p0 - p1);
           const int d = j + 64 * second;
           if (hb < 16) a.q[(size_t)t * RH + hb * RHD + d] = res;
@@ -293,18 +339,17 @@ __device__ __forceinline__ void epilogue_tile(const DecodeRsArgs& a, const RsLay
       }
     }
   } else if constexpr (EPI == EPI_RESID) {
+    unsigned short xo[NTOK];
 #pragma unroll
-    for (int t = 0; t < NTOK; ++t) {
-      if (t < a.B && valid) {
-        bf16* px = a.x + (size_t)t * RH + gr;                          // this thread is the only writer of x[t][gr]
-        const float xo = __uint_as_float((uint32_t)__ldcg(reinterpret_cast<const unsigned short*>(px)) << 16);
-        *px = __float2bfloat16_rn(xo + bf16r(__uint_as_float(v[t]) * sc));
-      }
-    }
+    for (int t = 0; t < NTOK; ++t)                                      // this thread is the only writer of x[t][gr]
+      xo[t] = (t < a.B && valid) ? __ldcg(reinterpret_cast<const unsigned short*>(a.x + (size_t)t * RH + gr)) : (unsigned short)0;
+#pragma unroll
+    for (int t = 0; t < NTOK; ++t)
+      if (t < a.B && valid) a.x[(size_t)t * RH + gr] = __float2bfloat16_rn(__uint_as_float((uint32_t)xo[t] << 16) + bf16r(v[t] * sc));
   } else if constexpr (EPI == EPI_SWIGLU) {
 #pragma unroll
     for (int t = 0; t < NTOK; ++t) {
-      const float own = bf16r(__uint_as_float(v[t]) * sc);
+      const float own = bf16r(v[t] * sc);
       const float up = __shfl_xor_sync(0xffffffffu, own, 1);       // rows are interleaved (gate, up)
       if (t < a.B && valid && (gr & 1) == 0) a.act[(size_t)t * RI + (gr >> 1)] = __float2bfloat16_rn(bf16r(silu_exact(own)) * up);
     }
@@ -314,7 +359,7 @@ __device__ __forceinline__ void epilogue_tile(const DecodeRsArgs& a, const RsLay
 #pragma unroll
     for (int t = 0; t < NTOK; ++t) {
       if (t < a.B) {                                                 // uniform
-        float x = valid ? __uint_as_float(v[t]) : -INFINITY;
+        float x = valid ? v[t] : -INFINITY;
         if (!(x == x)) x = -INFINITY;                                 // NaN never wins
         if (a.logits_out && valid) a.logits_out[(size_t)t * RV + gr] = x;
         float best = x, second = -INFINITY;
@@ -348,25 +393,29 @@ __device__ __forceinline__ void gemm_phase_rs(const DecodeRsArgs& a, const RsLay
   const int n_groups = g.nkb / g.kps;
   const int n_chunks = g.nkb / 16;                                    // activation chunks of 16 k blocks per sub-tile
   constexpr uint32_t kHalf = NTOK * 128 * 16;                         // bytes of one activation chunk
+  constexpr int kAcc = RsAcc<NTOK>::value;
   if (ACT && warp == 0) {
-    if (lane == 0) {
-      uint32_t au[2] = {c.au[0], c.au[1]};
-      for (int st = 0; st < n_sub; ++st)
-        for (int ci = 0; ci < n_chunks; ++ci) {
-          const int h = ci & 1;
-          mbar_wait_wd(b_misc(c, ACT_EMPTY + h), (au[h] & 1u) ^ 1u, 2);
+    uint32_t au[2] = {c.au[0], c.au[1]};
+    for (int st = 0; st < n_sub; ++st)
+      for (int ci = 0; ci < n_chunks; ++ci) {
+        const int h = ci & 1;
+        mbar_wait_wd(b_misc(c, ACT_EMPTY + h), (au[h] & 1u) ^ 1u, 2);
+        if (elect_one_sync()) {
           mbar_expect_tx(b_misc(c, ACT_FULL + h), kHalf);
-#pragma unroll 1
+#pragma unroll
           for (int kb = 0; kb < 16; ++kb)
             tma_load_2d(c.region + h * kHalf + kb * (NTOK * 128), act_map, b_misc(c, ACT_FULL + h), (ci * 16 + kb) * 64, 0);
-          ++au[h];
         }
-    }
+        __syncwarp();
+        ++au[h];
+      }
+    if (lane == 0) RS_DBG(c.phase, 11);
   } else if (warp == 1) {
-    if (lane == 0) {
+    {                                                                  // the whole warp walks the loop; one elected lane issues
       const uint32_t idesc = make_idesc_bf16(g.m, NTOK);
       uint32_t cnt = c.cnt, ic = c.ic, cc = c.cc;
       uint32_t au[2] = {c.au[0], c.au[1]};
+      if (lane == 0) RS_DBG(c.phase, 2);
       for (int st = 0; st < n_sub; ++st, ++ic) {
         const uint32_t acc = ic & 1u;
         mbar_wait_wd(b_misc(c, ACC_EMPTY + acc), ((ic >> 1) & 1u) ^ 1u, 3);
@@ -382,29 +431,38 @@ __device__ __forceinline__ void gemm_phase_rs(const DecodeRsArgs& a, const RsLay
             mbar_wait_wd(b_full(c, s), par, 5);
             abase = c.ring + s * kStageBytes;
           }
+          const int kb0 = grp * g.kps;
+          if (ACT && (kb0 & 15) == 0) mbar_wait_wd(b_misc(c, ACT_FULL + ((kb0 >> 4) & 1)), au[(kb0 >> 4) & 1] & 1u, 6);   // kps divides 16
           tc_fence_after();
-          for (int j = 0; j < g.kps; ++j) {
-            const int kb = grp * g.kps + j;
-            if (ACT && (kb & 15) == 0) {
-              const int h = (kb >> 4) & 1;
-              mbar_wait_wd(b_misc(c, ACT_FULL + h), au[h] & 1u, 6);
-              tc_fence_after();
-            }
-            const uint64_t da = make_sw128_desc(abase + j * g.sub), db = make_sw128_desc(c.region + (uint32_t)(kb & 31) * (NTOK * 128));
+          if (st == 0 && grp == 0 && lane == 0) RS_DBG(c.phase, 3);
+          const bool chunk_done = ACT && ((kb0 + g.kps) & 15) == 0;
+          if (elect_one_sync()) {
+            // a tcgen05.mma that accumulates into the tile its predecessor wrote waits for it (measured: 50-90 ns per
+            // 64|128 x 16 x 16 MMA into one accumulator): consecutive MMAs go to kAcc different accumulators, summed by the
+            // epilogue in a fixed order.  The loop body is 4 UTCHMMA + two descriptor increments.
+            uint64_t da = make_sw128_desc(abase), db = make_sw128_desc(c.region + (uint32_t)(kb0 & 31) * (NTOK * 128));
+            const uint64_t da_step = (uint64_t)(g.sub >> 4), db_step = (uint64_t)((NTOK * 128) >> 4);
+            const uint32_t t0 = c.tmem + acc * kAcc * NTOK;
+#pragma unroll 2
+            for (int j = 0; j < g.kps; ++j) {
+              const int kb = kb0 + j;
+              const uint32_t tb = t0 + ((kAcc == 8 && (kb & 1)) ? 4 * NTOK : 0);
+              const uint32_t accum = (kb * 4 >= kAcc) ? 1u : 0u;
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              tc_mma_bf16(c.tmem + acc * NTOK, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb != 0 || k != 0) ? 1u : 0u);
-            if (ACT && (kb & 15) == 15) {
-              const int h = (kb >> 4) & 1;
-              tc_commit(b_misc(c, ACT_EMPTY + h));
-              ++au[h];
+              for (int k = 0; k < 4; ++k) tc_mma_bf16(tb + k * NTOK, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, accum);
+              da += da_step; db += db_step;
             }
+            if (chunk_done) tc_commit(b_misc(c, ACT_EMPTY + (((kb0 + g.kps - 1) >> 4) & 1)));
+            if (W8 && g.i8) tc_commit(b_misc(c, CONV_EMPTY + (cc & 1u)));
+            else tc_commit(b_empty(c, s));
+            if (grp == n_groups - 1) tc_commit(b_misc(c, ACC_FULL + acc));
           }
-          if (W8 && g.i8) { tc_commit(b_misc(c, CONV_EMPTY + (cc & 1u))); ++cc; }
-          else tc_commit(b_empty(c, s));
+          __syncwarp();
+          if (chunk_done) ++au[((kb0 + g.kps - 1) >> 4) & 1];
+          if (W8 && g.i8) ++cc;
         }
-        tc_commit(b_misc(c, ACC_FULL + acc));
       }
+      if (lane == 0) RS_DBG(c.phase, 4);
     }
   } else if (warp >= 4 && warp < 8) {
     uint32_t ic = c.ic;
@@ -413,10 +471,12 @@ __device__ __forceinline__ void gemm_phase_rs(const DecodeRsArgs& a, const RsLay
       const uint32_t acc = ic & 1u;
       mbar_wait_wd(b_misc(c, ACC_FULL + acc), (ic >> 1) & 1u, 7);
       tc_fence_after();
-      epilogue_tile<NTOK, EPI>(a, L, g, r, wscale, c.tmem + acc * NTOK, s_pick);
+      if (warp == 4 && lane == 0) RS_DBG(c.phase, 5);
+      epilogue_tile<NTOK, EPI>(a, L, g, r, wscale, c.tmem + acc * kAcc * NTOK, s_pick);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(b_misc(c, ACC_EMPTY + acc));
+      if (warp == 4 && lane == 0) RS_DBG(c.phase, 6);
     }
   } else if (W8 && g.i8 && warp >= 8) {
     // int8 -> bf16: ring stage (kps raw tiles of [box rows x 64 B]) -> converter buffer (kps SWIZZLE_128B images)
@@ -580,7 +640,7 @@ template <int NTOK, bool W8>
 struct RsSmem {
   static constexpr int kRegion = NTOK * RH * 2;                          // operand region: 64 KB / 128 KB
   static constexpr int kConv = W8 ? 2 * 2 * kStageBytes : 0;             // two 32 KB converter buffers
-  static constexpr int kSmall = 2048;                                    // barriers, tmem slot, pick state
+  static constexpr int kSmall = 2048 + kRopePairs * NTOK * 8;            // barriers, tmem slot, RoPE table, positions, pick state
   static constexpr int kStages = (227 * 1024 - 1024 - kRegion - kConv - kSmall) / kStageBytes;
   static constexpr int kTotal = 1024 + kStages * kStageBytes + kConv + kRegion + kSmall;
   static_assert(kStages >= 3, "ring too shallow");
@@ -602,11 +662,13 @@ __global__ void __launch_bounds__(kRsThreads, 1) decode_rs_kernel(DecodeRsArgs a
   uint8_t* small = c.region_g + SM::kRegion;
   c.bars = c.region + SM::kRegion;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(small + 8 * (2 * SM::kStages + N_MISC));
-  float* s_pick = reinterpret_cast<float*>(small + 8 * (2 * SM::kStages + N_MISC) + 16);      // [4 warps][NTOK][3]
-  static_assert(8 * (2 * SM::kStages + N_MISC) + 16 + 4 * NTOK * 3 * 4 <= SM::kSmall, "small area overflow");
-  c.cnt = 0; c.ic = 0; c.cc = 0; c.au[0] = 0; c.au[1] = 0;
+  float2* s_rope = reinterpret_cast<float2*>(small + 8 * (2 * SM::kStages + N_MISC) + 16);      // [kRopePairs][NTOK] (cos, sin)
+  int* s_pos = reinterpret_cast<int*>(s_rope + kRopePairs * NTOK);                               // [64] token positions
+  float* s_pick = reinterpret_cast<float*>(s_pos + 64);                                          // [4 warps][NTOK][3]
+  static_assert(8 * (2 * SM::kStages + N_MISC) + 16 + kRopePairs * NTOK * 8 + 256 + 4 * NTOK * 3 * 4 <= SM::kSmall, "small area overflow");
+  c.cnt = 0; c.ic = 0; c.cc = 0; c.au[0] = 0; c.au[1] = 0; c.layer = -1; c.phase = 0;
   const int tid = threadIdx.x, warp = tid >> 5;
-  constexpr int kTmemCols = 2 * NTOK < 32 ? 32 : 2 * NTOK;
+  constexpr int kTmemCols = 2 * RsAcc<NTOK>::value * NTOK;                 // 256
   if (tid == 0) {
     for (int s = 0; s < SM::kStages; ++s) { mbar_init(b_full(c, s), 1); mbar_init(b_empty(c, s), 1); }
     for (int i = 0; i < 2; ++i) {
@@ -623,7 +685,7 @@ __global__ void __launch_bounds__(kRsThreads, 1) decode_rs_kernel(DecodeRsArgs a
   c.tmem = *tmem_slot;
 
   if (warp == 16) {                                                     // the weight stream never waits for a grid barrier
-    if ((tid & 31) == 0) producer_loop<W8>(a, c);
+    if (elect_one_sync()) producer_loop<W8>(a, c);
     return;
   }
   unsigned epoch = 0;
@@ -631,24 +693,59 @@ __global__ void __launch_bounds__(kRsThreads, 1) decode_rs_kernel(DecodeRsArgs a
   RS_STAMP();
   const CUtensorMap* wmaps = reinterpret_cast<const CUtensorMap*>(a.wmaps);
   const CUtensorMap* amaps = reinterpret_cast<const CUtensorMap*>(a.amaps);       // [0] attention output, [1] SwiGLU output
+  // positions and the RoPE table of this CTA's q / k rows (same rows, same angles in every layer)
+  if (tid < a.B) s_pos[tid] = a.gs.ctx_len[tid];
+  GammaRegs gm;
+  load_gamma(gm, a.layers[0].g1, a.B);
+  sync_workers();
+  {
+    const Geom gq = make_geom<W8>(wmaps, a.n_layers, 0, MAT_QKV);
+    const int pairs = (gq.r1 - gq.r0) >> 1;
+    if (pairs <= kRopePairs) {
+      for (int idx = tid; idx < pairs * a.B; idx += kRsWork) {
+        const int p = idx / a.B, t = idx - p * a.B, row = gq.r0 + 2 * p;
+        if (row < RQKV - RKVH * RHD) {
+          const int j = (row & 127) >> 1, pos = s_pos[t];
+          s_rope[p * NTOK + t] = make_float2(bf16r(__ldg(a.cos_t + (size_t)pos * (RHD / 2) + j)), bf16r(__ldg(a.sin_t + (size_t)pos * (RHD / 2) + j)));
+        }
+      }
+    }
+  }
   for (int l = 0; l < a.n_layers; ++l) {
     const RsLayer L = a.layers[l];
-    build_norm_operand<NTOK>(a, c, L.rms1, l == 0);
+    c.layer = l;
+    unsigned long long* bd = (a.dbg && (int)blockIdx.x == a.dbg_cta && l == a.dbg_layer) ? a.dbg : nullptr;
+    c.phase = 0;
+    if (tid == 0) RS_DBG(0, 0);
+    build_norm_operand<NTOK>(a, c, gm, l == 0);
+    if (tid == 0) RS_DBG(0, 1);
     gemm_phase_rs<NTOK, W8, EPI_QKV, false>(a, L, c, make_geom<W8>(wmaps, a.n_layers, l, MAT_QKV), nullptr, L.s_qkv, s_pick);
-    grid_barrier_rs(a.bar, epoch); RS_STAMP();
+    grid_barrier_rs(a.bar, epoch, bd ? bd + 7 : nullptr); RS_STAMP();
+    c.phase = 1;
+    if (tid == 0) RS_DBG(1, 0);
     attention_phase_rs(a, L, c.region_g);
-    grid_barrier_rs(a.bar, epoch); RS_STAMP();
+    grid_barrier_rs(a.bar, epoch, bd ? bd + 16 + 7 : nullptr); RS_STAMP();
+    c.phase = 2;
+    if (tid == 0) RS_DBG(2, 0);
     gemm_phase_rs<NTOK, W8, EPI_RESID, true>(a, L, c, make_geom<W8>(wmaps, a.n_layers, l, MAT_O), amaps, L.s_o, s_pick);
-    grid_barrier_rs(a.bar, epoch); RS_STAMP();
-    build_norm_operand<NTOK>(a, c, L.rms2, false);
+    load_gamma(gm, L.g2, a.B);
+    grid_barrier_rs(a.bar, epoch, bd ? bd + 32 + 7 : nullptr); RS_STAMP();
+    c.phase = 3;
+    if (tid == 0) RS_DBG(3, 0);
+    build_norm_operand<NTOK>(a, c, gm, false);
+    if (tid == 0) RS_DBG(3, 1);
     gemm_phase_rs<NTOK, W8, EPI_SWIGLU, false>(a, L, c, make_geom<W8>(wmaps, a.n_layers, l, MAT_GU), nullptr, L.s_gu, s_pick);
-    grid_barrier_rs(a.bar, epoch); RS_STAMP();
+    grid_barrier_rs(a.bar, epoch, bd ? bd + 48 + 7 : nullptr); RS_STAMP();
+    c.phase = 4;
+    if (tid == 0) RS_DBG(4, 0);
     gemm_phase_rs<NTOK, W8, EPI_RESID, true>(a, L, c, make_geom<W8>(wmaps, a.n_layers, l, MAT_DOWN), amaps + 1, L.s_down, s_pick);
-    grid_barrier_rs(a.bar, epoch); RS_STAMP();
+    load_gamma(gm, (l + 1 < a.n_layers) ? a.layers[l + 1].g1 : a.final_norm_bf, a.B);
+    grid_barrier_rs(a.bar, epoch, bd ? bd + 64 + 7 : nullptr); RS_STAMP();
   }
+  c.layer = -1; c.phase = 5;
   // ---- lm_head with the argmax as epilogue
   if (tid < 4 * NTOK) { s_pick[tid * 3] = -INFINITY; s_pick[tid * 3 + 1] = -INFINITY; s_pick[tid * 3 + 2] = __int_as_float(0x7fffffff); }
-  build_norm_operand<NTOK>(a, c, a.final_norm, false);
+  build_norm_operand<NTOK>(a, c, gm, false);
   {
     const RsLayer L0 = a.layers[0];
     gemm_phase_rs<NTOK, W8, EPI_HEAD, false>(a, L0, c, make_geom<W8>(wmaps, a.n_layers, 0, MAT_HEAD), nullptr, nullptr, s_pick);

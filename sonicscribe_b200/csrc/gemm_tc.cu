@@ -138,7 +138,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   pdl_launch_dependents();
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one_sync()) {
       int s = 0; uint32_t ph = 0;
       int kb = kb_begin;
       if constexpr (SWAP) {
@@ -168,7 +168,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one_sync()) {
       constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
       int s = 0; uint32_t ph = 0;
       int c = 0; uint32_t cph = 0;
@@ -536,7 +536,7 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one_sync()) {
       uint32_t cnt = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int batch = tile / (tiles_m * tiles_n), r = tile - batch * tiles_m * tiles_n;
@@ -552,7 +552,7 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one_sync()) {
       constexpr uint32_t idesc = make_idesc_bf16(BM, PBN);
       uint32_t cnt = 0, it = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {

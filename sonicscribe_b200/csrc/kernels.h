@@ -159,13 +159,13 @@ static constexpr int kPersistTcTokens = 64;   // token rows of the activation te
 
 // ---- decode_rs.cu: row-sliced persistent decode step for <= 32 segments (bf16) / <= 16 segments (int8 weight-only) ---------
 struct RsLayer {
-  const float *rms1, *rms2;
+  const bf16 *g1, *g2;                            // input / post-attention RMSNorm weights as bf16 (the fp32 vectors hold bf16-rounded values)
   const float *s_qkv, *s_o, *s_gu, *s_down;       // int8 mode: per-row scales (s_qkv in the interleaved row order of wqkv_il)
   bf16 *kc, *vc;                                  // this layer's K / V cache [max_batch][4][max_ctx][128]
 };
 struct DecodeRsArgs {
   const RsLayer* layers; int n_layers;
-  const bf16* embed; const float* final_norm;
+  const bf16* embed; const bf16* final_norm_bf;
   const float* cos_t; const float* sin_t;
   bf16 *x, *q, *attn, *act;       // residual stream [B][2048], rotated queries [B][2048], attention output [B][2048], SwiGLU output [B][6144]
   // device array of CUtensorMap: [4*l + {0: qkv (q/k rows interleaved), 1: o, 2: gate/up, 3: down}] with box rows decode_rs_box_rows(kind),
@@ -178,6 +178,7 @@ struct DecodeRsArgs {
   GreedyState gs;
   unsigned* bar;
   unsigned long long* timestamps; // optional: %globaltimer of CTA 0 after every grid barrier (5 * layers + 3 entries)
+  unsigned long long* dbg; int dbg_cta, dbg_layer;   // optional: 80 fine-grained stamps of one layer on one CTA (decode_rs.cu RS_DBG)
   int B, max_ctx, step;           // step: index of the token this launch produces
   float eps, scale;
 };

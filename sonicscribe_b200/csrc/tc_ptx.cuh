@@ -81,6 +81,19 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int m, int n) {
 }
 
 
+// One lane of a converged warp; code predicated on it is single-thread AND known-uniform to ptxas, so the uniform-register
+// operands of UTCHMMA / UTMALDG are fed directly.  (Under a plain `if (lane == 0)` ptxas wraps every such instruction in an
+// ELECT + 5 x R2UR.BROADCAST + BRA.U.ANY loop: ~100 clk per tcgen05.mma, ~70 ns per TMA issue, measured.)
+__device__ __forceinline__ uint32_t elect_one_sync() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\t"
+      "elect.sync _|P1, 0xffffffff;\n\t"
+      "selp.b32 %0, 1, 0, P1;\n\t}"
+      : "=r"(pred));
+  return pred;
+}
+
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
