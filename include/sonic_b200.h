@@ -134,6 +134,9 @@ SONIC_API int sonic_test_gemm_int8(sonic_handle h, int32_t swap, const float* A,
 /* back-to-back launches of one tcgen05 GEMM shape (zero-filled bf16 operands, weights rotated through > 126 MB so L2
  * never holds them); returns the average device time per launch in microseconds (CUDA events on the handle's stream). */
 SONIC_API int sonic_bench_gemm(sonic_handle h, int32_t swap, int32_t M, int32_t N, int32_t K, int32_t act, int32_t iters, float* avg_us);
+/* tcgen05.mma rate microbenchmark (one CTA): clocks per MMA of shape m x ntok x 16 (bf16, operands in shared memory) cycling through
+ * n_acc TMEM accumulators and n_tiles different 16 KB A tiles: issue-loop clocks and clocks until the last MMA has completed. */
+SONIC_API int sonic_bench_mma(sonic_handle h, int32_t m, int32_t ntok, int32_t n_mma, int32_t n_acc, int32_t n_tiles, float* issue_clk, float* total_clk);
 /* encoder attention alone (20 heads x 64, non-causal, scale 1/8) on a fused [segments*T, 3840] q|k|v buffer (host float32,
  * rounded to bf16 on the device): impl 0 = tcgen05 kernel, impl 1 = CUDA-core cross-check.  out: [segments*T, 1280]. */
 SONIC_API int sonic_test_enc_attention(sonic_handle h, int32_t impl, const float* qkv, float* out, int32_t segments, int32_t T);

@@ -1474,6 +1474,15 @@ int sonic_bench_gemm(sonic_handle h, int32_t swap, int32_t M, int32_t N, int32_t
   return 0;
 }
 
+int sonic_bench_mma(sonic_handle h, int32_t m, int32_t ntok, int32_t n_mma, int32_t n_acc, int32_t n_tiles, float* issue_clk, float* total_clk) {
+  ENTER();
+  if ((m != 64 && m != 128) || ntok < 8 || ntok > 256 || ntok % 8 || (m == 128 && ntok % 16) || n_acc < 1 || n_acc * ntok > 512 || n_tiles < 1 || n_tiles > 11 || n_mma < 1)
+    return fail(h, "sonic_bench_mma: bad shape");
+  CK(bench_mma_rate(m, ntok, n_mma, n_acc, n_tiles, issue_clk, total_clk, h->stream));
+  h->launches += 2;
+  return 0;
+}
+
 int sonic_test_enc_attention(sonic_handle h, int32_t impl, const float* qkv, float* out, int32_t segments, int32_t T) {
   ENTER();
   const size_t rows = (size_t)segments * T, nq = rows * 3 * kEncH, no = rows * kEncH;

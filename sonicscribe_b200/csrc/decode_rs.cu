@@ -82,7 +82,10 @@ __device__ __forceinline__ void mbar_wait_wd(uint32_t bar, uint32_t parity, int 
 }
 __device__ __forceinline__ void sync_workers() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
 __device__ __forceinline__ void sync_epilogue() { asm volatile("bar.sync 2, 128;" ::: "memory"); }
-__device__ __forceinline__ void sync_converters() { asm volatile("bar.sync 3, 256;" ::: "memory"); }
+__device__ __forceinline__ void sync_converters() { asm volatile("bar.sync 3, 128;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_n(uint32_t bar, uint32_t n) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(n) : "memory");
+}
 
 __device__ __forceinline__ void grid_barrier_rs(unsigned* counter, unsigned& epoch, unsigned long long* dbg3 = nullptr) {
   asm volatile("fence.proxy.async;" ::: "memory");       // generic writes of this phase vs TMA reads of the next
@@ -166,8 +169,8 @@ __device__ __forceinline__ Geom make_geom(const CUtensorMap* maps, int n_layers,
   return g;
 }
 
-// independent TMEM accumulators per output tile (see the MMA issue loop): 8 x 16 or 4 x 32 columns, double-buffered
-template <int NTOK> struct RsAcc { static constexpr int value = NTOK == 16 ? 8 : 4; };
+// independent TMEM accumulators per output tile (see the MMA issue loop): 8 x (16 | 32) columns, double-buffered
+template <int NTOK> struct RsAcc { static constexpr int value = 8; };
 
 struct RsCtx {
   uint32_t ring, region, conv, bars, tmem;
@@ -319,9 +322,10 @@ __device__ __forceinline__ void epilogue_tile(const DecodeRsArgs& a, const RsLay
     const bool tab = (g.r1 - g.r0) <= 2 * kRopePairs;
 #pragma unroll
     for (int t = 0; t < NTOK; ++t) {
+      if (t >= a.B) continue;                                            // uniform
       const float own = bf16r(v[t] * sc);
       const float other = __shfl_xor_sync(0xffffffffu, own, 1);
-      if (t < a.B && valid) {
+      if (valid) {
         const int pos = s_pos[t];
         if (is_qk) {
           float2 cs;
@@ -349,9 +353,10 @@ __device__ __forceinline__ void epilogue_tile(const DecodeRsArgs& a, const RsLay
   } else if constexpr (EPI == EPI_SWIGLU) {
 #pragma unroll
     for (int t = 0; t < NTOK; ++t) {
+      if (t >= a.B) continue;                                            // uniform
       const float own = bf16r(v[t] * sc);
       const float up = __shfl_xor_sync(0xffffffffu, own, 1);       // rows are interleaved (gate, up)
-      if (t < a.B && valid && (gr & 1) == 0) a.act[(size_t)t * RI + (gr >> 1)] = __float2bfloat16_rn(bf16r(silu_exact(own)) * up);
+      if (valid && (gr & 1) == 0) a.act[(size_t)t * RI + (gr >> 1)] = __float2bfloat16_rn(bf16r(silu_exact(own)) * up);
     }
   } else {
     // lm_head: fp32 logits; running (best, second, argmax) of this warp per token lives in shared memory
@@ -410,12 +415,16 @@ __device__ __forceinline__ void gemm_phase_rs(const DecodeRsArgs& a, const RsLay
         ++au[h];
       }
     if (lane == 0) RS_DBG(c.phase, 11);
-  } else if (warp == 1) {
-    {                                                                  // the whole warp walks the loop; one elected lane issues
+  } else if (warp >= 12) {
+    {
+      // FOUR issuing warps (one per SM sub-partition): warp 12 + m issues MMA k = m of every 64-wide k block into its own two
+      // accumulators (m for even, 4 + m for odd k blocks).  One warp sustains only ~1 tcgen05.mma per 25 ns (uniform-datapath
+      // bookkeeping around each UTCHMMA), which made the 128-384 MMAs of a full-K row slice the longest part of a phase.
+      const int m = warp - 12;
       const uint32_t idesc = make_idesc_bf16(g.m, NTOK);
       uint32_t cnt = c.cnt, ic = c.ic, cc = c.cc;
       uint32_t au[2] = {c.au[0], c.au[1]};
-      if (lane == 0) RS_DBG(c.phase, 2);
+      if (m == 0 && lane == 0) RS_DBG(c.phase, 2);
       for (int st = 0; st < n_sub; ++st, ++ic) {
         const uint32_t acc = ic & 1u;
         mbar_wait_wd(b_misc(c, ACC_EMPTY + acc), ((ic >> 1) & 1u) ^ 1u, 3);
@@ -434,22 +443,16 @@ __device__ __forceinline__ void gemm_phase_rs(const DecodeRsArgs& a, const RsLay
           const int kb0 = grp * g.kps;
           if (ACT && (kb0 & 15) == 0) mbar_wait_wd(b_misc(c, ACT_FULL + ((kb0 >> 4) & 1)), au[(kb0 >> 4) & 1] & 1u, 6);   // kps divides 16
           tc_fence_after();
-          if (st == 0 && grp == 0 && lane == 0) RS_DBG(c.phase, 3);
+          if (st == 0 && grp == 0 && m == 0 && lane == 0) RS_DBG(c.phase, 3);
           const bool chunk_done = ACT && ((kb0 + g.kps) & 15) == 0;
           if (elect_one_sync()) {
-            // a tcgen05.mma that accumulates into the tile its predecessor wrote waits for it (measured: 50-90 ns per
-            // 64|128 x 16 x 16 MMA into one accumulator): consecutive MMAs go to kAcc different accumulators, summed by the
-            // epilogue in a fixed order.  The loop body is 4 UTCHMMA + two descriptor increments.
-            uint64_t da = make_sw128_desc(abase), db = make_sw128_desc(c.region + (uint32_t)(kb0 & 31) * (NTOK * 128));
+            uint64_t da = make_sw128_desc(abase) + (uint64_t)(2 * m), db = make_sw128_desc(c.region + (uint32_t)(kb0 & 31) * (NTOK * 128)) + (uint64_t)(2 * m);
             const uint64_t da_step = (uint64_t)(g.sub >> 4), db_step = (uint64_t)((NTOK * 128) >> 4);
-            const uint32_t t0 = c.tmem + acc * kAcc * NTOK;
+            const uint32_t t0 = c.tmem + (acc * kAcc + m) * NTOK;
 #pragma unroll 2
             for (int j = 0; j < g.kps; ++j) {
               const int kb = kb0 + j;
-              const uint32_t tb = t0 + ((kAcc == 8 && (kb & 1)) ? 4 * NTOK : 0);
-              const uint32_t accum = (kb * 4 >= kAcc) ? 1u : 0u;
-#pragma unroll
-              for (int k = 0; k < 4; ++k) tc_mma_bf16(tb + k * NTOK, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, accum);
+              tc_mma_bf16(t0 + ((kb & 1) ? 4 * NTOK : 0), da, db, idesc, kb >= 2 ? 1u : 0u);
               da += da_step; db += db_step;
             }
             if (chunk_done) tc_commit(b_misc(c, ACT_EMPTY + (((kb0 + g.kps - 1) >> 4) & 1)));
@@ -462,7 +465,7 @@ __device__ __forceinline__ void gemm_phase_rs(const DecodeRsArgs& a, const RsLay
           if (W8 && g.i8) ++cc;
         }
       }
-      if (lane == 0) RS_DBG(c.phase, 4);
+      if (m == 0 && lane == 0) RS_DBG(c.phase, 4);
     }
   } else if (warp >= 4 && warp < 8) {
     uint32_t ic = c.ic;
@@ -478,7 +481,7 @@ __device__ __forceinline__ void gemm_phase_rs(const DecodeRsArgs& a, const RsLay
       if (lane == 0) mbar_arrive(b_misc(c, ACC_EMPTY + acc));
       if (warp == 4 && lane == 0) RS_DBG(c.phase, 6);
     }
-  } else if (W8 && g.i8 && warp >= 8) {
+  } else if (W8 && g.i8 && warp >= 8 && warp < 12) {
     // int8 -> bf16: ring stage (kps raw tiles of [box rows x 64 B]) -> converter buffer (kps SWIZZLE_128B images)
     const int tid = threadIdx.x - 256;
     uint32_t cnt = c.cnt, cc = c.cc;
@@ -490,7 +493,7 @@ __device__ __forceinline__ void gemm_phase_rs(const DecodeRsArgs& a, const RsLay
         mbar_wait_wd(b_misc(c, CONV_EMPTY + cb), ((cc >> 1) & 1u) ^ 1u, 9);
         const uint8_t* src = c.ring_g + (size_t)s * kStageBytes;
         uint8_t* dst = c.conv_g + (size_t)cb * (2 * kStageBytes);
-        for (int it = tid; it < g.kps * per_kb; it += 256) {
+        for (int it = tid; it < g.kps * per_kb; it += 128) {
           const int j = it / per_kb, rem = it - j * per_kb, row = rem >> 2, piece = rem & 3;
           const uint4 w = *reinterpret_cast<const uint4*>(src + (size_t)j * g.raw_sub + row * 64 + piece * 16);
           const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
@@ -513,8 +516,8 @@ __device__ __forceinline__ void gemm_phase_rs(const DecodeRsArgs& a, const RsLay
           *reinterpret_cast<uint4*>(drow + (((2 * piece + 1) ^ (row & 7)) << 4)) = make_uint4(o[4], o[5], o[6], o[7]);
         }
         fence_proxy_async_smem();
-        sync_converters();                                               // all 8 converter warps are done with this stage
-        if (tid == 0) { mbar_arrive(b_misc(c, CONV_FULL + cb)); mbar_arrive(b_empty(c, s)); }
+        sync_converters();                                               // all 4 converter warps are done with this stage
+        if (tid == 0) { mbar_arrive(b_misc(c, CONV_FULL + cb)); mbar_arrive_n(b_empty(c, s), 4); }   // the stage barrier counts the 4 MMA warps
       }
   }
   // mirrored counters (every worker thread advances them identically)
@@ -616,14 +619,31 @@ __device__ __forceinline__ void attention_phase_rs(const DecodeRsArgs& a, const 
       __threadfence();
       const int ph = tid >> 7, d = tid & 127;
       const float* wg = a.attn_ws + (size_t)grp * C * RG * (RHD + 2);
-      float M = -INFINITY;
-      for (int cidx = 0; cidx < n_chunks; ++cidx) M = fmaxf(M, __ldcg(wg + ((size_t)cidx * RG + ph) * (RHD + 2) + RHD));
-      float Ls = 0.f, o = 0.f;
-      for (int cidx = 0; cidx < n_chunks; ++cidx) {
-        const float* pc = wg + ((size_t)cidx * RG + ph) * (RHD + 2);
-        const float w = expf(__ldcg(pc + RHD) - M);
-        Ls += __ldcg(pc + RHD + 1) * w;
-        o += __ldcg(pc + d) * w;
+      float M = -INFINITY, Ls = 0.f, o = 0.f;
+      if (n_chunks <= 16) {                                              // every partial in flight at once: one L2 round trip
+        float mv[16], lv[16], ov[16];
+#pragma unroll
+        for (int cidx = 0; cidx < 16; ++cidx) {
+          mv[cidx] = -INFINITY; lv[cidx] = 0.f; ov[cidx] = 0.f;
+          if (cidx < n_chunks) {
+            const float* pc = wg + ((size_t)cidx * RG + ph) * (RHD + 2);
+            mv[cidx] = __ldcg(pc + RHD); lv[cidx] = __ldcg(pc + RHD + 1); ov[cidx] = __ldcg(pc + d);
+          }
+        }
+#pragma unroll
+        for (int cidx = 0; cidx < 16; ++cidx) M = fmaxf(M, mv[cidx]);
+#pragma unroll
+        for (int cidx = 0; cidx < 16; ++cidx) {                          // chunk order: deterministic
+          if (cidx < n_chunks) { const float w = expf(mv[cidx] - M); Ls += lv[cidx] * w; o += ov[cidx] * w; }
+        }
+      } else {
+        for (int cidx = 0; cidx < n_chunks; ++cidx) M = fmaxf(M, __ldcg(wg + ((size_t)cidx * RG + ph) * (RHD + 2) + RHD));
+        for (int cidx = 0; cidx < n_chunks; ++cidx) {
+          const float* pc = wg + ((size_t)cidx * RG + ph) * (RHD + 2);
+          const float w = expf(__ldcg(pc + RHD) - M);
+          Ls += __ldcg(pc + RHD + 1) * w;
+          o += __ldcg(pc + d) * w;
+        }
       }
       a.attn[(size_t)seg * RH + (size_t)(kvh * RG + ph) * RHD + d] = __float2bfloat16_rn(o / Ls);
     }
@@ -668,13 +688,13 @@ __global__ void __launch_bounds__(kRsThreads, 1) decode_rs_kernel(DecodeRsArgs a
   static_assert(8 * (2 * SM::kStages + N_MISC) + 16 + kRopePairs * NTOK * 8 + 256 + 4 * NTOK * 3 * 4 <= SM::kSmall, "small area overflow");
   c.cnt = 0; c.ic = 0; c.cc = 0; c.au[0] = 0; c.au[1] = 0; c.layer = -1; c.phase = 0;
   const int tid = threadIdx.x, warp = tid >> 5;
-  constexpr int kTmemCols = 2 * RsAcc<NTOK>::value * NTOK;                 // 256
+  constexpr int kTmemCols = 2 * RsAcc<NTOK>::value * NTOK;                 // 256 | 512
   if (tid == 0) {
-    for (int s = 0; s < SM::kStages; ++s) { mbar_init(b_full(c, s), 1); mbar_init(b_empty(c, s), 1); }
+    for (int s = 0; s < SM::kStages; ++s) { mbar_init(b_full(c, s), 1); mbar_init(b_empty(c, s), 4); }     // 4 MMA warps commit
     for (int i = 0; i < 2; ++i) {
-      mbar_init(b_misc(c, ACC_FULL + i), 1); mbar_init(b_misc(c, ACC_EMPTY + i), 4);
-      mbar_init(b_misc(c, ACT_FULL + i), 1); mbar_init(b_misc(c, ACT_EMPTY + i), 1);
-      mbar_init(b_misc(c, CONV_FULL + i), 1); mbar_init(b_misc(c, CONV_EMPTY + i), 1);
+      mbar_init(b_misc(c, ACC_FULL + i), 4); mbar_init(b_misc(c, ACC_EMPTY + i), 4);
+      mbar_init(b_misc(c, ACT_FULL + i), 1); mbar_init(b_misc(c, ACT_EMPTY + i), 4);
+      mbar_init(b_misc(c, CONV_FULL + i), 1); mbar_init(b_misc(c, CONV_EMPTY + i), 4);
     }
     fence_barrier_init();
   }
@@ -892,4 +912,66 @@ cudaError_t launch_decode_rs(const DecodeRsArgs& a, bool w8, int grid, cudaStrea
   return e;
 }
 
+}  // namespace sonic
+
+// ---- tcgen05.mma issue/execute rate microbenchmark (one CTA per SM, operands already in shared memory) ---------------------
+// Measures the clocks per MMA for M in {64,128}, N = ntok, K = 16 (kind::f16, SWIZZLE_128B K-major operands), cycling through
+// `n_acc` accumulators and `n_tiles` different A tiles; results feed the decode kernels' cost model.
+namespace sonic {
+__global__ void __launch_bounds__(128, 1) mma_rate_kernel(int m, int ntok, int n_mma, int n_acc, int n_tiles, unsigned long long* out) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t slot;
+  const int warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < (n_tiles * 16384 + 32768) / 4; i += 128) reinterpret_cast<uint32_t*>(smem_raw + (base - raw))[i] = 0x3c003c00u + i;
+  if (threadIdx.x == 0) { mbar_init(smem_u32(&bar), 1); fence_barrier_init(); }
+  if (warp == 1) tmem_alloc<512>(smem_u32(&slot));
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = slot;
+  if (warp == 0) {
+    unsigned long long t0 = 0, t1 = 0;
+    if (elect_one_sync()) {
+      const uint32_t idesc = make_idesc_bf16(m, ntok);
+      const uint32_t bop = base + n_tiles * 16384;
+      t0 = clock64();
+      for (int i = 0; i < n_mma; ++i) {
+        const uint64_t da = make_sw128_desc(base + (uint32_t)(i % n_tiles) * 16384) + (uint64_t)(2 * (i & 3));
+        const uint64_t db = make_sw128_desc(bop) + (uint64_t)(2 * (i & 3));
+        tc_mma_bf16(tmem + (uint32_t)(i % n_acc) * ntok, da, db, idesc, i >= n_acc ? 1u : 0u);
+      }
+      tc_commit(smem_u32(&bar));
+      t1 = clock64();
+    }
+    __syncwarp();
+    mbar_wait(smem_u32(&bar), 0);
+    const unsigned long long t2 = clock64();
+    if (elect_one_sync() && blockIdx.x == 0) { out[0] = t1 - t0; out[1] = t2 - t0; }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<512>(tmem);
+}
+
+cudaError_t bench_mma_rate(int m, int ntok, int n_mma, int n_acc, int n_tiles, float* issue_clk, float* total_clk, cudaStream_t st) {
+  unsigned long long* d = nullptr;
+  SONIC_CUDA_TRY(cudaMalloc(&d, 16));
+  const int smem = 1024 + n_tiles * 16384 + 32768;
+  cudaError_t e = cudaFuncSetAttribute(mma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e == cudaSuccess) {
+    mma_rate_kernel<<<1, 128, smem, st>>>(m, ntok, n_mma, n_acc, n_tiles, d);        // warm-up (instruction cache)
+    mma_rate_kernel<<<1, 128, smem, st>>>(m, ntok, n_mma, n_acc, n_tiles, d);
+    e = cudaStreamSynchronize(st);
+  }
+  unsigned long long h[2] = {0, 0};
+  if (e == cudaSuccess) e = cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  *issue_clk = (float)h[0] / n_mma;
+  *total_clk = (float)h[1] / n_mma;
+  return e;
+}
 }  // namespace sonic

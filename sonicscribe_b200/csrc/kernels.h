@@ -190,5 +190,7 @@ int decode_rs_occupancy();
 // dst <- fused qkv matrix with the q / k head rows interleaved for the RoPE epilogue (and the int8 row scales likewise)
 cudaError_t decode_rs_permute_qkv(const void* src, void* dst, int row_bytes, const float* scale_src, float* scale_dst, cudaStream_t st);
 cudaError_t launch_decode_rs(const DecodeRsArgs& a, bool w8, int grid, cudaStream_t st, int* mode);
+// clocks per tcgen05.mma (M x ntok x 16, operands in shared memory): issue time of the loop and time to completion
+cudaError_t bench_mma_rate(int m, int ntok, int n_mma, int n_acc, int n_tiles, float* issue_clk, float* total_clk, cudaStream_t st);
 
 }  // namespace sonic

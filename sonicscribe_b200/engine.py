@@ -74,6 +74,7 @@ def load_library():
         "sonic_test_enc_attention": (C.c_int, [H, C.c_int32, f32p, f32p, C.c_int32, C.c_int32]),
         "sonic_test_gemm_int8": (C.c_int, [H, C.c_int32, f32p, f32p, f32p, f32p, f32p, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
         "sonic_bench_gemm": (C.c_int, [H, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, f32p]),
+        "sonic_bench_mma": (C.c_int, [H, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, f32p, f32p]),
         "sonic_test_gemm": (C.c_int, [H, C.c_int32, C.c_int32, f32p, f32p, f32p, f32p, f32p, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
     }
     for name, (res, args) in protos.items():
@@ -300,6 +301,11 @@ class Engine:
         us = C.c_float()
         self._ck(self.lib.sonic_bench_gemm(self.h, 1 if swap else 0, M, N, K, act, iters, C.byref(us)))
         return float(us.value)
+
+    def bench_mma(self, m, ntok, n_mma=512, n_acc=8, n_tiles=4):
+        a, b = C.c_float(), C.c_float()
+        self._ck(self.lib.sonic_bench_mma(self.h, m, ntok, n_mma, n_acc, n_tiles, C.byref(a), C.byref(b)))
+        return float(a.value), float(b.value)
 
     def test_gemm_int8(self, A, W, bias=None, resid=None, act=0, swap=False):
         A = np.ascontiguousarray(A, dtype=np.float32)
