@@ -143,7 +143,7 @@ struct sonic_ctx {
   long long* offs_dev = nullptr;
   int* lens_dev = nullptr;
   unsigned *peak_bits = nullptr, *gmax_bits = nullptr;
-  float *mel_raw = nullptr, *mel_feat = nullptr;
+  float *mel_tile_min = nullptr, *mel_feat = nullptr;
   void* mel_tm = nullptr;
   std::vector<int> last_lens;           // lengths of the segments currently held in mel_tm
   int last_batch = 0;
@@ -345,8 +345,8 @@ struct Engine {
   static int mel(sonic_ctx* h, const float* pcm_dev, int batch, int max_len, int flags, float* feat_dev) {
     TAG(PC_MEL);
     CKL(launch_mel<T>(pcm_dev, h->offs_dev, h->lens_dev, batch, max_len, flags & 7, h->mel_tables, h->peak_bits, h->gmax_bits,
-                      h->mel_raw, feat_dev, reinterpret_cast<T*>(h->mel_tm), h->stream),
-        (flags & SONIC_FLAG_PEAK_NORM) ? 4 : 3);
+                      h->mel_tile_min, feat_dev, reinterpret_cast<T*>(h->mel_tm), h->stream),
+        2 + ((batch + 63) / 64) * ((flags & SONIC_FLAG_PEAK_NORM) ? 2 : 1));
     return 0;
   }
 
@@ -522,6 +522,7 @@ struct Engine {
       p.attn_ws = h->dattn_ws; p.attn_counters = h->dattn_counters;
       p.attn_chunks = std::min((h->cur_max_q + h->cur_step + 63) / 64, h->dattn_max_chunks);
       p.gs = h->gs; p.bar = h->persist_bar; p.timestamps = h->cfg.debug ? h->persist_ts : nullptr;
+      { const char* pf = getenv("SONIC_RS_L2_PREFETCH"); p.l2_prefetch = (pf && pf[0] == '1'); }    // measured slower (1.53 -> 1.71 ms at one segment): off
       if (h->cfg.debug) {
         const char* dc = getenv("SONIC_RS_DBG_CTA"); const char* dl = getenv("SONIC_RS_DBG_LAYER");
         p.dbg = h->persist_ts + 1024; p.dbg_cta = dc ? atoi(dc) : 0; p.dbg_layer = dl ? atoi(dl) : 1;
@@ -707,7 +708,7 @@ int alloc_all(sonic_ctx* h) {
   // mel
   DA(h->pcm_dev, (size_t)B * kWinSamples * 4); DA(h->offs_dev, B * 8); DA(h->lens_dev, B * 4);
   DA(h->peak_bits, B * 4); DA(h->gmax_bits, B * 4);
-  DA(h->mel_raw, (size_t)B * kMels * kFrames * 4); DA(h->mel_feat, (size_t)B * kMels * kFrames * 4);
+  DA(h->mel_tile_min, (size_t)B * mel_tiles_per_segment() * 4); DA(h->mel_feat, (size_t)B * kMels * kFrames * 4);
   DAZ(h->mel_tm, (size_t)B * (kFrames + 2) * kMels * E);
   // encoder
   DAZ(h->h1, (size_t)B * (kFrames + 2) * kEncH * E);     // pad rows 0 / 3001 stay zero forever
@@ -1326,7 +1327,6 @@ int sonic_debug_read(sonic_handle h, const char* name, float* out, size_t max_el
     if (!pt) return fail(h, "sonic_debug_read: that step was not registered with sonic_debug_set_logit_steps");
     src_f32 = pt; n = (size_t)h->probe_batch * kVocab;
   }
-  else if (nm == "mel_raw") { src_f32 = h->mel_raw; n = (size_t)h->last_batch * kMels * kFrames; }
   else if (h->probes_f32.count(nm)) { src_f32 = h->probes_f32[nm].first; n = h->probes_f32[nm].second; }
   else if (h->probes.count(nm)) { src_t = h->probes[nm].first; n = h->probes[nm].second; }
   else return fail(h, "sonic_debug_read: no such probe (create the handle with debug=1): " + nm);

@@ -1,18 +1,22 @@
-// Row-sliced persistent greedy-decode step for up to 32 segments (bf16 or int8 weight-only linears): ONE cooperative kernel
-// per generated token; every weight matrix is cut into 148 contiguous ROW slices (one per CTA) that are streamed over the
-// FULL K dimension by TMA into a shared-memory ring and multiplied on tcgen05 (weights = the M operand, 64- or 128-row MMA;
-// the <= 32 token rows = the N operand), accumulators in TMEM.
+// Row-sliced persistent greedy-decode step for up to 32 segments (bf16) / 16 segments (int8 weight-only linears): ONE
+// cooperative kernel per generated token; every weight matrix is cut into 148 contiguous ROW slices (one per CTA) that are
+// streamed over the FULL K dimension by TMA into a shared-memory ring and multiplied by mma.sync consumer warps that read
+// the 128B-swizzled stages with ldmatrix (int8: 16 B loads expanded to bf16 in registers).
 //
-// Why this shape (DESIGN.md §4):
+// Why this shape (DESIGN.md §4/§5):
 //   * a batch-1..32 decode step is a chain of ~140 dependent phases whose weight bytes (96 MB per layer) take 15 us at HBM
-//     speed while the dependency chain took 49 us with the split-K / mma.sync design of decode_persist.cu.  Here no phase
-//     produces split-K partials, so residual add, RoPE + KV append, SwiGLU and the argmax are epilogues of the GEMM that
-//     owns the rows, and RMSNorm is recomputed by every CTA while it builds its MMA operand in shared memory: 5 grid
+//     speed while the dependency chain took 49 us with the split-K design of decode_persist.cu.  Here no phase produces
+//     split-K partials in global memory, so residual add, RoPE + KV append, SwiGLU and the argmax are epilogues of the GEMM
+//     that owns the rows, and RMSNorm is recomputed by every CTA while it builds its operand in shared memory: 5 grid
 //     barriers per layer instead of 7, no fp32 partial traffic, no separate norm / embed / pick-scan phases;
 //   * weights do not depend on the token: a dedicated producer warp walks the CTA's whole weight schedule (all layers) and
-//     is throttled only by ring space, so the stream keeps flowing through grid barriers, attention and epilogues;
-//   * accumulation runs over K in one fixed order inside one accumulator: results do not depend on the batch size or on
-//     which other segments share the batch (bit-identical ids for a segment alone or in a batch).
+//     is throttled only by ring space, so the TMA stream keeps flowing through grid barriers, attention and epilogues (a TMA
+//     ring sustains ~2x the per-SM bandwidth of the 16 B register loads of decode_persist.cu's mma.sync classes);
+//   * why mma.sync and not tcgen05 for the multiplication: a tcgen05.mma costs 78-82 clocks whatever its shape up to N = 128
+//     (profiles/r02_tcgen05_mma_rate.txt), and a full-K row slice of 14-24 rows needs 128-384 of them per phase while using
+//     a quarter of the 64-row minimum tile: the first version of this kernel (tcgen05, TMEM accumulators) spent 3.4-10 us
+//     per phase just issuing MMAs.  Eight consumer warps with m16n8k16 fragments have no such floor;
+//   * accumulation order is fixed and independent of the batch: bit-identical ids for a segment alone or in any batch.
 //
 // Phases per layer:  P1 [u = rmsnorm(x) g1 -> smem] qkv slice, epilogue RoPE + q store + K/V append | barrier |
 //                    P2 attention (split over key chunks and CTAs, last-arriver merge)              | barrier |
@@ -21,8 +25,8 @@
 //                    P5 down slice (operand: act by TMA, 1024-k chunks), epilogue x += d            | barrier |
 // then lm_head slice with the argmax as epilogue | barrier | per-token merge + greedy bookkeeping.
 //
-// Warp roles (17 warps): w16 weight producer; w0 activation-chunk loader; w1 MMA issuer; w2 TMEM owner; w4-7 epilogue
-// (TMEM lane quadrants); w8-15 int8 -> bf16 converters (int8 mode); w0-15 build the normalised operand and run attention.
+// Warp roles (17 warps): w16 weight producer (TMA); w0 activation-chunk loader (TMA); w8-15 consumers (ldmatrix + mma.sync,
+// cross-warp reduction through shared memory, fused epilogues); w0-15 build the normalised operand and run attention.
 //
 // Replaces, for one new token per segment: LlamaDecoderLayer x28 + final norm + lm_head + argmax/EOS bookkeeping
 // (transformers/models/llama/modeling_llama.py:53-499, transformers/generation/utils.py:2743-2809), with the reference's
@@ -81,14 +85,11 @@ __device__ __forceinline__ void mbar_wait_wd(uint32_t bar, uint32_t parity, int 
   }
 }
 __device__ __forceinline__ void sync_workers() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
-__device__ __forceinline__ void sync_epilogue() { asm volatile("bar.sync 2, 128;" ::: "memory"); }
-__device__ __forceinline__ void sync_converters() { asm volatile("bar.sync 3, 128;" ::: "memory"); }
-__device__ __forceinline__ void mbar_arrive_n(uint32_t bar, uint32_t n) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(n) : "memory");
-}
-
+__device__ __forceinline__ void sync_consumers() { asm volatile("bar.sync 2, 256;" ::: "memory"); }
+// PROXY: the next phase reads this phase's global writes through TMA (async proxy): order the generic writes before it
+template <bool PROXY>
 __device__ __forceinline__ void grid_barrier_rs(unsigned* counter, unsigned& epoch, unsigned long long* dbg3 = nullptr) {
-  asm volatile("fence.proxy.async;" ::: "memory");       // generic writes of this phase vs TMA reads of the next
+  if (PROXY) asm volatile("fence.proxy.async;" ::: "memory");
   sync_workers();
   if (threadIdx.x == 0) {
     if (dbg3) dbg3[0] = gtime();
@@ -111,7 +112,7 @@ __device__ __forceinline__ void grid_barrier_rs(unsigned* counter, unsigned& epo
     if (dbg3) dbg3[2] = gtime();
   }
   sync_workers();
-  asm volatile("fence.proxy.async;" ::: "memory");
+  if (PROXY) asm volatile("fence.proxy.async;" ::: "memory");
 }
 
 __device__ __forceinline__ float bf16r(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
@@ -130,9 +131,10 @@ struct Geom {
   int box;           // rows per TMA box == rows per sub-tile
   int nkb;           // 64-wide k blocks
   int kps;           // k blocks per ring stage
-  int sub;           // bytes between the bf16 images of consecutive k blocks (1024-aligned, >= box * 128)
-  int raw_sub;       // int8 items: bytes between the raw int8 tiles of consecutive k blocks inside a ring stage
-  int m;             // MMA M (64 or 128)
+  int sub;           // bytes between the tiles of consecutive k blocks inside a ring stage (bf16: 1024-aligned; int8: 128-aligned)
+  int rtiles;        // 16-row tiles per sub-tile
+  int tpw;           // 16-row tiles per consumer warp (1 or 2)
+  int rsplit;        // consumer warps along rows (1, 2 or 4); the other 8 / rsplit split the k blocks
   int i8;            // weights arrive as int8
 };
 // box rows per matrix kind (multiples of 8 that cover the largest slice of a 148-CTA grid; other grids walk sub-tiles)
@@ -154,76 +156,105 @@ __device__ __forceinline__ Geom make_geom(const CUtensorMap* maps, int n_layers,
     if (kind == MAT_HEAD) { g.r0 = a0; g.r1 = a0 + full; } else { g.r0 = a0 + full; g.r1 = a1; }
   }
   g.map = maps + ((kind <= MAT_DOWN) ? 4 * layer + kind : 4 * n_layers + (kind - MAT_HEAD));
-  g.sub = (g.box * 128 + 1023) & ~1023;
-  g.m = g.box <= 64 ? 64 : 128;
-  int kps = kStageBytes / g.sub;                                       // bf16: the stage holds kps images
-  if (kps > 8) kps = 8;
-  while (g.nkb % kps) --kps;
-  if (g.i8) {                                                          // int8: twice the k blocks per stage, images go to a 32 KB converter buffer
-    g.raw_sub = (g.box * 64 + 127) & ~127;
-    kps = (2 * kStageBytes) / g.sub;
-    if (kps > 16) kps = 16;
-    while (g.nkb % kps || kps * g.raw_sub > kStageBytes) --kps;
-  } else g.raw_sub = 0;
+  g.sub = g.i8 ? ((g.box * 64 + 127) & ~127) : ((g.box * 128 + 1023) & ~1023);
+  int kps = kStageBytes / g.sub;
+  if (kps > 16) kps = 16;
+  while (g.nkb % kps || 16 % kps) --kps;                               // divides the k blocks of the matrix and of a 16-block activation chunk
   g.kps = kps;
+  g.rtiles = (g.box + 15) / 16;
+  g.tpw = g.rtiles >= 5 ? 2 : 1;                                       // 88 / 128 rows: two tiles per warp, k split in two (6 or 8 busy warps)
+  g.rsplit = g.rtiles >= 3 ? 4 : g.rtiles;
   return g;
 }
 
-// independent TMEM accumulators per output tile (see the MMA issue loop): 8 x (16 | 32) columns, double-buffered
-template <int NTOK> struct RsAcc { static constexpr int value = 8; };
-
 struct RsCtx {
-  uint32_t ring, region, conv, bars, tmem;
+  uint32_t ring, region, bars;
   uint8_t* region_g;     // generic pointer to the operand region (also the attention scratch)
   uint8_t* ring_g;
-  uint8_t* conv_g;
+  float* scratch;        // [8 k-slices][rows][NTOK + 1] partial sums of the consumer warps
   int n_stages;
   uint32_t cnt;          // ring stages consumed so far (all matrices)
-  uint32_t ic;           // accumulator uses so far
-  uint32_t cc;           // converter buffer uses so far (int8)
   uint32_t au[2];        // activation half-region loads so far
   int layer;             // current layer (debug stamps)
   int phase;             // current phase of the layer (debug stamps)
 };
-// barrier slots: full[NS] empty[NS] acc_full[2] acc_empty[2] act_full[2] act_empty[2] conv_full[2] conv_empty[2]
+// barrier slots: full[NS] empty[NS] act_full[2] act_empty[2]
 __device__ __forceinline__ uint32_t b_full(const RsCtx& c, uint32_t s) { return c.bars + 8u * s; }
 __device__ __forceinline__ uint32_t b_empty(const RsCtx& c, uint32_t s) { return c.bars + 8u * (c.n_stages + s); }
 __device__ __forceinline__ uint32_t b_misc(const RsCtx& c, uint32_t i) { return c.bars + 8u * (2 * c.n_stages + i); }
-enum { ACC_FULL = 0, ACC_EMPTY = 2, ACT_FULL = 4, ACT_EMPTY = 6, CONV_FULL = 8, CONV_EMPTY = 10, N_MISC = 12 };
+enum { ACT_FULL = 0, ACT_EMPTY = 2, N_MISC = 4 };
+constexpr int kConsumers = 8;                                          // warps 8..15
 
-// ---- the weight producer: one thread walks the CTA's whole schedule ----------------------------------------------------------
+// ---- the weight producer: one elected thread walks the CTA's whole schedule ---------------------------------------------------
+// Cursor over the CTA's weight schedule: every (layer, matrix, sub-tile, stage group) in consumption order.
 template <bool W8>
-__device__ __forceinline__ void produce_matrix(const RsCtx& c, const Geom& g, uint32_t& cnt) {
-  const uint32_t row_bytes = g.i8 ? 64u : 128u;
-  const uint32_t sub = g.i8 ? (uint32_t)g.raw_sub : (uint32_t)g.sub;
-  for (int r = g.r0; r < g.r1; r += g.box) {
-    for (int kb0 = 0; kb0 < g.nkb; kb0 += g.kps, ++cnt) {
-      const uint32_t s = cnt % c.n_stages, par = (cnt / c.n_stages) & 1u;
-      mbar_wait_wd(b_empty(c, s), par ^ 1u, 1);
-      mbar_expect_tx(b_full(c, s), (uint32_t)g.kps * g.box * row_bytes);
-      const uint32_t dst = c.ring + s * kStageBytes;
-#pragma unroll 1
-      for (int j = 0; j < g.kps; ++j) tma_load_2d(dst + j * sub, g.map, b_full(c, s), (kb0 + j) * 64, r);
+struct WCursor {
+  const CUtensorMap* maps; int n_layers;
+  int layer, kind, r, kb0;
+  Geom g;
+  bool done;
+  unsigned long long bytes;                 // bytes of the schedule before the cursor
+  __device__ __forceinline__ void load_geom() {
+    for (;;) {
+      if (layer >= n_layers && kind < MAT_HEAD) { kind = MAT_HEAD; }
+      if (kind > MAT_HEAD_TAIL) { done = true; return; }
+      g = make_geom<W8>(maps, n_layers, layer < n_layers ? layer : 0, kind);
+      if (g.r0 < g.r1) { r = g.r0; kb0 = 0; return; }
+      advance_matrix();
     }
   }
+  __device__ __forceinline__ void advance_matrix() {
+    if (kind < MAT_DOWN) ++kind;
+    else if (kind == MAT_DOWN) { kind = MAT_QKV; ++layer; }
+    else ++kind;                                                         // lm_head, lm_head tail, end
+  }
+  __device__ __forceinline__ void init(const CUtensorMap* m, int nl) { maps = m; n_layers = nl; layer = 0; kind = MAT_QKV; done = false; bytes = 0; load_geom(); }
+  __device__ __forceinline__ uint32_t stage_bytes() const { return (uint32_t)g.kps * g.box * (g.i8 ? 64u : 128u); }
+  __device__ __forceinline__ void next() {
+    bytes += stage_bytes();
+    kb0 += g.kps;
+    if (kb0 >= g.nkb) { kb0 = 0; r += g.box; if (r >= g.r1) { advance_matrix(); load_geom(); } }
+  }
+};
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1) : "memory");
 }
+// The ring holds ~100-150 KB per SM, a fifth of one layer's slice, so while a CTA sits in attention, epilogues and grid barriers
+// its ring is full and its share of HBM idle.  A second cursor runs up to kPrefetchAhead bytes in front of the loads and pulls
+// the coming boxes into L2 (126 MB: 148 x 384 KB = 57 MB), so the ring refills at L2 speed once it drains.
+constexpr unsigned long long kPrefetchAhead = 384u << 10;
 
 template <bool W8>
 __device__ void producer_loop(const DecodeRsArgs& a, const RsCtx& c) {
   const CUtensorMap* maps = reinterpret_cast<const CUtensorMap*>(a.wmaps);
+  WCursor<W8> ld, pf;
+  ld.init(maps, a.n_layers);
+  pf.init(maps, a.n_layers);
   uint32_t cnt = 0;
-  for (int l = 0; l < a.n_layers; ++l)
-    for (int k = MAT_QKV; k <= MAT_DOWN; ++k) {
-      produce_matrix<W8>(c, make_geom<W8>(maps, a.n_layers, l, k), cnt);
-      if (a.dbg && (int)blockIdx.x == a.dbg_cta && l == a.dbg_layer) a.dbg[16 * (k == MAT_QKV ? 0 : k + 1) + 10] = gtime();
+  while (!ld.done) {
+    while (a.l2_prefetch && !pf.done && pf.bytes < ld.bytes + kPrefetchAhead) {
+      if (pf.bytes >= ld.bytes + (unsigned long long)c.n_stages * kStageBytes) {        // what the ring itself will request soon is not prefetched
+#pragma unroll 1
+        for (int j = 0; j < pf.g.kps; ++j) tma_prefetch_2d(pf.g.map, (pf.kb0 + j) * 64, pf.r);
+      }
+      pf.next();
     }
-  produce_matrix<W8>(c, make_geom<W8>(maps, a.n_layers, 0, MAT_HEAD), cnt);
-  produce_matrix<W8>(c, make_geom<W8>(maps, a.n_layers, 0, MAT_HEAD_TAIL), cnt);
+    const uint32_t s = cnt % c.n_stages, par = (cnt / c.n_stages) & 1u;
+    mbar_wait_wd(b_empty(c, s), par ^ 1u, 1);
+    mbar_expect_tx(b_full(c, s), ld.stage_bytes());
+    const uint32_t dst = c.ring + s * kStageBytes;
+#pragma unroll 1
+    for (int j = 0; j < ld.g.kps; ++j) tma_load_2d(dst + j * ld.g.sub, ld.g.map, b_full(c, s), (ld.kb0 + j) * 64, ld.r);
+    if (a.dbg && (int)blockIdx.x == a.dbg_cta && ld.layer == a.dbg_layer && ld.kind <= MAT_DOWN && ld.kb0 + ld.g.kps >= ld.g.nkb && ld.r + ld.g.box >= ld.g.r1)
+      a.dbg[16 * (ld.kind == MAT_QKV ? 0 : ld.kind + 1) + 10] = gtime();
+    ld.next();
+    ++cnt;
+  }
 }
 
 // ---- operand builders ------------------------------------------------------------------------------------------------------
-// u[t] = gamma * bf16(x[t] * rsqrt(mean(x[t]^2) + eps)) for every token, written as the K-major SWIZZLE_128B operand the MMA
-// reads: k block kb is a [NTOK rows x 128 B] slab, 16 B chunk ch of row t sits at chunk (ch ^ (t & 7)).  One warp per token.
+// u[t] = gamma * bf16(x[t] * rsqrt(mean(x[t]^2) + eps)) for every token, written as the K-major SWIZZLE_128B operand the
+// consumers read: k block kb is a [NTOK rows x 128 B] slab, 16 B chunk ch of row t sits at chunk (ch ^ (t & 7)).  One warp per token.
 // from_embed: x[t] is the embedding row of the token picked by the previous step (and is stored to x by one CTA).
 struct GammaRegs { uint4 v[8]; };
 // bf16 image of an RMSNorm weight vector, the 8 chunks this lane multiplies with; issued BEFORE the grid barrier that precedes
@@ -277,112 +308,165 @@ __device__ __forceinline__ void build_norm_operand(const DecodeRsArgs& a, const 
   sync_workers();
 }
 
-// ---- epilogues -------------------------------------------------------------------------------------------------------------
+// ---- consumers -------------------------------------------------------------------------------------------------------------
 enum { EPI_QKV = 0, EPI_RESID = 1, EPI_SWIGLU = 2, EPI_HEAD = 3 };
-struct PickState { float best, second; int idx; };
 __device__ __forceinline__ void pick_merge2(float& mb, float& ms, int& mi, float ob, float os, int oi) {
   if (ob > mb || (ob == mb && oi < mi)) { ms = fmaxf(fmaxf(ms, os), mb); mb = ob; mi = oi; }
   else { ms = fmaxf(ms, ob); }
 }
+__device__ __forceinline__ void mma16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+// two's complement bytes -> bf16 pairs without integer conversion: b = low7 - 128 * bit7; bf16(0x4300 | low7) = 128 + low7 and
+// bf16(0x4300 | bit7 << 7) = 128 or 256 are exact, and so is their difference
+__device__ __forceinline__ void i8x4_to_bf16x2(uint32_t w, uint32_t& lo, uint32_t& hi) {
+  const uint32_t lo2 = __byte_perm(w, 0x43434343u, 0x4140), hi2 = __byte_perm(w, 0x43434343u, 0x4342);
+  const uint32_t m1 = 0xbf80bf80u;                                     // -1.0 in both halves
+  __nv_bfloat162 alo, blo, ahi, bhi;
+  *reinterpret_cast<uint32_t*>(&alo) = lo2 & 0xff7fff7fu; *reinterpret_cast<uint32_t*>(&blo) = lo2 & 0xff80ff80u;
+  *reinterpret_cast<uint32_t*>(&ahi) = hi2 & 0xff7fff7fu; *reinterpret_cast<uint32_t*>(&bhi) = hi2 & 0xff80ff80u;
+  const __nv_bfloat162 rlo = __hfma2(blo, *reinterpret_cast<const __nv_bfloat162*>(&m1), alo);
+  const __nv_bfloat162 rhi = __hfma2(bhi, *reinterpret_cast<const __nv_bfloat162*>(&m1), ahi);
+  lo = *reinterpret_cast<const uint32_t*>(&rlo);
+  hi = *reinterpret_cast<const uint32_t*>(&rhi);
+}
 
-template <int NTOK, int EPI>
-__device__ __forceinline__ void epilogue_tile(const DecodeRsArgs& a, const RsLayer& L, const Geom& g, int r, const float* __restrict__ wscale,
-                                              uint32_t taddr, float* s_pick) {
-  const int lane = threadIdx.x & 31, q = (threadIdx.x >> 5) & 3;
-  constexpr int kAcc = RsAcc<NTOK>::value;
-  float v[NTOK];
-  {
-    const uint32_t tq = taddr + ((uint32_t)(q * 32) << 16);
-    uint32_t t0[NTOK], t1[NTOK];
+// one 64-wide k block of one 16-row tile: acc[nt] += W[16 rows][64 k] . U[8 tokens of n-tile nt][64 k]^T
+// bf16: A fragments by ldmatrix from the SWIZZLE_128B stage tile, B fragments by ldmatrix from the operand slab (same swizzle)
+template <int NTOK>
+__device__ __forceinline__ void kblock_bf16(float (&acc)[NTOK / 8][4], uint32_t tile, uint32_t slab, int row0, int lane, int nt_used) {
+  const int mi = lane >> 3, ri = lane & 7;
+  const int arow = row0 + (mi & 1) * 8 + ri;                           // A: matrices (rows 0-7 | 8-15) x (k 0-7 | 8-15)
+  const uint32_t abase = tile + arow * 128, asw = (uint32_t)(arow & 7);
+  const int brow = (mi >> 1) * 8 + ri;                                 // B: matrices (n-tile 0 | 1) x (k 0-7 | 8-15)
+  uint32_t af[4][4], bf[4][NTOK / 16][4];
 #pragma unroll
-    for (int i = 0; i < NTOK; ++i) v[i] = 0.f;
+  for (int ks = 0; ks < 4; ++ks) {                                     // every fragment of the k block in flight before the first MMA
+    ldsm_x4(abase + (((uint32_t)(2 * ks + (mi >> 1)) ^ asw) << 4), af[ks][0], af[ks][1], af[ks][2], af[ks][3]);
 #pragma unroll
-    for (int ai = 0; ai < kAcc; ai += 2) {                             // fixed summation order
-      if constexpr (NTOK == 16) { tmem_ld16(tq + ai * NTOK, t0); tmem_ld16(tq + (ai + 1) * NTOK, t1); }
-      else { tmem_ld32(tq + ai * NTOK, t0); tmem_ld32(tq + (ai + 1) * NTOK, t1); }
-      tmem_ld_wait();
-#pragma unroll
-      for (int i = 0; i < NTOK; ++i) v[i] = (v[i] + __uint_as_float(t0[i])) + __uint_as_float(t1[i]);
+    for (int np = 0; np < NTOK / 16; ++np) {
+      const int n = np * 16 + brow;
+      ldsm_x4(slab + n * 128 + (((uint32_t)(2 * ks + (mi & 1)) ^ (uint32_t)(n & 7)) << 4), bf[ks][np][0], bf[ks][np][1], bf[ks][np][2], bf[ks][np][3]);
     }
   }
-  const int rl = (g.m == 64) ? (lane < 16 ? q * 16 + lane : -1) : q * 32 + lane;     // row of the tile held by this lane
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) {
+#pragma unroll
+    for (int np = 0; np < NTOK / 16; ++np) {
+      if (2 * np < nt_used) mma16816(acc[2 * np], af[ks][0], af[ks][1], af[ks][2], af[ks][3], bf[ks][np][0], bf[ks][np][1]);           // uniform
+      if (2 * np + 1 < nt_used) mma16816(acc[2 * np + 1], af[ks][0], af[ks][1], af[ks][2], af[ks][3], bf[ks][np][2], bf[ks][np][3]);
+    }
+  }
+}
+// int8: thread (g, t) owns bytes 16 t .. 16 t + 15 of rows g and g + 8 of the raw [rows][64 B] tile; the k order inside the
+// block is permuted identically for weights and activations (a dot product does not care)
+template <int NTOK>
+__device__ __forceinline__ void kblock_i8(float (&acc)[NTOK / 8][4], const uint8_t* tile, const uint8_t* slab, int row0, int lane, int nt_used) {
+  const int g = lane >> 2, t = lane & 3;
+  const uint4 wa = *reinterpret_cast<const uint4*>(tile + (row0 + g) * 64 + 16 * t);
+  const uint4 wb = *reinterpret_cast<const uint4*>(tile + (row0 + g + 8) * 64 + 16 * t);
+  const uint32_t ra[4] = {wa.x, wa.y, wa.z, wa.w}, rb[4] = {wb.x, wb.y, wb.z, wb.w};
+  uint32_t alo[4], ahi[4], blo[4], bhi[4];
+#pragma unroll
+  for (int s = 0; s < 4; ++s) { i8x4_to_bf16x2(ra[s], alo[s], ahi[s]); i8x4_to_bf16x2(rb[s], blo[s], bhi[s]); }
+#pragma unroll
+  for (int nt = 0; nt < NTOK / 8; ++nt) {
+    if (nt >= nt_used) break;                                           // uniform: 8-token tiles that hold no segment are skipped
+    const int n = nt * 8 + g;
+    const uint8_t* pr = slab + n * 128;
+    const uint4 x0 = *reinterpret_cast<const uint4*>(pr + (((2 * t) ^ (n & 7)) << 4));
+    const uint4 x1 = *reinterpret_cast<const uint4*>(pr + (((2 * t + 1) ^ (n & 7)) << 4));
+    mma16816(acc[nt], alo[0], blo[0], ahi[0], bhi[0], x0.x, x0.y);
+    mma16816(acc[nt], alo[1], blo[1], ahi[1], bhi[1], x0.z, x0.w);
+    mma16816(acc[nt], alo[2], blo[2], ahi[2], bhi[2], x1.x, x1.y);
+    mma16816(acc[nt], alo[3], blo[3], ahi[3], bhi[3], x1.z, x1.w);
+  }
+}
+
+// epilogue of one sub-tile from the consumers' partial sums: item = (row pair, token); the 256 consumer threads walk the items
+template <int NTOK, int EPI>
+__device__ __forceinline__ void epilogue_rs(const DecodeRsArgs& a, const RsLayer& L, const RsCtx& c, const Geom& g, int r, const float* __restrict__ wscale,
+                                            const int* s_pos, const float2* s_rope, float* s_pick) {
+  constexpr int P = NTOK + 1;                                          // scratch row pitch (floats)
+  const int tc = threadIdx.x - 256;
   const int nrows = min(g.box, g.r1 - r);
-  const bool valid = rl >= 0 && rl < nrows;
-  const int gr = r + (rl < 0 ? 0 : rl);
-  const float sc = (g.i8 && valid) ? __ldg(wscale + gr) : 1.0f;
-  if constexpr (EPI == EPI_QKV) {
-    // rows of q and k heads are interleaved (2j, 2j+1) = natural dims (j, j+64): the RoPE partner sits in the neighbouring lane
-    const bool is_qk = gr < (RQKV - RKVH * RHD);
-    const int hb = gr >> 7, i = gr & 127, j = i >> 1, second = i & 1;
-    // s_pick - 64 ints: token positions; before them the RoPE table of this CTA's q/k row pairs: [pair][token] (cos, sin), bf16-rounded,
-    // filled once per launch (the rows a CTA owns, and so the rotation angles it needs, are the same in every layer)
-    const int* s_pos = reinterpret_cast<const int*>(s_pick) - 64;
-    const float2* s_rope = reinterpret_cast<const float2*>(s_pos) - kRopePairs * NTOK;
-    const int pair = ((r - g.r0) + (rl < 0 ? 0 : rl)) >> 1;
-    const bool tab = (g.r1 - g.r0) <= 2 * kRopePairs;
+  const int ksw = kConsumers / g.rsplit;
+  const int slice = g.rtiles * 16 * P;                                 // floats per k-slice
+  if constexpr (EPI == EPI_HEAD) {
+    // argmax per token: warp w takes tokens w, w + 8, ...; lanes stride the rows
+    const int lane = tc & 31, w = tc >> 5;
+    for (int t = w; t < a.B; t += kConsumers) {
+      float best = -INFINITY, second = -INFINITY;
+      int bi = 0x7fffffff;
+      for (int rl = lane; rl < nrows; rl += 32) {
+        float x = 0.f;
+        for (int ks = 0; ks < ksw; ++ks) x += c.scratch[ks * slice + rl * P + t];
+        if (!(x == x)) x = -INFINITY;                                   // NaN never wins
+        if (a.logits_out) a.logits_out[(size_t)t * RV + r + rl] = x;
+        if (x > best) { second = best; best = x; bi = r + rl; }
+        else if (x > second) second = x;
+      }
 #pragma unroll
-    for (int t = 0; t < NTOK; ++t) {
-      if (t >= a.B) continue;                                            // uniform
-      const float own = bf16r(v[t] * sc);
-      const float other = __shfl_xor_sync(0xffffffffu, own, 1);
-      if (valid) {
-        const int pos = s_pos[t];
-        if (is_qk) {
-          float2 cs;
-          if (tab) cs = s_rope[pair * NTOK + t];
-          else cs = make_float2(bf16r(__ldg(a.cos_t + (size_t)pos * (RHD / 2) + j)), bf16r(__ldg(a.sin_t + (size_t)pos * (RHD / 2) + j)));
-          const float p0 = bf16r(own * cs.x), p1 = bf16r(other * cs.y);
-          const bf16 res = __float2bfloat16_rn(second ? p0 + p1 : p0 - p1);
-          const int d = j + 64 * second;
-          if (hb < 16) a.q[(size_t)t * RH + hb * RHD + d] = res;
-          else L.kc[((size_t)(t * RKVH + (hb - 16)) * a.max_ctx + pos) * RHD + d] = res;
-        } else {
-          const int vr = gr - (RQKV - RKVH * RHD);
-          L.vc[((size_t)(t * RKVH + (vr >> 7)) * a.max_ctx + pos) * RHD + (vr & 127)] = __float2bfloat16_rn(own);
-        }
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ob = __shfl_xor_sync(0xffffffffu, best, o), os = __shfl_xor_sync(0xffffffffu, second, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        pick_merge2(best, second, bi, ob, os, oi);
+      }
+      if (lane == 0) {                                                  // token t is always handled by this warp: private running state
+        float* sp = s_pick + t * 3;
+        float mb = sp[0], ms = sp[1];
+        int mi = __float_as_int(sp[2]);
+        pick_merge2(mb, ms, mi, best, second, bi);
+        sp[0] = mb; sp[1] = ms; sp[2] = __int_as_float(mi);
       }
     }
-  } else if constexpr (EPI == EPI_RESID) {
-    unsigned short xo[NTOK];
-#pragma unroll
-    for (int t = 0; t < NTOK; ++t)                                      // this thread is the only writer of x[t][gr]
-      xo[t] = (t < a.B && valid) ? __ldcg(reinterpret_cast<const unsigned short*>(a.x + (size_t)t * RH + gr)) : (unsigned short)0;
-#pragma unroll
-    for (int t = 0; t < NTOK; ++t)
-      if (t < a.B && valid) a.x[(size_t)t * RH + gr] = __float2bfloat16_rn(__uint_as_float((uint32_t)xo[t] << 16) + bf16r(v[t] * sc));
-  } else if constexpr (EPI == EPI_SWIGLU) {
-#pragma unroll
-    for (int t = 0; t < NTOK; ++t) {
-      if (t >= a.B) continue;                                            // uniform
-      const float own = bf16r(v[t] * sc);
-      const float up = __shfl_xor_sync(0xffffffffu, own, 1);       // rows are interleaved (gate, up)
-      if (valid && (gr & 1) == 0) a.act[(size_t)t * RI + (gr >> 1)] = __float2bfloat16_rn(bf16r(silu_exact(own)) * up);
+    return;
+  }
+  const int pairs = (nrows + 1) >> 1;
+  for (int it = tc; it < pairs * a.B; it += 32 * kConsumers) {
+    const int p = it / a.B, t = it - p * a.B;
+    const int rl = 2 * p, gr = r + rl;
+    float v0 = 0.f, v1 = 0.f;
+    for (int ks = 0; ks < ksw; ++ks) {                                  // k-slice order: deterministic
+      v0 += c.scratch[ks * slice + rl * P + t];
+      v1 += c.scratch[ks * slice + (rl + 1) * P + t];
     }
-  } else {
-    // lm_head: fp32 logits; running (best, second, argmax) of this warp per token lives in shared memory
-    const int warp4 = (threadIdx.x >> 5) & 3;
-#pragma unroll
-    for (int t = 0; t < NTOK; ++t) {
-      if (t < a.B) {                                                 // uniform
-        float x = valid ? v[t] : -INFINITY;
-        if (!(x == x)) x = -INFINITY;                                 // NaN never wins
-        if (a.logits_out && valid) a.logits_out[(size_t)t * RV + gr] = x;
-        float best = x, second = -INFINITY;
-        int bi = valid ? gr : 0x7fffffff;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          const float ob = __shfl_xor_sync(0xffffffffu, best, o), os = __shfl_xor_sync(0xffffffffu, second, o);
-          const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-          pick_merge2(best, second, bi, ob, os, oi);
-        }
-        if (lane == 0) {
-          float* sp = s_pick + (warp4 * NTOK + t) * 3;
-          float mb = sp[0], ms = sp[1];
-          int mi = __float_as_int(sp[2]);
-          pick_merge2(mb, ms, mi, best, second, bi);
-          sp[0] = mb; sp[1] = ms; sp[2] = __int_as_float(mi);
-        }
+    const bool has1 = rl + 1 < nrows;
+    if (g.i8) { v0 *= __ldg(wscale + gr); if (has1) v1 *= __ldg(wscale + gr + 1); }
+    if constexpr (EPI == EPI_QKV) {
+      // rows of q and k heads are interleaved (2j, 2j+1) = natural dims (j, j+64); slices are even-aligned, so has1 holds
+      const float x = bf16r(v0), y = bf16r(v1);
+      const int pos = s_pos[t];
+      if (gr < RQKV - RKVH * RHD) {
+        const int hb = gr >> 7, j = (gr & 127) >> 1;
+        float2 cs;
+        const int pair = (gr - g.r0) >> 1;
+        if ((g.r1 - g.r0) <= 2 * kRopePairs) cs = s_rope[pair * NTOK + t];
+        else cs = make_float2(bf16r(__ldg(a.cos_t + (size_t)pos * (RHD / 2) + j)), bf16r(__ldg(a.sin_t + (size_t)pos * (RHD / 2) + j)));
+        const bf16 o0 = __float2bfloat16_rn(bf16r(x * cs.x) - bf16r(y * cs.y));
+        const bf16 o1 = __float2bfloat16_rn(bf16r(y * cs.x) + bf16r(x * cs.y));
+        bf16* dst = (hb < 16) ? a.q + (size_t)t * RH + hb * RHD : L.kc + ((size_t)(t * RKVH + (hb - 16)) * a.max_ctx + pos) * RHD;
+        dst[j] = o0; dst[j + 64] = o1;
+      } else {
+        const int vr = gr - (RQKV - RKVH * RHD);
+        bf16* dst = L.vc + ((size_t)(t * RKVH + (vr >> 7)) * a.max_ctx + pos) * RHD + (vr & 127);
+        dst[0] = __float2bfloat16_rn(x); dst[1] = __float2bfloat16_rn(y);
       }
+    } else if constexpr (EPI == EPI_RESID) {
+      bf16* px = a.x + (size_t)t * RH + gr;                            // this thread is the only writer of these two elements
+      const float x0 = __uint_as_float((uint32_t)__ldcg(reinterpret_cast<const unsigned short*>(px)) << 16);
+      px[0] = __float2bfloat16_rn(x0 + bf16r(v0));
+      if (has1) {
+        const float x1 = __uint_as_float((uint32_t)__ldcg(reinterpret_cast<const unsigned short*>(px + 1)) << 16);
+        px[1] = __float2bfloat16_rn(x1 + bf16r(v1));
+      }
+    } else {                                                            // SwiGLU: rows are interleaved (gate, up)
+      a.act[(size_t)t * RI + (gr >> 1)] = __float2bfloat16_rn(bf16r(silu_exact(bf16r(v0))) * bf16r(v1));
     }
   }
 }
@@ -392,13 +476,13 @@ __device__ __forceinline__ void epilogue_tile(const DecodeRsArgs& a, const RsLay
 // region already holds the normalised operand for the whole K = 2048.
 template <int NTOK, bool W8, int EPI, bool ACT>
 __device__ __forceinline__ void gemm_phase_rs(const DecodeRsArgs& a, const RsLayer& L, RsCtx& c, const Geom& g, const CUtensorMap* act_map,
-                                              const float* __restrict__ wscale, float* s_pick) {
+                                              const float* __restrict__ wscale, const int* s_pos, const float2* s_rope, float* s_pick) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_sub = (g.r1 - g.r0 + g.box - 1) / g.box;
   const int n_groups = g.nkb / g.kps;
   const int n_chunks = g.nkb / 16;                                    // activation chunks of 16 k blocks per sub-tile
   constexpr uint32_t kHalf = NTOK * 128 * 16;                         // bytes of one activation chunk
-  constexpr int kAcc = RsAcc<NTOK>::value;
+  constexpr int P = NTOK + 1;
   if (ACT && warp == 0) {
     uint32_t au[2] = {c.au[0], c.au[1]};
     for (int st = 0; st < n_sub; ++st)
@@ -415,115 +499,75 @@ __device__ __forceinline__ void gemm_phase_rs(const DecodeRsArgs& a, const RsLay
         ++au[h];
       }
     if (lane == 0) RS_DBG(c.phase, 11);
-  } else if (warp >= 12) {
-    {
-      // FOUR issuing warps (one per SM sub-partition): warp 12 + m issues MMA k = m of every 64-wide k block into its own two
-      // accumulators (m for even, 4 + m for odd k blocks).  One warp sustains only ~1 tcgen05.mma per 25 ns (uniform-datapath
-      // bookkeeping around each UTCHMMA), which made the 128-384 MMAs of a full-K row slice the longest part of a phase.
-      const int m = warp - 12;
-      const uint32_t idesc = make_idesc_bf16(g.m, NTOK);
-      uint32_t cnt = c.cnt, ic = c.ic, cc = c.cc;
-      uint32_t au[2] = {c.au[0], c.au[1]};
-      if (m == 0 && lane == 0) RS_DBG(c.phase, 2);
-      for (int st = 0; st < n_sub; ++st, ++ic) {
-        const uint32_t acc = ic & 1u;
-        mbar_wait_wd(b_misc(c, ACC_EMPTY + acc), ((ic >> 1) & 1u) ^ 1u, 3);
-        tc_fence_after();
-        for (int grp = 0; grp < n_groups; ++grp, ++cnt) {
-          const uint32_t s = cnt % c.n_stages, par = (cnt / c.n_stages) & 1u;
-          uint32_t abase;
-          if (W8 && g.i8) {
-            const uint32_t cb = cc & 1u;
-            mbar_wait_wd(b_misc(c, CONV_FULL + cb), (cc >> 1) & 1u, 4);
-            abase = c.conv + cb * (2 * kStageBytes);
-          } else {
-            mbar_wait_wd(b_full(c, s), par, 5);
-            abase = c.ring + s * kStageBytes;
-          }
-          const int kb0 = grp * g.kps;
-          if (ACT && (kb0 & 15) == 0) mbar_wait_wd(b_misc(c, ACT_FULL + ((kb0 >> 4) & 1)), au[(kb0 >> 4) & 1] & 1u, 6);   // kps divides 16
-          tc_fence_after();
-          if (st == 0 && grp == 0 && m == 0 && lane == 0) RS_DBG(c.phase, 3);
-          const bool chunk_done = ACT && ((kb0 + g.kps) & 15) == 0;
-          if (elect_one_sync()) {
-            uint64_t da = make_sw128_desc(abase) + (uint64_t)(2 * m), db = make_sw128_desc(c.region + (uint32_t)(kb0 & 31) * (NTOK * 128)) + (uint64_t)(2 * m);
-            const uint64_t da_step = (uint64_t)(g.sub >> 4), db_step = (uint64_t)((NTOK * 128) >> 4);
-            const uint32_t t0 = c.tmem + (acc * kAcc + m) * NTOK;
-#pragma unroll 2
-            for (int j = 0; j < g.kps; ++j) {
-              const int kb = kb0 + j;
-              tc_mma_bf16(t0 + ((kb & 1) ? 4 * NTOK : 0), da, db, idesc, kb >= 2 ? 1u : 0u);
-              da += da_step; db += db_step;
-            }
-            if (chunk_done) tc_commit(b_misc(c, ACT_EMPTY + (((kb0 + g.kps - 1) >> 4) & 1)));
-            if (W8 && g.i8) tc_commit(b_misc(c, CONV_EMPTY + (cc & 1u)));
-            else tc_commit(b_empty(c, s));
-            if (grp == n_groups - 1) tc_commit(b_misc(c, ACC_FULL + acc));
-          }
-          __syncwarp();
-          if (chunk_done) ++au[((kb0 + g.kps - 1) >> 4) & 1];
-          if (W8 && g.i8) ++cc;
-        }
-      }
-      if (m == 0 && lane == 0) RS_DBG(c.phase, 4);
-    }
-  } else if (warp >= 4 && warp < 8) {
-    uint32_t ic = c.ic;
+  } else if (warp >= 8) {
+    const int wc = warp - 8;
+    const int rg = wc % g.rsplit, ksl = wc / g.rsplit, ksw = kConsumers / g.rsplit;
+    const int rt0 = rg * g.tpw;                                         // first 16-row tile of this warp
+    const int nt_used = (a.B + 7) >> 3;
+    const bool active = rt0 < g.rtiles, two = g.tpw == 2 && rt0 + 1 < g.rtiles;
+    uint32_t cnt = c.cnt;
+    uint32_t au[2] = {c.au[0], c.au[1]};
     int r = g.r0;
-    for (int st = 0; st < n_sub; ++st, ++ic, r += g.box) {
-      const uint32_t acc = ic & 1u;
-      mbar_wait_wd(b_misc(c, ACC_FULL + acc), (ic >> 1) & 1u, 7);
-      tc_fence_after();
-      if (warp == 4 && lane == 0) RS_DBG(c.phase, 5);
-      epilogue_tile<NTOK, EPI>(a, L, g, r, wscale, c.tmem + acc * kAcc * NTOK, s_pick);
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(b_misc(c, ACC_EMPTY + acc));
-      if (warp == 4 && lane == 0) RS_DBG(c.phase, 6);
-    }
-  } else if (W8 && g.i8 && warp >= 8 && warp < 12) {
-    // int8 -> bf16: ring stage (kps raw tiles of [box rows x 64 B]) -> converter buffer (kps SWIZZLE_128B images)
-    const int tid = threadIdx.x - 256;
-    uint32_t cnt = c.cnt, cc = c.cc;
-    const int per_kb = g.box * 4;                                     // 16 B pieces per k block
-    for (int st = 0; st < n_sub; ++st)
-      for (int grp = 0; grp < n_groups; ++grp, ++cnt, ++cc) {
-        const uint32_t s = cnt % c.n_stages, par = (cnt / c.n_stages) & 1u, cb = cc & 1u;
-        mbar_wait_wd(b_full(c, s), par, 8);
-        mbar_wait_wd(b_misc(c, CONV_EMPTY + cb), ((cc >> 1) & 1u) ^ 1u, 9);
-        const uint8_t* src = c.ring_g + (size_t)s * kStageBytes;
-        uint8_t* dst = c.conv_g + (size_t)cb * (2 * kStageBytes);
-        for (int it = tid; it < g.kps * per_kb; it += 128) {
-          const int j = it / per_kb, rem = it - j * per_kb, row = rem >> 2, piece = rem & 3;
-          const uint4 w = *reinterpret_cast<const uint4*>(src + (size_t)j * g.raw_sub + row * 64 + piece * 16);
-          const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
-          uint32_t o[8];
+    if (wc == 0 && lane == 0) RS_DBG(c.phase, 2);
+    for (int st = 0; st < n_sub; ++st, r += g.box) {
+      float acc[2][NTOK / 8][4];
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            // two's complement byte b = low7 - 128 * bit7: bf16(0x4300 | low7) = 128 + low7, bf16(0x4300 | bit7 << 7) = 128 or 256
-            const uint32_t lo2 = __byte_perm(ww[e], 0x43434343u, 0x4140), hi2 = __byte_perm(ww[e], 0x43434343u, 0x4342);
-            const uint32_t one = 0xbf80bf80u;                         // -1.0 in both bf16 halves
-            __nv_bfloat162 alo, blo, ahi, bhi;
-            *reinterpret_cast<uint32_t*>(&alo) = lo2 & 0xff7fff7fu; *reinterpret_cast<uint32_t*>(&blo) = lo2 & 0xff80ff80u;
-            *reinterpret_cast<uint32_t*>(&ahi) = hi2 & 0xff7fff7fu; *reinterpret_cast<uint32_t*>(&bhi) = hi2 & 0xff80ff80u;
-            const __nv_bfloat162 m1 = *reinterpret_cast<const __nv_bfloat162*>(&one);
-            const __nv_bfloat162 rlo = __hfma2(blo, m1, alo), rhi = __hfma2(bhi, m1, ahi);
-            o[2 * e] = *reinterpret_cast<const uint32_t*>(&rlo);
-            o[2 * e + 1] = *reinterpret_cast<const uint32_t*>(&rhi);
+      for (int h2 = 0; h2 < 2; ++h2)
+#pragma unroll
+        for (int nt = 0; nt < NTOK / 8; ++nt) { acc[h2][nt][0] = acc[h2][nt][1] = acc[h2][nt][2] = acc[h2][nt][3] = 0.f; }
+      for (int grp = 0; grp < n_groups; ++grp, ++cnt) {
+        const uint32_t s = cnt % c.n_stages, par = (cnt / c.n_stages) & 1u;
+        const int kb0 = grp * g.kps;
+        mbar_wait_wd(b_full(c, s), par, 5);
+        if (ACT && (kb0 & 15) == 0) mbar_wait_wd(b_misc(c, ACT_FULL + ((kb0 >> 4) & 1)), au[(kb0 >> 4) & 1] & 1u, 6);   // kps divides 16
+        if (st == 0 && grp == 0 && wc == 0 && lane == 0) RS_DBG(c.phase, 3);
+        if (active) {
+          // rows of this warp's tile(s); k blocks kb = kb0 + j with (kb % ksw) == ksl (a fixed partition: the sum order never changes)
+          for (int j = (ksl - kb0) & (ksw - 1); j < g.kps; j += ksw) {        // ksw is a power of two
+            const int kb = kb0 + j;
+            const uint32_t slab = (uint32_t)(kb & 31) * (NTOK * 128);
+            if (W8 && g.i8) {
+              const uint8_t* tile = c.ring_g + (size_t)s * kStageBytes + (size_t)j * g.sub;
+              kblock_i8<NTOK>(acc[0], tile, c.region_g + slab, rt0 * 16, lane, nt_used);
+              if (two) kblock_i8<NTOK>(acc[1], tile, c.region_g + slab, rt0 * 16 + 16, lane, nt_used);
+            } else {
+              const uint32_t tile = c.ring + s * kStageBytes + j * g.sub;
+              kblock_bf16<NTOK>(acc[0], tile, c.region + slab, rt0 * 16, lane, nt_used);
+              if (two) kblock_bf16<NTOK>(acc[1], tile, c.region + slab, rt0 * 16 + 16, lane, nt_used);
+            }
           }
-          uint8_t* drow = dst + (size_t)j * g.sub + row * 128;
-          *reinterpret_cast<uint4*>(drow + (((2 * piece) ^ (row & 7)) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
-          *reinterpret_cast<uint4*>(drow + (((2 * piece + 1) ^ (row & 7)) << 4)) = make_uint4(o[4], o[5], o[6], o[7]);
         }
-        fence_proxy_async_smem();
-        sync_converters();                                               // all 4 converter warps are done with this stage
-        if (tid == 0) { mbar_arrive(b_misc(c, CONV_FULL + cb)); mbar_arrive_n(b_empty(c, s), 4); }   // the stage barrier counts the 4 MMA warps
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(b_empty(c, s));                                  // 8 consumer warps free a stage
+          if (ACT && ((kb0 + g.kps) & 15) == 0) mbar_arrive(b_misc(c, ACT_EMPTY + (((kb0 + g.kps - 1) >> 4) & 1)));
+        }
+        if (ACT && ((kb0 + g.kps) & 15) == 0) ++au[((kb0 + g.kps - 1) >> 4) & 1];
       }
+      if (wc == 0 && lane == 0) RS_DBG(c.phase, 4);
+      // partial sums -> scratch[k-slice][row][token]
+      if (active) {
+        const int gq = lane >> 2, tq = lane & 3;
+#pragma unroll
+        for (int h2 = 0; h2 < 2; ++h2) {
+          if (h2 == 1 && !two) break;
+          float* sp = c.scratch + ksl * (g.rtiles * 16 * P) + ((rt0 + h2) * 16 + gq) * P + 2 * tq;
+#pragma unroll
+          for (int nt = 0; nt < NTOK / 8; ++nt) {
+            sp[nt * 8] = acc[h2][nt][0]; sp[nt * 8 + 1] = acc[h2][nt][1];
+            sp[8 * P + nt * 8] = acc[h2][nt][2]; sp[8 * P + nt * 8 + 1] = acc[h2][nt][3];
+          }
+        }
+      }
+      sync_consumers();
+      if (wc == 0 && lane == 0) RS_DBG(c.phase, 5);
+      epilogue_rs<NTOK, EPI>(a, L, c, g, r, wscale, s_pos, s_rope, s_pick);
+      if (wc == 0 && lane == 0) RS_DBG(c.phase, 6);
+      if (st + 1 < n_sub || EPI == EPI_HEAD) sync_consumers();         // the scratch is rewritten by the next sub-tile
+    }
   }
   // mirrored counters (every worker thread advances them identically)
   c.cnt += (uint32_t)(n_sub * n_groups);
-  c.ic += (uint32_t)n_sub;
-  if (W8 && g.i8) c.cc += (uint32_t)(n_sub * n_groups);
   if (ACT) { c.au[0] += (uint32_t)(n_sub * ((n_chunks + 1) / 2)); c.au[1] += (uint32_t)(n_sub * (n_chunks / 2)); }
 }
 
@@ -659,10 +703,10 @@ __device__ __forceinline__ void attention_phase_rs(const DecodeRsArgs& a, const 
 template <int NTOK, bool W8>
 struct RsSmem {
   static constexpr int kRegion = NTOK * RH * 2;                          // operand region: 64 KB / 128 KB
-  static constexpr int kConv = W8 ? 2 * 2 * kStageBytes : 0;             // two 32 KB converter buffers
-  static constexpr int kSmall = 2048 + kRopePairs * NTOK * 8;            // barriers, tmem slot, RoPE table, positions, pick state
-  static constexpr int kStages = (227 * 1024 - 1024 - kRegion - kConv - kSmall) / kStageBytes;
-  static constexpr int kTotal = 1024 + kStages * kStageBytes + kConv + kRegion + kSmall;
+  static constexpr int kScratch = 256 * (NTOK + 1) * 4;                  // consumer partial sums: max over matrices of k-slices x rows (2 x 128)
+  static constexpr int kSmall = 1024 + kRopePairs * NTOK * 8 + kScratch; // barriers, positions, pick state, RoPE table, scratch
+  static constexpr int kStages = (227 * 1024 - 1024 - kRegion - kSmall) / kStageBytes;
+  static constexpr int kTotal = 1024 + kStages * kStageBytes + kRegion + kSmall;
   static_assert(kStages >= 3, "ring too shallow");
   static_assert(kRegion >= kAttnCK * kAttnKRow + kAttnCK * RHD * 2 + (RG * RHD + RG * kAttnCK + 40) * 4, "attention scratch does not fit the operand region");
 };
@@ -677,37 +721,28 @@ __global__ void __launch_bounds__(kRsThreads, 1) decode_rs_kernel(DecodeRsArgs a
   RsCtx c;
   c.n_stages = SM::kStages;
   c.ring = base; c.ring_g = sg;
-  c.conv = base + SM::kStages * kStageBytes; c.conv_g = sg + SM::kStages * kStageBytes;
-  c.region = c.conv + SM::kConv; c.region_g = c.conv_g + SM::kConv;
+  c.region = base + SM::kStages * kStageBytes; c.region_g = sg + SM::kStages * kStageBytes;
   uint8_t* small = c.region_g + SM::kRegion;
   c.bars = c.region + SM::kRegion;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(small + 8 * (2 * SM::kStages + N_MISC));
-  float2* s_rope = reinterpret_cast<float2*>(small + 8 * (2 * SM::kStages + N_MISC) + 16);      // [kRopePairs][NTOK] (cos, sin)
-  int* s_pos = reinterpret_cast<int*>(s_rope + kRopePairs * NTOK);                               // [64] token positions
-  float* s_pick = reinterpret_cast<float*>(s_pos + 64);                                          // [4 warps][NTOK][3]
-  static_assert(8 * (2 * SM::kStages + N_MISC) + 16 + kRopePairs * NTOK * 8 + 256 + 4 * NTOK * 3 * 4 <= SM::kSmall, "small area overflow");
-  c.cnt = 0; c.ic = 0; c.cc = 0; c.au[0] = 0; c.au[1] = 0; c.layer = -1; c.phase = 0;
+  static_assert(8 * (2 * SM::kStages + N_MISC) + 256 + NTOK * 3 * 4 <= 1024, "small area overflow");
+  int* s_pos = reinterpret_cast<int*>(small + 8 * (2 * SM::kStages + N_MISC));                   // [64] token positions
+  float* s_pick = reinterpret_cast<float*>(s_pos + 64);                                          // [NTOK][3] running argmax state
+  float2* s_rope = reinterpret_cast<float2*>(small + 1024);                                      // [kRopePairs][NTOK] (cos, sin)
+  c.scratch = reinterpret_cast<float*>(small + 1024 + kRopePairs * NTOK * 8);
+  c.cnt = 0; c.au[0] = 0; c.au[1] = 0; c.layer = -1; c.phase = 0;
   const int tid = threadIdx.x, warp = tid >> 5;
-  constexpr int kTmemCols = 2 * RsAcc<NTOK>::value * NTOK;                 // 256 | 512
   if (tid == 0) {
-    for (int s = 0; s < SM::kStages; ++s) { mbar_init(b_full(c, s), 1); mbar_init(b_empty(c, s), 4); }     // 4 MMA warps commit
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(b_misc(c, ACC_FULL + i), 4); mbar_init(b_misc(c, ACC_EMPTY + i), 4);
-      mbar_init(b_misc(c, ACT_FULL + i), 1); mbar_init(b_misc(c, ACT_EMPTY + i), 4);
-      mbar_init(b_misc(c, CONV_FULL + i), 1); mbar_init(b_misc(c, CONV_EMPTY + i), 4);
-    }
+    for (int s = 0; s < SM::kStages; ++s) { mbar_init(b_full(c, s), 1); mbar_init(b_empty(c, s), kConsumers); }
+    for (int i = 0; i < 2; ++i) { mbar_init(b_misc(c, ACT_FULL + i), 1); mbar_init(b_misc(c, ACT_EMPTY + i), kConsumers); }
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc<kTmemCols>(smem_u32(tmem_slot));
-  tc_fence_before();
   __syncthreads();
-  tc_fence_after();
-  c.tmem = *tmem_slot;
 
   if (warp == 16) {                                                     // the weight stream never waits for a grid barrier
     if (elect_one_sync()) producer_loop<W8>(a, c);
     return;
   }
+
   unsigned epoch = 0;
   int n_stamp = 0;
   RS_STAMP();
@@ -739,54 +774,46 @@ __global__ void __launch_bounds__(kRsThreads, 1) decode_rs_kernel(DecodeRsArgs a
     if (tid == 0) RS_DBG(0, 0);
     build_norm_operand<NTOK>(a, c, gm, l == 0);
     if (tid == 0) RS_DBG(0, 1);
-    gemm_phase_rs<NTOK, W8, EPI_QKV, false>(a, L, c, make_geom<W8>(wmaps, a.n_layers, l, MAT_QKV), nullptr, L.s_qkv, s_pick);
-    grid_barrier_rs(a.bar, epoch, bd ? bd + 7 : nullptr); RS_STAMP();
+    gemm_phase_rs<NTOK, W8, EPI_QKV, false>(a, L, c, make_geom<W8>(wmaps, a.n_layers, l, MAT_QKV), nullptr, L.s_qkv, s_pos, s_rope, s_pick);
+    grid_barrier_rs<false>(a.bar, epoch, bd ? bd + 7 : nullptr); RS_STAMP();
     c.phase = 1;
     if (tid == 0) RS_DBG(1, 0);
     attention_phase_rs(a, L, c.region_g);
-    grid_barrier_rs(a.bar, epoch, bd ? bd + 16 + 7 : nullptr); RS_STAMP();
+    grid_barrier_rs<true>(a.bar, epoch, bd ? bd + 16 + 7 : nullptr); RS_STAMP();      // attn is read by TMA
     c.phase = 2;
     if (tid == 0) RS_DBG(2, 0);
-    gemm_phase_rs<NTOK, W8, EPI_RESID, true>(a, L, c, make_geom<W8>(wmaps, a.n_layers, l, MAT_O), amaps, L.s_o, s_pick);
+    gemm_phase_rs<NTOK, W8, EPI_RESID, true>(a, L, c, make_geom<W8>(wmaps, a.n_layers, l, MAT_O), amaps, L.s_o, s_pos, s_rope, s_pick);
     load_gamma(gm, L.g2, a.B);
-    grid_barrier_rs(a.bar, epoch, bd ? bd + 32 + 7 : nullptr); RS_STAMP();
+    grid_barrier_rs<false>(a.bar, epoch, bd ? bd + 32 + 7 : nullptr); RS_STAMP();
     c.phase = 3;
     if (tid == 0) RS_DBG(3, 0);
     build_norm_operand<NTOK>(a, c, gm, false);
     if (tid == 0) RS_DBG(3, 1);
-    gemm_phase_rs<NTOK, W8, EPI_SWIGLU, false>(a, L, c, make_geom<W8>(wmaps, a.n_layers, l, MAT_GU), nullptr, L.s_gu, s_pick);
-    grid_barrier_rs(a.bar, epoch, bd ? bd + 48 + 7 : nullptr); RS_STAMP();
+    gemm_phase_rs<NTOK, W8, EPI_SWIGLU, false>(a, L, c, make_geom<W8>(wmaps, a.n_layers, l, MAT_GU), nullptr, L.s_gu, s_pos, s_rope, s_pick);
+    grid_barrier_rs<true>(a.bar, epoch, bd ? bd + 48 + 7 : nullptr); RS_STAMP();      // act is read by TMA
     c.phase = 4;
     if (tid == 0) RS_DBG(4, 0);
-    gemm_phase_rs<NTOK, W8, EPI_RESID, true>(a, L, c, make_geom<W8>(wmaps, a.n_layers, l, MAT_DOWN), amaps + 1, L.s_down, s_pick);
+    gemm_phase_rs<NTOK, W8, EPI_RESID, true>(a, L, c, make_geom<W8>(wmaps, a.n_layers, l, MAT_DOWN), amaps + 1, L.s_down, s_pos, s_rope, s_pick);
     load_gamma(gm, (l + 1 < a.n_layers) ? a.layers[l + 1].g1 : a.final_norm_bf, a.B);
-    grid_barrier_rs(a.bar, epoch, bd ? bd + 64 + 7 : nullptr); RS_STAMP();
+    grid_barrier_rs<false>(a.bar, epoch, bd ? bd + 64 + 7 : nullptr); RS_STAMP();
   }
   c.layer = -1; c.phase = 5;
   // ---- lm_head with the argmax as epilogue
-  if (tid < 4 * NTOK) { s_pick[tid * 3] = -INFINITY; s_pick[tid * 3 + 1] = -INFINITY; s_pick[tid * 3 + 2] = __int_as_float(0x7fffffff); }
+  if (tid < NTOK) { s_pick[tid * 3] = -INFINITY; s_pick[tid * 3 + 1] = -INFINITY; s_pick[tid * 3 + 2] = __int_as_float(0x7fffffff); }
   build_norm_operand<NTOK>(a, c, gm, false);
   {
     const RsLayer L0 = a.layers[0];
-    gemm_phase_rs<NTOK, W8, EPI_HEAD, false>(a, L0, c, make_geom<W8>(wmaps, a.n_layers, 0, MAT_HEAD), nullptr, nullptr, s_pick);
-    gemm_phase_rs<NTOK, W8, EPI_HEAD, false>(a, L0, c, make_geom<W8>(wmaps, a.n_layers, 0, MAT_HEAD_TAIL), nullptr, nullptr, s_pick);
+    gemm_phase_rs<NTOK, W8, EPI_HEAD, false>(a, L0, c, make_geom<W8>(wmaps, a.n_layers, 0, MAT_HEAD), nullptr, nullptr, s_pos, s_rope, s_pick);
+    gemm_phase_rs<NTOK, W8, EPI_HEAD, false>(a, L0, c, make_geom<W8>(wmaps, a.n_layers, 0, MAT_HEAD_TAIL), nullptr, nullptr, s_pos, s_rope, s_pick);
   }
-  if (warp >= 4 && warp < 8) {
-    sync_epilogue();
-    if (warp == 4) {
-      for (int t = tid & 31; t < a.B; t += 32) {
-        float mb = -INFINITY, ms = -INFINITY;
-        int mi = 0x7fffffff;
-        for (int w = 0; w < 4; ++w) {
-          const float* sp = s_pick + (w * NTOK + t) * 3;
-          pick_merge2(mb, ms, mi, sp[0], sp[1], __float_as_int(sp[2]));
-        }
-        float* pp = a.pick_scratch + ((size_t)t * gridDim.x + blockIdx.x) * 4;
-        pp[0] = mb; pp[1] = ms; pp[2] = __int_as_float(mi);
-      }
+  if (warp >= 8) {
+    sync_consumers();
+    for (int t = tid - 256; t < a.B; t += 32 * kConsumers) {
+      float* pp = a.pick_scratch + ((size_t)t * gridDim.x + blockIdx.x) * 4;
+      pp[0] = s_pick[t * 3]; pp[1] = s_pick[t * 3 + 1]; pp[2] = s_pick[t * 3 + 2];
     }
   }
-  grid_barrier_rs(a.bar, epoch); RS_STAMP();
+  grid_barrier_rs<false>(a.bar, epoch); RS_STAMP();
   for (int b = blockIdx.x; b < a.B; b += gridDim.x) {
     if (tid < 32) {
       float best = -INFINITY, second = -INFINITY;
@@ -819,9 +846,6 @@ __global__ void __launch_bounds__(kRsThreads, 1) decode_rs_kernel(DecodeRsArgs a
   }
   if (blockIdx.x == 0 && tid == 0) *a.gs.step = a.step + 1;      // the other decode paths read the step from device memory
   RS_STAMP();
-  tc_fence_before();
-  sync_workers();
-  if (warp == 2) tmem_dealloc<kTmemCols>(c.tmem);
 }
 
 typedef void (*RsKernel)(DecodeRsArgs);

@@ -19,8 +19,9 @@ void mel_build_tables(void* host_out, const int* tap_start, const int* tap_count
 cudaError_t mel_setup();
 template <typename T>
 cudaError_t launch_mel(const float* pcm, const long long* offs, const int* lens, int batch, int max_len, int flags,
-                       const void* tables, unsigned* peak_bits, unsigned* gmax_bits, float* raw, float* feat, T* feat_tm,
-                       cudaStream_t st);
+                       const void* tables, unsigned* peak_bits, unsigned* gmax_bits, float* tile_min /*[batch][mel_tiles_per_segment()]*/,
+                       float* feat, T* feat_tm, cudaStream_t st);
+int mel_tiles_per_segment();
 
 // ---- gemm: C[b][M,N] = epilogue(A[b][M,K] * W[N,K]^T) ---------------------------------------------------------------
 enum { ACT_NONE = 0, ACT_GELU = 1, ACT_SWIGLU = 2 };   // SWIGLU: columns are (gate,up) pairs; writes N/2 columns
@@ -178,6 +179,7 @@ struct DecodeRsArgs {
   GreedyState gs;
   unsigned* bar;
   unsigned long long* timestamps; // optional: %globaltimer of CTA 0 after every grid barrier (5 * layers + 3 entries)
+  int l2_prefetch;                // 1: the producer prefetches the coming weight boxes into L2 ahead of the ring
   unsigned long long* dbg; int dbg_cta, dbg_layer;   // optional: 80 fine-grained stamps of one layer on one CTA (decode_rs.cu RS_DBG)
   int B, max_ctx, step;           // step: index of the token this launch produces
   float eps, scale;

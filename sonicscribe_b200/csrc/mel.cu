@@ -5,14 +5,18 @@
 // n_fft=400 hop=160 periodic Hann, |.|^2, 128-bin slaney mel, log10 clamp, max-8 floor, (x+4)/4).
 //
 // Kernels
-//   mel_peak_kernel     per-segment max|x| (the peak-normalise reduction)                       HBM read N*4 B
-//   mel_frames_kernel   pre-step on load -> smem framing/windowing -> 400-point FFT of frame PAIRS (two real frames
-//                       as one complex transform, 400 = 16 x 25 Cooley-Tukey held in registers per thread, exchanged
-//                       through shared memory) -> power -> sparse mel (<=9 taps) -> log10 -> raw log-mel + segment max
-//   mel_finalize_kernel max(x, gmax-8), (x+4)/4; writes fp32 [B,128,3000] (API/parity) and/or the time-major
-//                       encoder input [B,3002,128] (row 0 and 3001 are the conv padding rows)
-//
-// Frames that only see zero padding are never transformed: their value is exactly log10(1e-10) = -10.
+//   mel_peak_kernel     per-segment max|x| (the peak-normalise reduction).  Launched per group of <= 64 segments right before
+//                       that group's frames kernel, so the second read of the PCM comes from the 126 MB L2, not from HBM.
+//   mel_frames_kernel   pre-step on load (float4 loads on the aligned interior) -> smem framing/windowing -> 400-point FFT of
+//                       frame PAIRS (two real frames as one complex transform, 400 = 16 x 25 Cooley-Tukey held in registers per
+//                       thread, exchanged through shared memory) -> power -> sparse mel (<=9 taps) -> log10 -> (x+4)/4 written
+//                       ONCE, unclamped, in the final layouts: fp32 [B,128,3000] (API/parity) and/or the time-major encoder
+//                       input [B,3002,128]; per-tile minimum and per-segment maximum on the side.
+//   mel_fixup_kernel    the max(x, gmax-8) clamp needs the segment maximum, known only after the last frame: this pass
+//                       fills the frames that only see zero padding (never transformed: exactly log10(1e-10) = -10) and
+//                       re-touches only the 32-frame tiles whose minimum is below gmax-8 (silence), instead of streaming a
+//                       raw fp32 copy out and back in (round 1: 7.2 MB of traffic per segment against 2.8 MB algorithmic).
+#include <stdlib.h>
 #include "common.cuh"
 #include "kernels.h"
 
@@ -30,7 +34,7 @@ static constexpr int kMaxTaps = 12;
 
 struct MelTables {             // built once on the host (api.cu) from the slaney filter bank, uploaded to global
   float window[kNfft];
-  float2 w400[kNfft];
+  float2 tw[16 * 25];        // step-1 twiddles W400^(n2*k1) laid out [k1][n2]: consecutive lanes (n2) read consecutive entries
   float tapw[kMels * kMaxTaps];
   int tap_start[kMels];
   int tap_count[kMels];
@@ -108,23 +112,25 @@ __global__ void mel_peak_kernel(const float* __restrict__ pcm, const long long* 
   if (threadIdx.x == 0 && m > 0.f) atomicMax(peak_bits + b, __float_as_uint(m));   // non-negative floats order as uints
 }
 
+template <typename TM>
 __global__ void __launch_bounds__(kMelThreads, 2)
 mel_frames_kernel(const float* __restrict__ pcm, const long long* __restrict__ offs, const int* __restrict__ lens,
-                  const unsigned* __restrict__ peak_bits, const MelTables* __restrict__ tab, int flags, int batch, int tiles_per_seg,
-                  float* __restrict__ raw /*[B][128][3000]*/, unsigned* __restrict__ gmax_bits /*[B]*/) {
+                  const unsigned* __restrict__ peak_bits, const MelTables* __restrict__ tab, int flags, int batch, int tiles_per_seg, int tile_min_stride,
+                  float* __restrict__ feat /*[B][128][3000] or null*/, TM* __restrict__ feat_tm /*[B][3002][128] or null*/,
+                  float* __restrict__ tile_min /*[B][94]*/, unsigned* __restrict__ gmax_bits /*[B]*/) {
   extern __shared__ float smem[];
   float* s_samp = smem;                              // kSpan
   float* s_re = s_samp + kSpan;                      // kPairs*kStride
   float* s_im = s_re + kPairs * kStride;             // kPairs*kStride   (base offset == 16 mod 32 banks)
   float* s_win = s_im + kPairs * kStride;            // 400
-  float2* s_w400 = reinterpret_cast<float2*>(s_win + kNfft);   // 400
-  float* s_tapw = reinterpret_cast<float*>(s_w400 + kNfft);    // 128*12
+  float2* s_tw = reinterpret_cast<float2*>(s_win + kNfft);     // 16 x 25
+  float* s_tapw = reinterpret_cast<float*>(s_tw + kNfft);      // 128*12
   int* s_tstart = reinterpret_cast<int*>(s_tapw + kMels * kMaxTaps);
   int* s_tcount = s_tstart + kMels;
   __shared__ float red[32];
 
   const int tid = threadIdx.x;
-  for (int i = tid; i < kNfft; i += kMelThreads) { s_win[i] = tab->window[i]; s_w400[i] = tab->w400[i]; }
+  for (int i = tid; i < kNfft; i += kMelThreads) { s_win[i] = tab->window[i]; s_tw[i] = tab->tw[i]; }
   for (int i = tid; i < kMels * kMaxTaps; i += kMelThreads) s_tapw[i] = tab->tapw[i];
   for (int i = tid; i < kMels; i += kMelThreads) { s_tstart[i] = tab->tap_start[i]; s_tcount[i] = tab->tap_count[i]; }
 
@@ -141,8 +147,30 @@ mel_frames_kernel(const float* __restrict__ pcm, const long long* __restrict__ o
     const int t0 = tile * kTileFrames;
     __syncthreads();                                  // previous item's readers are done with smem
     const int j0 = t0 * kHop - 200;
-    {
-      // all of a thread's loads are issued before the first value is transformed (kSpan / 256 = 21 independent loads)
+    const bool interior = j0 >= 0 && j0 + kSpan <= n && !(flags & SONIC_MEL_S16) && (((base + j0) & 3) == 0);
+    if (interior) {
+      // the whole span lies inside the segment and is 16 B aligned: float4 loads, all issued before the first value is used
+      constexpr int kPer4 = (kSpan / 4 + kMelThreads - 1) / kMelThreads;                    // 1340 float4 -> 6 per thread
+      const float4* x4 = reinterpret_cast<const float4*>(pcm + base + j0);
+      float4 rawv[kPer4];
+#pragma unroll
+      for (int q = 0; q < kPer4; ++q) {
+        const int i = tid + q * kMelThreads;
+        rawv[q] = (i < kSpan / 4) ? __ldg(x4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int q = 0; q < kPer4; ++q) {
+        const int i = tid + q * kMelThreads;
+        float v[4] = {rawv[q].x, rawv[q].y, rawv[q].z, rawv[q].w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          if ((flags & SONIC_MEL_PEAK_NORM) && gate > 0.f) v[e] = v[e] / peak;              // asr.py:266-267 (true division)
+          if (flags & SONIC_MEL_PCM16) v[e] = rintf(v[e] * 32767.0f) * (1.0f / 32768.0f);   // soundfile PCM_16 write + float read
+        }
+        if (i < kSpan / 4) *reinterpret_cast<float4*>(s_samp + 4 * i) = make_float4(v[0], v[1], v[2], v[3]);
+      }
+    } else {
+      // edges (reflection, zero padding), int16 input or unaligned base: scalar loads, still all in flight together
       constexpr int kPer = (kSpan + kMelThreads - 1) / kMelThreads;
       float rawv[kPer];
 #pragma unroll
@@ -180,7 +208,7 @@ mel_frames_kernel(const float* __restrict__ pcm, const long long* __restrict__ o
       for (int s = 0; s < 16; ++s) {
         const int k1 = (s >> 2) + 4 * (s & 3);
         float2 y = v[s];
-        if (k1 != 0 && n2 != 0) y = cmul(y, s_w400[n2 * k1]);      // n2*k1 <= 24*15 = 360 < 400
+        if (k1 != 0 && n2 != 0) y = cmul(y, s_tw[k1 * 25 + n2]);   // W400^(n2 k1); [k1][n2] layout: no bank conflicts across n2
         s_re[tr * kStride + k1 * 25 + n2] = y.x;
         s_im[tr * kStride + k1 * 25 + n2] = y.y;
       }
@@ -217,7 +245,9 @@ mel_frames_kernel(const float* __restrict__ pcm, const long long* __restrict__ o
       s_im[a0] = 0.25f * (br * br + bi * bi);
     }
     __syncthreads();
-    // ---- sparse mel + log10: lane = frame of the tile, warp strides over mel bins
+    // ---- sparse mel + log10: lane = frame of the tile, warp strides over mel bins; (l + 4) / 4 staged as a [128][33] tile
+    float* s_out = s_samp;                               // the sample span is dead after step 1 (5360 >= 128 * 33 floats)
+    float lmin = 0.f;
     {
       const int lane = tid & 31, warp = tid >> 5;
       const int t = t0 + lane;
@@ -230,51 +260,86 @@ mel_frames_kernel(const float* __restrict__ pcm, const long long* __restrict__ o
           acc = fmaf(s_tapw[m * kMaxTaps + j], P[(k & 15) * 25 + (k >> 4)], acc);
         }
         // log10 via MUFU lg2 (relative error 2^-22: < 2e-7 in the log, far below the 1e-4 parity bar)
-        const float l = __log2f(fmaxf(acc, 1e-10f)) * 0.30102999566398120f;
-        if (t < n_active) {
-          raw[((size_t)b * kMels + m) * kFrames + t] = l;
-          lmax = fmaxf(lmax, l);
-        }
+        float l = __log2f(fmaxf(acc, 1e-10f)) * 0.30102999566398120f;
+        if (t < n_active) lmax = fmaxf(lmax, l);
+        else l = -10.0f;                                   // frames of the tile that only see zero padding
+        if (t < kFrames) lmin = fminf(lmin, l);
+        s_out[m * 33 + lane] = (l + 4.0f) * 0.25f;
+      }
+    }
+    __syncthreads();
+    if (feat) {                                            // [m][t]: a warp writes 32 consecutive frames of one mel row
+      const int lane = tid & 31, warp = tid >> 5;
+      const int t = t0 + lane;
+      if (t < kFrames)
+        for (int m = warp; m < kMels; m += kMelThreads / 32) feat[((size_t)b * kMels + m) * kFrames + t] = s_out[m * 33 + lane];
+    }
+    if (feat_tm) {                                         // [t][m]: 128 consecutive mels of one frame
+      const int m = tid & (kMels - 1);
+      for (int r = tid >> 7; r < kTileFrames; r += kMelThreads / kMels) {
+        const int t = t0 + r;
+        if (t < kFrames) feat_tm[((size_t)b * (kFrames + 2) + 1 + t) * kMels + m] = from_f32<TM>(s_out[m * 33 + r]);
       }
     }
     lmax = block_max(lmax, red);
-    if (tid == 0) atomicMax(gmax_bits + b, f32_to_ordered(lmax));
+    lmin = -block_max(-lmin, red);
+    if (tid == 0) {
+      atomicMax(gmax_bits + b, f32_to_ordered(lmax));
+      tile_min[(size_t)b * tile_min_stride + tile] = lmin;
+    }
   }
 }
 
+// The clamp max(x, gmax - 8) in the written domain y = (x + 4) / 4 (a monotone map: clamping y at (gmax - 8 + 4) / 4 gives the
+// same bits as clamping x first).  grid (94 tiles, segments).
 template <typename T>
-__global__ void mel_finalize_kernel(const float* __restrict__ raw, const unsigned* __restrict__ gmax_bits,
-                                    const int* __restrict__ lens, float* __restrict__ feat /*[B][128][3000] or null*/,
-                                    T* __restrict__ feat_tm /*[B][3002][128] or null*/) {
-  // tile: 32 frames x 128 mels; blockDim = (32, 8)
-  __shared__ float tile[kMels][33];
-  const int b = blockIdx.y, t0 = blockIdx.x * 32;
+__global__ void __launch_bounds__(256) mel_fixup_kernel(const unsigned* __restrict__ gmax_bits, const int* __restrict__ lens,
+                                                        const float* __restrict__ tile_min, int tiles_per_seg, float* __restrict__ feat, T* __restrict__ feat_tm) {
+  const int b = blockIdx.y, tile = blockIdx.x, t0 = tile * kTileFrames;
   const int n = min(lens[b], kWin);
   const int n_active = min(kFrames, (n + 200 + kHop - 1) / kHop);
-  const float g = ordered_to_f32(gmax_bits[b]);
-  const float floor_v = g - 8.0f;
-  const int tx = threadIdx.x, ty = threadIdx.y;
-  for (int m = ty; m < kMels; m += 8) {
-    const int t = t0 + tx;
-    float v = 0.f;
-    if (t < kFrames) {
-      const float l = (t < n_active) ? raw[((size_t)b * kMels + m) * kFrames + t] : -10.0f;
-      v = (fmaxf(l, floor_v) + 4.0f) * 0.25f;
-      if (feat) feat[((size_t)b * kMels + m) * kFrames + t] = v;
+  const float fl = ordered_to_f32(gmax_bits[b]) - 8.0f;
+  const float y_floor = (fl + 4.0f) * 0.25f;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (feat_tm && tile == 0 && tid < kMels) {               // conv padding rows of the time-major copy
+    feat_tm[((size_t)b * (kFrames + 2)) * kMels + tid] = from_f32<T>(0.f);
+    feat_tm[((size_t)b * (kFrames + 2) + kFrames + 1) * kMels + tid] = from_f32<T>(0.f);
+  }
+  if (t0 >= n_active) {                                    // never transformed: the constant value of silence after the clamp
+    const float y_pad = (fmaxf(-10.0f, fl) + 4.0f) * 0.25f;
+    if (feat) {
+      const int t = t0 + lane;
+      if (t < kFrames)
+        for (int m = warp; m < kMels; m += 8) feat[((size_t)b * kMels + m) * kFrames + t] = y_pad;
     }
-    tile[m][tx] = v;
+    if (feat_tm) {
+      const int m = tid & (kMels - 1);
+      for (int r = tid >> 7; r < kTileFrames; r += 2) {
+        const int t = t0 + r;
+        if (t < kFrames) feat_tm[((size_t)b * (kFrames + 2) + 1 + t) * kMels + m] = from_f32<T>(y_pad);
+      }
+    }
+    return;
   }
-  if (!feat_tm) return;
-  __syncthreads();
-  const int flat = ty * 32 + tx;                        // 256 threads; each row of 128 mels = 128 threads
-  for (int r = flat / kMels; r < 32; r += 2) {
-    const int t = t0 + r, m = flat % kMels;
-    if (t < kFrames) feat_tm[((size_t)b * (kFrames + 2) + 1 + t) * kMels + m] = from_f32<T>(tile[m][r]);
+  if (!(tile_min[(size_t)b * tiles_per_seg + tile] < fl)) return;     // nothing below the floor in this tile: written once, done
+  if (feat) {
+    const int t = t0 + lane;
+    if (t < kFrames)
+      for (int m = warp; m < kMels; m += 8) {
+        float* p = feat + ((size_t)b * kMels + m) * kFrames + t;
+        if (*p < y_floor) *p = y_floor;
+      }
   }
-  // conv padding rows
-  if (blockIdx.x == 0 && flat < kMels) {
-    feat_tm[((size_t)b * (kFrames + 2)) * kMels + flat] = from_f32<T>(0.f);
-    feat_tm[((size_t)b * (kFrames + 2) + kFrames + 1) * kMels + flat] = from_f32<T>(0.f);
+  if (feat_tm) {
+    const int m = tid & (kMels - 1);
+    const T yf = from_f32<T>(y_floor);
+    for (int r = tid >> 7; r < kTileFrames; r += 2) {
+      const int t = t0 + r;
+      if (t < kFrames) {
+        T* p = feat_tm + ((size_t)b * (kFrames + 2) + 1 + t) * kMels + m;
+        if (to_f32(*p) < to_f32(yf)) *p = yf;
+      }
+    }
   }
 }
 
@@ -291,8 +356,12 @@ void mel_build_tables(void* host_out, const int* tap_start, const int* tap_count
   for (int i = 0; i < kNfft; ++i) {
     // torch.hann_window(400) (periodic) is evaluated in fp32 by torch; the fp64->fp32 rounded value differs by <=1 ulp
     t->window[i] = (float)(0.5 - 0.5 * cos(two_pi * i / kNfft));
-    t->w400[i] = make_float2((float)cos(two_pi * i / kNfft), (float)(-sin(two_pi * i / kNfft)));
   }
+  for (int k1 = 0; k1 < 16; ++k1)
+    for (int n2 = 0; n2 < 25; ++n2) {
+      const int e = (n2 * k1) % kNfft;
+      t->tw[k1 * 25 + n2] = make_float2((float)cos(two_pi * e / kNfft), (float)(-sin(two_pi * e / kNfft)));
+    }
   for (int m = 0; m < kMels; ++m) {
     t->tap_start[m] = tap_start[m];
     t->tap_count[m] = tap_count[m];
@@ -305,33 +374,45 @@ static size_t mel_smem_bytes() {
 }
 
 cudaError_t mel_setup() {
-  return cudaFuncSetAttribute(mel_frames_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mel_smem_bytes());
+  SONIC_CUDA_TRY(cudaFuncSetAttribute(mel_frames_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mel_smem_bytes()));
+  return cudaFuncSetAttribute(mel_frames_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mel_smem_bytes());
 }
+
+int mel_tiles_per_segment() { return cdiv(kFrames, kTileFrames); }
 
 template <typename T>
 cudaError_t launch_mel(const float* pcm, const long long* offs, const int* lens, int batch, int max_len, int flags,
-                       const void* tables, unsigned* peak_bits, unsigned* gmax_bits, float* raw, float* feat, T* feat_tm,
+                       const void* tables, unsigned* peak_bits, unsigned* gmax_bits, float* tile_min, float* feat, T* feat_tm,
                        cudaStream_t st) {
   if (batch <= 0) return cudaSuccess;
   mel_init_kernel<<<cdiv(batch, 128), 128, 0, st>>>(peak_bits, gmax_bits, batch);
   SONIC_LAUNCH_CHECK();
-  if (flags & SONIC_MEL_PEAK_NORM) {
-    int gx = max(1, min(cdiv(max_len, 256 * 8), 64));
-    mel_peak_kernel<<<dim3(gx, batch), 256, 0, st>>>(pcm, offs, lens, peak_bits, flags);
-    SONIC_LAUNCH_CHECK();
-  }
   const int n_eff = min(max_len, kWin);
   const int max_active = min(kFrames, (n_eff + 200 + kHop - 1) / kHop);
-  const int tiles = cdiv(max_active, kTileFrames);
+  const int tiles = cdiv(max_active, kTileFrames);                     // tiles that can hold transformed frames
+  const int tps = mel_tiles_per_segment();
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const long long total = (long long)tiles * batch;
-  const int grid = (int)(total < 2LL * sms ? total : 2LL * sms);      // two resident CTAs per SM, persistent
-  mel_frames_kernel<<<grid, kMelThreads, mel_smem_bytes(), st>>>(
-      pcm, offs, lens, peak_bits, reinterpret_cast<const MelTables*>(tables), flags, batch, tiles, raw, gmax_bits);
-  SONIC_LAUNCH_CHECK();
-  mel_finalize_kernel<T><<<dim3(cdiv(kFrames, 32), batch), dim3(32, 8), 0, st>>>(raw, gmax_bits, lens, feat, feat_tm);
+  // groups of <= 64 segments (82 MB of fp32 PCM): the frames kernel of a group re-reads from L2 what its peak pass just read
+  // (measured at 1024 segments: 620 GB/s in groups of 64, 684 GB/s as one launch that reads the PCM twice from HBM; SONIC_MEL_GROUP)
+  static const int kGroup = [] { const char* v = getenv("SONIC_MEL_GROUP"); const int g = v ? atoi(v) : 64; return g > 0 ? g : 64; }();
+  for (int g0 = 0; g0 < batch; g0 += kGroup) {
+    const int gb = min(kGroup, batch - g0);
+    if (flags & SONIC_MEL_PEAK_NORM) {
+      int gx = max(1, min(cdiv(max_len, 256 * 8), 64));
+      mel_peak_kernel<<<dim3(gx, gb), 256, 0, st>>>(pcm, offs + g0, lens + g0, peak_bits + g0, flags);
+      SONIC_LAUNCH_CHECK();
+    }
+    const long long total = (long long)tiles * gb;
+    const int grid = (int)(total < 2LL * sms ? total : 2LL * sms);      // two resident CTAs per SM, persistent
+    mel_frames_kernel<T><<<grid, kMelThreads, mel_smem_bytes(), st>>>(
+        pcm, offs + g0, lens + g0, peak_bits + g0, reinterpret_cast<const MelTables*>(tables), flags, gb, tiles, tps,
+        feat ? feat + (size_t)g0 * kMels * kFrames : nullptr, feat_tm ? feat_tm + (size_t)g0 * (kFrames + 2) * kMels : nullptr,
+        tile_min + (size_t)g0 * tps, gmax_bits + g0);
+    SONIC_LAUNCH_CHECK();
+  }
+  mel_fixup_kernel<T><<<dim3(tps, batch), 256, 0, st>>>(gmax_bits, lens, tile_min, tps, feat, feat_tm);
   SONIC_LAUNCH_CHECK();
   return cudaSuccess;
 }
