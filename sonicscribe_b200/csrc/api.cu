@@ -88,6 +88,25 @@ __global__ void __launch_bounds__(256) quantize_rows_kernel(const TS* __restrict
   }
   if (threadIdx.x == 0) scale[dr] = sc / 127.0f;
 }
+// int8 -> bf16 (exact: |q| <= 127), 16 values per thread step.  int8 mode keeps the encoder / prefill weights as int8 in HBM and
+// expands one matrix at a time into a scratch buffer that the persistent bf16 tcgen05 GEMM multiplies; the row scale stays an
+// fp32 factor in the GEMM epilogue, so the arithmetic is the one of the int8 tile kernel, at the bf16 kernel's speed.
+__global__ void expand_i8_kernel(const int8_t* __restrict__ src, bf16* __restrict__ dst, long long n16) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (long long)gridDim.x * blockDim.x) {
+    const uint4 w = __ldg(reinterpret_cast<const uint4*>(src) + i);
+    const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+    uint32_t o[8];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      __nv_bfloat162 lo = __floats2bfloat162_rn((float)(int)(int8_t)(ww[e] & 0xff), (float)(int)(int8_t)((ww[e] >> 8) & 0xff));
+      __nv_bfloat162 hi = __floats2bfloat162_rn((float)(int)(int8_t)((ww[e] >> 16) & 0xff), (float)(int)(int8_t)(ww[e] >> 24));
+      o[2 * e] = *reinterpret_cast<uint32_t*>(&lo); o[2 * e + 1] = *reinterpret_cast<uint32_t*>(&hi);
+    }
+    uint4* d = reinterpret_cast<uint4*>(dst) + 2 * i;
+    d[0] = make_uint4(o[0], o[1], o[2], o[3]);
+    d[1] = make_uint4(o[4], o[5], o[6], o[7]);
+  }
+}
 __global__ void set_int_kernel(int* p, int v, int n) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = v;
@@ -118,6 +137,7 @@ struct sonic_ctx {
   bool is_f32 = false;
   bool is_int8 = false;                 // bf16 activations, int8 weight-only linears (lm_head / embedding / convs stay bf16)
   float *s_proj1 = nullptr, *s_proj2 = nullptr;
+  bf16* i8_scratch = nullptr;           // int8 mode: bf16 image of the matrix the next token-major GEMM multiplies (largest: gate/up)
   bool force_simt = false;
   bool use_pdl = true;                  // SONIC_NO_PDL=1 disables programmatic dependent launch in the decode step
   bool pdl_now = false;
@@ -316,6 +336,13 @@ struct Engine {
     g.pdl = h->pdl_now ? 1 : 0;
     if (std::is_same<T, float>::value) { CKL(launch_gemm_simt<float>(g, h->stream), 1); return 0; }
     if (h->force_simt) { CKL(launch_gemm_simt<bf16>(g, h->stream), 1); return 0; }
+    if (!swap && g.w_int8 && h->i8_scratch && g.conv_cin == 0 && ((long long)g.N * g.K) % 16 == 0) {
+      const long long n16 = (long long)g.N * g.K / 16;
+      CKL((expand_i8_kernel<<<(unsigned)std::min<long long>((n16 + 255) / 256, 148 * 16), 256, 0, h->stream>>>(
+               reinterpret_cast<const int8_t*>(g.W), h->i8_scratch, n16), cudaGetLastError()), 1);
+      g.W = h->i8_scratch;
+      g.w_int8 = 0;                    // the row scale (g.wscale) is applied by the bf16 kernel's epilogue
+    }
     CKL(launch_gemm_tc(g, swap, h->stream), 1);
     return 0;
   }
@@ -668,7 +695,7 @@ int alloc_all(sonic_ctx* h) {
   DA(h->conv1_b, kEncH * 4); DA(h->conv2_b, kEncH * 4); DA(h->enc_norm_g, kEncH * 4); DA(h->enc_norm_b, kEncH * 4);
   DA(h->proj1_w, (size_t)2 * kDecH * kEncInter * Q); DA(h->proj1_b, 2 * kDecH * 4);
   DA(h->proj2_w, (size_t)kDecH * 2 * kDecH * Q); DA(h->proj2_b, kDecH * 4);
-  if (h->is_int8) { DA(h->s_proj1, 2 * kDecH * 4); DA(h->s_proj2, kDecH * 4); }
+  if (h->is_int8) { DA(h->s_proj1, 2 * kDecH * 4); DA(h->s_proj2, kDecH * 4); DA(h->i8_scratch, (size_t)2 * kDecInter * kDecH * 2); }
   DA(h->embed, (size_t)kVocab * kDecH * E); DA(h->lm_head, (size_t)kVocab * kDecH * E); DA(h->final_norm, kDecH * 4);
   h->enc.resize(c.enc_layers);
   for (auto& w : h->enc) {

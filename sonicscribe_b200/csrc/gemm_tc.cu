@@ -430,6 +430,13 @@ static constexpr int kPersistGemmThreads = 384;
 
 template <typename TC>
 __device__ __forceinline__ void epilogue_chunk32(const TcEpi& e, float (&x)[32], int m, int n, TC* Cb, const TC* Rb) {
+  if (e.wscale) {                                                       // weights were int8 rows expanded to bf16: per-feature dequantisation scale
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      const float4 sv = __ldg(reinterpret_cast<const float4*>(e.wscale + n + j));
+      x[j] *= sv.x; x[j + 1] *= sv.y; x[j + 2] *= sv.z; x[j + 3] *= sv.w;
+    }
+  }
   if (e.bias) {
 #pragma unroll
     for (int j = 0; j < 32; j += 4) {
