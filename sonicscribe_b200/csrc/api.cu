@@ -194,7 +194,7 @@ struct sonic_ctx {
   float* probe_logits = nullptr;       // [probe_steps][max_batch][vocab]
   int cur_step = 0;                    // index of the token the next decode step produces (host-side mirror of gs.step)
   int probe_batch = 0;
-  bool persist_tc = false;             // batch class 33..64 of the persistent kernel runs its GEMM phases on tcgen05
+  bool persist_tc = false;             // live batches of 17..64 segments run the GEMM phases of the persistent kernel on tcgen05 (bf16)
   bool use_persist = false;            // one cooperative kernel per greedy step (bf16 mode; SONIC_DECODE=graph disables)
   DecLayerDev* dev_layers = nullptr;
   void* persist_kv_maps = nullptr;     // device CUtensorMap[2]: K cache, V cache (decode attention phase)
@@ -580,6 +580,9 @@ struct Engine {
       p.w8 = h->is_int8 ? 1 : 0;
       p.tmaps = h->persist_tc ? h->persist_tmaps : nullptr;
       p.kv_maps = h->persist_kv_maps; p.kc_base = reinterpret_cast<const bf16*>(h->kcache);
+      { const char* pd = getenv("SONIC_PERSIST_PRE"); p.tc_pre_depth = pd ? atoi(pd) : 6; }
+      { const char* df = getenv("SONIC_PERSIST_DBGFLAGS"); p.dbg_flags = (h->cfg.debug && df) ? atoi(df) : 0; }
+      { const char* dc = getenv("SONIC_PERSIST_DBG_CTA"); p.dbg_cta = (h->cfg.debug && dc) ? atoi(dc) : -1; }
       p.B = B; p.Bpad = (B + 7) / 8 * 8; p.max_ctx = h->max_ctx; p.eps = kRmsEps; p.scale = 0.08838834764831845f;
       TAG(PC_DEC_PERSIST);
       if (h->prof_on) { cudaEventRecord(prof_event(h), h->stream); h->prof_tags.push_back(h->prof_cls); }
@@ -1150,7 +1153,7 @@ int sonic_finalize_weights(sonic_handle h) {
       CK(cudaMemcpy(h->persist_kv_maps, kvm, sizeof(kvm), cudaMemcpyHostToDevice));
     }
     const char* ptc = getenv("SONIC_PERSIST_TC");
-    h->persist_tc = !h->is_int8 && h->cfg.max_batch > 32 && !(ptc && ptc[0] == '0');
+    h->persist_tc = !h->is_int8 && h->cfg.max_batch > 16 && !(ptc && ptc[0] == '0');
     if (h->persist_tc) {
       // weight maps: {K, rows} with a 64 x 128 box; activation maps: {K, 64 token rows} with a 64 x 64 box (128B swizzle)
       const int L = h->cfg.dec_layers;
@@ -1159,10 +1162,10 @@ int sonic_finalize_weights(sonic_handle h) {
         const DecLayerW& w = h->dec[l];
         CK(make_tensor_map_2d(&maps[4 * l + 0], w.wqkv, kDecH, kQkvDec, kDecH, 64, 128));
         CK(make_tensor_map_2d(&maps[4 * l + 1], w.wo, kDecH, kDecH, kDecH, 64, 128));
-        CK(make_tensor_map_2d(&maps[4 * l + 2], w.wgu, kDecH, 2 * kDecInter, kDecH, 64, 128));
+        CK(make_tensor_map_2d(&maps[4 * l + 2], w.wgu, kDecH, 2 * kDecInter, kDecH, 64, kPersistGuTileRows));
         CK(make_tensor_map_2d(&maps[4 * l + 3], w.wdown, kDecInter, kDecH, kDecInter, 64, 128));
       }
-      CK(make_tensor_map_2d(&maps[4 * L], h->lm_head, kDecH, kVocab, kDecH, 64, 128));
+      CK(make_tensor_map_2d(&maps[4 * L], h->lm_head, kDecH, kVocab, kDecH, 64, kPersistLmTileRows));
       CK(make_tensor_map_2d(&maps[4 * L + 1], h->du, kDecH, kPersistTcTokens, kDecH, 64, kPersistTcTokens));
       CK(make_tensor_map_2d(&maps[4 * L + 2], h->dattn, kDecH, kPersistTcTokens, kDecH, 64, kPersistTcTokens));
       CK(make_tensor_map_2d(&maps[4 * L + 3], h->dact, kDecInter, kPersistTcTokens, kDecInter, 64, kPersistTcTokens));
@@ -1325,6 +1328,18 @@ int sonic_debug_read(sonic_handle h, const char* name, float* out, size_t max_el
     if (max_elems < 80) return fail(h, "sonic_debug_read: output buffer too small");
     for (int i = 0; i < 80; ++i) out[i] = ts[i] ? (float)((double)(ts[i] - ts[0]) * 1e-3) : -1.0f;
     if (n_elems) *n_elems = 80;
+    return 0;
+  }
+  else if (nm == "persist_dbg" && h->persist_ts) {
+    // raw debug stamps persist_ts[1024..2047] in microseconds relative to the smallest one (unset entries: -1)
+    std::vector<unsigned long long> ts(1024);
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaMemcpy(ts.data(), h->persist_ts + 1024, 1024 * 8, cudaMemcpyDeviceToHost));
+    if (max_elems < 1024) return fail(h, "sonic_debug_read: output buffer too small");
+    unsigned long long t0 = ~0ull;
+    for (auto t : ts) if (t && t < t0) t0 = t;
+    for (int i = 0; i < 1024; ++i) out[i] = ts[i] ? (float)((double)(ts[i] - t0) * 1e-3) : -1.0f;
+    if (n_elems) *n_elems = 1024;
     return 0;
   }
   else if (nm == "rs_ts" && h->persist_ts) {

@@ -43,27 +43,44 @@ __device__ __forceinline__ void mma16816(float (&c)[4], uint32_t a0, uint32_t a1
                : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 __device__ __forceinline__ float bf16r(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
+__device__ __forceinline__ unsigned long long gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)::"memory");     // "memory": stays on its side of barriers
+  return t;
+}
 
 // grid-wide barrier: monotonically increasing arrival counter (zeroed by the host before the launch).  The gpu-scope fences
 // order every thread's global writes before the arrival and invalidate L1 after the wait, so plain loads see fresh data.
 template <bool PROXY = false>
-__device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& epoch) {
+__device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& epoch, int flags = 0, unsigned long long* dbg = nullptr) {
   // PROXY: the next phase may read this phase's global writes, or overwrite shared memory it used, through the async proxy
   // (TMA); order the generic-proxy accesses of every thread before that
-  if (PROXY) asm volatile("fence.proxy.async;" ::: "memory");
+  const bool wdbg = dbg && (int)blockIdx.x == (flags >> 8) && (threadIdx.x & 31) == 0;
+  if (wdbg) dbg[960 + (threadIdx.x >> 5)] = gtimer();
+  if (PROXY && !(flags & 1)) asm volatile("fence.proxy.async.global;" ::: "memory");
+  if (wdbg) dbg[980 + (threadIdx.x >> 5)] = gtimer();
   __syncthreads();
+  if (wdbg) dbg[1000 + (threadIdx.x >> 5)] = gtimer();
   if (threadIdx.x == 0) {
     epoch += gridDim.x;
-    __threadfence();
-    atomicAdd(counter, 1u);
+    // release-arrive without waiting for the atomic's return value (one L2 round trip less than fence + atomicAdd), relaxed
+    // polling, one acquire fence at the end (it also invalidates L1 for the whole CTA)
     unsigned v;
+    if (dbg) {                                             // debug: arrival with a return value, so that its completion can be stamped
+      dbg[480 + blockIdx.x] = gtimer();
+      asm volatile("atom.release.gpu.global.add.u32 %0, [%1], 1;" : "=r"(v) : "l"(counter) : "memory");
+      dbg[640 + blockIdx.x] = gtimer() + (v & 0u);
+    } else {
+      asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
+    }
     do {
-      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+      asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
     } while (v < epoch);
-    __threadfence();
+    if (dbg) dbg[800 + blockIdx.x] = gtimer();
+    asm volatile("fence.acq_rel.gpu;" ::: "memory");
   }
   __syncthreads();
-  if (PROXY) asm volatile("fence.proxy.async;" ::: "memory");
+  if (PROXY && !(flags & 2)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
 // ---- GEMM phase: part[s][tok][n] = sum_{k in slice s} W[n][k] * X[tok][k] ------------------------------------------------
@@ -246,10 +263,13 @@ __device__ __forceinline__ void gemm_dispatch(const void* W, const float* wscale
 static constexpr int kTcStages = 6;                   // 8 measured no faster
 static constexpr int kTcStageA = 128 * 64 * 2, kTcStageB = kPersistTcTokens * 64 * 2;
 static constexpr int kTcRingBytes = kTcStages * (kTcStageA + kTcStageB) + 1024;     // + alignment slack
+static constexpr int kTcEpiBytes = 8 * 32 * 32 * 4;   // epilogue transpose buffers (TcCtx::epi)
 struct TcCtx {
   uint32_t ringA, ringB, bars, tmem;
   uint32_t kb_count, item_count;
   uint32_t pre;                  // k blocks of the coming phase whose weight tile is already in flight (tc_prefetch_weights)
+  uint32_t pre_depth;            // how many stages tc_prefetch_weights may fill before a grid barrier (<= kTcStages)
+  float* epi;                    // 8 epilogue warps x [32 tokens][32 features] fp32 transpose buffers
 };
 __device__ __forceinline__ uint32_t tc_full(const TcCtx& c, uint32_t s) { return c.bars + 8u * s; }
 __device__ __forceinline__ uint32_t tc_empty(const TcCtx& c, uint32_t s) { return c.bars + 8u * (kTcStages + s); }
@@ -259,18 +279,18 @@ __device__ __forceinline__ uint32_t tc_acc_empty(const TcCtx& c, uint32_t a) { r
 // Weights do not depend on the previous phase: thread 0 (the producer) puts the weight tiles of this CTA's first k blocks of
 // the NEXT tcgen05 phase in flight (arming the stage for weight + activation bytes) before the grid barrier / while a
 // non-GEMM phase runs; the producer of that phase then only adds the activation tiles.  Every thread computes `pre`.
-__device__ __forceinline__ void tc_prefetch_weights(const CUtensorMap* wmap, int N, int K, int splits, TcCtx& tc) {
-  const int tiles = N >> 7, nkb = K >> 6, n_items = tiles * splits;
+__device__ __forceinline__ void tc_prefetch_weights(const CUtensorMap* wmap, int N, int K, int splits, TcCtx& tc, int tile_rows = 128) {
+  const int tiles = (N + tile_rows - 1) / tile_rows, nkb = K >> 6, n_items = tiles * splits;
   uint32_t n = 0;
-  for (int item = blockIdx.x; item < n_items && n < (uint32_t)kTcStages; item += gridDim.x) {
+  for (int item = blockIdx.x; item < n_items && n < tc.pre_depth; item += gridDim.x) {
     const int tile = item / splits, ks = item - tile * splits;
     const int kb0 = (ks * nkb) / splits, kb1 = ((ks + 1) * nkb) / splits;
-    for (int kb = kb0; kb < kb1 && n < (uint32_t)kTcStages; ++kb, ++n) {
+    for (int kb = kb0; kb < kb1 && n < tc.pre_depth; ++kb, ++n) {
       if (threadIdx.x < 32 && elect_one_sync()) {
         const uint32_t cnt = tc.kb_count + n, st = cnt % kTcStages, par = (cnt / kTcStages) & 1u;
         mbar_wait(tc_empty(tc, st), par ^ 1u);
-        mbar_expect_tx(tc_full(tc, st), kTcStageA + kTcStageB);
-        tma_load_2d(tc.ringA + st * kTcStageA, wmap, tc_full(tc, st), kb * 64, tile * 128);
+        mbar_expect_tx(tc_full(tc, st), tile_rows * 128 + kTcStageB);
+        tma_load_2d(tc.ringA + st * kTcStageA, wmap, tc_full(tc, st), kb * 64, tile * tile_rows);
       }
     }
   }
@@ -279,11 +299,16 @@ __device__ __forceinline__ void tc_prefetch_weights(const CUtensorMap* wmap, int
 
 template <int EPI>
 __device__ __forceinline__ void gemm_phase_tc(const CUtensorMap* wmap, const CUtensorMap* xmap, int N, int K, int splits, int B, int Bpad,
-                                              float* __restrict__ out32, bf16* __restrict__ act, TcCtx& tc) {
+                                              float* __restrict__ out32, bf16* __restrict__ act, TcCtx& tc, int tile_rows = 128,
+                                              unsigned long long* dbg = nullptr, int dbgf = 0) {
+  // tile_rows: weight rows per item (the box height of `wmap`).  128 fills the MMA tile; a smaller value (gate/up: 84, so that
+  // 147 whole-K items cover the 12288 rows, one per CTA) leaves the remaining rows of the 128-row shared-memory tile stale:
+  // they only feed accumulator rows the epilogue never reads.  Rows past N are zero-filled by TMA.
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tiles = N >> 7, nkb = K >> 6, n_items = tiles * splits;
+  const int tiles = (N + tile_rows - 1) / tile_rows, nkb = K >> 6, n_items = tiles * splits;
   if (warp == 0) {
     if (elect_one_sync()) {
+      if (dbg) dbg[0] = gtimer();
       uint32_t cnt = tc.kb_count, idx = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         const int tile = item / splits, ks = item - tile * splits;
@@ -292,11 +317,12 @@ __device__ __forceinline__ void gemm_phase_tc(const CUtensorMap* wmap, const CUt
           const uint32_t st = cnt % kTcStages, par = (cnt / kTcStages) & 1u;
           if (idx >= tc.pre) {
             mbar_wait(tc_empty(tc, st), par ^ 1u);
-            mbar_expect_tx(tc_full(tc, st), kTcStageA + kTcStageB);
-            tma_load_2d(tc.ringA + st * kTcStageA, wmap, tc_full(tc, st), kb * 64, tile * 128);
+            mbar_expect_tx(tc_full(tc, st), tile_rows * 128 + kTcStageB);
+            tma_load_2d(tc.ringA + st * kTcStageA, wmap, tc_full(tc, st), kb * 64, tile * tile_rows);
           }
           tma_load_2d(tc.ringB + st * kTcStageB, xmap, tc_full(tc, st), kb * 64, 0);
         }
+        if (dbg) dbg[1 + (item >= (int)gridDim.x)] = gtimer();       // producer: all loads of item 0 / 1 issued
       }
     }
   } else if (warp == 1) {
@@ -313,6 +339,7 @@ __device__ __forceinline__ void gemm_phase_tc(const CUtensorMap* wmap, const CUt
           const uint32_t st = cnt % kTcStages, par = (cnt / kTcStages) & 1u;
           mbar_wait(tc_full(tc, st), par);
           tc_fence_after();
+          if (dbg && kb == kb0) dbg[3 + (item >= (int)gridDim.x)] = gtimer();   // first stage of item 0 / 1 landed
           const uint64_t da = make_sw128_desc(tc.ringA + st * kTcStageA), db = make_sw128_desc(tc.ringB + st * kTcStageB);
 #pragma unroll
           for (int k = 0; k < 4; ++k)
@@ -320,39 +347,61 @@ __device__ __forceinline__ void gemm_phase_tc(const CUtensorMap* wmap, const CUt
           tc_commit(tc_empty(tc, st));
         }
         tc_commit(tc_acc_full(tc, acc));
+        if (dbg) dbg[5 + (item >= (int)gridDim.x)] = gtimer();       // all MMAs of item 0 / 1 issued
       }
     }
   } else if (warp >= 4 && warp < 12) {
+    // Epilogue: lane = weight row (TMEM lane), registers = 32 tokens.  The outputs are token-major, so the 32 x 32 block is
+    // transposed through a per-warp shared-memory buffer and leaves as 16 B vectors: lane (tr, fc) handles token rows
+    // tr + 4 i (i = 0..7), features fc..fc+3 — 8 vector stores per lane instead of 32 scalar ones (measured: the scalar
+    // version spent 1.3 us issuing the fp32 stores and 3.8 us in the SwiGLU stores of one item).
     const int q = warp & 3, half = (warp - 4) >> 2;
+    float* eb = tc.epi + (warp - 4) * 1024;
+    const int tr = lane >> 3, fc = (lane & 7) * 4;
     uint32_t ic = tc.item_count;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++ic) {
       const int tile = item / splits, ks = item - tile * splits;
       const uint32_t acc = ic & 1u, apar = (ic >> 1) & 1u;
       mbar_wait(tc_acc_full(tc, acc), apar);
       tc_fence_after();
-      uint32_t v[32];
-      tmem_ld32(tc.tmem + ((uint32_t)(q * 32) << 16) + acc * kPersistTcTokens + half * 32, v);
-      tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(tc_acc_empty(tc, acc));           // the accumulator is in registers: the next item may start
-      const int row = tile * 128 + q * 32 + lane;
-      if (EPI == EPI_SWIGLU) {
+      unsigned long long* dw = (dbg && warp == 4 && lane == 0) ? dbg + 8 + 8 * (item >= (int)gridDim.x) : nullptr;
+      if (dw) dw[0] = gtimer();                                     // accumulator complete
+      {
+        uint32_t v[32];
+        tmem_ld32(tc.tmem + ((uint32_t)(q * 32) << 16) + acc * kPersistTcTokens + half * 32, v);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tc_acc_empty(tc, acc));         // the accumulator is in registers: the next item may start
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float x = __uint_as_float(v[j]);
-          const float up = __shfl_xor_sync(0xffffffffu, x, 1);       // rows are interleaved (gate, up)
-          const int tok = half * 32 + j;
-          if ((lane & 1) == 0 && tok < B) act[(size_t)tok * (N >> 1) + (row >> 1)] = __float2bfloat16_rn(silu(x) * up);
+        for (int j = 0; j < 32; ++j) eb[j * 32 + lane] = __uint_as_float(v[j]);
+      }
+      __syncwarp();
+      const int feat = tile * tile_rows + q * 32 + fc;              // first of this lane's 4 features
+      const bool fvalid = (q * 32 + fc < tile_rows) && (feat < N);  // tile_rows and N are multiples of 4
+      if (EPI == EPI_SWIGLU) {
+        // rows are interleaved (gate, up): features (fc, fc+1) and (fc+2, fc+3) are two (gate, up) pairs
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int tl = i * 4 + tr, tok = half * 32 + tl;
+          // accumulator rows past the tile come from stale shared memory (possibly NaN / denormal bit patterns, for which the
+          // division takes its slow path: measured 5 us on the CTAs whose ring never held a 128-row tile): no arithmetic on them
+          if (fvalid && tok < B) {
+            const float4 x = *reinterpret_cast<const float4*>(eb + tl * 32 + fc);
+            __nv_bfloat162 ob = __floats2bfloat162_rn(silu(x.x) * x.y, silu(x.z) * x.w);
+            *reinterpret_cast<uint32_t*>(act + (size_t)tok * (N >> 1) + (feat >> 1)) = *reinterpret_cast<uint32_t*>(&ob);
+          }
         }
       } else {
-        float* o = out32 + (size_t)ks * Bpad * N + row;
+        float* o = out32 + (size_t)ks * Bpad * N + feat;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int tok = half * 32 + j;
-          if (tok < B) o[(size_t)tok * N] = __uint_as_float(v[j]);
+        for (int i = 0; i < 8; ++i) {
+          const int tl = i * 4 + tr, tok = half * 32 + tl;
+          if (fvalid && tok < B) *reinterpret_cast<float4*>(o + (size_t)tok * N) = *reinterpret_cast<const float4*>(eb + tl * 32 + fc);
         }
       }
+      if (dw) dw[5] = gtimer();
+      __syncwarp();                                                 // the buffer is rewritten by the next item
     }
   }
   for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
@@ -764,18 +813,13 @@ __device__ __forceinline__ void attention_phase_mma(const DecodePersistArgs& a, 
   __syncthreads();
 }
 
-__device__ __forceinline__ unsigned long long gtimer() {
-  unsigned long long t;
-  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-  return t;
-}
 #define STAMP()                                                                      \
   do {                                                                               \
     if (a.timestamps && blockIdx.x == 0 && threadIdx.x == 0) a.timestamps[n_stamp++] = gtimer(); \
   } while (0)
 
 // K splits of the tcgen05 phases (items = tiles x splits ~ one per CTA of a 148-SM grid): qkv 24 tiles x 6, o 16 x 9,
-// gate/up 96 x 1 (the SwiGLU epilogue needs whole sums), down 16 x 9, lm_head 463 x 1
+// gate/up 147 tiles of kPersistGuTileRows = 84 rows x 1 (whole K: the SwiGLU epilogue needs whole sums), down 16 x 9, lm_head 570 tiles of kPersistLmTileRows = 104 rows x 1 (four waves of 104 rows instead of four of 128)
 static constexpr int kTcSplitQkv = 6, kTcSplitO = 9, kTcSplitDown = 9;
 
 template <bool W8, int NT, bool TC>
@@ -806,6 +850,7 @@ __global__ void __launch_bounds__(kPThreads, 1) decode_persist_kernel(DecodePers
     tc.ringB = tc.ringA + kTcStages * kTcStageA;
     tc.bars = smem_u32(tc_bars);
     tc.kb_count = 0; tc.item_count = 0; tc.pre = 0;
+    tc.pre_depth = (uint32_t)min(max(a.tc_pre_depth, 0), kTcStages);
     if (tid == 32) {
       for (int s = 0; s < kTcStages; ++s) { mbar_init(tc_full(tc, s), 1); mbar_init(tc_empty(tc, s), 1); }
       for (int i = 0; i < 2; ++i) { mbar_init(tc_acc_full(tc, i), 1); mbar_init(tc_acc_empty(tc, i), 8); }
@@ -823,6 +868,7 @@ __global__ void __launch_bounds__(kPThreads, 1) decode_persist_kernel(DecodePers
   const uint32_t ring_off = ((smem_u32(smem) + 1023u) & ~1023u) - smem_u32(smem);
   uint8_t* smem_kv = smem + ring_off;                     // 1024 B aligned (TMA swizzle atoms)
   uint8_t* smem_small = smem + ring_off + (TC ? (size_t)kTcStages * (kTcStageA + kTcStageB) : attn_kv_smem<ATW>());
+  if (TC) tc.epi = reinterpret_cast<float*>(smem + ((ring_off + (size_t)kTcStages * (kTcStageA + kTcStageB) + 2 * attn_small_smem<8>() + 15) & ~(size_t)15));
 
   // ---- phase 0: x = E[cur_tok]; u = rmsnorm(x) * g(layer 0 input norm)
   for (int b = blockIdx.x; b < B; b += gridDim.x) {
@@ -853,7 +899,7 @@ __global__ void __launch_bounds__(kPThreads, 1) decode_persist_kernel(DecodePers
     grid_barrier<TC>(a.bar, epoch); STAMP();
     if (TC) {
       gemm_phase_tc<EPI_F32>(tmaps + 4 * l + 1, xmaps + 1, PH, PH, kTcSplitO, B, Bpad, a.part, nullptr, tc);
-      tc_prefetch_weights(tmaps + 4 * l + 2, 2 * PI, PH, 1, tc);
+      tc_prefetch_weights(tmaps + 4 * l + 2, 2 * PI, PH, 1, tc, kPersistGuTileRows);
       grid_barrier<TC>(a.bar, epoch); STAMP();
       residual_norm_phase<kTcSplitO>(a.part, B, Bpad, a.x, a.u, L.rms2, a.eps, red);
     } else {
@@ -862,16 +908,25 @@ __global__ void __launch_bounds__(kPThreads, 1) decode_persist_kernel(DecodePers
       residual_norm_phase<0>(nullptr, B, Bpad, a.x, a.u, L.rms2, a.eps, red);
     }
     grid_barrier<TC>(a.bar, epoch); STAMP();
+    // debug (dbg_cta == -2): per-CTA stamps around the gate/up phase of layer 1: [cta] start, [160 + cta] work done, [320 + cta] barrier passed
+    const bool dbg_all = a.timestamps && a.dbg_cta == -2 && l == 1;      // CTA-uniform
+    if (dbg_all && tid == 0) a.timestamps[1024 + blockIdx.x] = gtimer();
     if (TC) {
-      gemm_phase_tc<EPI_SWIGLU>(tmaps + 4 * l + 2, xmaps, 2 * PI, PH, 1, B, Bpad, nullptr, a.act, tc);
+      gemm_phase_tc<EPI_SWIGLU>(tmaps + 4 * l + 2, xmaps, 2 * PI, PH, 1, B, Bpad, nullptr, a.act, tc, kPersistGuTileRows,
+                                (a.timestamps && l == 1 && (int)blockIdx.x == a.dbg_cta) ? a.timestamps + 1024 : nullptr, a.dbg_flags);
+      const bool wd = a.timestamps && l == 1 && (int)blockIdx.x == a.dbg_cta && (tid & 31) == 0;
+      if (wd) a.timestamps[1024 + 40 + (tid >> 5)] = gtimer();
       tc_prefetch_weights(tmaps + 4 * l + 3, PH, PI, kTcSplitDown, tc);
+      if (wd) a.timestamps[1024 + 60 + (tid >> 5)] = gtimer();
     } else gemm_dispatch<EPI_SWIGLU, W8, NT>(L.wgu, L.sgu, 2 * PI, PH, a.u, B, Bpad, nullptr, nullptr, a.act, smem);
-    grid_barrier<TC>(a.bar, epoch); STAMP();
+    if (dbg_all) { __syncthreads(); if (tid == 0) a.timestamps[1024 + 160 + blockIdx.x] = gtimer(); }
+    grid_barrier<TC>(a.bar, epoch, a.dbg_flags, dbg_all ? a.timestamps + 1024 : nullptr); STAMP();
+    if (dbg_all && tid == 0) a.timestamps[1024 + 320 + blockIdx.x] = gtimer();
     const float* next_gamma = (l + 1 < a.n_layers) ? a.layers[l + 1].rms1 : a.final_norm;
     if (TC) {
       gemm_phase_tc<EPI_F32>(tmaps + 4 * l + 3, xmaps + 2, PH, PI, kTcSplitDown, B, Bpad, a.part, nullptr, tc);
       if (l + 1 < a.n_layers) tc_prefetch_weights(tmaps + 4 * (l + 1), PQKV, PH, kTcSplitQkv, tc);
-      else tc_prefetch_weights(tmaps + 4 * a.n_layers, PV_, PH, 1, tc);
+      else tc_prefetch_weights(tmaps + 4 * a.n_layers, PV_, PH, 1, tc, kPersistLmTileRows);
       grid_barrier<TC>(a.bar, epoch); STAMP();
       residual_norm_phase<kTcSplitDown>(a.part, B, Bpad, a.x, a.u, next_gamma, a.eps, red);
     } else {
@@ -883,7 +938,7 @@ __global__ void __launch_bounds__(kPThreads, 1) decode_persist_kernel(DecodePers
   }
 
   // ---- lm_head + greedy pick: every CTA scans its slice of the vocabulary for all tokens, CTA b merges token b
-  if (TC) gemm_phase_tc<EPI_F32>(tmaps + 4 * a.n_layers, xmaps, PV_, PH, 1, B, Bpad, a.part, nullptr, tc);
+  if (TC) gemm_phase_tc<EPI_F32>(tmaps + 4 * a.n_layers, xmaps, PV_, PH, 1, B, Bpad, a.part, nullptr, tc, kPersistLmTileRows);
   else gemm_dispatch<EPI_F32, false, NT>(a.lm_head, nullptr, PV_, PH, a.u, B, Bpad, a.part, nullptr, nullptr, smem);
   grid_barrier<TC>(a.bar, epoch); STAMP();
   {
@@ -972,7 +1027,7 @@ static size_t persist_smem_for(bool tc) {
   if (attn_mma16 > m) m = attn_mma16;
   if (attn_mma8 > m) m = attn_mma8;
   // tcgen05 class: TMA ring (the attention K/V buffers overlay it) + the per-team attention arrays after it
-  if (tc) m = kTcRingBytes + 2 * attn_small_smem<8>();
+  if (tc) m = kTcRingBytes + 2 * attn_small_smem<8>() + 16 + kTcEpiBytes;
   return m;
 }
 size_t decode_persist_smem_bytes() { return persist_smem_for(true); }
@@ -991,7 +1046,7 @@ static PersistKernel persist_variant(int i) {
 }
 static PersistKernel persist_kernel_for(bool w8, int B, bool tc) {
   const int cls = B <= 8 ? 0 : (B <= 16 ? 1 : (B <= 32 ? 2 : 3));
-  if (tc && !w8 && cls == 3) return persist_variant(8);
+  if (tc && !w8 && cls >= 2) return persist_variant(8);           // 17..64 segments, bf16: tcgen05 phases
   return persist_variant((w8 ? 4 : 0) + cls);
 }
 

@@ -140,14 +140,21 @@ struct DecodePersistArgs {
   int B, Bpad, max_ctx;
   int w8;                         // 1: decoder linears are int8 weight-only (lm_head / embedding stay bf16)
   // batch class 33..64, bf16 weights: the GEMM phases run on tcgen05 fed by TMA.  Device array of CUtensorMap (128 B each):
-  // [4*l + {0: qkv, 1: o, 2: gate/up, 3: down}] weight maps (box 64 k x 128 rows), [4*n_layers] lm_head,
+  // [4*l + {0: qkv, 1: o, 2: gate/up, 3: down}] weight maps (box 64 k x 128 rows; gate/up: x kPersistGuTileRows), [4*n_layers] lm_head,
   // [4*n_layers + 1 + {0: u, 1: attn, 2: act}] activation maps (box 64 k x 64 token rows).  nullptr: mma.sync phases.
   const void* tmaps;
   // attention phase: device array of two CUtensorMap over the whole K and V caches ({128 dims, layers*batch*4*max_ctx key rows},
   // box 64 dims x 64 keys, 128B swizzle); kc_base = first element of the K cache (row 0 of the maps)
   const void* kv_maps; const bf16* kc_base;
+  int tc_pre_depth;               // tcgen05 classes: ring stages of the NEXT phase's weights put in flight before each grid barrier
+  int dbg_flags;                  // timing experiments (SONIC_PERSIST_DBGFLAGS; results are wrong with them): 1 / 2 skip the proxy fence before / after the gate/up barrier, 4 skip the SwiGLU stores
+  int dbg_cta;                    // debug handles: CTA whose gate/up phase of layer 1 writes fine-grained stamps to timestamps + 1024 (-1: none)
   float eps, scale;
 };
+// weight rows per gate/up item of the tcgen05 decode classes = box height of the gate/up weight map: 147 items of 84 rows cover
+// the 12288 interleaved (gate, up) rows, one whole-K item per CTA of a 148-SM grid (128-row tiles would occupy 96 CTAs)
+static constexpr int kPersistGuTileRows = 84;
+static constexpr int kPersistLmTileRows = 104;  // lm_head: 570 items = 3.85 per CTA
 size_t decode_persist_smem_bytes();
 size_t decode_persist_part_floats(int Bpad);
 size_t decode_persist_pick_floats(int max_batch, int num_sms);
