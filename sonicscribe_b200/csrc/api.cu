@@ -194,6 +194,7 @@ struct sonic_ctx {
   float* probe_logits = nullptr;       // [probe_steps][max_batch][vocab]
   int cur_step = 0;                    // index of the token the next decode step produces (host-side mirror of gs.step)
   int probe_batch = 0;
+  int persist_tc_min = 1;              // smallest live batch that uses the tcgen05 class (SONIC_PERSIST_TC_MIN; measured faster at every batch size)
   bool persist_tc = false;             // live batches of 17..64 segments run the GEMM phases of the persistent kernel on tcgen05 (bf16)
   bool use_persist = false;            // one cooperative kernel per greedy step (bf16 mode; SONIC_DECODE=graph disables)
   DecLayerDev* dev_layers = nullptr;
@@ -575,10 +576,17 @@ struct Engine {
       p.act = reinterpret_cast<bf16*>(h->dact); p.part = h->persist_part; p.logits_out = probe_target(h, h->cur_step); p.pick_scratch = h->persist_pick;
       p.attn_ws = h->dattn_ws; p.attn_counters = h->dattn_counters;
       // 128-key chunks over separate CTAs while that still leaves CTAs idle; otherwise one CTA walks all chunks of a group
-      p.attn_chunks = (B * kDecKv * ((h->decode_chunks + 1) / 2) <= h->persist_grid) ? (h->decode_chunks + 1) / 2 : 1;
+      // few segments: the keys of a (segment, kv head) group are split over CTAs, 64 keys per item while every item still gets
+      // its own CTA, else 128; otherwise one team of warps walks all chunks of a group.  The choice depends on the batch and on
+      // the handle's maximum context only — never on max_new_tokens — so a call with a larger token budget reproduces the ids
+      // of a shorter one (interim vs committed decode of the same audio)
+      const int c64 = h->dattn_max_chunks, c128 = (c64 + 1) / 2;
+      if (B * kDecKv * c64 <= h->persist_grid) { p.attn_chunks = c64; p.attn_chunk_keys = 64; }
+      else if (B * kDecKv * c128 <= h->persist_grid) { p.attn_chunks = c128; p.attn_chunk_keys = 128; }
+      else { p.attn_chunks = 1; p.attn_chunk_keys = 128; }
       p.gs = h->gs; p.bar = h->persist_bar; p.timestamps = h->cfg.debug ? h->persist_ts : nullptr;
       p.w8 = h->is_int8 ? 1 : 0;
-      p.tmaps = h->persist_tc ? h->persist_tmaps : nullptr;
+      p.tmaps = (h->persist_tc && B >= h->persist_tc_min) ? h->persist_tmaps : nullptr;
       p.kv_maps = h->persist_kv_maps; p.kc_base = reinterpret_cast<const bf16*>(h->kcache);
       { const char* pd = getenv("SONIC_PERSIST_PRE"); p.tc_pre_depth = pd ? atoi(pd) : 6; }
       { const char* df = getenv("SONIC_PERSIST_DBGFLAGS"); p.dbg_flags = (h->cfg.debug && df) ? atoi(df) : 0; }
@@ -1153,17 +1161,18 @@ int sonic_finalize_weights(sonic_handle h) {
       CK(cudaMemcpy(h->persist_kv_maps, kvm, sizeof(kvm), cudaMemcpyHostToDevice));
     }
     const char* ptc = getenv("SONIC_PERSIST_TC");
-    h->persist_tc = !h->is_int8 && h->cfg.max_batch > 16 && !(ptc && ptc[0] == '0');
+    h->persist_tc = !h->is_int8 && !(ptc && ptc[0] == '0');
+    { const char* tm = getenv("SONIC_PERSIST_TC_MIN"); h->persist_tc_min = tm ? atoi(tm) : 1; }
     if (h->persist_tc) {
       // weight maps: {K, rows} with a 64 x 128 box; activation maps: {K, 64 token rows} with a 64 x 64 box (128B swizzle)
       const int L = h->cfg.dec_layers;
       std::vector<CUtensorMap> maps(4 * L + 4);
       for (int l = 0; l < L; ++l) {
         const DecLayerW& w = h->dec[l];
-        CK(make_tensor_map_2d(&maps[4 * l + 0], w.wqkv, kDecH, kQkvDec, kDecH, 64, 128));
-        CK(make_tensor_map_2d(&maps[4 * l + 1], w.wo, kDecH, kDecH, kDecH, 64, 128));
+        CK(make_tensor_map_2d(&maps[4 * l + 0], w.wqkv, kDecH, kQkvDec, kDecH, 64, kPersistQkvTileRows));
+        CK(make_tensor_map_2d(&maps[4 * l + 1], w.wo, kDecH, kDecH, kDecH, 64, kPersistOTileRows));
         CK(make_tensor_map_2d(&maps[4 * l + 2], w.wgu, kDecH, 2 * kDecInter, kDecH, 64, kPersistGuTileRows));
-        CK(make_tensor_map_2d(&maps[4 * l + 3], w.wdown, kDecInter, kDecH, kDecInter, 64, 128));
+        CK(make_tensor_map_2d(&maps[4 * l + 3], w.wdown, kDecInter, kDecH, kDecInter, 64, kPersistDownTileRows));
       }
       CK(make_tensor_map_2d(&maps[4 * L], h->lm_head, kDecH, kVocab, kDecH, 64, kPersistLmTileRows));
       CK(make_tensor_map_2d(&maps[4 * L + 1], h->du, kDecH, kPersistTcTokens, kDecH, 64, kPersistTcTokens));

@@ -268,6 +268,7 @@ struct TcCtx {
   uint32_t ringA, ringB, bars, tmem;
   uint32_t kb_count, item_count;
   uint32_t pre;                  // k blocks of the coming phase whose weight tile is already in flight (tc_prefetch_weights)
+  uint64_t wpolicy;              // L2 policy of the weight / KV streams (evict_first), or 0: default
   uint32_t pre_depth;            // how many stages tc_prefetch_weights may fill before a grid barrier (<= kTcStages)
   float* epi;                    // 8 epilogue warps x [32 tokens][32 features] fp32 transpose buffers
 };
@@ -290,7 +291,8 @@ __device__ __forceinline__ void tc_prefetch_weights(const CUtensorMap* wmap, int
         const uint32_t cnt = tc.kb_count + n, st = cnt % kTcStages, par = (cnt / kTcStages) & 1u;
         mbar_wait(tc_empty(tc, st), par ^ 1u);
         mbar_expect_tx(tc_full(tc, st), tile_rows * 128 + kTcStageB);
-        tma_load_2d(tc.ringA + st * kTcStageA, wmap, tc_full(tc, st), kb * 64, tile * tile_rows);
+        if (tc.wpolicy) tma_load_2d_hint(tc.ringA + st * kTcStageA, wmap, tc_full(tc, st), kb * 64, tile * tile_rows, tc.wpolicy);
+        else tma_load_2d(tc.ringA + st * kTcStageA, wmap, tc_full(tc, st), kb * 64, tile * tile_rows);
       }
     }
   }
@@ -318,7 +320,8 @@ __device__ __forceinline__ void gemm_phase_tc(const CUtensorMap* wmap, const CUt
           if (idx >= tc.pre) {
             mbar_wait(tc_empty(tc, st), par ^ 1u);
             mbar_expect_tx(tc_full(tc, st), tile_rows * 128 + kTcStageB);
-            tma_load_2d(tc.ringA + st * kTcStageA, wmap, tc_full(tc, st), kb * 64, tile * tile_rows);
+            if (tc.wpolicy) tma_load_2d_hint(tc.ringA + st * kTcStageA, wmap, tc_full(tc, st), kb * 64, tile * tile_rows, tc.wpolicy);
+            else tma_load_2d(tc.ringA + st * kTcStageA, wmap, tc_full(tc, st), kb * 64, tile * tile_rows);
           }
           tma_load_2d(tc.ringB + st * kTcStageB, xmap, tc_full(tc, st), kb * 64, 0);
         }
@@ -465,7 +468,11 @@ __device__ __forceinline__ void residual_norm_phase(const float* part, int B, in
 // section and rotates it; the item owning the newest position also rotates k and appends k, v to the cache.  Each item writes
 // an (m, l, o) partial; the item arriving last at the (segment, kv head) counter merges the partials in chunk order.
 template <int KSQ>
-__device__ __forceinline__ void attention_phase(const DecodePersistArgs& a, const DecLayerDev& L, uint8_t* smem) {
+__device__ __forceinline__ void attention_phase(const DecodePersistArgs& a, const DecLayerDev& L, uint8_t* smem, const int* s_ctx,
+                                                unsigned long long* dbg = nullptr) {
+  int n_dbg = 0;
+#define ASTAMP() do { if (dbg && threadIdx.x == 0 && n_dbg < 16) dbg[n_dbg++] = gtimer(); } while (0)
+  ASTAMP();
   uint8_t* sK = smem;                                          // AKEYS * kAKRow
   bf16* sV = reinterpret_cast<bf16*>(smem + AKEYS * kAKRow);   // AKEYS * 128
   float* sQ = reinterpret_cast<float*>(smem + AKEYS * kAKRow + AKEYS * PHD * 2);   // [4][128]
@@ -477,16 +484,32 @@ __device__ __forceinline__ void attention_phase(const DecodePersistArgs& a, cons
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int C = a.attn_chunks;
   const int n_items = a.B * PKVH * C;
+  const int CKEYS = a.attn_chunk_keys;                          // 64 or 128 keys per item (<= AKEYS)
   for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
     const int chunk = item % C, grp = item / C;                  // grp = seg * 4 + kvh
     const int seg = grp / PKVH, kvh = grp - seg * PKVH;
-    const int pos = a.gs.ctx_len[seg], kv_len = pos + 1;
-    const int n_chunks = (kv_len + AKEYS - 1) / AKEYS;
+    const int pos = s_ctx[seg], kv_len = pos + 1;
+    const int n_chunks = (kv_len + CKEYS - 1) / CKEYS;
     float* ws = a.attn_ws + ((size_t)grp * C + chunk) * PG * (PHD + 2);
     if (chunk < n_chunks) {
       bf16* kc = L.kc + ((size_t)seg * PKVH + kvh) * a.max_ctx * PHD;
       bf16* vc = L.vc + ((size_t)seg * PKVH + kvh) * a.max_ctx * PHD;
-      const bool owner = (chunk == pos / AKEYS);
+      const bool owner = (chunk == pos / CKEYS);
+      const int k0 = chunk * CKEYS;
+      const int nk = min(CKEYS, kv_len - k0);
+      // the chunk's cached K / V rows do not depend on this step's q, k, v: their loads are issued first and land while the
+      // partial sums / RoPE below wait for theirs
+      uint4 kreg[AKEYS * (PHD / 8) / kPThreads], vreg[AKEYS * (PHD / 8) / kPThreads];
+#pragma unroll
+      for (int it = 0; it < AKEYS * (PHD / 8) / kPThreads; ++it) {
+        const int i = tid + it * kPThreads, r = i / (PHD / 8), c8 = i - r * (PHD / 8);
+        kreg[it] = make_uint4(0, 0, 0, 0); vreg[it] = make_uint4(0, 0, 0, 0);
+        if (r < nk && k0 + r != pos) {
+          kreg[it] = __ldcg(reinterpret_cast<const uint4*>(kc + (size_t)(k0 + r) * PHD + c8 * 8));
+          vreg[it] = __ldcg(reinterpret_cast<const uint4*>(vc + (size_t)(k0 + r) * PHD + c8 * 8));
+        }
+      }
+      ASTAMP();                                                    // K / V loads issued
       const int n_pairs = (owner ? PG + 2 : PG) * (PHD / 2);
       for (int i = tid; i < n_pairs; i += kPThreads) {
         const int hh = i / (PHD / 2), j = i - hh * (PHD / 2);     // hh < 4: query head; 4: key; 5: value (pair j, j+64)
@@ -500,35 +523,29 @@ __device__ __forceinline__ void attention_phase(const DecodePersistArgs& a, cons
           else { sKV[j] = rx; sKV[j + PHD / 2] = ry; }
         } else { sKV[PHD + j] = x; sKV[PHD + j + PHD / 2] = y; }
       }
-      __syncthreads();
+      __syncthreads(); ASTAMP();
       if (owner) {
         if (tid < PHD) kc[(size_t)pos * PHD + tid] = __float2bfloat16_rn(sKV[tid]);
         else if (tid < 2 * PHD) vc[(size_t)pos * PHD + tid - PHD] = __float2bfloat16_rn(sKV[tid]);
       }
-      const int k0 = chunk * AKEYS;
-      const int nk = min(AKEYS, kv_len - k0);
-      for (int i = tid; i < AKEYS * (PHD / 8); i += kPThreads) {
-        const int r = i / (PHD / 8), c8 = i - r * (PHD / 8);
-        uint4 kk = make_uint4(0, 0, 0, 0), vv = make_uint4(0, 0, 0, 0);
-        if (r < nk) {
-          if (k0 + r == pos) {                                   // the row this CTA appends: take it from shared memory
-            uint32_t wk[4], wv[4];
 #pragma unroll
-            for (int e2 = 0; e2 < 4; ++e2) {
-              __nv_bfloat162 pk = __floats2bfloat162_rn(sKV[c8 * 8 + 2 * e2], sKV[c8 * 8 + 2 * e2 + 1]);
-              __nv_bfloat162 pv = __floats2bfloat162_rn(sKV[PHD + c8 * 8 + 2 * e2], sKV[PHD + c8 * 8 + 2 * e2 + 1]);
-              wk[e2] = *reinterpret_cast<uint32_t*>(&pk); wv[e2] = *reinterpret_cast<uint32_t*>(&pv);
-            }
-            kk = make_uint4(wk[0], wk[1], wk[2], wk[3]); vv = make_uint4(wv[0], wv[1], wv[2], wv[3]);
-          } else {
-            kk = __ldcg(reinterpret_cast<const uint4*>(kc + (size_t)(k0 + r) * PHD + c8 * 8));
-            vv = __ldcg(reinterpret_cast<const uint4*>(vc + (size_t)(k0 + r) * PHD + c8 * 8));
+      for (int it = 0; it < AKEYS * (PHD / 8) / kPThreads; ++it) {
+        const int i = tid + it * kPThreads, r = i / (PHD / 8), c8 = i - r * (PHD / 8);
+        uint4 kk = kreg[it], vv = vreg[it];
+        if (r < nk && k0 + r == pos) {                           // the row this CTA appends: take it from shared memory
+          uint32_t wk[4], wv[4];
+#pragma unroll
+          for (int e2 = 0; e2 < 4; ++e2) {
+            __nv_bfloat162 pk = __floats2bfloat162_rn(sKV[c8 * 8 + 2 * e2], sKV[c8 * 8 + 2 * e2 + 1]);
+            __nv_bfloat162 pv = __floats2bfloat162_rn(sKV[PHD + c8 * 8 + 2 * e2], sKV[PHD + c8 * 8 + 2 * e2 + 1]);
+            wk[e2] = *reinterpret_cast<uint32_t*>(&pk); wv[e2] = *reinterpret_cast<uint32_t*>(&pv);
           }
+          kk = make_uint4(wk[0], wk[1], wk[2], wk[3]); vv = make_uint4(wv[0], wv[1], wv[2], wv[3]);
         }
         *reinterpret_cast<uint4*>(sK + r * kAKRow + c8 * 16) = kk;
         *reinterpret_cast<uint4*>(sV + r * PHD + c8 * 8) = vv;
       }
-      __syncthreads();
+      __syncthreads(); ASTAMP();
       const int head = warp & 3, kgrp = warp >> 2;               // scores: 4 heads x 4 groups of 32 keys
       const int r = kgrp * 32 + lane;
       float sc = -INFINITY;
@@ -548,18 +565,25 @@ __device__ __forceinline__ void attention_phase(const DecodePersistArgs& a, cons
       }
       const float wmax = warp_max(sc);
       if (lane == 0) sMax[head * 4 + kgrp] = wmax;
-      __syncthreads();
+      __syncthreads(); ASTAMP();
       const float cmax = fmaxf(fmaxf(sMax[head * 4], sMax[head * 4 + 1]), fmaxf(sMax[head * 4 + 2], sMax[head * 4 + 3]));
       const float p = (sc == -INFINITY) ? 0.f : expf(sc - cmax);
       sP[head * AKEYS + r] = p;
       const float wsum = warp_sum(p);
       if (lane == 0) sSum[head * 4 + kgrp] = wsum;
-      __syncthreads();
+      __syncthreads(); ASTAMP();
       {
         const int ph = tid >> 7, d = tid & 127;                  // PV: thread = (head, dim)
         float acc = 0.f;
         const float* pp = sP + ph * AKEYS;
-        for (int j = 0; j < nk; ++j) acc = fmaf(pp[j], __bfloat162float(sV[j * PHD + d]), acc);
+        // rows >= nk hold p = 0 and zero V rows: the loop runs over the whole chunk, 8 independent loads per step
+        for (int j0 = 0; j0 < CKEYS; j0 += 8) {
+          float pv[8], vv[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) { pv[u] = pp[j0 + u]; vv[u] = __bfloat162float(sV[(j0 + u) * PHD + d]); }
+#pragma unroll
+          for (int u = 0; u < 8; ++u) acc = fmaf(pv[u], vv[u], acc);
+        }
         ws[(size_t)ph * (PHD + 2) + d] = acc;
         if (d == 0) {
           ws[(size_t)ph * (PHD + 2) + PHD] = fmaxf(fmaxf(sMax[ph * 4], sMax[ph * 4 + 1]), fmaxf(sMax[ph * 4 + 2], sMax[ph * 4 + 3]));
@@ -569,31 +593,47 @@ __device__ __forceinline__ void attention_phase(const DecodePersistArgs& a, cons
     }
     // arrival + last-arriver merge (chunk order => deterministic)
     __threadfence();
-    __syncthreads();
+    __syncthreads(); ASTAMP();
     if (tid == 0) {
       const int prev = atomicAdd(a.attn_counters + grp, 1);
       s_last = (prev == C - 1) ? 1 : 0;
       if (s_last) a.attn_counters[grp] = 0;
     }
-    __syncthreads();
+    __syncthreads(); ASTAMP();
     if (s_last) {
       __threadfence();
       const int ph = tid >> 7, d = tid & 127;
       const float* wg = a.attn_ws + (size_t)grp * C * PG * (PHD + 2);
-      float M = -INFINITY;
-      for (int c = 0; c < n_chunks; ++c) M = fmaxf(M, __ldcg(wg + ((size_t)c * PG + ph) * (PHD + 2) + PHD));
-      float Ls = 0.f, acc = 0.f;
-      for (int c = 0; c < n_chunks; ++c) {
-        const float* pc = wg + ((size_t)c * PG + ph) * (PHD + 2);
-        const float w = expf(__ldcg(pc + PHD) - M);
-        Ls += __ldcg(pc + PHD + 1) * w;
-        acc += __ldcg(pc + d) * w;
+      // four chunks' partials in flight per step; accumulation stays in chunk order
+      float M = -INFINITY, Ls = 0.f, acc = 0.f;
+      for (int c0 = 0; c0 < n_chunks; c0 += 4) {
+        float mv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) mv[u] = (c0 + u < n_chunks) ? __ldcg(wg + ((size_t)(c0 + u) * PG + ph) * (PHD + 2) + PHD) : -INFINITY;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) M = fmaxf(M, mv[u]);
+      }
+      for (int c0 = 0; c0 < n_chunks; c0 += 4) {
+        float mv[4], lv[4], av[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const float* pc = wg + ((size_t)(c0 + u) * PG + ph) * (PHD + 2);
+          const bool ok = c0 + u < n_chunks;
+          mv[u] = ok ? __ldcg(pc + PHD) : -INFINITY; lv[u] = ok ? __ldcg(pc + PHD + 1) : 0.f; av[u] = ok ? __ldcg(pc + d) : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const float w = (c0 + u < n_chunks) ? expf(mv[u] - M) : 0.f;
+          Ls += lv[u] * w;
+          acc += av[u] * w;
+        }
       }
       a.attn[(size_t)seg * PH + (size_t)(kvh * PG + ph) * PHD + d] = __float2bfloat16_rn(acc / Ls);
     }
-    __syncthreads();
+    __syncthreads(); ASTAMP();
   }
 }
+#undef ASTAMP
 
 // ---- attention phase on mma.sync (used when every CTA has at least one (segment, kv head) group to itself) -----------------
 // Per 128-key chunk: S[4 heads(16) x 128 keys] = Q.K^T with warp w owning keys 8w..8w+7 (8 k-steps over head_dim), online
@@ -630,7 +670,7 @@ __device__ __forceinline__ uint32_t kv_sw(int r, int c16, int half_bytes) {
 
 template <int KSQ, int TW>
 __device__ __forceinline__ void attention_phase_mma(const DecodePersistArgs& a, const DecLayerDev& L, uint8_t* smem_kv, uint8_t* smem_small,
-                                                    uint32_t bars, uint32_t& n_chunk) {
+                                                    uint32_t bars, uint32_t& n_chunk, const int* s_ctx) {
   constexpr int CK = 8 * TW;                              // keys per chunk
   constexpr int TT = 32 * TW;                             // threads per team
   constexpr int NTEAM = kPWarps / TW;
@@ -651,6 +691,7 @@ __device__ __forceinline__ void attention_phase_mma(const DecodePersistArgs& a, 
   const int n_items = a.B * PKVH;
   const int item_stride = gridDim.x * NTEAM;
   auto bar_of = [&](uint32_t b) { return bars + 8u * (team * 2 + b); };
+  const uint64_t kvpol = l2_policy_evict_first();          // every cached key / value is read once per step
   // one thread asks TMA for the whole chunk: [64 keys x 64 dims] boxes of the K and V caches (one 2-D map per cache over all
   // layers, segments and kv heads; row = key), landing as SWIZZLE_128B halves.  Rows past the context are finite cache
   // contents (masked below); the row appended this step is overwritten from sKV after the chunk has landed.
@@ -662,15 +703,15 @@ __device__ __forceinline__ void attention_phase_mma(const DecodePersistArgs& a, 
       for (int s2 = 0; s2 < CK / 64; ++s2) {
 #pragma unroll
         for (int h2 = 0; h2 < 2; ++h2) {
-          tma_load_2d(dst + h2 * kHalfB + s2 * 8192, kmap, bar_of(b), 64 * h2, row0 + k0 + 64 * s2);
-          tma_load_2d(dst + 2 * kHalfB + h2 * kHalfB + s2 * 8192, vmap, bar_of(b), 64 * h2, row0 + k0 + 64 * s2);
+          tma_load_2d_hint(dst + h2 * kHalfB + s2 * 8192, kmap, bar_of(b), 64 * h2, row0 + k0 + 64 * s2, kvpol);
+          tma_load_2d_hint(dst + 2 * kHalfB + h2 * kHalfB + s2 * 8192, vmap, bar_of(b), 64 * h2, row0 + k0 + 64 * s2, kvpol);
         }
       }
     }
   };
   auto group_of = [&](int item, int& seg, int& kvh, int& pos, int& row0) {
     seg = item / PKVH; kvh = item - seg * PKVH;
-    pos = a.gs.ctx_len[seg];
+    pos = s_ctx[seg];
     row0 = (int)((L.kc - a.kc_base) / PHD) + (seg * PKVH + kvh) * a.max_ctx;
   };
   int item = blockIdx.x * NTEAM + team;
@@ -820,6 +861,8 @@ __device__ __forceinline__ void attention_phase_mma(const DecodePersistArgs& a, 
 
 // K splits of the tcgen05 phases (items = tiles x splits ~ one per CTA of a 148-SM grid): qkv 24 tiles x 6, o 16 x 9,
 // gate/up 147 tiles of kPersistGuTileRows = 84 rows x 1 (whole K: the SwiGLU epilogue needs whole sums), down 16 x 9, lm_head 570 tiles of kPersistLmTileRows = 104 rows x 1 (four waves of 104 rows instead of four of 128)
+// (measured: 84 / 56 / 72-row tiles with 4 / 4 / 5 splits, i.e. 145-148 items and fewer partials, are slower — 50 vs 46.5 us per
+// layer at 64 segments: a CTA then issues 2-3 x as many MMAs (>= 80 clk each) behind its last weight bytes)
 static constexpr int kTcSplitQkv = 6, kTcSplitO = 9, kTcSplitDown = 9;
 
 template <bool W8, int NT, bool TC>
@@ -830,6 +873,7 @@ __global__ void __launch_bounds__(kPThreads, 1) decode_persist_kernel(DecodePers
   __shared__ __align__(8) uint64_t tc_bars[2 * kTcStages + 4];
   __shared__ uint32_t tc_tmem_slot;
   __shared__ __align__(8) uint64_t attn_bars[4];                  // [team][buffer] K/V chunk arrival
+  __shared__ int s_ctx[64];                                       // context length of every segment (constant until the pick phase)
   unsigned epoch = 0;
   int n_stamp = 0;
   STAMP();
@@ -851,6 +895,7 @@ __global__ void __launch_bounds__(kPThreads, 1) decode_persist_kernel(DecodePers
     tc.bars = smem_u32(tc_bars);
     tc.kb_count = 0; tc.item_count = 0; tc.pre = 0;
     tc.pre_depth = (uint32_t)min(max(a.tc_pre_depth, 0), kTcStages);
+    tc.wpolicy = (a.dbg_flags & 8) ? 0ull : l2_policy_evict_first();
     if (tid == 32) {
       for (int s = 0; s < kTcStages; ++s) { mbar_init(tc_full(tc, s), 1); mbar_init(tc_empty(tc, s), 1); }
       for (int i = 0; i < 2; ++i) { mbar_init(tc_acc_full(tc, i), 1); mbar_init(tc_acc_empty(tc, i), 8); }
@@ -861,7 +906,7 @@ __global__ void __launch_bounds__(kPThreads, 1) decode_persist_kernel(DecodePers
     __syncthreads();
     tc_fence_after();
     tc.tmem = tc_tmem_slot;
-    tc_prefetch_weights(tmaps, PQKV, PH, kTcSplitQkv, tc);
+    tc_prefetch_weights(tmaps, PQKV, PH, kTcSplitQkv, tc, kPersistQkvTileRows);
   }
   // attention: K/V chunk buffers overlay the (then idle) TMA ring / GEMM staging area, the small per-team arrays sit after it
   constexpr int ATW = (NT == 8) ? 8 : 16;                 // attention team width of this batch class
@@ -870,6 +915,7 @@ __global__ void __launch_bounds__(kPThreads, 1) decode_persist_kernel(DecodePers
   uint8_t* smem_small = smem + ring_off + (TC ? (size_t)kTcStages * (kTcStageA + kTcStageB) : attn_kv_smem<ATW>());
   if (TC) tc.epi = reinterpret_cast<float*>(smem + ((ring_off + (size_t)kTcStages * (kTcStageA + kTcStageB) + 2 * attn_small_smem<8>() + 15) & ~(size_t)15));
 
+  if (tid < 64) s_ctx[tid] = (tid < B) ? a.gs.ctx_len[tid] : 0;     // visible after the first grid barrier's __syncthreads
   // ---- phase 0: x = E[cur_tok]; u = rmsnorm(x) * g(layer 0 input norm)
   for (int b = blockIdx.x; b < B; b += gridDim.x) {
     const int tok = a.gs.cur_tok[b];
@@ -890,15 +936,20 @@ __global__ void __launch_bounds__(kPThreads, 1) decode_persist_kernel(DecodePers
   for (int l = 0; l < a.n_layers; ++l) {
     const DecLayerDev L = a.layers[l];
     if (TC) {
-      gemm_phase_tc<EPI_F32>(tmaps + 4 * l, xmaps, PQKV, PH, kTcSplitQkv, B, Bpad, a.part, nullptr, tc);
+      gemm_phase_tc<EPI_F32>(tmaps + 4 * l, xmaps, PQKV, PH, kTcSplitQkv, B, Bpad, a.part, nullptr, tc, kPersistQkvTileRows);
     } else gemm_dispatch<EPI_F32, W8, NT>(L.wqkv, L.sqkv, PQKV, PH, a.u, B, Bpad, a.part, nullptr, nullptr, smem);
     grid_barrier<TC>(a.bar, epoch); STAMP();
-    if (!TC && a.attn_chunks > 1) attention_phase<1>(a, L, smem);          // few segments: split the keys over CTAs
-    else attention_phase_mma<TC ? kTcSplitQkv : 1, ATW>(a, L, smem_kv, smem_small, smem_u32(attn_bars), attn_chunks_done);
-    if (TC) tc_prefetch_weights(tmaps + 4 * l + 1, PH, PH, kTcSplitO, tc);      // the ring is free again
+    if (a.attn_chunks > 1) attention_phase<TC ? kTcSplitQkv : 1>(a, L, TC ? smem_kv : smem, s_ctx, (a.timestamps && l == 1 && (int)blockIdx.x == a.dbg_cta) ? a.timestamps + 1024 + 900 : nullptr);   // few segments: split the keys over CTAs
+    else attention_phase_mma<TC ? kTcSplitQkv : 1, ATW>(a, L, smem_kv, smem_small, smem_u32(attn_bars), attn_chunks_done, s_ctx);
+    if (TC) {
+      // the attention phase read / wrote the ring's shared memory through the generic proxy; TMA overwrites it next
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncthreads();
+      tc_prefetch_weights(tmaps + 4 * l + 1, PH, PH, kTcSplitO, tc, kPersistOTileRows);      // the ring is free again
+    }
     grid_barrier<TC>(a.bar, epoch); STAMP();
     if (TC) {
-      gemm_phase_tc<EPI_F32>(tmaps + 4 * l + 1, xmaps + 1, PH, PH, kTcSplitO, B, Bpad, a.part, nullptr, tc);
+      gemm_phase_tc<EPI_F32>(tmaps + 4 * l + 1, xmaps + 1, PH, PH, kTcSplitO, B, Bpad, a.part, nullptr, tc, kPersistOTileRows);
       tc_prefetch_weights(tmaps + 4 * l + 2, 2 * PI, PH, 1, tc, kPersistGuTileRows);
       grid_barrier<TC>(a.bar, epoch); STAMP();
       residual_norm_phase<kTcSplitO>(a.part, B, Bpad, a.x, a.u, L.rms2, a.eps, red);
@@ -916,7 +967,7 @@ __global__ void __launch_bounds__(kPThreads, 1) decode_persist_kernel(DecodePers
                                 (a.timestamps && l == 1 && (int)blockIdx.x == a.dbg_cta) ? a.timestamps + 1024 : nullptr, a.dbg_flags);
       const bool wd = a.timestamps && l == 1 && (int)blockIdx.x == a.dbg_cta && (tid & 31) == 0;
       if (wd) a.timestamps[1024 + 40 + (tid >> 5)] = gtimer();
-      tc_prefetch_weights(tmaps + 4 * l + 3, PH, PI, kTcSplitDown, tc);
+      tc_prefetch_weights(tmaps + 4 * l + 3, PH, PI, kTcSplitDown, tc, kPersistDownTileRows);
       if (wd) a.timestamps[1024 + 60 + (tid >> 5)] = gtimer();
     } else gemm_dispatch<EPI_SWIGLU, W8, NT>(L.wgu, L.sgu, 2 * PI, PH, a.u, B, Bpad, nullptr, nullptr, a.act, smem);
     if (dbg_all) { __syncthreads(); if (tid == 0) a.timestamps[1024 + 160 + blockIdx.x] = gtimer(); }
@@ -924,8 +975,8 @@ __global__ void __launch_bounds__(kPThreads, 1) decode_persist_kernel(DecodePers
     if (dbg_all && tid == 0) a.timestamps[1024 + 320 + blockIdx.x] = gtimer();
     const float* next_gamma = (l + 1 < a.n_layers) ? a.layers[l + 1].rms1 : a.final_norm;
     if (TC) {
-      gemm_phase_tc<EPI_F32>(tmaps + 4 * l + 3, xmaps + 2, PH, PI, kTcSplitDown, B, Bpad, a.part, nullptr, tc);
-      if (l + 1 < a.n_layers) tc_prefetch_weights(tmaps + 4 * (l + 1), PQKV, PH, kTcSplitQkv, tc);
+      gemm_phase_tc<EPI_F32>(tmaps + 4 * l + 3, xmaps + 2, PH, PI, kTcSplitDown, B, Bpad, a.part, nullptr, tc, kPersistDownTileRows);
+      if (l + 1 < a.n_layers) tc_prefetch_weights(tmaps + 4 * (l + 1), PQKV, PH, kTcSplitQkv, tc, kPersistQkvTileRows);
       else tc_prefetch_weights(tmaps + 4 * a.n_layers, PV_, PH, 1, tc, kPersistLmTileRows);
       grid_barrier<TC>(a.bar, epoch); STAMP();
       residual_norm_phase<kTcSplitDown>(a.part, B, Bpad, a.x, a.u, next_gamma, a.eps, red);
@@ -1046,7 +1097,7 @@ static PersistKernel persist_variant(int i) {
 }
 static PersistKernel persist_kernel_for(bool w8, int B, bool tc) {
   const int cls = B <= 8 ? 0 : (B <= 16 ? 1 : (B <= 32 ? 2 : 3));
-  if (tc && !w8 && cls >= 2) return persist_variant(8);           // 17..64 segments, bf16: tcgen05 phases
+  if (tc && !w8) return persist_variant(8);                       // bf16 and the caller passed tensor maps: tcgen05 phases
   return persist_variant((w8 ? 4 : 0) + cls);
 }
 

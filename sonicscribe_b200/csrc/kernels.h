@@ -134,6 +134,7 @@ struct DecodePersistArgs {
   float* logits_out;              // optional [B][vocab]
   float* pick_scratch;            // decode_persist_pick_floats(max_batch, num_sms)
   float* attn_ws; int* attn_counters; int attn_chunks;   // split-KV partials [B*4][attn_chunks][4][130], counters [B*4] (zeroed)
+  int attn_chunk_keys;            // keys per split-KV item when attn_chunks > 1: 64 or 128
   GreedyState gs;
   unsigned* bar;                  // grid barrier counter
   unsigned long long* timestamps; // optional: %globaltimer after every grid barrier (CTA 0), 1 + 8*layers + 3 entries
@@ -154,6 +155,7 @@ struct DecodePersistArgs {
 // weight rows per gate/up item of the tcgen05 decode classes = box height of the gate/up weight map: 147 items of 84 rows cover
 // the 12288 interleaved (gate, up) rows, one whole-K item per CTA of a 148-SM grid (128-row tiles would occupy 96 CTAs)
 static constexpr int kPersistGuTileRows = 84;
+static constexpr int kPersistQkvTileRows = 128, kPersistOTileRows = 128, kPersistDownTileRows = 128;   // x K splits 6 / 9 / 9 (decode_persist.cu)
 static constexpr int kPersistLmTileRows = 104;  // lm_head: 570 items = 3.85 per CTA
 size_t decode_persist_smem_bytes();
 size_t decode_persist_part_floats(int Bpad);
