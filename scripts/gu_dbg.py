@@ -16,12 +16,14 @@ for i in range(2):
         names[8 + 8 * i + j] = f"epi{i}:{n}"
 for cta in sys.argv[2:] or ["0", "100", "147"]:
     os.environ["SONIC_PERSIST_DBG_CTA"] = cta
-    eng = Engine(1, L, mode="bf16", device=0, max_batch=B, max_prompt=320, max_new=64, debug=True)
+    eng = Engine(1, L, mode=os.environ.get("MODE", "bf16"), device=0, max_batch=B, max_prompt=320, max_new=64, debug=True)
     eng.load_state_dict(sd)
     segs = [synth_audio("speech", 320000, seed=i) for i in range(B)]
     prompts = [synthetic_prompt_ids(num_audio_tokens(320000)) for _ in range(B)]
     eng.transcribe_ids(segs, prompts, 24)
     d = eng.debug_read("rs_dbg", 80)
+    dd = eng.debug_read("persist_dbg", 1024)
+    print('      converter warp 2, per k block (raw landed, slot free, converted):', np.round(dd[100:130].reshape(10, 3) - dd[0], 2).tolist())
     print(f"cta {cta}: " + "  ".join(f"{names[i]}={d[i]:.2f}" for i in sorted(names) if d[i] >= 0 or i == 0))
     print('      per-warp end of phase', np.round(d[40:56], 2), ' after prefetch', np.round(d[60:76], 2))
     eng.close()

@@ -194,7 +194,8 @@ struct sonic_ctx {
   float* probe_logits = nullptr;       // [probe_steps][max_batch][vocab]
   int cur_step = 0;                    // index of the token the next decode step produces (host-side mirror of gs.step)
   int probe_batch = 0;
-  int persist_tc_min = 1;              // smallest live batch that uses the tcgen05 class (SONIC_PERSIST_TC_MIN; measured faster at every batch size)
+  int persist_tc_min = 1;              // smallest live batch that uses the tcgen05 class (SONIC_PERSIST_TC_MIN): bf16 1 (measured faster at every
+                                       // batch size), int8 17 (its converter warps are ALU-bound: below that the register-streaming class wins)
   bool persist_tc = false;             // live batches of 17..64 segments run the GEMM phases of the persistent kernel on tcgen05 (bf16)
   bool use_persist = false;            // one cooperative kernel per greedy step (bf16 mode; SONIC_DECODE=graph disables)
   DecLayerDev* dev_layers = nullptr;
@@ -588,6 +589,7 @@ struct Engine {
       p.w8 = h->is_int8 ? 1 : 0;
       p.tmaps = (h->persist_tc && B >= h->persist_tc_min) ? h->persist_tmaps : nullptr;
       p.kv_maps = h->persist_kv_maps; p.kc_base = reinterpret_cast<const bf16*>(h->kcache);
+      { const char* nt = getenv("SONIC_PERSIST_NTOK"); p.tc_ntok = nt ? atoi(nt) : (B <= 16 ? 16 : (B <= 32 ? 32 : 64)); if (p.tc_ntok < B || (p.tc_ntok != 16 && p.tc_ntok != 32)) p.tc_ntok = 64; }
       { const char* pd = getenv("SONIC_PERSIST_PRE"); p.tc_pre_depth = pd ? atoi(pd) : 6; }
       { const char* df = getenv("SONIC_PERSIST_DBGFLAGS"); p.dbg_flags = (h->cfg.debug && df) ? atoi(df) : 0; }
       { const char* dc = getenv("SONIC_PERSIST_DBG_CTA"); p.dbg_cta = (h->cfg.debug && dc) ? atoi(dc) : -1; }
@@ -768,7 +770,7 @@ int alloc_all(sonic_ctx* h) {
     DAZ(h->persist_ts, 2048 * 8);
     DA(h->persist_pick, decode_persist_pick_floats(B, h->num_sms) * 4);
     DA(h->dev_layers, (size_t)c.dec_layers * sizeof(DecLayerDev));
-    DA(h->persist_tmaps, (size_t)(4 * c.dec_layers + 4) * sizeof(CUtensorMap));
+    DA(h->persist_tmaps, (size_t)(4 * c.dec_layers + 10) * sizeof(CUtensorMap));
     DA(h->persist_kv_maps, 2 * sizeof(CUtensorMap));
   }
   if (h->use_rs) {
@@ -1161,23 +1163,34 @@ int sonic_finalize_weights(sonic_handle h) {
       CK(cudaMemcpy(h->persist_kv_maps, kvm, sizeof(kvm), cudaMemcpyHostToDevice));
     }
     const char* ptc = getenv("SONIC_PERSIST_TC");
-    h->persist_tc = !h->is_int8 && !(ptc && ptc[0] == '0');
-    { const char* tm = getenv("SONIC_PERSIST_TC_MIN"); h->persist_tc_min = tm ? atoi(tm) : 1; }
+    h->persist_tc = !(ptc && ptc[0] == '0');
+    { const char* tm = getenv("SONIC_PERSIST_TC_MIN"); h->persist_tc_min = tm ? atoi(tm) : (h->is_int8 ? 17 : 1); }
     if (h->persist_tc) {
-      // weight maps: {K, rows} with a 64 x 128 box; activation maps: {K, 64 token rows} with a 64 x 64 box (128B swizzle)
+      // weight maps: {K, rows} with a 64-k box of the phase's tile rows (bf16: 128B swizzle; int8: raw rows of 64 B, expanded by
+      // the kernel's converter warps); activation maps: {K, 64 token rows} with a 64 x 64 box (128B swizzle)
       const int L = h->cfg.dec_layers;
-      std::vector<CUtensorMap> maps(4 * L + 4);
+      std::vector<CUtensorMap> maps(4 * L + 10);
       for (int l = 0; l < L; ++l) {
         const DecLayerW& w = h->dec[l];
-        CK(make_tensor_map_2d(&maps[4 * l + 0], w.wqkv, kDecH, kQkvDec, kDecH, 64, kPersistQkvTileRows));
-        CK(make_tensor_map_2d(&maps[4 * l + 1], w.wo, kDecH, kDecH, kDecH, 64, kPersistOTileRows));
-        CK(make_tensor_map_2d(&maps[4 * l + 2], w.wgu, kDecH, 2 * kDecInter, kDecH, 64, kPersistGuTileRows));
-        CK(make_tensor_map_2d(&maps[4 * l + 3], w.wdown, kDecInter, kDecH, kDecInter, 64, kPersistDownTileRows));
+        if (h->is_int8) {
+          CK(make_tensor_map_2d_u8(&maps[4 * l + 0], w.wqkv, kDecH, kQkvDec, kDecH, 64, kPersistQkvTileRows));
+          CK(make_tensor_map_2d_u8(&maps[4 * l + 1], w.wo, kDecH, kDecH, kDecH, 64, kPersistOTileRows));
+          CK(make_tensor_map_2d_u8(&maps[4 * l + 2], w.wgu, kDecH, 2 * kDecInter, kDecH, 64, kPersistGuTileRows));
+          CK(make_tensor_map_2d_u8(&maps[4 * l + 3], w.wdown, kDecInter, kDecH, kDecInter, 64, kPersistDownTileRows));
+        } else {
+          CK(make_tensor_map_2d(&maps[4 * l + 0], w.wqkv, kDecH, kQkvDec, kDecH, 64, kPersistQkvTileRows));
+          CK(make_tensor_map_2d(&maps[4 * l + 1], w.wo, kDecH, kDecH, kDecH, 64, kPersistOTileRows));
+          CK(make_tensor_map_2d(&maps[4 * l + 2], w.wgu, kDecH, 2 * kDecInter, kDecH, 64, kPersistGuTileRows));
+          CK(make_tensor_map_2d(&maps[4 * l + 3], w.wdown, kDecInter, kDecH, kDecInter, 64, kPersistDownTileRows));
+        }
       }
       CK(make_tensor_map_2d(&maps[4 * L], h->lm_head, kDecH, kVocab, kDecH, 64, kPersistLmTileRows));
-      CK(make_tensor_map_2d(&maps[4 * L + 1], h->du, kDecH, kPersistTcTokens, kDecH, 64, kPersistTcTokens));
-      CK(make_tensor_map_2d(&maps[4 * L + 2], h->dattn, kDecH, kPersistTcTokens, kDecH, 64, kPersistTcTokens));
-      CK(make_tensor_map_2d(&maps[4 * L + 3], h->dact, kDecInter, kPersistTcTokens, kDecInter, 64, kPersistTcTokens));
+      for (int w = 0; w < 3; ++w) {                                 // token-tile widths 64, 32, 16
+        const int nt = 64 >> w;
+        CK(make_tensor_map_2d(&maps[4 * L + 1 + 3 * w], h->du, kDecH, kPersistTcTokens, kDecH, 64, nt));
+        CK(make_tensor_map_2d(&maps[4 * L + 2 + 3 * w], h->dattn, kDecH, kPersistTcTokens, kDecH, 64, nt));
+        CK(make_tensor_map_2d(&maps[4 * L + 3 + 3 * w], h->dact, kDecInter, kPersistTcTokens, kDecInter, 64, nt));
+      }
       CK(cudaMemcpy(h->persist_tmaps, maps.data(), maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice));
     }
   }

@@ -264,23 +264,46 @@ static constexpr int kTcStages = 6;                   // 8 measured no faster
 static constexpr int kTcStageA = 128 * 64 * 2, kTcStageB = kPersistTcTokens * 64 * 2;
 static constexpr int kTcRingBytes = kTcStages * (kTcStageA + kTcStageB) + 1024;     // + alignment slack
 static constexpr int kTcEpiBytes = 8 * 32 * 32 * 4;   // epilogue transpose buffers (TcCtx::epi)
+// int8 weights (W8): the 96 KB weight area of the ring holds six raw int8 stages (128 rows x 64 B = 8 KB, no swizzle) followed by
+// three bf16 slots (16 KB, SWIZZLE_128B) that warps 2..15 fill from the raw stages; the MMA reads the slots
+static constexpr int kTcRawA = 128 * 64, kTcConvSlots = 3, kTcConvWarps = 14;
+static constexpr int kTcConvBase = kTcStages * kTcRawA;
 struct TcCtx {
   uint32_t ringA, ringB, bars, tmem;
   uint32_t kb_count, item_count;
   uint32_t pre;                  // k blocks of the coming phase whose weight tile is already in flight (tc_prefetch_weights)
+  uint32_t ntok;                 // token rows of the activation tiles / MMA N of this launch: 16, 32 or 64 (>= live batch)
   uint64_t wpolicy;              // L2 policy of the weight / KV streams (evict_first), or 0: default
   uint32_t pre_depth;            // how many stages tc_prefetch_weights may fill before a grid barrier (<= kTcStages)
   float* epi;                    // 8 epilogue warps x [32 tokens][32 features] fp32 transpose buffers
+  uint8_t* ring_gen;             // generic-address view of ringA (int8 converter warps)
 };
 __device__ __forceinline__ uint32_t tc_full(const TcCtx& c, uint32_t s) { return c.bars + 8u * s; }
 __device__ __forceinline__ uint32_t tc_empty(const TcCtx& c, uint32_t s) { return c.bars + 8u * (kTcStages + s); }
 __device__ __forceinline__ uint32_t tc_acc_full(const TcCtx& c, uint32_t a) { return c.bars + 8u * (2 * kTcStages + a); }
 __device__ __forceinline__ uint32_t tc_acc_empty(const TcCtx& c, uint32_t a) { return c.bars + 8u * (2 * kTcStages + 2 + a); }
+__device__ __forceinline__ uint32_t tc_conv_full(const TcCtx& c, uint32_t s) { return c.bars + 8u * (2 * kTcStages + 4 + s); }
+__device__ __forceinline__ uint32_t tc_conv_empty(const TcCtx& c, uint32_t s) { return c.bars + 8u * (2 * kTcStages + 4 + kTcConvSlots + s); }
+// (An fp16 expansion — one PRMT per two values — would halve the ALU work of the converters, but tcgen05 kind::f16 rejects an fp16 A
+// operand next to a bf16 B operand: illegal instruction, measured.)
+// four int8 of a word (already XORed with 0x80808080: bytes are value + 128) -> two bf16 pairs, exactly: the byte is placed in the
+// low mantissa bits of 2^23 and (2^23 + 128) is subtracted — one PRMT + one FADD per value instead of an I2F
+__device__ __forceinline__ void u8x4_to_bf16x2(uint32_t w, uint32_t& lo, uint32_t& hi) {
+  const float f0 = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7540)) - 8388736.0f;
+  const float f1 = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7541)) - 8388736.0f;
+  const float f2 = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7542)) - 8388736.0f;
+  const float f3 = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7543)) - 8388736.0f;
+  __nv_bfloat162 a = __floats2bfloat162_rn(f0, f1), b = __floats2bfloat162_rn(f2, f3);
+  lo = *reinterpret_cast<uint32_t*>(&a);
+  hi = *reinterpret_cast<uint32_t*>(&b);
+}
 
 // Weights do not depend on the previous phase: thread 0 (the producer) puts the weight tiles of this CTA's first k blocks of
 // the NEXT tcgen05 phase in flight (arming the stage for weight + activation bytes) before the grid barrier / while a
 // non-GEMM phase runs; the producer of that phase then only adds the activation tiles.  Every thread computes `pre`.
+template <bool W8 = false>
 __device__ __forceinline__ void tc_prefetch_weights(const CUtensorMap* wmap, int N, int K, int splits, TcCtx& tc, int tile_rows = 128) {
+  constexpr int kRowB = W8 ? 64 : 128, kStA = W8 ? kTcRawA : kTcStageA;
   const int tiles = (N + tile_rows - 1) / tile_rows, nkb = K >> 6, n_items = tiles * splits;
   uint32_t n = 0;
   for (int item = blockIdx.x; item < n_items && n < tc.pre_depth; item += gridDim.x) {
@@ -290,19 +313,20 @@ __device__ __forceinline__ void tc_prefetch_weights(const CUtensorMap* wmap, int
       if (threadIdx.x < 32 && elect_one_sync()) {
         const uint32_t cnt = tc.kb_count + n, st = cnt % kTcStages, par = (cnt / kTcStages) & 1u;
         mbar_wait(tc_empty(tc, st), par ^ 1u);
-        mbar_expect_tx(tc_full(tc, st), tile_rows * 128 + kTcStageB);
-        if (tc.wpolicy) tma_load_2d_hint(tc.ringA + st * kTcStageA, wmap, tc_full(tc, st), kb * 64, tile * tile_rows, tc.wpolicy);
-        else tma_load_2d(tc.ringA + st * kTcStageA, wmap, tc_full(tc, st), kb * 64, tile * tile_rows);
+        mbar_expect_tx(tc_full(tc, st), tile_rows * kRowB + tc.ntok * 128);
+        if (tc.wpolicy) tma_load_2d_hint(tc.ringA + st * kStA, wmap, tc_full(tc, st), kb * 64, tile * tile_rows, tc.wpolicy);
+        else tma_load_2d(tc.ringA + st * kStA, wmap, tc_full(tc, st), kb * 64, tile * tile_rows);
       }
     }
   }
   tc.pre = n;
 }
 
-template <int EPI>
+template <int EPI, bool W8 = false>
 __device__ __forceinline__ void gemm_phase_tc(const CUtensorMap* wmap, const CUtensorMap* xmap, int N, int K, int splits, int B, int Bpad,
                                               float* __restrict__ out32, bf16* __restrict__ act, TcCtx& tc, int tile_rows = 128,
-                                              unsigned long long* dbg = nullptr, int dbgf = 0) {
+                                              unsigned long long* dbg = nullptr, int dbgf = 0, const float* __restrict__ wscale = nullptr) {
+  constexpr int kRowB = W8 ? 64 : 128, kStA = W8 ? kTcRawA : kTcStageA;
   // tile_rows: weight rows per item (the box height of `wmap`).  128 fills the MMA tile; a smaller value (gate/up: 84, so that
   // 147 whole-K items cover the 12288 rows, one per CTA) leaves the remaining rows of the 128-row shared-memory tile stale:
   // they only feed accumulator rows the epilogue never reads.  Rows past N are zero-filled by TMA.
@@ -319,9 +343,9 @@ __device__ __forceinline__ void gemm_phase_tc(const CUtensorMap* wmap, const CUt
           const uint32_t st = cnt % kTcStages, par = (cnt / kTcStages) & 1u;
           if (idx >= tc.pre) {
             mbar_wait(tc_empty(tc, st), par ^ 1u);
-            mbar_expect_tx(tc_full(tc, st), tile_rows * 128 + kTcStageB);
-            if (tc.wpolicy) tma_load_2d_hint(tc.ringA + st * kTcStageA, wmap, tc_full(tc, st), kb * 64, tile * tile_rows, tc.wpolicy);
-            else tma_load_2d(tc.ringA + st * kTcStageA, wmap, tc_full(tc, st), kb * 64, tile * tile_rows);
+            mbar_expect_tx(tc_full(tc, st), tile_rows * kRowB + tc.ntok * 128);
+            if (tc.wpolicy) tma_load_2d_hint(tc.ringA + st * kStA, wmap, tc_full(tc, st), kb * 64, tile * tile_rows, tc.wpolicy);
+            else tma_load_2d(tc.ringA + st * kStA, wmap, tc_full(tc, st), kb * 64, tile * tile_rows);
           }
           tma_load_2d(tc.ringB + st * kTcStageB, xmap, tc_full(tc, st), kb * 64, 0);
         }
@@ -330,7 +354,7 @@ __device__ __forceinline__ void gemm_phase_tc(const CUtensorMap* wmap, const CUt
     }
   } else if (warp == 1) {
     if (elect_one_sync()) {
-      constexpr uint32_t idesc = make_idesc_bf16(128, kPersistTcTokens);
+      const uint32_t idesc = make_idesc_bf16(128, (int)tc.ntok);
       uint32_t cnt = tc.kb_count, ic = tc.item_count;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++ic) {
         const int tile = item / splits, ks = item - tile * splits;
@@ -340,35 +364,96 @@ __device__ __forceinline__ void gemm_phase_tc(const CUtensorMap* wmap, const CUt
         tc_fence_after();
         for (int kb = kb0; kb < kb1; ++kb, ++cnt) {
           const uint32_t st = cnt % kTcStages, par = (cnt / kTcStages) & 1u;
-          mbar_wait(tc_full(tc, st), par);
+          const uint32_t cs = cnt % kTcConvSlots, cpar = (cnt / kTcConvSlots) & 1u;
+          if (W8) mbar_wait(tc_conv_full(tc, cs), cpar);              // the converters waited for the raw stage (and its X tile)
+          else mbar_wait(tc_full(tc, st), par);
           tc_fence_after();
           if (dbg && kb == kb0) dbg[3 + (item >= (int)gridDim.x)] = gtimer();   // first stage of item 0 / 1 landed
-          const uint64_t da = make_sw128_desc(tc.ringA + st * kTcStageA), db = make_sw128_desc(tc.ringB + st * kTcStageB);
+          const uint64_t da = make_sw128_desc(W8 ? tc.ringA + kTcConvBase + cs * kTcStageA : tc.ringA + st * kTcStageA);
+          const uint64_t db = make_sw128_desc(tc.ringB + st * kTcStageB);
 #pragma unroll
           for (int k = 0; k < 4; ++k)
             tc_mma_bf16(tc.tmem + acc * kPersistTcTokens, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb > kb0 || k != 0) ? 1u : 0u);
           tc_commit(tc_empty(tc, st));
+          if (W8) tc_commit(tc_conv_empty(tc, cs));
         }
         tc_commit(tc_acc_full(tc, acc));
         if (dbg) dbg[5 + (item >= (int)gridDim.x)] = gtimer();       // all MMAs of item 0 / 1 issued
       }
     }
-  } else if (warp >= 4 && warp < 12) {
-    // Epilogue: lane = weight row (TMEM lane), registers = 32 tokens.  The outputs are token-major, so the 32 x 32 block is
-    // transposed through a per-warp shared-memory buffer and leaves as 16 B vectors: lane (tr, fc) handles token rows
+  } else if (warp >= 2 && (W8 || (warp >= 4 && warp < 12))) {
+    // Warps 4..11: epilogue — lane = weight row (TMEM lane), registers = 32 tokens.  The outputs are token-major, so the 32 x 32
+    // block is transposed through a per-warp shared-memory buffer and leaves as 16 B vectors: lane (tr, fc) handles token rows
     // tr + 4 i (i = 0..7), features fc..fc+3 — 8 vector stores per lane instead of 32 scalar ones (measured: the scalar
     // version spent 1.3 us issuing the fp32 stores and 3.8 us in the SwiGLU stores of one item).
+    // int8 weights: warps 2..15 (the epilogue warps included — every int8 phase has at most one item per CTA, so they are idle
+    // until its accumulator completes) first expand the item's raw int8 stages to bf16: thread piece = (row r, 16 values j) of
+    // a stage, 16 B in, two 16 B chunks out at their SWIZZLE_128B places (chunk c of row r lives at c ^ (r & 7)); rows past the
+    // tile are left alone.
+    const bool is_epi = warp >= 4 && warp < 12;
     const int q = warp & 3, half = (warp - 4) >> 2;
     float* eb = tc.epi + (warp - 4) * 1024;
     const int tr = lane >> 3, fc = (lane & 7) * 4;
-    uint32_t ic = tc.item_count;
+    uint32_t ic = tc.item_count, ccnt = tc.kb_count;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++ic) {
       const int tile = item / splits, ks = item - tile * splits;
+      if (W8) {
+        const int kb0 = (ks * nkb) / splits, kb1 = ((ks + 1) * nkb) / splits;
+        const int n_pieces = min(tile_rows, N - tile * tile_rows) * 4;
+        // this thread's (at most two) pieces: offsets are the same for every k block
+        const int i0 = (warp - 2) * 32 + lane, i1 = i0 + kTcConvWarps * 32;
+        const bool v0 = i0 < n_pieces, v1 = i1 < n_pieces;
+        const int r0 = i0 >> 2, j0 = i0 & 3, r1 = i1 >> 2, j1 = i1 & 3;
+        const int s0 = i0 * 16, s1 = i1 * 16;
+        const int d00 = r0 * 128 + (((2 * j0) ^ (r0 & 7)) << 4), d01 = r0 * 128 + (((2 * j0 + 1) ^ (r0 & 7)) << 4);
+        const int d10 = r1 * 128 + (((2 * j1) ^ (r1 & 7)) << 4), d11 = r1 * 128 + (((2 * j1 + 1) ^ (r1 & 7)) << 4);
+        uint32_t st = ccnt % kTcStages, par = (ccnt / kTcStages) & 1u;
+        uint32_t cs = ccnt % kTcConvSlots, cpar = (ccnt / kTcConvSlots) & 1u;
+        for (int kb = kb0; kb < kb1; ++kb, ++ccnt) {
+          unsigned long long* dc = (dbg && warp == 2 && lane == 0 && kb - kb0 < 10) ? dbg + 100 + 3 * (kb - kb0) : nullptr;
+          mbar_wait(tc_full(tc, st), par);
+          if (dc) dc[0] = gtimer();
+          mbar_wait(tc_conv_empty(tc, cs), cpar ^ 1u);
+          if (dc) dc[1] = gtimer();
+          const uint8_t* raw = tc.ring_gen + st * kTcRawA;
+          uint8_t* dst = tc.ring_gen + kTcConvBase + cs * kTcStageA;
+          uint4 w0 = make_uint4(0, 0, 0, 0), w1 = make_uint4(0, 0, 0, 0);
+          if (v0) w0 = *reinterpret_cast<const uint4*>(raw + s0);
+          if (v1) w1 = *reinterpret_cast<const uint4*>(raw + s1);
+          if (v0) {
+            uint32_t o[8];
+            u8x4_to_bf16x2(w0.x ^ 0x80808080u, o[0], o[1]); u8x4_to_bf16x2(w0.y ^ 0x80808080u, o[2], o[3]);
+            u8x4_to_bf16x2(w0.z ^ 0x80808080u, o[4], o[5]); u8x4_to_bf16x2(w0.w ^ 0x80808080u, o[6], o[7]);
+            *reinterpret_cast<uint4*>(dst + d00) = make_uint4(o[0], o[1], o[2], o[3]);
+            *reinterpret_cast<uint4*>(dst + d01) = make_uint4(o[4], o[5], o[6], o[7]);
+          }
+          if (v1) {
+            uint32_t o[8];
+            u8x4_to_bf16x2(w1.x ^ 0x80808080u, o[0], o[1]); u8x4_to_bf16x2(w1.y ^ 0x80808080u, o[2], o[3]);
+            u8x4_to_bf16x2(w1.z ^ 0x80808080u, o[4], o[5]); u8x4_to_bf16x2(w1.w ^ 0x80808080u, o[6], o[7]);
+            *reinterpret_cast<uint4*>(dst + d10) = make_uint4(o[0], o[1], o[2], o[3]);
+            *reinterpret_cast<uint4*>(dst + d11) = make_uint4(o[4], o[5], o[6], o[7]);
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tc_conv_full(tc, cs));
+          if (dc) dc[2] = gtimer();
+          if (++st == (uint32_t)kTcStages) { st = 0; par ^= 1u; }
+          if (++cs == (uint32_t)kTcConvSlots) { cs = 0; cpar ^= 1u; }
+        }
+      }
+      if (!is_epi) continue;
       const uint32_t acc = ic & 1u, apar = (ic >> 1) & 1u;
       mbar_wait(tc_acc_full(tc, acc), apar);
       tc_fence_after();
       unsigned long long* dw = (dbg && warp == 4 && lane == 0) ? dbg + 8 + 8 * (item >= (int)gridDim.x) : nullptr;
       if (dw) dw[0] = gtimer();                                     // accumulator complete
+      if (half * 32 >= (int)tc.ntok) {                              // no token of this half exists at this tile width
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tc_acc_empty(tc, acc));
+        continue;
+      }
       {
         uint32_t v[32];
         tmem_ld32(tc.tmem + ((uint32_t)(q * 32) << 16) + acc * kPersistTcTokens + half * 32, v);
@@ -376,8 +461,10 @@ __device__ __forceinline__ void gemm_phase_tc(const CUtensorMap* wmap, const CUt
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(tc_acc_empty(tc, acc));         // the accumulator is in registers: the next item may start
+        float rs = 1.0f;                                           // int8 weights: dequantisation scale of this lane's weight row
+        if (W8) { const int lr = q * 32 + lane, row = tile * tile_rows + lr; rs = (lr < tile_rows && row < N) ? __ldg(wscale + row) : 0.f; }
 #pragma unroll
-        for (int j = 0; j < 32; ++j) eb[j * 32 + lane] = __uint_as_float(v[j]);
+        for (int j = 0; j < 32; ++j) eb[j * 32 + lane] = W8 ? __uint_as_float(v[j]) * rs : __uint_as_float(v[j]);
       }
       __syncwarp();
       const int feat = tile * tile_rows + q * 32 + fc;              // first of this lane's 4 features
@@ -867,10 +954,10 @@ static constexpr int kTcSplitQkv = 6, kTcSplitO = 9, kTcSplitDown = 9;
 
 template <bool W8, int NT, bool TC>
 __global__ void __launch_bounds__(kPThreads, 1) decode_persist_kernel(DecodePersistArgs a) {
-  static_assert(!TC || (!W8 && NT == 8), "tcgen05 phases: bf16 weights, 64-token class");
+  static_assert(!TC || NT == 8, "tcgen05 phases: one instantiation (64-token tiles) per weight type");
   extern __shared__ __align__(16) uint8_t smem[];
   __shared__ float red[32];
-  __shared__ __align__(8) uint64_t tc_bars[2 * kTcStages + 4];
+  __shared__ __align__(8) uint64_t tc_bars[2 * kTcStages + 4 + 2 * kTcConvSlots];
   __shared__ uint32_t tc_tmem_slot;
   __shared__ __align__(8) uint64_t attn_bars[4];                  // [team][buffer] K/V chunk arrival
   __shared__ int s_ctx[64];                                       // context length of every segment (constant until the pick phase)
@@ -887,18 +974,22 @@ __global__ void __launch_bounds__(kPThreads, 1) decode_persist_kernel(DecodePers
   }
   if (!TC) __syncthreads();
   const CUtensorMap* tmaps = reinterpret_cast<const CUtensorMap*>(a.tmaps);
-  const CUtensorMap* xmaps = tmaps + 4 * a.n_layers + 1;                    // u, attn, act
+  // activation maps {u, attn, act} x token-tile widths {64, 32, 16}
+  const CUtensorMap* xmaps = tmaps + 4 * a.n_layers + 1 + (a.tc_ntok == 64 ? 0 : (a.tc_ntok == 32 ? 3 : 6));
   if (TC) {
     const uint32_t raw = smem_u32(smem);
     tc.ringA = (raw + 1023u) & ~1023u;
     tc.ringB = tc.ringA + kTcStages * kTcStageA;
     tc.bars = smem_u32(tc_bars);
+    tc.ring_gen = smem + (tc.ringA - raw);
     tc.kb_count = 0; tc.item_count = 0; tc.pre = 0;
     tc.pre_depth = (uint32_t)min(max(a.tc_pre_depth, 0), kTcStages);
+    tc.ntok = (uint32_t)a.tc_ntok;
     tc.wpolicy = (a.dbg_flags & 8) ? 0ull : l2_policy_evict_first();
     if (tid == 32) {
       for (int s = 0; s < kTcStages; ++s) { mbar_init(tc_full(tc, s), 1); mbar_init(tc_empty(tc, s), 1); }
       for (int i = 0; i < 2; ++i) { mbar_init(tc_acc_full(tc, i), 1); mbar_init(tc_acc_empty(tc, i), 8); }
+      for (int i = 0; i < kTcConvSlots; ++i) { mbar_init(tc_conv_full(tc, i), kTcConvWarps); mbar_init(tc_conv_empty(tc, i), 1); }
       fence_barrier_init();
     }
     if ((tid >> 5) == 2) tmem_alloc<2 * kPersistTcTokens>(smem_u32(&tc_tmem_slot));
@@ -906,7 +997,7 @@ __global__ void __launch_bounds__(kPThreads, 1) decode_persist_kernel(DecodePers
     __syncthreads();
     tc_fence_after();
     tc.tmem = tc_tmem_slot;
-    tc_prefetch_weights(tmaps, PQKV, PH, kTcSplitQkv, tc, kPersistQkvTileRows);
+    tc_prefetch_weights<W8>(tmaps, PQKV, PH, kTcSplitQkv, tc, kPersistQkvTileRows);
   }
   // attention: K/V chunk buffers overlay the (then idle) TMA ring / GEMM staging area, the small per-team arrays sit after it
   constexpr int ATW = (NT == 8) ? 8 : 16;                 // attention team width of this batch class
@@ -936,7 +1027,7 @@ __global__ void __launch_bounds__(kPThreads, 1) decode_persist_kernel(DecodePers
   for (int l = 0; l < a.n_layers; ++l) {
     const DecLayerDev L = a.layers[l];
     if (TC) {
-      gemm_phase_tc<EPI_F32>(tmaps + 4 * l, xmaps, PQKV, PH, kTcSplitQkv, B, Bpad, a.part, nullptr, tc, kPersistQkvTileRows);
+      gemm_phase_tc<EPI_F32, W8>(tmaps + 4 * l, xmaps, PQKV, PH, kTcSplitQkv, B, Bpad, a.part, nullptr, tc, kPersistQkvTileRows, nullptr, 0, L.sqkv);
     } else gemm_dispatch<EPI_F32, W8, NT>(L.wqkv, L.sqkv, PQKV, PH, a.u, B, Bpad, a.part, nullptr, nullptr, smem);
     grid_barrier<TC>(a.bar, epoch); STAMP();
     if (a.attn_chunks > 1) attention_phase<TC ? kTcSplitQkv : 1>(a, L, TC ? smem_kv : smem, s_ctx, (a.timestamps && l == 1 && (int)blockIdx.x == a.dbg_cta) ? a.timestamps + 1024 + 900 : nullptr);   // few segments: split the keys over CTAs
@@ -945,12 +1036,12 @@ __global__ void __launch_bounds__(kPThreads, 1) decode_persist_kernel(DecodePers
       // the attention phase read / wrote the ring's shared memory through the generic proxy; TMA overwrites it next
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncthreads();
-      tc_prefetch_weights(tmaps + 4 * l + 1, PH, PH, kTcSplitO, tc, kPersistOTileRows);      // the ring is free again
+      tc_prefetch_weights<W8>(tmaps + 4 * l + 1, PH, PH, kTcSplitO, tc, kPersistOTileRows);      // the ring is free again
     }
     grid_barrier<TC>(a.bar, epoch); STAMP();
     if (TC) {
-      gemm_phase_tc<EPI_F32>(tmaps + 4 * l + 1, xmaps + 1, PH, PH, kTcSplitO, B, Bpad, a.part, nullptr, tc, kPersistOTileRows);
-      tc_prefetch_weights(tmaps + 4 * l + 2, 2 * PI, PH, 1, tc, kPersistGuTileRows);
+      gemm_phase_tc<EPI_F32, W8>(tmaps + 4 * l + 1, xmaps + 1, PH, PH, kTcSplitO, B, Bpad, a.part, nullptr, tc, kPersistOTileRows, nullptr, 0, L.so);
+      tc_prefetch_weights<W8>(tmaps + 4 * l + 2, 2 * PI, PH, 1, tc, kPersistGuTileRows);
       grid_barrier<TC>(a.bar, epoch); STAMP();
       residual_norm_phase<kTcSplitO>(a.part, B, Bpad, a.x, a.u, L.rms2, a.eps, red);
     } else {
@@ -963,11 +1054,11 @@ __global__ void __launch_bounds__(kPThreads, 1) decode_persist_kernel(DecodePers
     const bool dbg_all = a.timestamps && a.dbg_cta == -2 && l == 1;      // CTA-uniform
     if (dbg_all && tid == 0) a.timestamps[1024 + blockIdx.x] = gtimer();
     if (TC) {
-      gemm_phase_tc<EPI_SWIGLU>(tmaps + 4 * l + 2, xmaps, 2 * PI, PH, 1, B, Bpad, nullptr, a.act, tc, kPersistGuTileRows,
-                                (a.timestamps && l == 1 && (int)blockIdx.x == a.dbg_cta) ? a.timestamps + 1024 : nullptr, a.dbg_flags);
+      gemm_phase_tc<EPI_SWIGLU, W8>(tmaps + 4 * l + 2, xmaps, 2 * PI, PH, 1, B, Bpad, nullptr, a.act, tc, kPersistGuTileRows,
+                                (a.timestamps && l == 1 && (int)blockIdx.x == a.dbg_cta) ? a.timestamps + 1024 : nullptr, a.dbg_flags, L.sgu);
       const bool wd = a.timestamps && l == 1 && (int)blockIdx.x == a.dbg_cta && (tid & 31) == 0;
       if (wd) a.timestamps[1024 + 40 + (tid >> 5)] = gtimer();
-      tc_prefetch_weights(tmaps + 4 * l + 3, PH, PI, kTcSplitDown, tc, kPersistDownTileRows);
+      tc_prefetch_weights<W8>(tmaps + 4 * l + 3, PH, PI, kTcSplitDown, tc, kPersistDownTileRows);
       if (wd) a.timestamps[1024 + 60 + (tid >> 5)] = gtimer();
     } else gemm_dispatch<EPI_SWIGLU, W8, NT>(L.wgu, L.sgu, 2 * PI, PH, a.u, B, Bpad, nullptr, nullptr, a.act, smem);
     if (dbg_all) { __syncthreads(); if (tid == 0) a.timestamps[1024 + 160 + blockIdx.x] = gtimer(); }
@@ -975,9 +1066,14 @@ __global__ void __launch_bounds__(kPThreads, 1) decode_persist_kernel(DecodePers
     if (dbg_all && tid == 0) a.timestamps[1024 + 320 + blockIdx.x] = gtimer();
     const float* next_gamma = (l + 1 < a.n_layers) ? a.layers[l + 1].rms1 : a.final_norm;
     if (TC) {
-      gemm_phase_tc<EPI_F32>(tmaps + 4 * l + 3, xmaps + 2, PH, PI, kTcSplitDown, B, Bpad, a.part, nullptr, tc, kPersistDownTileRows);
-      if (l + 1 < a.n_layers) tc_prefetch_weights(tmaps + 4 * (l + 1), PQKV, PH, kTcSplitQkv, tc, kPersistQkvTileRows);
-      else tc_prefetch_weights(tmaps + 4 * a.n_layers, PV_, PH, 1, tc, kPersistLmTileRows);
+      gemm_phase_tc<EPI_F32, W8>(tmaps + 4 * l + 3, xmaps + 2, PH, PI, kTcSplitDown, B, Bpad, a.part, nullptr, tc, kPersistDownTileRows, nullptr, 0, L.sdown);
+      if (l + 1 < a.n_layers) tc_prefetch_weights<W8>(tmaps + 4 * (l + 1), PQKV, PH, kTcSplitQkv, tc, kPersistQkvTileRows);
+      else {
+        // the lm_head stays bf16 in int8 mode: its 16 KB stages overlay the raw stages / converter slots, so every MMA of the
+        // int8 layout must have retired (all epilogue warps have drained their accumulators) before the first load lands
+        if (W8) __syncthreads();
+        tc_prefetch_weights<false>(tmaps + 4 * a.n_layers, PV_, PH, 1, tc, kPersistLmTileRows);
+      }
       grid_barrier<TC>(a.bar, epoch); STAMP();
       residual_norm_phase<kTcSplitDown>(a.part, B, Bpad, a.x, a.u, next_gamma, a.eps, red);
     } else {
@@ -989,7 +1085,7 @@ __global__ void __launch_bounds__(kPThreads, 1) decode_persist_kernel(DecodePers
   }
 
   // ---- lm_head + greedy pick: every CTA scans its slice of the vocabulary for all tokens, CTA b merges token b
-  if (TC) gemm_phase_tc<EPI_F32>(tmaps + 4 * a.n_layers, xmaps, PV_, PH, 1, B, Bpad, a.part, nullptr, tc, kPersistLmTileRows);
+  if (TC) gemm_phase_tc<EPI_F32, false>(tmaps + 4 * a.n_layers, xmaps, PV_, PH, 1, B, Bpad, a.part, nullptr, tc, kPersistLmTileRows);
   else gemm_dispatch<EPI_F32, false, NT>(a.lm_head, nullptr, PV_, PH, a.u, B, Bpad, a.part, nullptr, nullptr, smem);
   grid_barrier<TC>(a.bar, epoch); STAMP();
   {
@@ -1087,17 +1183,18 @@ size_t decode_persist_part_floats(int Bpad) { return (size_t)PV_ * Bpad; }     /
 size_t decode_persist_pick_floats(int max_batch, int num_sms) { return (size_t)max_batch * num_sms * 4; }
 
 typedef void (*PersistKernel)(DecodePersistArgs);
-static constexpr int kPersistVariants = 9;
+static constexpr int kPersistVariants = 10;
 static PersistKernel persist_variant(int i) {
   static const PersistKernel tab[kPersistVariants] = {
       decode_persist_kernel<false, 1, false>, decode_persist_kernel<false, 2, false>, decode_persist_kernel<false, 4, false>,
       decode_persist_kernel<false, 8, false>, decode_persist_kernel<true, 1, false>,  decode_persist_kernel<true, 2, false>,
-      decode_persist_kernel<true, 4, false>,  decode_persist_kernel<true, 8, false>,  decode_persist_kernel<false, 8, true>};
+      decode_persist_kernel<true, 4, false>,  decode_persist_kernel<true, 8, false>,  decode_persist_kernel<false, 8, true>,
+      decode_persist_kernel<true, 8, true>};
   return tab[i];
 }
 static PersistKernel persist_kernel_for(bool w8, int B, bool tc) {
   const int cls = B <= 8 ? 0 : (B <= 16 ? 1 : (B <= 32 ? 2 : 3));
-  if (tc && !w8) return persist_variant(8);                       // bf16 and the caller passed tensor maps: tcgen05 phases
+  if (tc) return persist_variant(w8 ? 9 : 8);                     // the caller passed tensor maps: tcgen05 phases
   return persist_variant((w8 ? 4 : 0) + cls);
 }
 
@@ -1105,7 +1202,7 @@ int decode_persist_occupancy() {
   int worst = 1 << 30;
   for (int i = 0; i < kPersistVariants; ++i) {
     int per_sm = -1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, persist_variant(i), kPThreads, persist_smem_for(i == 8));
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, persist_variant(i), kPThreads, persist_smem_for(i >= 8));
     if (per_sm < worst) worst = per_sm;
   }
   return worst;
@@ -1121,7 +1218,7 @@ int decode_persist_max_grid(int num_sms) {
 
 cudaError_t decode_persist_configure() {
   for (int i = 0; i < kPersistVariants; ++i)
-    SONIC_CUDA_TRY(cudaFuncSetAttribute(persist_variant(i), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)persist_smem_for(i == 8)));
+    SONIC_CUDA_TRY(cudaFuncSetAttribute(persist_variant(i), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)persist_smem_for(i >= 8)));
   return cudaSuccess;
 }
 
@@ -1129,7 +1226,7 @@ cudaError_t launch_decode_persist(const DecodePersistArgs& a, int grid, cudaStre
   if (grid < 1 || a.B < 1 || a.B > 64) return cudaErrorInvalidConfiguration;
   const int num_sms = grid;
   PersistKernel kern = persist_kernel_for(a.w8 != 0, a.B, a.tmaps != nullptr);
-  const size_t smem_bytes = persist_smem_for(kern == persist_variant(8));
+  const size_t smem_bytes = persist_smem_for(kern == persist_variant(8) || kern == persist_variant(9));
   {
     cudaError_t me = cudaMemsetAsync(a.bar, 0, sizeof(unsigned), st);
     if (me != cudaSuccess) { fprintf(stderr, "[sonicscribe_b200] barrier memset failed: %s\n", cudaGetErrorName(me)); return me; }
