@@ -7,8 +7,8 @@ mkdir -p "$OUT"
 CS="${COMPUTE_SANITIZER:-/usr/local/cuda/bin/compute-sanitizer}"
 SUMMARY="$OUT/summary.txt"
 : > "$SUMMARY"
-for tool in memcheck racecheck; do
-  for c in smoke_fp32 smoke_bf16 b3 b20 b64 int8_b2; do
+for tool in ${SANITIZE_TOOLS:-memcheck racecheck}; do
+  for c in ${SANITIZE_CASES:-smoke_fp32 smoke_bf16 b3 b20 b64 int8_b2 int8_b20}; do
     log="$OUT/${tool}_${c}.log"
     SANITIZE_TOKENS=3 timeout "${SANITIZE_TIMEOUT:-420}" "$CS" --tool "$tool" --error-exitcode 7 --print-limit 20 \
         python scripts/sanitize_target.py "$c" > "$log" 2>&1

@@ -1,5 +1,5 @@
 """Target of scripts/sanitize.sh: a short pass over every kernel family on the tiny (2+2 layer) model — the smoke path
-(fp32 + bf16, one segment) and persistent decode steps at 64 / 20 / 3 segments (bf16) and 2 segments (int8)."""
+(fp32 + bf16, one segment) and persistent decode steps at 64 / 20 / 3 segments (bf16) and 2 / 20 segments (int8: register-streaming class / tcgen05 class with converter warps)."""
 import os
 import sys
 
@@ -14,7 +14,7 @@ from sonicscribe_b200.weights import ModelDims, synthetic_state_dict  # noqa: E4
 what = sys.argv[1] if len(sys.argv) > 1 else "all"
 steps = int(os.environ.get("SANITIZE_TOKENS", "3"))
 sd = synthetic_state_dict(ModelDims(enc_layers=2, dec_layers=2), seed=0)
-cases = {"smoke_fp32": ("fp32", 1), "smoke_bf16": ("bf16", 1), "b64": ("bf16", 64), "b20": ("bf16", 20), "b3": ("bf16", 3), "int8_b2": ("int8", 2)}
+cases = {"smoke_fp32": ("fp32", 1), "smoke_bf16": ("bf16", 1), "b64": ("bf16", 64), "b20": ("bf16", 20), "b3": ("bf16", 3), "int8_b2": ("int8", 2), "int8_b20": ("int8", 20)}
 for name, (mode, B) in cases.items():
     if what not in ("all", name):
         continue
