@@ -261,9 +261,9 @@ __device__ __forceinline__ void gemm_dispatch(const void* W, const float* wscale
 // The ring / accumulator barriers live for the whole kernel; their phase is derived from running counters that every thread
 // advances identically.
 static constexpr int kTcStages = 6;                   // 8 measured no faster
-static constexpr int kTcStageA = 128 * 64 * 2, kTcStageB = kPersistTcTokens * 64 * 2;
+static constexpr int kTcStageA = 128 * 64 * 2, kTcStageB = kPersistTcMaxTokens * 64 * 2;
 static constexpr int kTcRingBytes = kTcStages * (kTcStageA + kTcStageB) + 1024;     // + alignment slack
-static constexpr int kTcEpiBytes = 8 * 32 * 32 * 4;   // epilogue transpose buffers (TcCtx::epi)
+static constexpr int kTcEpiBytes = 8 * 16 * 32 * 4;   // epilogue transpose buffers (TcCtx::epi): [16 tokens][32 features] fp32 per warp
 // int8 weights (W8): the 96 KB weight area of the ring holds six raw int8 stages (128 rows x 64 B = 8 KB, no swizzle) followed by
 // three bf16 slots (16 KB, SWIZZLE_128B) that warps 2..15 fill from the raw stages; the MMA reads the slots
 static constexpr int kTcRawA = 128 * 64, kTcConvSlots = 3, kTcConvWarps = 14;
@@ -373,7 +373,7 @@ __device__ __forceinline__ void gemm_phase_tc(const CUtensorMap* wmap, const CUt
           const uint64_t db = make_sw128_desc(tc.ringB + st * kTcStageB);
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            tc_mma_bf16(tc.tmem + acc * kPersistTcTokens, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb > kb0 || k != 0) ? 1u : 0u);
+            tc_mma_bf16(tc.tmem + acc * kPersistTcMaxTokens, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb > kb0 || k != 0) ? 1u : 0u);
           tc_commit(tc_empty(tc, st));
           if (W8) tc_commit(tc_conv_empty(tc, cs));
         }
@@ -392,7 +392,7 @@ __device__ __forceinline__ void gemm_phase_tc(const CUtensorMap* wmap, const CUt
     // tile are left alone.
     const bool is_epi = warp >= 4 && warp < 12;
     const int q = warp & 3, half = (warp - 4) >> 2;
-    float* eb = tc.epi + (warp - 4) * 1024;
+    float* eb = tc.epi + (warp - 4) * 512;
     const int tr = lane >> 3, fc = (lane & 7) * 4;
     uint32_t ic = tc.item_count, ccnt = tc.kb_count;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++ic) {
@@ -448,50 +448,58 @@ __device__ __forceinline__ void gemm_phase_tc(const CUtensorMap* wmap, const CUt
       tc_fence_after();
       unsigned long long* dw = (dbg && warp == 4 && lane == 0) ? dbg + 8 + 8 * (item >= (int)gridDim.x) : nullptr;
       if (dw) dw[0] = gtimer();                                     // accumulator complete
-      if (half * 32 >= (int)tc.ntok) {                              // no token of this half exists at this tile width
+      float rs = 1.0f;                                             // int8 weights: dequantisation scale of this lane's weight row
+      if (W8) { const int lr = q * 32 + lane, row = tile * tile_rows + lr; rs = (lr < tile_rows && row < N) ? __ldg(wscale + row) : 0.f; }
+      const int feat = tile * tile_rows + q * 32 + fc;              // first of this lane's 4 features
+      const bool fvalid = (q * 32 + fc < tile_rows) && (feat < N);  // tile_rows and N are multiples of 4
+      // this warp drains the 32-token column blocks `half` and `half + 2` of the accumulator (those below the tile width)
+      const int n_blk = (half * 32 >= (int)tc.ntok) ? 0 : ((half + 2) * 32 < (int)tc.ntok ? 2 : 1);
+      if (n_blk == 0) {
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(tc_acc_empty(tc, acc));
-        continue;
       }
-      {
+      for (int bi = 0; bi < n_blk; ++bi) {
+        const int blk = half + 2 * bi;
         uint32_t v[32];
-        tmem_ld32(tc.tmem + ((uint32_t)(q * 32) << 16) + acc * kPersistTcTokens + half * 32, v);
+        tmem_ld32(tc.tmem + ((uint32_t)(q * 32) << 16) + acc * kPersistTcMaxTokens + blk * 32, v);
         tmem_ld_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(tc_acc_empty(tc, acc));         // the accumulator is in registers: the next item may start
-        float rs = 1.0f;                                           // int8 weights: dequantisation scale of this lane's weight row
-        if (W8) { const int lr = q * 32 + lane, row = tile * tile_rows + lr; rs = (lr < tile_rows && row < N) ? __ldg(wscale + row) : 0.f; }
-#pragma unroll
-        for (int j = 0; j < 32; ++j) eb[j * 32 + lane] = W8 ? __uint_as_float(v[j]) * rs : __uint_as_float(v[j]);
-      }
-      __syncwarp();
-      const int feat = tile * tile_rows + q * 32 + fc;              // first of this lane's 4 features
-      const bool fvalid = (q * 32 + fc < tile_rows) && (feat < N);  // tile_rows and N are multiples of 4
-      if (EPI == EPI_SWIGLU) {
-        // rows are interleaved (gate, up): features (fc, fc+1) and (fc+2, fc+3) are two (gate, up) pairs
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int tl = i * 4 + tr, tok = half * 32 + tl;
-          // accumulator rows past the tile come from stale shared memory (possibly NaN / denormal bit patterns, for which the
-          // division takes its slow path: measured 5 us on the CTAs whose ring never held a 128-row tile): no arithmetic on them
-          if (fvalid && tok < B) {
-            const float4 x = *reinterpret_cast<const float4*>(eb + tl * 32 + fc);
-            __nv_bfloat162 ob = __floats2bfloat162_rn(silu(x.x) * x.y, silu(x.z) * x.w);
-            *reinterpret_cast<uint32_t*>(act + (size_t)tok * (N >> 1) + (feat >> 1)) = *reinterpret_cast<uint32_t*>(&ob);
-          }
+        if (bi == n_blk - 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tc_acc_empty(tc, acc));       // the accumulator is in registers: the next item may start
         }
-      } else {
-        float* o = out32 + (size_t)ks * Bpad * N + feat;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int tl = i * 4 + tr, tok = half * 32 + tl;
-          if (fvalid && tok < B) *reinterpret_cast<float4*>(o + (size_t)tok * N) = *reinterpret_cast<const float4*>(eb + tl * 32 + fc);
+        for (int p = 0; p < 2; ++p) {                               // two passes of 16 tokens through the [16][32] transpose buffer
+#pragma unroll
+          for (int j = 0; j < 16; ++j) eb[j * 32 + lane] = W8 ? __uint_as_float(v[16 * p + j]) * rs : __uint_as_float(v[16 * p + j]);
+          __syncwarp();
+          if (EPI == EPI_SWIGLU) {
+            // rows are interleaved (gate, up): features (fc, fc+1) and (fc+2, fc+3) are two (gate, up) pairs
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int tl = i * 4 + tr, tok = blk * 32 + 16 * p + tl;
+              // accumulator rows past the tile come from stale shared memory (possibly NaN / denormal bit patterns, for which
+              // the division takes its slow path: measured 5 us on the CTAs whose ring never held a 128-row tile): no
+              // arithmetic on them
+              if (fvalid && tok < B) {
+                const float4 x = *reinterpret_cast<const float4*>(eb + tl * 32 + fc);
+                __nv_bfloat162 ob = __floats2bfloat162_rn(silu(x.x) * x.y, silu(x.z) * x.w);
+                *reinterpret_cast<uint32_t*>(act + (size_t)tok * (N >> 1) + (feat >> 1)) = *reinterpret_cast<uint32_t*>(&ob);
+              }
+            }
+          } else {
+            float* o = out32 + (size_t)ks * Bpad * N + feat;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int tl = i * 4 + tr, tok = blk * 32 + 16 * p + tl;
+              if (fvalid && tok < B) *reinterpret_cast<float4*>(o + (size_t)tok * N) = *reinterpret_cast<const float4*>(eb + tl * 32 + fc);
+            }
+          }
+          __syncwarp();                                             // the buffer is rewritten by the next pass / item
         }
       }
       if (dw) dw[5] = gtimer();
-      __syncwarp();                                                 // the buffer is rewritten by the next item
     }
   }
   for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
@@ -960,7 +968,7 @@ __global__ void __launch_bounds__(kPThreads, 1) decode_persist_kernel(DecodePers
   __shared__ __align__(8) uint64_t tc_bars[2 * kTcStages + 4 + 2 * kTcConvSlots];
   __shared__ uint32_t tc_tmem_slot;
   __shared__ __align__(8) uint64_t attn_bars[4];                  // [team][buffer] K/V chunk arrival
-  __shared__ int s_ctx[64];                                       // context length of every segment (constant until the pick phase)
+  __shared__ int s_ctx[kPersistTcMaxTokens];                                       // context length of every segment (constant until the pick phase)
   unsigned epoch = 0;
   int n_stamp = 0;
   STAMP();
@@ -974,8 +982,8 @@ __global__ void __launch_bounds__(kPThreads, 1) decode_persist_kernel(DecodePers
   }
   if (!TC) __syncthreads();
   const CUtensorMap* tmaps = reinterpret_cast<const CUtensorMap*>(a.tmaps);
-  // activation maps {u, attn, act} x token-tile widths {64, 32, 16}
-  const CUtensorMap* xmaps = tmaps + 4 * a.n_layers + 1 + (a.tc_ntok == 64 ? 0 : (a.tc_ntok == 32 ? 3 : 6));
+  // activation maps {u, attn, act} x token-tile widths {64, 32, 16, 128}
+  const CUtensorMap* xmaps = tmaps + 4 * a.n_layers + 1 + (a.tc_ntok == 64 ? 0 : (a.tc_ntok == 32 ? 3 : (a.tc_ntok == 16 ? 6 : 9)));
   if (TC) {
     const uint32_t raw = smem_u32(smem);
     tc.ringA = (raw + 1023u) & ~1023u;
@@ -992,7 +1000,7 @@ __global__ void __launch_bounds__(kPThreads, 1) decode_persist_kernel(DecodePers
       for (int i = 0; i < kTcConvSlots; ++i) { mbar_init(tc_conv_full(tc, i), kTcConvWarps); mbar_init(tc_conv_empty(tc, i), 1); }
       fence_barrier_init();
     }
-    if ((tid >> 5) == 2) tmem_alloc<2 * kPersistTcTokens>(smem_u32(&tc_tmem_slot));
+    if ((tid >> 5) == 2) tmem_alloc<2 * kPersistTcMaxTokens>(smem_u32(&tc_tmem_slot));
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -1006,7 +1014,7 @@ __global__ void __launch_bounds__(kPThreads, 1) decode_persist_kernel(DecodePers
   uint8_t* smem_small = smem + ring_off + (TC ? (size_t)kTcStages * (kTcStageA + kTcStageB) : attn_kv_smem<ATW>());
   if (TC) tc.epi = reinterpret_cast<float*>(smem + ((ring_off + (size_t)kTcStages * (kTcStageA + kTcStageB) + 2 * attn_small_smem<8>() + 15) & ~(size_t)15));
 
-  if (tid < 64) s_ctx[tid] = (tid < B) ? a.gs.ctx_len[tid] : 0;     // visible after the first grid barrier's __syncthreads
+  if (tid < kPersistTcMaxTokens) s_ctx[tid] = (tid < B) ? a.gs.ctx_len[tid] : 0;     // visible after the first grid barrier's __syncthreads
   // ---- phase 0: x = E[cur_tok]; u = rmsnorm(x) * g(layer 0 input norm)
   for (int b = blockIdx.x; b < B; b += gridDim.x) {
     const int tok = a.gs.cur_tok[b];
@@ -1162,7 +1170,7 @@ __global__ void __launch_bounds__(kPThreads, 1) decode_persist_kernel(DecodePers
   if (TC) {
     tc_fence_before();
     __syncthreads();
-    if ((tid >> 5) == 2) tmem_dealloc<2 * kPersistTcTokens>(tc.tmem);
+    if ((tid >> 5) == 2) tmem_dealloc<2 * kPersistTcMaxTokens>(tc.tmem);
   }
 }
 
@@ -1223,7 +1231,7 @@ cudaError_t decode_persist_configure() {
 }
 
 cudaError_t launch_decode_persist(const DecodePersistArgs& a, int grid, cudaStream_t st, int* mode) {
-  if (grid < 1 || a.B < 1 || a.B > 64) return cudaErrorInvalidConfiguration;
+  if (grid < 1 || a.B < 1 || a.B > (a.tmaps ? kPersistTcMaxTokens : 64)) return cudaErrorInvalidConfiguration;
   const int num_sms = grid;
   PersistKernel kern = persist_kernel_for(a.w8 != 0, a.B, a.tmaps != nullptr);
   const size_t smem_bytes = persist_smem_for(kern == persist_variant(8) || kern == persist_variant(9));

@@ -481,7 +481,8 @@ def _pin_oracle(sd, tag, i, x, ids):
     return _pin_cache[key]
 
 
-@pytest.mark.parametrize("mode,B", [("bf16", 64), ("bf16", 36), ("int8", 64), ("bf16", 16), ("bf16", 24), ("int8", 8), ("bf16", 1)])
+@pytest.mark.parametrize("mode,B", [("bf16", 64), ("bf16", 36), ("int8", 64), ("bf16", 16), ("bf16", 24), ("int8", 8), ("bf16", 1),
+                                    ("bf16", 128), ("bf16", 100), ("int8", 128)])
 def test_decode_step_logits_pinned_to_oracle(tiny_sd, mode, B):
     lens, segs, prompts = _pin_case(B)
     eng = Engine(2, 2, mode=mode, device=0, max_batch=B, max_prompt=300, max_new=24, debug=True)
