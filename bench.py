@@ -547,7 +547,7 @@ def run_file1h(args):
     cuts = cut_long_segments(0, total_samples, 16000, SEG_SECONDS)
     n_seg = len(cuts)
     mine = shard_indices(n_seg, world, rank)
-    B = min(args.batch, 128)
+    B = min(args.batch, 256)
     eng, dims, _ = make_engine(args, local, rank, world, max_batch=B)
     asr = ASRModel("synthetic", device=f"cuda:{local}", mode={"bf16": "native"}.get(args.mode, args.mode), engine=eng)
     # the hour is the concatenation of per-cut synthetic utterances (seed = cut index): every rank materialises only its shard
@@ -615,7 +615,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="file20s", choices=["file20s", "realtime", "file1h"])
-    ap.add_argument("--batch", type=int, default=int(os.environ.get("SONIC_BENCH_BATCH", "128")))
+    ap.add_argument("--batch", type=int, default=int(os.environ.get("SONIC_BENCH_BATCH", "256")))
     ap.add_argument("--max-new", type=int, default=128)
     ap.add_argument("--mode", default="bf16", choices=["bf16", "fp32", "int8"])
     ap.add_argument("--enc-layers", type=int, default=32)
@@ -624,6 +624,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-api-threads", action="store_true")
     args = ap.parse_args()
+    if args.mode == "int8" and args.batch > 128:
+        args.batch = 128                       # the int8 tcgen05 decode class tiles at most 128 segments per launch
     if args.impl == "reference":
         run_reference(args)
     elif args.workload == "realtime":

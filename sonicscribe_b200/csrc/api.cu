@@ -567,7 +567,7 @@ struct Engine {
               cudaGetErrorName(pe), h->rs_grid, B);
       h->use_rs = false;
     }
-    if (h->use_persist && B <= (h->persist_tc ? kPersistTcMaxTokens : 64) && std::is_same<T, bf16>::value) {   // the tcgen05 classes tile up to 128 tokens
+    if (h->use_persist && B <= (h->persist_tc ? (h->is_int8 ? 128 : kPersistTcMaxTokens) : 64) && std::is_same<T, bf16>::value) {   // the tcgen05 classes tile up to 128 tokens
       DecodePersistArgs p;
       memset(&p, 0, sizeof(p));
       p.layers = h->dev_layers; p.n_layers = h->cfg.dec_layers;
@@ -589,7 +589,7 @@ struct Engine {
       p.w8 = h->is_int8 ? 1 : 0;
       p.tmaps = (h->persist_tc && B >= h->persist_tc_min) ? h->persist_tmaps : nullptr;
       p.kv_maps = h->persist_kv_maps; p.kc_base = reinterpret_cast<const bf16*>(h->kcache);
-      { const char* nt = getenv("SONIC_PERSIST_NTOK"); p.tc_ntok = nt ? atoi(nt) : (B <= 16 ? 16 : (B <= 32 ? 32 : 64)); if (p.tc_ntok < B || (p.tc_ntok != 16 && p.tc_ntok != 32)) p.tc_ntok = B <= 64 ? 64 : 128; }
+      { const char* nt = getenv("SONIC_PERSIST_NTOK"); p.tc_ntok = nt ? atoi(nt) : (B <= 16 ? 16 : (B <= 32 ? 32 : 64)); if (p.tc_ntok < B || (p.tc_ntok != 16 && p.tc_ntok != 32)) p.tc_ntok = B <= 64 ? 64 : (B <= 128 ? 128 : 256); }
       { const char* pd = getenv("SONIC_PERSIST_PRE"); p.tc_pre_depth = pd ? atoi(pd) : 6; }
       { const char* df = getenv("SONIC_PERSIST_DBGFLAGS"); p.dbg_flags = (h->cfg.debug && df) ? atoi(df) : 0; }
       { const char* dc = getenv("SONIC_PERSIST_DBG_CTA"); p.dbg_cta = (h->cfg.debug && dc) ? atoi(dc) : -1; }
@@ -770,7 +770,7 @@ int alloc_all(sonic_ctx* h) {
     DAZ(h->persist_ts, 2048 * 8);
     DA(h->persist_pick, decode_persist_pick_floats(B, h->num_sms) * 4);
     DA(h->dev_layers, (size_t)c.dec_layers * sizeof(DecLayerDev));
-    DA(h->persist_tmaps, (size_t)(4 * c.dec_layers + 13) * sizeof(CUtensorMap));
+    DA(h->persist_tmaps, (size_t)(4 * c.dec_layers + 16) * sizeof(CUtensorMap));
     DA(h->persist_kv_maps, 2 * sizeof(CUtensorMap));
   }
   if (h->use_rs) {
@@ -943,7 +943,7 @@ int do_generate(sonic_ctx* h, const int32_t* ids, const int32_t* id_offsets, int
   // greedy steps 2..max_new: one CUDA graph per (batch, max_new) replayed; no per-token host sync.
   h->decode_chunks = (max_q + max_new + 63) / 64;
   if (h->decode_chunks > h->dattn_max_chunks) h->decode_chunks = h->dattn_max_chunks;
-  if (max_new > 1 && (h->prof_on || !h->probe_steps.empty() || (h->use_persist && batch <= (h->persist_tc ? kPersistTcMaxTokens : 64) && !h->is_f32))) {
+  if (max_new > 1 && (h->prof_on || !h->probe_steps.empty() || (h->use_persist && batch <= (h->persist_tc ? (h->is_int8 ? 128 : kPersistTcMaxTokens) : 64) && !h->is_f32))) {
     int* flag = h->h_pinned + h->h_pinned_ints - 16;
     for (int step = 1; step < max_new; ++step) {
       h->cur_step = step;
@@ -1169,7 +1169,7 @@ int sonic_finalize_weights(sonic_handle h) {
       // weight maps: {K, rows} with a 64-k box of the phase's tile rows (bf16: 128B swizzle; int8: raw rows of 64 B, expanded by
       // the kernel's converter warps); activation maps: {K, 64 token rows} with a 64 x 64 box (128B swizzle)
       const int L = h->cfg.dec_layers;
-      std::vector<CUtensorMap> maps(4 * L + 13);
+      std::vector<CUtensorMap> maps(4 * L + 16);
       for (int l = 0; l < L; ++l) {
         const DecLayerW& w = h->dec[l];
         if (h->is_int8) {
@@ -1185,8 +1185,8 @@ int sonic_finalize_weights(sonic_handle h) {
         }
       }
       CK(make_tensor_map_2d(&maps[4 * L], h->lm_head, kDecH, kVocab, kDecH, 64, kPersistLmTileRows));
-      for (int w = 0; w < 4; ++w) {                                 // token-tile widths 64, 32, 16, 128
-        const int nt = w < 3 ? 64 >> w : 128;
+      for (int w = 0; w < 5; ++w) {                                 // token-tile widths 64, 32, 16, 128, 256
+        const int nt = w < 3 ? 64 >> w : (w == 3 ? 128 : 256);
         CK(make_tensor_map_2d(&maps[4 * L + 1 + 3 * w], h->du, kDecH, nt, kDecH, 64, nt));
         CK(make_tensor_map_2d(&maps[4 * L + 2 + 3 * w], h->dattn, kDecH, nt, kDecH, 64, nt));
         CK(make_tensor_map_2d(&maps[4 * L + 3 + 3 * w], h->dact, kDecInter, nt, kDecInter, 64, nt));

@@ -261,7 +261,7 @@ __device__ __forceinline__ void gemm_dispatch(const void* W, const float* wscale
 // The ring / accumulator barriers live for the whole kernel; their phase is derived from running counters that every thread
 // advances identically.
 static constexpr int kTcStages = 6;                   // 8 measured no faster
-static constexpr int kTcStageA = 128 * 64 * 2, kTcStageB = kPersistTcMaxTokens * 64 * 2;
+static constexpr int kTcStageA = 128 * 64 * 2, kTcStageB = 128 * 64 * 2;
 static constexpr int kTcRingBytes = kTcStages * (kTcStageA + kTcStageB) + 1024;     // + alignment slack
 static constexpr int kTcEpiBytes = 8 * 16 * 32 * 4;   // epilogue transpose buffers (TcCtx::epi): [16 tokens][32 features] fp32 per warp
 // int8 weights (W8): the 96 KB weight area of the ring holds six raw int8 stages (128 rows x 64 B = 8 KB, no swizzle) followed by
@@ -272,7 +272,8 @@ struct TcCtx {
   uint32_t ringA, ringB, bars, tmem;
   uint32_t kb_count, item_count;
   uint32_t pre;                  // k blocks of the coming phase whose weight tile is already in flight (tc_prefetch_weights)
-  uint32_t ntok;                 // token rows of the activation tiles / MMA N of this launch: 16, 32 or 64 (>= live batch)
+  uint32_t ntok;                 // token rows of the activation tiles / MMA N of this launch: 16, 32, 64, 128 or 256 (>= live batch)
+  uint32_t stages, bstride;      // ring depth and activation-stage stride: 6 x (16 KB + 16 KB), or 4 x (16 KB + 32 KB) at 256 tokens
   uint64_t wpolicy;              // L2 policy of the weight / KV streams (evict_first), or 0: default
   uint32_t pre_depth;            // how many stages tc_prefetch_weights may fill before a grid barrier (<= kTcStages)
   float* epi;                    // 8 epilogue warps x [32 tokens][32 features] fp32 transpose buffers
@@ -311,7 +312,7 @@ __device__ __forceinline__ void tc_prefetch_weights(const CUtensorMap* wmap, int
     const int kb0 = (ks * nkb) / splits, kb1 = ((ks + 1) * nkb) / splits;
     for (int kb = kb0; kb < kb1 && n < tc.pre_depth; ++kb, ++n) {
       if (threadIdx.x < 32 && elect_one_sync()) {
-        const uint32_t cnt = tc.kb_count + n, st = cnt % kTcStages, par = (cnt / kTcStages) & 1u;
+        const uint32_t cnt = tc.kb_count + n, st = cnt % tc.stages, par = (cnt / tc.stages) & 1u;
         mbar_wait(tc_empty(tc, st), par ^ 1u);
         mbar_expect_tx(tc_full(tc, st), tile_rows * kRowB + tc.ntok * 128);
         if (tc.wpolicy) tma_load_2d_hint(tc.ringA + st * kStA, wmap, tc_full(tc, st), kb * 64, tile * tile_rows, tc.wpolicy);
@@ -340,14 +341,14 @@ __device__ __forceinline__ void gemm_phase_tc(const CUtensorMap* wmap, const CUt
         const int tile = item / splits, ks = item - tile * splits;
         const int kb0 = (ks * nkb) / splits, kb1 = ((ks + 1) * nkb) / splits;
         for (int kb = kb0; kb < kb1; ++kb, ++cnt, ++idx) {
-          const uint32_t st = cnt % kTcStages, par = (cnt / kTcStages) & 1u;
+          const uint32_t st = cnt % tc.stages, par = (cnt / tc.stages) & 1u;
           if (idx >= tc.pre) {
             mbar_wait(tc_empty(tc, st), par ^ 1u);
             mbar_expect_tx(tc_full(tc, st), tile_rows * kRowB + tc.ntok * 128);
             if (tc.wpolicy) tma_load_2d_hint(tc.ringA + st * kStA, wmap, tc_full(tc, st), kb * 64, tile * tile_rows, tc.wpolicy);
             else tma_load_2d(tc.ringA + st * kStA, wmap, tc_full(tc, st), kb * 64, tile * tile_rows);
           }
-          tma_load_2d(tc.ringB + st * kTcStageB, xmap, tc_full(tc, st), kb * 64, 0);
+          tma_load_2d(tc.ringB + st * tc.bstride, xmap, tc_full(tc, st), kb * 64, 0);
         }
         if (dbg) dbg[1 + (item >= (int)gridDim.x)] = gtimer();       // producer: all loads of item 0 / 1 issued
       }
@@ -363,14 +364,14 @@ __device__ __forceinline__ void gemm_phase_tc(const CUtensorMap* wmap, const CUt
         mbar_wait(tc_acc_empty(tc, acc), apar ^ 1u);
         tc_fence_after();
         for (int kb = kb0; kb < kb1; ++kb, ++cnt) {
-          const uint32_t st = cnt % kTcStages, par = (cnt / kTcStages) & 1u;
+          const uint32_t st = cnt % tc.stages, par = (cnt / tc.stages) & 1u;
           const uint32_t cs = cnt % kTcConvSlots, cpar = (cnt / kTcConvSlots) & 1u;
           if (W8) mbar_wait(tc_conv_full(tc, cs), cpar);              // the converters waited for the raw stage (and its X tile)
           else mbar_wait(tc_full(tc, st), par);
           tc_fence_after();
           if (dbg && kb == kb0) dbg[3 + (item >= (int)gridDim.x)] = gtimer();   // first stage of item 0 / 1 landed
           const uint64_t da = make_sw128_desc(W8 ? tc.ringA + kTcConvBase + cs * kTcStageA : tc.ringA + st * kTcStageA);
-          const uint64_t db = make_sw128_desc(tc.ringB + st * kTcStageB);
+          const uint64_t db = make_sw128_desc(tc.ringB + st * tc.bstride);
 #pragma unroll
           for (int k = 0; k < 4; ++k)
             tc_mma_bf16(tc.tmem + acc * kPersistTcMaxTokens, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb > kb0 || k != 0) ? 1u : 0u);
@@ -407,7 +408,7 @@ __device__ __forceinline__ void gemm_phase_tc(const CUtensorMap* wmap, const CUt
         const int s0 = i0 * 16, s1 = i1 * 16;
         const int d00 = r0 * 128 + (((2 * j0) ^ (r0 & 7)) << 4), d01 = r0 * 128 + (((2 * j0 + 1) ^ (r0 & 7)) << 4);
         const int d10 = r1 * 128 + (((2 * j1) ^ (r1 & 7)) << 4), d11 = r1 * 128 + (((2 * j1 + 1) ^ (r1 & 7)) << 4);
-        uint32_t st = ccnt % kTcStages, par = (ccnt / kTcStages) & 1u;
+        uint32_t st = ccnt % tc.stages, par = (ccnt / tc.stages) & 1u;
         uint32_t cs = ccnt % kTcConvSlots, cpar = (ccnt / kTcConvSlots) & 1u;
         for (int kb = kb0; kb < kb1; ++kb, ++ccnt) {
           unsigned long long* dc = (dbg && warp == 2 && lane == 0 && kb - kb0 < 10) ? dbg + 100 + 3 * (kb - kb0) : nullptr;
@@ -438,7 +439,7 @@ __device__ __forceinline__ void gemm_phase_tc(const CUtensorMap* wmap, const CUt
           __syncwarp();
           if (lane == 0) mbar_arrive(tc_conv_full(tc, cs));
           if (dc) dc[2] = gtimer();
-          if (++st == (uint32_t)kTcStages) { st = 0; par ^= 1u; }
+          if (++st == tc.stages) { st = 0; par ^= 1u; }
           if (++cs == (uint32_t)kTcConvSlots) { cs = 0; cpar ^= 1u; }
         }
       }
@@ -453,7 +454,7 @@ __device__ __forceinline__ void gemm_phase_tc(const CUtensorMap* wmap, const CUt
       const int feat = tile * tile_rows + q * 32 + fc;              // first of this lane's 4 features
       const bool fvalid = (q * 32 + fc < tile_rows) && (feat < N);  // tile_rows and N are multiples of 4
       // this warp drains the 32-token column blocks `half` and `half + 2` of the accumulator (those below the tile width)
-      const int n_blk = (half * 32 >= (int)tc.ntok) ? 0 : ((half + 2) * 32 < (int)tc.ntok ? 2 : 1);
+      const int n_blk = max(0, ((int)tc.ntok / 32 + (tc.ntok == 16 ? 1 : 0) - half + 1) / 2);    // blocks half, half + 2, ... below the tile width
       if (n_blk == 0) {
         tc_fence_before();
         __syncwarp();
@@ -982,17 +983,19 @@ __global__ void __launch_bounds__(kPThreads, 1) decode_persist_kernel(DecodePers
   }
   if (!TC) __syncthreads();
   const CUtensorMap* tmaps = reinterpret_cast<const CUtensorMap*>(a.tmaps);
-  // activation maps {u, attn, act} x token-tile widths {64, 32, 16, 128}
-  const CUtensorMap* xmaps = tmaps + 4 * a.n_layers + 1 + (a.tc_ntok == 64 ? 0 : (a.tc_ntok == 32 ? 3 : (a.tc_ntok == 16 ? 6 : 9)));
+  // activation maps {u, attn, act} x token-tile widths {64, 32, 16, 128, 256}
+  const CUtensorMap* xmaps = tmaps + 4 * a.n_layers + 1 + (a.tc_ntok == 64 ? 0 : (a.tc_ntok == 32 ? 3 : (a.tc_ntok == 16 ? 6 : (a.tc_ntok == 128 ? 9 : 12))));
   if (TC) {
     const uint32_t raw = smem_u32(smem);
     tc.ringA = (raw + 1023u) & ~1023u;
-    tc.ringB = tc.ringA + kTcStages * kTcStageA;
+    tc.ntok = (uint32_t)a.tc_ntok;
+    tc.stages = tc.ntok > 128 ? 4u : (uint32_t)kTcStages;
+    tc.bstride = tc.ntok > 128 ? 2u * kTcStageB : (uint32_t)kTcStageB;
+    tc.ringB = tc.ringA + tc.stages * kTcStageA;
     tc.bars = smem_u32(tc_bars);
     tc.ring_gen = smem + (tc.ringA - raw);
     tc.kb_count = 0; tc.item_count = 0; tc.pre = 0;
-    tc.pre_depth = (uint32_t)min(max(a.tc_pre_depth, 0), kTcStages);
-    tc.ntok = (uint32_t)a.tc_ntok;
+    tc.pre_depth = min((uint32_t)max(a.tc_pre_depth, 0), tc.stages);
     tc.wpolicy = (a.dbg_flags & 8) ? 0ull : l2_policy_evict_first();
     if (tid == 32) {
       for (int s = 0; s < kTcStages; ++s) { mbar_init(tc_full(tc, s), 1); mbar_init(tc_empty(tc, s), 1); }

@@ -142,12 +142,12 @@ struct DecodePersistArgs {
   int w8;                         // 1: decoder linears are int8 weight-only (lm_head / embedding stay bf16)
   // batch class 33..64, bf16 weights: the GEMM phases run on tcgen05 fed by TMA.  Device array of CUtensorMap (128 B each):
   // [4*l + {0: qkv, 1: o, 2: gate/up, 3: down}] weight maps (box 64 k x 128 rows; gate/up: x kPersistGuTileRows), [4*n_layers] lm_head,
-  // [4*n_layers + 1 + 3*w + {0: u, 1: attn, 2: act}] activation maps (box 64 k x {64, 32, 16, 128}[w] token rows).  nullptr: mma.sync phases.
+  // [4*n_layers + 1 + 3*w + {0: u, 1: attn, 2: act}] activation maps (box 64 k x {64, 32, 16, 128, 256}[w] token rows).  nullptr: mma.sync phases.
   const void* tmaps;
   // attention phase: device array of two CUtensorMap over the whole K and V caches ({128 dims, layers*batch*4*max_ctx key rows},
   // box 64 dims x 64 keys, 128B swizzle); kc_base = first element of the K cache (row 0 of the maps)
   const void* kv_maps; const bf16* kc_base;
-  int tc_ntok;                    // tcgen05 classes: token rows per activation tile = MMA N: 16, 32, 64 or 128, >= B
+  int tc_ntok;                    // tcgen05 classes: token rows per activation tile = MMA N: 16, 32, 64, 128 or 256, >= B
   int tc_pre_depth;               // tcgen05 classes: ring stages of the NEXT phase's weights put in flight before each grid barrier
   int dbg_flags;                  // timing experiments (SONIC_PERSIST_DBGFLAGS; results are wrong with them): 1 / 2 skip the proxy fence before / after the gate/up barrier, 4 skip the SwiGLU stores
   int dbg_cta;                    // debug handles: CTA whose gate/up phase of layer 1 writes fine-grained stamps to timestamps + 1024 (-1: none)
@@ -167,7 +167,7 @@ int decode_persist_occupancy();
 // *mode: per-handle launch API state (0 on first use); advanced when a launch API is refused
 cudaError_t launch_decode_persist(const DecodePersistArgs& a, int grid, cudaStream_t st, int* mode);
 static constexpr int kPersistTcTokens = 64;   // token rows of the widest activation tensor maps of the row-sliced kernel (decode_rs.cu)
-static constexpr int kPersistTcMaxTokens = 128;   // largest live batch of the tcgen05 decode classes (activation tiles of 16 / 32 / 64 / 128 token rows)
+static constexpr int kPersistTcMaxTokens = 256;   // largest live batch of the tcgen05 decode classes (activation tiles of 16 ... 256 token rows; int8: 128)
 
 // ---- decode_rs.cu: row-sliced persistent decode step for <= 32 segments (bf16) / <= 16 segments (int8 weight-only) ---------
 struct RsLayer {
