@@ -1,0 +1,9 @@
+#!/bin/bash
+# A/B of the int8 batch-1 decode step across library builds (SONIC_LIB): .scratch/<commit>/sonicscribe_b200/libsonic_b200.so
+for c in b1973f4 2c7727a 86dd6f9 HEAD; do
+  if [ "$c" = HEAD ]; then unset SONIC_LIB; else export SONIC_LIB=$PWD/.scratch/$c/sonicscribe_b200/libsonic_b200.so; fi
+  for m in int8 bf16; do
+  timeout 200 python bench.py --batch 1 --mode $m --no-cpu-baseline --no-api-threads --steps 3 2>/dev/null | python -c "
+import json,sys; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('$c $m', round(d['decode']['ms_per_token_step'],4), d['stage_ms_last_step'])"
+  done
+done

@@ -181,10 +181,11 @@ __device__ __forceinline__ void gemm_phase(const void* __restrict__ Wv, const fl
             x0 = *reinterpret_cast<const uint4*>(px);
             x1 = *reinterpret_cast<const uint4*>(px + 16);
           } else {
-            // rows >= B of the activation buffers are allocated (prefill sizes them) and their columns are never stored
+            // token rows >= B are not read (their accumulator columns are never stored): at one segment the activation
+            // footprint in L1 is one row instead of eight
             const bf16* px = X + (size_t)(tok0 + nt * 8 + g) * K + (size_t)gs * 2048 + warp * 128 + 64 * v + 16 * t;
-            x0 = *reinterpret_cast<const uint4*>(px);
-            x1 = *reinterpret_cast<const uint4*>(px + 8);
+            x0 = x1 = make_uint4(0, 0, 0, 0);
+            if (tok0 + nt * 8 + g < B) { x0 = *reinterpret_cast<const uint4*>(px); x1 = *reinterpret_cast<const uint4*>(px + 8); }
           }
 #pragma unroll
           for (int rbl = 0; rbl < RBW; ++rbl) {
@@ -204,7 +205,8 @@ __device__ __forceinline__ void gemm_phase(const void* __restrict__ Wv, const fl
           if (STAGE) {
             xv = *reinterpret_cast<const uint4*>(sX + (size_t)(nt * 8 + g) * kXRowBytes + (warp * 128 + 32 * u + 8 * t) * 2);
           } else {
-            xv = *reinterpret_cast<const uint4*>(X + (size_t)(tok0 + nt * 8 + g) * K + (size_t)gs * 2048 + warp * 128 + 32 * u + 8 * t);
+            xv = make_uint4(0, 0, 0, 0);
+            if (tok0 + nt * 8 + g < B) xv = *reinterpret_cast<const uint4*>(X + (size_t)(tok0 + nt * 8 + g) * K + (size_t)gs * 2048 + warp * 128 + 32 * u + 8 * t);
           }
           mma16816(acc[0][nt], wa[u].x, wb[u].x, wa[u].y, wb[u].y, xv.x, xv.y);
           mma16816(acc[0][nt], wa[u].z, wb[u].z, wa[u].w, wb[u].w, xv.z, xv.w);
@@ -969,7 +971,12 @@ __global__ void __launch_bounds__(kPThreads, 1) decode_persist_kernel(DecodePers
   __shared__ __align__(8) uint64_t tc_bars[2 * kTcStages + 4 + 2 * kTcConvSlots];
   __shared__ uint32_t tc_tmem_slot;
   __shared__ __align__(8) uint64_t attn_bars[4];                  // [team][buffer] K/V chunk arrival
-  __shared__ int s_ctx[kPersistTcMaxTokens];                                       // context length of every segment (constant until the pick phase)
+  // context length of every segment (constant until the pick phase).  The register-streaming classes (<= 64 segments) keep the
+  // array at 64 entries: their 194 KB of dynamic shared memory plus the static arrays must stay within the 196 KB carve-out —
+  // 512 B more selects the 228 KB one, leaves 28 KB instead of 60 KB of L1 for the activation rows they re-read, and cost
+  // 18 % of the int8 batch-1 step (1.29 -> 1.53 ms per token, measured)
+  constexpr int kCtxSlots = TC ? kPersistTcMaxTokens : 64;
+  __shared__ int s_ctx[kCtxSlots];
   unsigned epoch = 0;
   int n_stamp = 0;
   STAMP();
@@ -1017,7 +1024,7 @@ __global__ void __launch_bounds__(kPThreads, 1) decode_persist_kernel(DecodePers
   uint8_t* smem_small = smem + ring_off + (TC ? (size_t)kTcStages * (kTcStageA + kTcStageB) : attn_kv_smem<ATW>());
   if (TC) tc.epi = reinterpret_cast<float*>(smem + ((ring_off + (size_t)kTcStages * (kTcStageA + kTcStageB) + 2 * attn_small_smem<8>() + 15) & ~(size_t)15));
 
-  if (tid < kPersistTcMaxTokens) s_ctx[tid] = (tid < B) ? a.gs.ctx_len[tid] : 0;     // visible after the first grid barrier's __syncthreads
+  if (tid < kCtxSlots) s_ctx[tid] = (tid < B) ? a.gs.ctx_len[tid] : 0;     // visible after the first grid barrier's __syncthreads
   // ---- phase 0: x = E[cur_tok]; u = rmsnorm(x) * g(layer 0 input norm)
   for (int b = blockIdx.x; b < B; b += gridDim.x) {
     const int tok = a.gs.cur_tok[b];
@@ -1177,9 +1184,16 @@ __global__ void __launch_bounds__(kPThreads, 1) decode_persist_kernel(DecodePers
   }
 }
 
-static size_t persist_smem_for(bool tc) {
+// dynamic shared memory of variant i (persist_variant): the register-streaming classes that do not stage activations (NT = 1: <= 8
+// segments, NT = 8: 33..64) need only the attention buffers and the 64 KB fragment exchange — 133 KB, which selects the 164 KB
+// carve-out and leaves 92 KB of L1 for the activation rows they re-read from global memory; the staged classes (NT = 2, 4) add the
+// 130 KB staging area.
+static size_t persist_smem_for(int variant) {
+  const bool tc = variant >= 8;
+  const int nt = tc ? 8 : (1 << (variant & 3));
   const size_t attn = (size_t)AKEYS * kAKRow + (size_t)AKEYS * PHD * 2 + (PG * PHD + PG * AKEYS + 2 * PHD + 32 + 16) * 4;
-  const size_t exch = (size_t)kXStageBytes + (size_t)kPWarps * 2 * 4 * 128 * 4;    // staged activations + 16 warps x NT(4) x 128 fp32 (>= the unstaged NT = 8 exchange)
+  const size_t xchg = (size_t)kPWarps * 2 * 4 * 128 * 4;                            // 16 warps x NT(4) x 128 fp32 x RBW 2 (>= the NT = 8 exchange)
+  const size_t exch = ((nt == 2 || nt == 4) ? (size_t)kXStageBytes : 0) + xchg;     // staged activations + fragment exchange
   const size_t attn_mma16 = 1024 + attn_kv_smem<16>() + attn_small_smem<16>(), attn_mma8 = 1024 + attn_kv_smem<8>() + 2 * attn_small_smem<8>();
   size_t m = attn > exch ? attn : exch;
   if (attn_mma16 > m) m = attn_mma16;
@@ -1188,7 +1202,7 @@ static size_t persist_smem_for(bool tc) {
   if (tc) m = kTcRingBytes + 2 * attn_small_smem<8>() + 16 + kTcEpiBytes;
   return m;
 }
-size_t decode_persist_smem_bytes() { return persist_smem_for(true); }
+size_t decode_persist_smem_bytes() { return persist_smem_for(8); }
 
 size_t decode_persist_part_floats(int Bpad) { return (size_t)PV_ * Bpad; }     // >= qkv (3072) and 3 down sections (6144)
 size_t decode_persist_pick_floats(int max_batch, int num_sms) { return (size_t)max_batch * num_sms * 4; }
@@ -1213,7 +1227,7 @@ int decode_persist_occupancy() {
   int worst = 1 << 30;
   for (int i = 0; i < kPersistVariants; ++i) {
     int per_sm = -1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, persist_variant(i), kPThreads, persist_smem_for(i >= 8));
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, persist_variant(i), kPThreads, persist_smem_for(i));
     if (per_sm < worst) worst = per_sm;
   }
   return worst;
@@ -1229,7 +1243,7 @@ int decode_persist_max_grid(int num_sms) {
 
 cudaError_t decode_persist_configure() {
   for (int i = 0; i < kPersistVariants; ++i)
-    SONIC_CUDA_TRY(cudaFuncSetAttribute(persist_variant(i), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)persist_smem_for(i >= 8)));
+    SONIC_CUDA_TRY(cudaFuncSetAttribute(persist_variant(i), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)persist_smem_for(i)));
   return cudaSuccess;
 }
 
@@ -1237,7 +1251,9 @@ cudaError_t launch_decode_persist(const DecodePersistArgs& a, int grid, cudaStre
   if (grid < 1 || a.B < 1 || a.B > (a.tmaps ? kPersistTcMaxTokens : 64)) return cudaErrorInvalidConfiguration;
   const int num_sms = grid;
   PersistKernel kern = persist_kernel_for(a.w8 != 0, a.B, a.tmaps != nullptr);
-  const size_t smem_bytes = persist_smem_for(kern == persist_variant(8) || kern == persist_variant(9));
+  int variant = 0;
+  while (variant < kPersistVariants - 1 && persist_variant(variant) != kern) ++variant;
+  const size_t smem_bytes = persist_smem_for(variant);
   {
     cudaError_t me = cudaMemsetAsync(a.bar, 0, sizeof(unsigned), st);
     if (me != cudaSuccess) { fprintf(stderr, "[sonicscribe_b200] barrier memset failed: %s\n", cudaGetErrorName(me)); return me; }

@@ -7,11 +7,18 @@
 // Kernels
 //   mel_peak_kernel     per-segment max|x| (the peak-normalise reduction).  Launched per group of <= 64 segments right before
 //                       that group's frames kernel, so the second read of the PCM comes from the 126 MB L2, not from HBM.
-//   mel_frames_kernel   pre-step on load (float4 loads on the aligned interior) -> smem framing/windowing -> 400-point FFT of
-//                       frame PAIRS (two real frames as one complex transform, 400 = 16 x 25 Cooley-Tukey held in registers per
-//                       thread, exchanged through shared memory) -> power -> sparse mel (<=9 taps) -> log10 -> (x+4)/4 written
-//                       ONCE, unclamped, in the final layouts: fp32 [B,128,3000] (API/parity) and/or the time-major encoder
-//                       input [B,3002,128]; per-tile minimum and per-segment maximum on the side.
+//   mel_frames_kernel   persistent CTAs over 32-frame tiles.  Per tile:
+//                         load    the 5360-sample span: float4 loads issued during the PREVIOUS tile's mel phase (registers),
+//                                 pre-step (exact division by two FMA corrections of v * rcp(peak), PCM16 rint) -> smem
+//                         step 1  frame PAIRS as one complex transform (z = w fA + i w fB), 400 = 16 x 25 Cooley-Tukey:
+//                                 16-point DFTs in registers (packed fp32x2 butterflies), twiddled, float2 rows to smem
+//                         step 2  25-point DFTs in registers; the two real spectra are separated WITHOUT a pass over smem:
+//                                 bin k of a pair lives in thread (k mod 16), bin 400 - k in thread (16 - k mod 16) of the same
+//                                 half-warp, so one shuffle per value fetches the partner and every thread writes one power
+//                                 (frame A for k <= 200, frame B for the mirrored bins) in natural bin order
+//                         mel     lane = frame, warp strides over mel bins: taps in float4 groups, log10 via lg2, (x+4)/4
+//                                 stored straight to the fp32 [B,128,3000] features (coalesced 128 B rows) and / or staged for
+//                                 the time-major encoder input [B,3002,128]; per-tile minimum, per-segment maximum on the side
 //   mel_fixup_kernel    the max(x, gmax-8) clamp needs the segment maximum, known only after the last frame: this pass
 //                       fills the frames that only see zero padding (never transformed: exactly log10(1e-10) = -10) and
 //                       re-touches only the 32-frame tiles whose minimum is below gmax-8 (silence), instead of streaming a
@@ -26,9 +33,12 @@ static constexpr int kNfft = 400, kHop = 160, kBins = 201, kMels = 128, kFrames 
 static constexpr int kPairs = 16;                 // complex transforms per CTA tile
 static constexpr int kTileFrames = 2 * kPairs;    // 32 frames per tile
 static constexpr int kSpan = (kTileFrames - 1) * kHop + kNfft;   // 5360 samples
-static constexpr int kStride = 401;               // padded transform stride (bank-conflict-free mel reads)
+static constexpr int kPStride = kBins;            // power rows [frame][bin]: odd stride, lanes (frames) hit distinct banks
+static constexpr int kPFloats = kTileFrames * kPStride + 16;     // + slack for the zero-weight taps of the last float4 group
 static constexpr int kMelThreads = 256;
 static constexpr int kMaxTaps = 12;
+static constexpr int kPer4 = (kSpan / 4 + kMelThreads - 1) / kMelThreads;    // 1340 float4 -> 6 per thread
+static constexpr int kPer1 = (kSpan + kMelThreads - 1) / kMelThreads;        // 21 scalars per thread (edge tiles)
 
 #include "mel_twiddles.inc"   // __constant__ float2 c_w16[16], c_w25[25]  (e^{-2 pi i k/n})
 
@@ -40,33 +50,38 @@ struct MelTables {             // built once on the host (api.cu) from the slane
   int tap_count[kMels];
 };
 
+// ---- packed fp32x2 arithmetic (one issue slot per complex add / scaled add) ----------------------------------------------
+__device__ __forceinline__ float2 padd(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 psub(float2 a, float2 b) { return __ffma2_rn(b, make_float2(-1.f, -1.f), a); }
+__device__ __forceinline__ float2 pfma(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ float2 pmul(float2 a, float2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ float2 cswap(float2 a) { return make_float2(a.y, a.x); }
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
-__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
 
 // forward 4-point DFT in place: (a0..a3) -> (X0..X3)
 __device__ __forceinline__ void dft4(float2& a0, float2& a1, float2& a2, float2& a3) {
-  float2 t0 = cadd(a0, a2), t1 = csub(a0, a2), t2 = cadd(a1, a3), t3 = csub(a1, a3);
-  float2 mi = make_float2(t3.y, -t3.x);          // -i * t3
-  a0 = cadd(t0, t2);
-  a2 = csub(t0, t2);
-  a1 = cadd(t1, mi);
-  a3 = csub(t1, mi);
+  const float2 t0 = padd(a0, a2), t1 = psub(a0, a2), t2 = padd(a1, a3), t3 = psub(a1, a3);
+  const float2 sw = cswap(t3);                                    // -i t3 = (t3.y, -t3.x)
+  a0 = padd(t0, t2);
+  a2 = psub(t0, t2);
+  a1 = pfma(sw, make_float2(1.f, -1.f), t1);
+  a3 = pfma(sw, make_float2(-1.f, 1.f), t1);
 }
 // forward 5-point DFT in place
 __device__ __forceinline__ void dft5(float2& a0, float2& a1, float2& a2, float2& a3, float2& a4) {
   const float c1 = 0.30901699437494745f, c2 = -0.8090169943749473f, s1 = 0.9510565162951535f, s2 = 0.5877852522924732f;
-  float2 p = cadd(a1, a4), q = cadd(a2, a3), d1 = csub(a1, a4), d2 = csub(a2, a3);
-  float2 x0 = make_float2(a0.x + p.x + q.x, a0.y + p.y + q.y);
-  float2 p1 = make_float2(a0.x + c1 * p.x + c2 * q.x, a0.y + c1 * p.y + c2 * q.y);
-  float2 p2 = make_float2(a0.x + c2 * p.x + c1 * q.x, a0.y + c2 * p.y + c1 * q.y);
-  float2 q1 = make_float2(s1 * d1.x + s2 * d2.x, s1 * d1.y + s2 * d2.y);
-  float2 q2 = make_float2(s2 * d1.x - s1 * d2.x, s2 * d1.y - s1 * d2.y);
+  const float2 C1 = make_float2(c1, c1), C2 = make_float2(c2, c2), S1 = make_float2(s1, s1), S2 = make_float2(s2, s2), NS1 = make_float2(-s1, -s1);
+  const float2 p = padd(a1, a4), q = padd(a2, a3), d1 = psub(a1, a4), d2 = psub(a2, a3);
+  const float2 x0 = padd(padd(a0, p), q);
+  const float2 p1 = pfma(q, C2, pfma(p, C1, a0));
+  const float2 p2 = pfma(q, C1, pfma(p, C2, a0));
+  const float2 q1 = cswap(pfma(d2, S2, pmul(d1, S1)));           // (q1.y, q1.x)
+  const float2 q2 = cswap(pfma(d2, NS1, pmul(d1, S2)));
   a0 = x0;
-  a1 = make_float2(p1.x + q1.y, p1.y - q1.x);    // p1 - i q1
-  a4 = make_float2(p1.x - q1.y, p1.y + q1.x);    // p1 + i q1
-  a2 = make_float2(p2.x + q2.y, p2.y - q2.x);
-  a3 = make_float2(p2.x - q2.y, p2.y + q2.x);
+  a1 = pfma(q1, make_float2(1.f, -1.f), p1);                     // p1 - i q1 = (p1.x + q1.y, p1.y - q1.x)
+  a4 = pfma(q1, make_float2(-1.f, 1.f), p1);                     // p1 + i q1
+  a2 = pfma(q2, make_float2(1.f, -1.f), p2);
+  a3 = pfma(q2, make_float2(-1.f, 1.f), p2);
 }
 // 16-point forward DFT. Input x[n], n = 4*m1 + m2. Output X[j1 + 4*j2] is left in slot 4*j1 + j2.
 __device__ __forceinline__ void dft16(float2 (&x)[16]) {
@@ -90,6 +105,7 @@ __device__ __forceinline__ void dft25(float2 (&x)[25]) {
 #pragma unroll
   for (int j1 = 0; j1 < 5; ++j1) dft5(x[5 * j1], x[5 * j1 + 1], x[5 * j1 + 2], x[5 * j1 + 3], x[5 * j1 + 4]);
 }
+__host__ __device__ constexpr int dft25_slot(int k2) { return 5 * (k2 % 5) + k2 / 5; }      // slot that holds X[k2]
 
 // ------------------------------------------------------------------------------------------------------------
 // sample j of a segment whose first sample is element `base` of the PCM buffer: float32, or int16 scaled by 1/32768 (the
@@ -106,11 +122,36 @@ __global__ void mel_peak_kernel(const float* __restrict__ pcm, const long long* 
   const long long base = offs[b];
   float m = 0.f;
   // the reference normalises by the peak of the WHOLE input segment (asr.py:265), before the 30 s truncation
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) m = fmaxf(m, fabsf(load_pcm(pcm, base, i, flags)));
+  if (!(flags & SONIC_MEL_S16) && ((base & 3) == 0)) {
+    const float4* x4 = reinterpret_cast<const float4*>(pcm + base);
+    const int n4 = n >> 2;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
+      const float4 v = __ldg(x4 + i);
+      m = fmaxf(fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
+    }
+    for (int i = 4 * n4 + blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) m = fmaxf(m, fabsf(__ldg(pcm + base + i)));
+  } else {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) m = fmaxf(m, fabsf(load_pcm(pcm, base, i, flags)));
+  }
   __shared__ float red[32];
   m = block_max(m, red);
   if (threadIdx.x == 0 && m > 0.f) atomicMax(peak_bits + b, __float_as_uint(m));   // non-negative floats order as uints
 }
+
+// the reference pre-step on one sample: v / peak (asr.py:266-267; IEEE division reproduced as q = v * RN(1/peak) followed by
+// two FMA corrections — the second one is Markstein's correctly-rounding step) and the PCM_16 write + float read (asr.py:276)
+__device__ __forceinline__ float prestep(float v, float peak, float rpeak, bool norm, bool pcm16) {
+  if (norm) {
+    float q = v * rpeak;
+    q = fmaf(fmaf(-q, peak, v), rpeak, q);
+    q = fmaf(fmaf(-q, peak, v), rpeak, q);
+    v = q;
+  }
+  if (pcm16) v = rintf(v * 32767.0f) * (1.0f / 32768.0f);
+  return v;
+}
+
+struct TileItem { int b, tile, n, n_active; long long base; float peak; bool interior; };
 
 template <typename TM>
 __global__ void __launch_bounds__(kMelThreads, 2)
@@ -118,163 +159,182 @@ mel_frames_kernel(const float* __restrict__ pcm, const long long* __restrict__ o
                   const unsigned* __restrict__ peak_bits, const MelTables* __restrict__ tab, int flags, int batch, int tiles_per_seg, int tile_min_stride,
                   float* __restrict__ feat /*[B][128][3000] or null*/, TM* __restrict__ feat_tm /*[B][3002][128] or null*/,
                   float* __restrict__ tile_min /*[B][94]*/, unsigned* __restrict__ gmax_bits /*[B]*/) {
-  extern __shared__ float smem[];
-  float* s_samp = smem;                              // kSpan
-  float* s_re = s_samp + kSpan;                      // kPairs*kStride
-  float* s_im = s_re + kPairs * kStride;             // kPairs*kStride   (base offset == 16 mod 32 banks)
-  float* s_win = s_im + kPairs * kStride;            // 400
-  float2* s_tw = reinterpret_cast<float2*>(s_win + kNfft);     // 16 x 25
-  float* s_tapw = reinterpret_cast<float*>(s_tw + kNfft);      // 128*12
-  int* s_tstart = reinterpret_cast<int*>(s_tapw + kMels * kMaxTaps);
-  int* s_tcount = s_tstart + kMels;
+  extern __shared__ __align__(16) float smem[];
+  float* s_samp = smem;                                            // kSpan
+  float2* s_z = reinterpret_cast<float2*>(s_samp + kSpan);         // [pair][k1][n2]  (16 x 400 float2)
+  float* s_P = reinterpret_cast<float*>(s_z + kPairs * kNfft);     // [frame][bin] powers
+  float* s_win = s_P + kPFloats;                                   // 400
+  float2* s_tw = reinterpret_cast<float2*>(s_win + kNfft);         // [k1][n2]
+  float4* s_tapw = reinterpret_cast<float4*>(s_tw + kNfft);        // [128][3] float4 groups (zero beyond the tap count)
+  int* s_tstart = reinterpret_cast<int*>(s_tapw + kMels * (kMaxTaps / 4));
+  int* s_tcnt4 = s_tstart + kMels;
+  float* s_out = reinterpret_cast<float*>(s_z);                    // [128][33] staging of the time-major copy (s_z is dead after step 2)
   __shared__ float red[32];
 
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (int i = tid; i < kNfft; i += kMelThreads) { s_win[i] = tab->window[i]; s_tw[i] = tab->tw[i]; }
-  for (int i = tid; i < kMels * kMaxTaps; i += kMelThreads) s_tapw[i] = tab->tapw[i];
-  for (int i = tid; i < kMels; i += kMelThreads) { s_tstart[i] = tab->tap_start[i]; s_tcount[i] = tab->tap_count[i]; }
+  for (int i = tid; i < kMels * kMaxTaps; i += kMelThreads) reinterpret_cast<float*>(s_tapw)[i] = tab->tapw[i];
+  for (int i = tid; i < kMels; i += kMelThreads) { s_tstart[i] = tab->tap_start[i]; s_tcnt4[i] = (tab->tap_count[i] + 3) >> 2; }
+  for (int i = tid; i < 16; i += kMelThreads) s_P[kTileFrames * kPStride + i] = 0.f;
 
-  // persistent CTAs: work item = (segment, tile of 32 frames); the tables above are loaded once per CTA
-  for (int work = blockIdx.x; work < batch * tiles_per_seg; work += gridDim.x) {
-    const int b = work / tiles_per_seg, tile = work - b * tiles_per_seg;
-    const int n = min(lens[b], kWin);
-    const int n_active = min(kFrames, (n + 200 + kHop - 1) / kHop);
-    if (tile * kTileFrames >= n_active) continue;               // CTA-uniform
-    const long long base = offs[b];
-    const float peak = __uint_as_float(peak_bits[b]);
-    const float gate = (peak > 1e-6f) ? 1.f : 0.f;
-    float lmax = -10.0f;
-    const int t0 = tile * kTileFrames;
-    __syncthreads();                                  // previous item's readers are done with smem
-    const int j0 = t0 * kHop - 200;
-    const bool interior = j0 >= 0 && j0 + kSpan <= n && !(flags & SONIC_MEL_S16) && (((base + j0) & 3) == 0);
-    if (interior) {
-      // the whole span lies inside the segment and is 16 B aligned: float4 loads, all issued before the first value is used
-      constexpr int kPer4 = (kSpan / 4 + kMelThreads - 1) / kMelThreads;                    // 1340 float4 -> 6 per thread
-      const float4* x4 = reinterpret_cast<const float4*>(pcm + base + j0);
-      float4 rawv[kPer4];
+  const bool norm_flag = (flags & SONIC_MEL_PEAK_NORM) != 0, pcm16 = (flags & SONIC_MEL_PCM16) != 0;
+  const int total = batch * tiles_per_seg;
+  // work item = (segment, tile of 32 frames); tiles that hold no transformed frame are skipped (CTA-uniform)
+  auto describe = [&](int work, TileItem& it) -> bool {
+    it.b = work / tiles_per_seg; it.tile = work - it.b * tiles_per_seg;
+    it.n = min(lens[it.b], kWin);
+    it.n_active = min(kFrames, (it.n + 200 + kHop - 1) / kHop);
+    if (it.tile * kTileFrames >= it.n_active) return false;
+    it.base = offs[it.b];
+    it.peak = __uint_as_float(peak_bits[it.b]);
+    const int j0 = it.tile * kTileFrames * kHop - 200;
+    it.interior = j0 >= 0 && j0 + kSpan <= it.n && !(flags & SONIC_MEL_S16) && (((it.base + j0) & 3) == 0);
+    return true;
+  };
+  auto next_item = [&](int work, TileItem& it) -> int {
+    while (work < total && !describe(work, it)) work += gridDim.x;
+    return work;
+  };
+  // span loads in two halves: issue (global -> registers, all in flight together) and commit (pre-step -> smem)
+  float rawv[4 * kPer4];
+  auto issue_loads = [&](const TileItem& it) {
+    const int j0 = it.tile * kTileFrames * kHop - 200;
+    if (it.interior) {      // the whole span lies inside the segment and is 16 B aligned: float4 loads
+      const float4* x4 = reinterpret_cast<const float4*>(pcm + it.base + j0);
 #pragma unroll
       for (int q = 0; q < kPer4; ++q) {
         const int i = tid + q * kMelThreads;
-        rawv[q] = (i < kSpan / 4) ? __ldg(x4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 v = (i < kSpan / 4) ? __ldg(x4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        rawv[4 * q] = v.x; rawv[4 * q + 1] = v.y; rawv[4 * q + 2] = v.z; rawv[4 * q + 3] = v.w;
       }
+    } else {                // edges (reflection, zero padding), int16 input or unaligned base: scalar loads
 #pragma unroll
-      for (int q = 0; q < kPer4; ++q) {
-        const int i = tid + q * kMelThreads;
-        float v[4] = {rawv[q].x, rawv[q].y, rawv[q].z, rawv[q].w};
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          if ((flags & SONIC_MEL_PEAK_NORM) && gate > 0.f) v[e] = v[e] / peak;              // asr.py:266-267 (true division)
-          if (flags & SONIC_MEL_PCM16) v[e] = rintf(v[e] * 32767.0f) * (1.0f / 32768.0f);   // soundfile PCM_16 write + float read
-        }
-        if (i < kSpan / 4) *reinterpret_cast<float4*>(s_samp + 4 * i) = make_float4(v[0], v[1], v[2], v[3]);
-      }
-    } else {
-      // edges (reflection, zero padding), int16 input or unaligned base: scalar loads, still all in flight together
-      constexpr int kPer = (kSpan + kMelThreads - 1) / kMelThreads;
-      float rawv[kPer];
-#pragma unroll
-      for (int q = 0; q < kPer; ++q) {
+      for (int q = 0; q < kPer1; ++q) {
         const int i = tid + q * kMelThreads;
         int j = j0 + i;
         if (j < 0) j = -j;
         if (j >= kWin) j = 2 * (kWin - 1) - j;
-        rawv[q] = (i < kSpan && j < n) ? load_pcm(pcm, base, j, flags) : 0.f;
-      }
-#pragma unroll
-      for (int q = 0; q < kPer; ++q) {
-        const int i = tid + q * kMelThreads;
-        float v = rawv[q];
-        if ((flags & SONIC_MEL_PEAK_NORM) && gate > 0.f) v = v / peak;              // asr.py:266-267 (true division)
-        if (flags & SONIC_MEL_PCM16) v = rintf(v * 32767.0f) * (1.0f / 32768.0f);   // soundfile PCM_16 write + float read
-        if (i < kSpan) s_samp[i] = v;
+        rawv[q] = (i < kSpan && j < it.n) ? load_pcm(pcm, it.base, j, flags) : 0.f;
       }
     }
-    __syncthreads();
+  };
+  auto commit_loads = [&](const TileItem& it) {
+    const bool norm = norm_flag && it.peak > 1e-6f;
+    const float rpeak = norm ? __frcp_rn(it.peak) : 0.f;
+    if (it.interior) {
+#pragma unroll
+      for (int q = 0; q < kPer4; ++q) {
+        const int i = tid + q * kMelThreads;
+        float4 v;
+        v.x = prestep(rawv[4 * q], it.peak, rpeak, norm, pcm16); v.y = prestep(rawv[4 * q + 1], it.peak, rpeak, norm, pcm16);
+        v.z = prestep(rawv[4 * q + 2], it.peak, rpeak, norm, pcm16); v.w = prestep(rawv[4 * q + 3], it.peak, rpeak, norm, pcm16);
+        if (i < kSpan / 4) *reinterpret_cast<float4*>(s_samp + 4 * i) = v;
+      }
+    } else {
+#pragma unroll
+      for (int q = 0; q < kPer1; ++q) {
+        const int i = tid + q * kMelThreads;
+        if (i < kSpan) s_samp[i] = prestep(rawv[q], it.peak, rpeak, norm, pcm16);
+      }
+    }
+  };
 
-    // ---- step 1: for each (pair, n2): 16-point DFT over n1 of z[25*n1+n2], z = wA*fA + i*wB*fB; twiddle W400^{n2*k1}
+  TileItem cur, nxt;
+  int work = next_item(blockIdx.x, cur);
+  if (work < total) { issue_loads(cur); commit_loads(cur); }
+  while (work < total) {
+    const int work_next = next_item(work + gridDim.x, nxt);
+    const int b = cur.b, tile = cur.tile, n_active = cur.n_active, t0 = tile * kTileFrames;
+    __syncthreads();                                  // the span is in smem; the previous item's readers of s_P / s_out are done
+
+    // ---- step 1: for each (pair, n2): 16-point DFT over n1 of z[25*n1+n2], z = w*fA + i*w*fB; twiddle W400^{n2*k1}
     for (int it = tid; it < kPairs * 25; it += kMelThreads) {
       const int tr = it / 25, n2 = it - tr * 25;
-      const float* fa = s_samp + (2 * tr) * kHop;
+      const float* fa = s_samp + (2 * tr) * kHop + n2;
+      const float* wp = s_win + n2;
       float2 v[16];
 #pragma unroll
       for (int n1 = 0; n1 < 16; ++n1) {
-        const int idx = 25 * n1 + n2;
-        const float w = s_win[idx];
-        v[n1] = make_float2(fa[idx] * w, fa[idx + kHop] * w);
+        const float w = wp[25 * n1];
+        v[n1] = make_float2(fa[25 * n1] * w, fa[25 * n1 + kHop] * w);
       }
       dft16(v);
+      float2* zo = s_z + tr * kNfft + n2;
+      const float2* twp = s_tw + n2;
 #pragma unroll
       for (int s = 0; s < 16; ++s) {
         const int k1 = (s >> 2) + 4 * (s & 3);
         float2 y = v[s];
-        if (k1 != 0 && n2 != 0) y = cmul(y, s_tw[k1 * 25 + n2]);   // W400^(n2 k1); [k1][n2] layout: no bank conflicts across n2
-        s_re[tr * kStride + k1 * 25 + n2] = y.x;
-        s_im[tr * kStride + k1 * 25 + n2] = y.y;
+        if (k1 != 0) y = cmul(y, twp[k1 * 25]);        // W400^(n2 k1) (n2 = 0: exactly 1); [k1][n2] layout: no bank conflicts across n2
+        zo[k1 * 25] = y;
       }
     }
     __syncthreads();
-    // ---- step 2: for each (pair, k1): 25-point DFT over n2 -> Z[k1 + 16*k2], kept in place at k1*25 + k2
-    for (int it = tid; it < kPairs * 16; it += kMelThreads) {
-      const int tr = it >> 4, k1 = it & 15;
-      float* pr = s_re + tr * kStride + k1 * 25;
-      float* pi = s_im + tr * kStride + k1 * 25;
+    // ---- step 2: thread (pair, k1): 25-point DFT over n2 -> Z[k1 + 16*k2]; then the split of the two real spectra.
+    // Z = X_A + i X_B, so |X_A[k]|^2 = |Z[k] + conj Z[400-k]|^2 / 4 and |X_B[k]|^2 = |Z[k] - conj Z[400-k]|^2 / 4.  Bin 400 - k
+    // sits in thread (16 - k1) & 15 of the same half-warp, slot 24 - k2 (k1 = 0: own slot (25 - k2) % 25).  The holder of
+    // k <= 200 writes frame A's power of bin k, the holder of k > 200 frame B's power of bin 400 - k (same modulus seen from
+    // the mirrored side); the self-mirrored bins 0 and 200 write both.
+    {
+      const int tr = tid >> 4, k1 = tid & 15;
+      const float2* zi = s_z + tr * kNfft + k1 * 25;
       float2 v[25];
 #pragma unroll
-      for (int i = 0; i < 25; ++i) v[i] = make_float2(pr[i], pi[i]);
+      for (int i = 0; i < 25; ++i) v[i] = zi[i];
       dft25(v);
+      const int partner = (lane & 16) | ((16 - k1) & 15);
+      float* PA = s_P + (2 * tr) * kPStride;
+      float* PB = PA + kPStride;
 #pragma unroll
-      for (int s = 0; s < 25; ++s) {
-        const int k2 = (s / 5) + 5 * (s % 5);
-        pr[k2] = v[s].x;
-        pi[k2] = v[s].y;
+      for (int k2 = 0; k2 < 25; ++k2) {
+        const float2 z = v[dft25_slot(k2)];
+        const float2 off = v[dft25_slot(24 - k2)];                         // what the partner wants from this thread
+        float pr = __shfl_sync(0xffffffffu, off.x, partner), pi = __shfl_sync(0xffffffffu, off.y, partner);
+        if (k1 == 0) { const float2 own = v[dft25_slot((25 - k2) % 25)]; pr = own.x; pi = own.y; }
+        const int k = k1 + 16 * k2;
+        const bool is_a = (k2 < 12) || (k2 == 12 && k1 <= 8);              // k <= 200
+        const float sg = is_a ? 1.f : -1.f;
+        const float ar = fmaf(sg, pr, z.x), ai = fmaf(-sg, pi, z.y);
+        const float pw = 0.25f * (ar * ar + ai * ai);
+        if (is_a) PA[k] = pw; else PB[kNfft - k] = pw;
+        if ((k2 == 0 && k1 == 0) || (k2 == 12 && k1 == 8)) {               // bins 0 and 200 mirror onto themselves
+          const float br = z.x - pr, bi = z.y + pi;
+          PB[k] = 0.25f * (br * br + bi * bi);
+        }
       }
     }
     __syncthreads();
-    // ---- split the two real spectra and take |.|^2 in place: re <- P_A[k], im <- P_B[k], k = 0..200
-    for (int it = tid; it < kPairs * kBins; it += kMelThreads) {
-      const int tr = it / kBins, k = it - tr * kBins;
-      const int kk = (k == 0) ? 0 : (kNfft - k);
-      const int a0 = tr * kStride + (k & 15) * 25 + (k >> 4);
-      const int a1 = tr * kStride + (kk & 15) * 25 + (kk >> 4);
-      const float zr = s_re[a0], zi = s_im[a0], yr = s_re[a1], yi = s_im[a1];
-      const float ar = zr + yr, ai = zi - yi;        // 2*X_A
-      const float br = zr - yr, bi = zi + yi;        // 2*i*X_B (same modulus)
-      // in-place is safe: a1 addresses bins >= 200, which no item writes (k = 200 maps to itself)
-      s_re[a0] = 0.25f * (ar * ar + ai * ai);
-      s_im[a0] = 0.25f * (br * br + bi * bi);
-    }
-    __syncthreads();
-    // ---- sparse mel + log10: lane = frame of the tile, warp strides over mel bins; (l + 4) / 4 staged as a [128][33] tile
-    float* s_out = s_samp;                               // the sample span is dead after step 1 (5360 >= 128 * 33 floats)
-    float lmin = 0.f;
+    // ---- the next item's PCM loads fly during the mel phase (the span buffer is free: step 1 was its last reader)
+    if (work_next < total) issue_loads(nxt);
+    // ---- sparse mel + log10: lane = frame of the tile, warp strides over mel bins
+    float lmax = -10.0f, lmin = 0.f;
     {
-      const int lane = tid & 31, warp = tid >> 5;
       const int t = t0 + lane;
-      const float* P = ((lane & 1) ? s_im : s_re) + (lane >> 1) * kStride;
+      const float* P = s_P + lane * kPStride;
+      float* frow = feat ? feat + ((size_t)b * kMels) * kFrames + t : nullptr;
+#pragma unroll 2
       for (int m = warp; m < kMels; m += kMelThreads / 32) {
-        const int ks = s_tstart[m], kc = s_tcount[m];
+        const float* p = P + s_tstart[m];
+        const int c4 = s_tcnt4[m];
         float acc = 0.f;
-        for (int j = 0; j < kc; ++j) {
-          const int k = ks + j;
-          acc = fmaf(s_tapw[m * kMaxTaps + j], P[(k & 15) * 25 + (k >> 4)], acc);
+        for (int c = 0; c < c4; ++c) {
+          const float4 w = s_tapw[m * (kMaxTaps / 4) + c];
+          acc = fmaf(w.x, p[4 * c], acc); acc = fmaf(w.y, p[4 * c + 1], acc);
+          acc = fmaf(w.z, p[4 * c + 2], acc); acc = fmaf(w.w, p[4 * c + 3], acc);
         }
         // log10 via MUFU lg2 (relative error 2^-22: < 2e-7 in the log, far below the 1e-4 parity bar)
         float l = __log2f(fmaxf(acc, 1e-10f)) * 0.30102999566398120f;
         if (t < n_active) lmax = fmaxf(lmax, l);
         else l = -10.0f;                                   // frames of the tile that only see zero padding
         if (t < kFrames) lmin = fminf(lmin, l);
-        s_out[m * 33 + lane] = (l + 4.0f) * 0.25f;
+        const float y = (l + 4.0f) * 0.25f;
+        if (frow && t < kFrames) frow[(size_t)m * kFrames] = y;     // a warp writes 32 consecutive frames of one mel row
+        if (feat_tm) s_out[m * 33 + lane] = y;
       }
     }
-    __syncthreads();
-    if (feat) {                                            // [m][t]: a warp writes 32 consecutive frames of one mel row
-      const int lane = tid & 31, warp = tid >> 5;
-      const int t = t0 + lane;
-      if (t < kFrames)
-        for (int m = warp; m < kMels; m += kMelThreads / 32) feat[((size_t)b * kMels + m) * kFrames + t] = s_out[m * 33 + lane];
-    }
+    if (work_next < total) commit_loads(nxt);
     if (feat_tm) {                                         // [t][m]: 128 consecutive mels of one frame
+      __syncthreads();
       const int m = tid & (kMels - 1);
       for (int r = tid >> 7; r < kTileFrames; r += kMelThreads / kMels) {
         const int t = t0 + r;
@@ -287,6 +347,8 @@ mel_frames_kernel(const float* __restrict__ pcm, const long long* __restrict__ o
       atomicMax(gmax_bits + b, f32_to_ordered(lmax));
       tile_min[(size_t)b * tile_min_stride + tile] = lmin;
     }
+    cur = nxt;
+    work = work_next;
   }
 }
 
@@ -370,7 +432,7 @@ void mel_build_tables(void* host_out, const int* tap_start, const int* tap_count
 }
 
 static size_t mel_smem_bytes() {
-  return sizeof(float) * (kSpan + 2 * kPairs * kStride + kNfft + 2 * kNfft + kMels * kMaxTaps) + sizeof(int) * 2 * kMels;
+  return sizeof(float) * (kSpan + 2 * kPairs * kNfft + kPFloats + kNfft + 2 * kNfft + kMels * kMaxTaps) + sizeof(int) * 2 * kMels;
 }
 
 cudaError_t mel_setup() {
