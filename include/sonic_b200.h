@@ -45,6 +45,8 @@ enum { SONIC_DTYPE_F32 = 0, SONIC_DTYPE_BF16 = 1 };
                                         float32 / 32768 on the device, as transcription_manager.py:45-51 does on the host        */
 #define SONIC_FLAG_PCM_DEVICE  0x10  /* pcm pointer is device memory (bench: inputs resident in HBM)            */
 #define SONIC_FLAG_OUT_DEVICE  0x20  /* features pointer of sonic_mel is device memory                          */
+#define SONIC_FLAG_FEATURES_ONLY 0x40 /* sonic_mel writes `features` only, not the encoder's time-major copy (front-end
+                                        bandwidth sweep, BASELINE.json configs[4]); a following sonic_encode is refused   */
 #define SONIC_FLAG_REFERENCE_PRESTEP (SONIC_FLAG_PEAK_NORM | SONIC_FLAG_PCM16)
 
 typedef struct {

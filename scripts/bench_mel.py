@@ -5,10 +5,12 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import ctypes as C
 import numpy as np
 import torch
-from sonicscribe_b200.engine import Engine, FLAG_PCM_DEVICE, FLAG_OUT_DEVICE, FLAG_REFERENCE_PRESTEP
+from sonicscribe_b200.engine import Engine, FLAG_PCM_DEVICE, FLAG_OUT_DEVICE, FLAG_REFERENCE_PRESTEP, FLAG_FEATURES_ONLY
 from sonicscribe_b200.synth import synth_audio
 
 N = 320000
+# MEL_WITH_TM=1: also write the encoder's time-major bf16 copy (what sonic_mel does inside the transcription path)
+EXTRA = 0 if os.environ.get('MEL_WITH_TM') else FLAG_FEATURES_ONLY
 maxB = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
 eng = Engine(1, 1, mode="bf16", device=0, max_batch=maxB, max_prompt=32, max_new=2)
 base = np.stack([synth_audio("speech", N, seed=i) for i in range(8)])
@@ -28,7 +30,7 @@ while B <= maxB:
     nfr = np.zeros(B, dtype=np.int32)
     def call():
         rc = eng.lib.sonic_mel(eng.h, C.c_void_p(pcm.data_ptr()), offs.ctypes.data_as(C.POINTER(C.c_int64)), lens.ctypes.data_as(C.POINTER(C.c_int32)),
-                               B, FLAG_REFERENCE_PRESTEP | FLAG_PCM_DEVICE | FLAG_OUT_DEVICE, C.c_void_p(feat.data_ptr()), nfr.ctypes.data_as(C.POINTER(C.c_int32)))
+                               B, FLAG_REFERENCE_PRESTEP | FLAG_PCM_DEVICE | FLAG_OUT_DEVICE | EXTRA, C.c_void_p(feat.data_ptr()), nfr.ctypes.data_as(C.POINTER(C.c_int32)))
         assert rc == 0, eng.lib.sonic_last_error(eng.h)
     for _ in range(3):
         call()

@@ -374,7 +374,7 @@ struct Engine {
   static int mel(sonic_ctx* h, const float* pcm_dev, int batch, int max_len, int flags, float* feat_dev) {
     TAG(PC_MEL);
     CKL(launch_mel<T>(pcm_dev, h->offs_dev, h->lens_dev, batch, max_len, flags & 7, h->mel_tables, h->peak_bits, h->gmax_bits,
-                      h->mel_tile_min, feat_dev, reinterpret_cast<T*>(h->mel_tm), h->stream),
+                      h->mel_tile_min, feat_dev, (flags & SONIC_FLAG_FEATURES_ONLY) ? nullptr : reinterpret_cast<T*>(h->mel_tm), h->stream),
         2 + ((batch + 63) / 64) * ((flags & SONIC_FLAG_PEAK_NORM) ? 2 : 1));
     return 0;
   }
@@ -846,7 +846,8 @@ int do_mel(sonic_ctx* h, const void* pcm_any, const int64_t* offsets, const int3
     h->last_lens[b] = lengths[b];
     if (n_frames) n_frames[b] = n_valid_frames(lengths[b]);
   }
-  h->last_batch = batch;
+  if ((flags & SONIC_FLAG_FEATURES_ONLY) && !features) return fail(h, "sonic_mel: SONIC_FLAG_FEATURES_ONLY without a features pointer");
+  h->last_batch = (flags & SONIC_FLAG_FEATURES_ONLY) ? 0 : batch;      // features only: nothing for sonic_encode to consume
   CK(cudaMemcpyAsync(h->offs_dev, h_offs, batch * 8, cudaMemcpyHostToDevice, h->stream));
   CK(cudaMemcpyAsync(h->lens_dev, h_lens, batch * 4, cudaMemcpyHostToDevice, h->stream));
   float* feat_dev = nullptr;

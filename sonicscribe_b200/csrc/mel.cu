@@ -24,6 +24,7 @@
 //                       re-touches only the 32-frame tiles whose minimum is below gmax-8 (silence), instead of streaming a
 //                       raw fp32 copy out and back in (round 1: 7.2 MB of traffic per segment against 2.8 MB algorithmic).
 #include <stdlib.h>
+#include <type_traits>
 #include "common.cuh"
 #include "kernels.h"
 
@@ -48,6 +49,8 @@ struct MelTables {             // built once on the host (api.cu) from the slane
   float tapw[kMels * kMaxTaps];
   int tap_start[kMels];
   int tap_count[kMels];
+  int meta[kMels];           // mel bins ordered by their number of float4 tap groups (1, 2, 3): bin | first tap << 8
+  int cls_end[4];            // [c]: entries of `meta` with at most c + 1 groups
 };
 
 // ---- packed fp32x2 arithmetic (one issue slot per complex add / scaled add) ----------------------------------------------
@@ -151,6 +154,9 @@ __device__ __forceinline__ float prestep(float v, float peak, float rpeak, bool 
   return v;
 }
 
+__device__ __forceinline__ void store_pair(float* p, float a, float b) { *reinterpret_cast<float2*>(p) = make_float2(a, b); }
+__device__ __forceinline__ void store_pair(bf16* p, float a, float b) { *reinterpret_cast<__nv_bfloat162*>(p) = __floats2bfloat162_rn(a, b); }
+
 struct TileItem { int b, tile, n, n_active; long long base; float peak; bool interior; };
 
 template <typename TM>
@@ -166,15 +172,15 @@ mel_frames_kernel(const float* __restrict__ pcm, const long long* __restrict__ o
   float* s_win = s_P + kPFloats;                                   // 400
   float2* s_tw = reinterpret_cast<float2*>(s_win + kNfft);         // [k1][n2]
   float4* s_tapw = reinterpret_cast<float4*>(s_tw + kNfft);        // [128][3] float4 groups (zero beyond the tap count)
-  int* s_tstart = reinterpret_cast<int*>(s_tapw + kMels * (kMaxTaps / 4));
-  int* s_tcnt4 = s_tstart + kMels;
-  float* s_out = reinterpret_cast<float*>(s_z);                    // [128][33] staging of the time-major copy (s_z is dead after step 2)
-  __shared__ float red[32];
+  int* s_meta = reinterpret_cast<int*>(s_tapw + kMels * (kMaxTaps / 4));
+  float* s_out = reinterpret_cast<float*>(s_z);                    // [32 frames][129] staging of the time-major copy (s_z is dead after step 2)
+  __shared__ unsigned s_ext[2][2];                                 // [slot][max, min] of a tile, order-preserving encoding
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (int i = tid; i < kNfft; i += kMelThreads) { s_win[i] = tab->window[i]; s_tw[i] = tab->tw[i]; }
   for (int i = tid; i < kMels * kMaxTaps; i += kMelThreads) reinterpret_cast<float*>(s_tapw)[i] = tab->tapw[i];
-  for (int i = tid; i < kMels; i += kMelThreads) { s_tstart[i] = tab->tap_start[i]; s_tcnt4[i] = (tab->tap_count[i] + 3) >> 2; }
+  for (int i = tid; i < kMels; i += kMelThreads) s_meta[i] = tab->meta[i];
+  const int cls1 = tab->cls_end[0], cls2 = tab->cls_end[1];
   for (int i = tid; i < 16; i += kMelThreads) s_P[kTileFrames * kPStride + i] = 0.f;
 
   const bool norm_flag = (flags & SONIC_MEL_PEAK_NORM) != 0, pcm16 = (flags & SONIC_MEL_PCM16) != 0;
@@ -240,12 +246,25 @@ mel_frames_kernel(const float* __restrict__ pcm, const long long* __restrict__ o
   };
 
   TileItem cur, nxt;
+  int prev_b = -1, prev_tile = 0, slot = 0;
+  if (tid == 0) { s_ext[0][0] = s_ext[1][0] = f32_to_ordered(-10.0f); s_ext[0][1] = s_ext[1][1] = f32_to_ordered(0.f); }
   int work = next_item(blockIdx.x, cur);
   if (work < total) { issue_loads(cur); commit_loads(cur); }
   while (work < total) {
-    const int work_next = next_item(work + gridDim.x, nxt);
+    // the next candidate item's segment fields are fetched now and looked at after step 2 (no dependent-load stall per tile)
+    const int cand = work + gridDim.x, cand_b = cand / tiles_per_seg;
+    int c_len = 0; long long c_off = 0; unsigned c_peak = 0;
+    if (cand < total) { c_len = lens[cand_b]; c_off = offs[cand_b]; c_peak = peak_bits[cand_b]; }
     const int b = cur.b, tile = cur.tile, n_active = cur.n_active, t0 = tile * kTileFrames;
     __syncthreads();                                  // the span is in smem; the previous item's readers of s_P / s_out are done
+    if (tid == 0) {
+      if (prev_b >= 0) {                              // publish the previous tile's extrema
+        atomicMax(gmax_bits + prev_b, s_ext[slot ^ 1][0]);
+        tile_min[(size_t)prev_b * tile_min_stride + prev_tile] = ordered_to_f32(s_ext[slot ^ 1][1]);
+      }
+      // re-arm the slot the NEXT tile will use (its last reader ran above one iteration ago): maximum -10, minimum 0
+      s_ext[slot ^ 1][0] = f32_to_ordered(-10.0f); s_ext[slot ^ 1][1] = f32_to_ordered(0.f);
+    }
 
     // ---- step 1: for each (pair, n2): 16-point DFT over n1 of z[25*n1+n2], z = w*fA + i*w*fB; twiddle W400^{n2*k1}
     for (int it = tid; it < kPairs * 25; it += kMelThreads) {
@@ -305,102 +324,145 @@ mel_frames_kernel(const float* __restrict__ pcm, const long long* __restrict__ o
     }
     __syncthreads();
     // ---- the next item's PCM loads fly during the mel phase (the span buffer is free: step 1 was its last reader)
+    int work_next = cand;
+    if (cand < total) {
+      nxt.b = cand_b; nxt.tile = cand - cand_b * tiles_per_seg;
+      nxt.n = min(c_len, kWin);
+      nxt.n_active = min(kFrames, (nxt.n + 200 + kHop - 1) / kHop);
+      if (nxt.tile * kTileFrames >= nxt.n_active) work_next = next_item(cand + gridDim.x, nxt);     // skipped tile: look further (rare)
+      else {
+        nxt.base = c_off; nxt.peak = __uint_as_float(c_peak);
+        const int j0 = nxt.tile * kTileFrames * kHop - 200;
+        nxt.interior = j0 >= 0 && j0 + kSpan <= nxt.n && !(flags & SONIC_MEL_S16) && (((nxt.base + j0) & 3) == 0);
+      }
+    }
     if (work_next < total) issue_loads(nxt);
-    // ---- sparse mel + log10: lane = frame of the tile, warp strides over mel bins
+    // ---- sparse mel + log10: lane = frame of the tile; a warp takes every 8th entry of the bin list, which is ordered by the
+    // number of float4 tap groups so that each of the three loops below is fully unrolled
     float lmax = -10.0f, lmin = 0.f;
     {
       const int t = t0 + lane;
+      const bool valid = t < n_active, inrange = t < kFrames;
       const float* P = s_P + lane * kPStride;
-      float* frow = feat ? feat + ((size_t)b * kMels) * kFrames + t : nullptr;
-#pragma unroll 2
-      for (int m = warp; m < kMels; m += kMelThreads / 32) {
-        const float* p = P + s_tstart[m];
-        const int c4 = s_tcnt4[m];
+      float* frow = (feat && inrange) ? feat + ((size_t)b * kMels) * kFrames + t : nullptr;
+      float* orow = s_out + lane * 129;
+      auto one = [&](int i, auto groups) {
+        constexpr int G = decltype(groups)::value;
+        const int meta = s_meta[i], m = meta & 127;
+        const float* p = P + (meta >> 8);
+        const float4* w4 = s_tapw + m * (kMaxTaps / 4);
         float acc = 0.f;
-        for (int c = 0; c < c4; ++c) {
-          const float4 w = s_tapw[m * (kMaxTaps / 4) + c];
+#pragma unroll
+        for (int c = 0; c < G; ++c) {
+          const float4 w = w4[c];
           acc = fmaf(w.x, p[4 * c], acc); acc = fmaf(w.y, p[4 * c + 1], acc);
           acc = fmaf(w.z, p[4 * c + 2], acc); acc = fmaf(w.w, p[4 * c + 3], acc);
         }
-        // log10 via MUFU lg2 (relative error 2^-22: < 2e-7 in the log, far below the 1e-4 parity bar)
-        float l = __log2f(fmaxf(acc, 1e-10f)) * 0.30102999566398120f;
-        if (t < n_active) lmax = fmaxf(lmax, l);
-        else l = -10.0f;                                   // frames of the tile that only see zero padding
-        if (t < kFrames) lmin = fminf(lmin, l);
-        const float y = (l + 4.0f) * 0.25f;
-        if (frow && t < kFrames) frow[(size_t)m * kFrames] = y;     // a warp writes 32 consecutive frames of one mel row
-        if (feat_tm) s_out[m * 33 + lane] = y;
-      }
+        // log10 via MUFU lg2 (relative error 2^-22: < 2e-7 in the log, far below the 1e-4 parity bar); the argument is >= 1e-10
+        float l;
+        asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(fmaxf(acc, 1e-10f)));
+        l = valid ? l * 0.30102999566398120f : -10.0f;     // frames of the tile that only see zero padding: log10(1e-10)
+        lmax = fmaxf(lmax, l);
+        lmin = fminf(lmin, inrange ? l : 0.f);
+        const float y = fmaf(l, 0.25f, 1.0f);              // (l + 4) / 4: the same value (scaling by 1/4 commutes with the rounding)
+        if (frow) frow[(size_t)m * kFrames] = y;           // a warp writes 32 consecutive frames of one mel row
+        if (feat_tm) orow[m] = y;
+      };
+      int i = warp;
+      for (; i < cls1; i += kMelThreads / 32) one(i, std::integral_constant<int, 1>());
+      for (; i < cls2; i += kMelThreads / 32) one(i, std::integral_constant<int, 2>());
+      for (; i < kMels; i += kMelThreads / 32) one(i, std::integral_constant<int, 3>());
     }
     if (work_next < total) commit_loads(nxt);
-    if (feat_tm) {                                         // [t][m]: 128 consecutive mels of one frame
+    if (feat_tm) {                                         // [t][m]: 128 consecutive mels of one frame, two per thread and store
       __syncthreads();
-      const int m = tid & (kMels - 1);
-      for (int r = tid >> 7; r < kTileFrames; r += kMelThreads / kMels) {
-        const int t = t0 + r;
-        if (t < kFrames) feat_tm[((size_t)b * (kFrames + 2) + 1 + t) * kMels + m] = from_f32<TM>(s_out[m * 33 + r]);
+      TM* dst = feat_tm + ((size_t)b * (kFrames + 2) + 1 + t0) * kMels;
+#pragma unroll
+      for (int q = 0; q < kTileFrames * (kMels / 2) / kMelThreads; ++q) {
+        const int j = tid + q * kMelThreads, r = j >> 6, mp = j & 63;
+        if (t0 + r < kFrames) store_pair(dst + r * kMels + 2 * mp, s_out[r * 129 + 2 * mp], s_out[r * 129 + 2 * mp + 1]);
       }
     }
-    lmax = block_max(lmax, red);
-    lmin = -block_max(-lmin, red);
-    if (tid == 0) {
-      atomicMax(gmax_bits + b, f32_to_ordered(lmax));
-      tile_min[(size_t)b * tile_min_stride + tile] = lmin;
-    }
+    // tile extrema: warp shuffles, then one shared-memory atomic per warp into this tile's slot (two alternating slots: the
+    // result is published after the next tile's first barrier, or after the loop — no extra barrier per tile)
+    lmax = warp_max(lmax);
+    lmin = -warp_max(-lmin);
+    if (lane == 0) { atomicMax(&s_ext[slot][0], f32_to_ordered(lmax)); atomicMin(&s_ext[slot][1], f32_to_ordered(lmin)); }
+    prev_b = b; prev_tile = tile;
+    slot ^= 1;
     cur = nxt;
     work = work_next;
+  }
+  __syncthreads();
+  if (tid == 0 && prev_b >= 0) {
+    atomicMax(gmax_bits + prev_b, s_ext[slot ^ 1][0]);
+    tile_min[(size_t)prev_b * tile_min_stride + prev_tile] = ordered_to_f32(s_ext[slot ^ 1][1]);
   }
 }
 
 // The clamp max(x, gmax - 8) in the written domain y = (x + 4) / 4 (a monotone map: clamping y at (gmax - 8 + 4) / 4 gives the
-// same bits as clamping x first).  grid (94 tiles, segments).
+// same bits as clamping x first).  grid (16, segments): CTA (s, b) fills the never-transformed frames [pad0, 3000) of mel rows
+// 8 s .. 8 s + 7 with 16 B stores (pad0 = first tile without a transformed frame), one sixteenth of the contiguous padded block
+// of the time-major copy, and re-touches the transformed tiles s, s + 16, ... whose minimum lies below the floor.
 template <typename T>
 __global__ void __launch_bounds__(256) mel_fixup_kernel(const unsigned* __restrict__ gmax_bits, const int* __restrict__ lens,
                                                         const float* __restrict__ tile_min, int tiles_per_seg, float* __restrict__ feat, T* __restrict__ feat_tm) {
-  const int b = blockIdx.y, tile = blockIdx.x, t0 = tile * kTileFrames;
+  const int b = blockIdx.y, s = blockIdx.x, ns = gridDim.x;
   const int n = min(lens[b], kWin);
   const int n_active = min(kFrames, (n + 200 + kHop - 1) / kHop);
+  const int active_tiles = (n_active + kTileFrames - 1) / kTileFrames;
+  const int pad0 = min(kFrames, active_tiles * kTileFrames);
   const float fl = ordered_to_f32(gmax_bits[b]) - 8.0f;
   const float y_floor = (fl + 4.0f) * 0.25f;
+  const float y_pad = (fmaxf(-10.0f, fl) + 4.0f) * 0.25f;   // the constant value of silence after the clamp
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (feat_tm && tile == 0 && tid < kMels) {               // conv padding rows of the time-major copy
+  if (feat_tm && s == 0 && tid < kMels) {                  // conv padding rows of the time-major copy
     feat_tm[((size_t)b * (kFrames + 2)) * kMels + tid] = from_f32<T>(0.f);
     feat_tm[((size_t)b * (kFrames + 2) + kFrames + 1) * kMels + tid] = from_f32<T>(0.f);
   }
-  if (t0 >= n_active) {                                    // never transformed: the constant value of silence after the clamp
-    const float y_pad = (fmaxf(-10.0f, fl) + 4.0f) * 0.25f;
-    if (feat) {
+  if (pad0 < kFrames) {
+    if (feat) {                                            // rows are 12000 B and pad0 is a multiple of 32 frames: 16 B aligned
+      const float4 v4 = make_float4(y_pad, y_pad, y_pad, y_pad);
+      const int n4 = (kFrames - pad0) >> 2;
+      for (int m = s * (kMels / ns) + warp; m < (s + 1) * (kMels / ns); m += 8) {
+        float4* row = reinterpret_cast<float4*>(feat + ((size_t)b * kMels + m) * kFrames + pad0);
+        for (int i = lane; i < n4; i += 32) row[i] = v4;
+      }
+    }
+    if (feat_tm) {                                         // frames [pad0, 3000) x 128 mels are one contiguous block
+      constexpr int kPer16 = 16 / (int)sizeof(T);
+      __align__(16) T fill[kPer16];
+#pragma unroll
+      for (int i = 0; i < kPer16; ++i) fill[i] = from_f32<T>(y_pad);
+      const uint4 v16 = *reinterpret_cast<const uint4*>(fill);
+      uint4* blk = reinterpret_cast<uint4*>(feat_tm + ((size_t)b * (kFrames + 2) + 1 + pad0) * kMels);
+      const int n16 = (kFrames - pad0) * kMels / kPer16;
+      for (int i = s * 256 + tid; i < n16; i += ns * 256) blk[i] = v16;
+    }
+  }
+  for (int tile = s; tile < active_tiles; tile += ns) {
+    if (!(tile_min[(size_t)b * tiles_per_seg + tile] < fl)) continue;     // nothing below the floor in this tile: written once, done
+    const int t0 = tile * kTileFrames;
+    if (feat) {                                            // all 16 loads of a thread in flight, then the (rare) stores
       const int t = t0 + lane;
-      if (t < kFrames)
-        for (int m = warp; m < kMels; m += 8) feat[((size_t)b * kMels + m) * kFrames + t] = y_pad;
+      float* p = feat + ((size_t)b * kMels + warp) * kFrames + t;
+      float v[kMels / 8];
+#pragma unroll
+      for (int i = 0; i < kMels / 8; ++i) v[i] = (t < kFrames) ? p[(size_t)i * 8 * kFrames] : y_floor;
+#pragma unroll
+      for (int i = 0; i < kMels / 8; ++i)
+        if (v[i] < y_floor) p[(size_t)i * 8 * kFrames] = y_floor;
     }
     if (feat_tm) {
-      const int m = tid & (kMels - 1);
-      for (int r = tid >> 7; r < kTileFrames; r += 2) {
-        const int t = t0 + r;
-        if (t < kFrames) feat_tm[((size_t)b * (kFrames + 2) + 1 + t) * kMels + m] = from_f32<T>(y_pad);
-      }
-    }
-    return;
-  }
-  if (!(tile_min[(size_t)b * tiles_per_seg + tile] < fl)) return;     // nothing below the floor in this tile: written once, done
-  if (feat) {
-    const int t = t0 + lane;
-    if (t < kFrames)
-      for (int m = warp; m < kMels; m += 8) {
-        float* p = feat + ((size_t)b * kMels + m) * kFrames + t;
-        if (*p < y_floor) *p = y_floor;
-      }
-  }
-  if (feat_tm) {
-    const int m = tid & (kMels - 1);
-    const T yf = from_f32<T>(y_floor);
-    for (int r = tid >> 7; r < kTileFrames; r += 2) {
-      const int t = t0 + r;
-      if (t < kFrames) {
-        T* p = feat_tm + ((size_t)b * (kFrames + 2) + 1 + t) * kMels + m;
-        if (to_f32(*p) < to_f32(yf)) *p = yf;
-      }
+      const int m = tid & (kMels - 1), r0 = tid >> 7;
+      const T yf = from_f32<T>(y_floor);
+      T* p = feat_tm + ((size_t)b * (kFrames + 2) + 1 + t0 + r0) * kMels + m;
+      T v[kTileFrames / 2];
+#pragma unroll
+      for (int i = 0; i < kTileFrames / 2; ++i) v[i] = (t0 + r0 + 2 * i < kFrames) ? p[(size_t)i * 2 * kMels] : yf;
+#pragma unroll
+      for (int i = 0; i < kTileFrames / 2; ++i)
+        if (to_f32(v[i]) < to_f32(yf)) p[(size_t)i * 2 * kMels] = yf;
     }
   }
 }
@@ -427,12 +489,21 @@ void mel_build_tables(void* host_out, const int* tap_start, const int* tap_count
   for (int m = 0; m < kMels; ++m) {
     t->tap_start[m] = tap_start[m];
     t->tap_count[m] = tap_count[m];
-    for (int j = 0; j < kMaxTaps; ++j) t->tapw[m * kMaxTaps + j] = tapw[m * kMaxTaps + j];
+    for (int j = 0; j < kMaxTaps; ++j) t->tapw[m * kMaxTaps + j] = (j < tap_count[m]) ? tapw[m * kMaxTaps + j] : 0.f;
   }
+  int n = 0;
+  for (int g = 1; g <= kMaxTaps / 4; ++g) {
+    for (int m = 0; m < kMels; ++m) {
+      const int groups = tap_count[m] <= 0 ? 1 : (tap_count[m] + 3) / 4;
+      if (groups == g) t->meta[n++] = m | (tap_start[m] << 8);
+    }
+    t->cls_end[g - 1] = n;
+  }
+  t->cls_end[3] = n;
 }
 
 static size_t mel_smem_bytes() {
-  return sizeof(float) * (kSpan + 2 * kPairs * kNfft + kPFloats + kNfft + 2 * kNfft + kMels * kMaxTaps) + sizeof(int) * 2 * kMels;
+  return sizeof(float) * (kSpan + 2 * kPairs * kNfft + kPFloats + kNfft + 2 * kNfft + kMels * kMaxTaps) + sizeof(int) * kMels;
 }
 
 cudaError_t mel_setup() {
@@ -474,7 +545,7 @@ cudaError_t launch_mel(const float* pcm, const long long* offs, const int* lens,
         tile_min + (size_t)g0 * tps, gmax_bits + g0);
     SONIC_LAUNCH_CHECK();
   }
-  mel_fixup_kernel<T><<<dim3(tps, batch), 256, 0, st>>>(gmax_bits, lens, tile_min, tps, feat, feat_tm);
+  mel_fixup_kernel<T><<<dim3(16, batch), 256, 0, st>>>(gmax_bits, lens, tile_min, tps, feat, feat_tm);
   SONIC_LAUNCH_CHECK();
   return cudaSuccess;
 }

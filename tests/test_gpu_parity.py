@@ -84,6 +84,20 @@ def test_mel_time_major_copy(eng_fp32, eng_bf16):
         assert np.array_equal(tm[1:-1], want)
 
 
+def test_mel_features_only_flag(eng_bf16):
+    """SONIC_FLAG_FEATURES_ONLY (the front-end sweep's call): the same feature bits, no time-major copy, and a following
+    sonic_encode is refused instead of consuming a stale copy."""
+    from sonicscribe_b200.engine import FLAG_FEATURES_ONLY, FLAG_REFERENCE_PRESTEP
+    xs = [mo.synth_audio("speech", 52000, 3), mo.synth_audio("noise", 16000, 4)]
+    full, nfr = eng_bf16.mel(xs)
+    only, nfr2 = eng_bf16.mel(xs, flags=FLAG_REFERENCE_PRESTEP | FLAG_FEATURES_ONLY)
+    assert np.array_equal(full, only) and np.array_equal(nfr, nfr2)
+    with pytest.raises(RuntimeError):
+        eng_bf16.encode(want_embeds=False)
+    eng_bf16.mel(xs)                     # the handle recovers with the next ordinary call
+    eng_bf16.encode(want_embeds=False)
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 # tcgen05 GEMM against a float64 product of the bf16-rounded operands
 # ---------------------------------------------------------------------------------------------------------------------
