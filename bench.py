@@ -509,7 +509,9 @@ def run_realtime(args):
         "config": {"workload": "BASELINE.json configs[1]: one realtime stream, int16 64 ms chunks; interim decode once per second on the last 20 chunks "
                                "(20480 samples, max_new_tokens=15), committed decode of the 20 s utterance (max_new_tokens=150); full-size random-init "
                                "GLM-ASR-Nano-2512; latency = wall clock of TranscriptionManager.transcribe_temporary/committed (bytes in, text out)",
-                   "utterances": args.steps, "interim_calls": len(lat_i), "mode": args.mode},
+                   "utterances": args.steps, "interim_calls": len(lat_i), "mode": args.mode,
+                   "interim_encoder_window": ("short (opt-in SONIC_FLAG_SHORT_WINDOW via SONIC_SHORT_WINDOW_MAX_NEW: NOT the reference's numerics)"
+                                              if int(os.environ.get("SONIC_SHORT_WINDOW_MAX_NEW", "0")) >= 15 else "full 30 s window (the reference's)")},
         "interim_ms": {"p50": p(lat_i, 50), "p95": p(lat_i, 95), "max": max(lat_i), "stage_ms": stage_i},
         "committed_ms": {"p50": p(lat_c, 50), "p95": p(lat_c, 95), "max": max(lat_c), "stage_ms": stage_c},
         "interim_budget_ms": 1000.0, "interim_share_of_budget": p(lat_i, 95) / 1000.0,

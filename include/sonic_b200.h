@@ -47,6 +47,12 @@ enum { SONIC_DTYPE_F32 = 0, SONIC_DTYPE_BF16 = 1 };
 #define SONIC_FLAG_OUT_DEVICE  0x20  /* features pointer of sonic_mel is device memory                          */
 #define SONIC_FLAG_FEATURES_ONLY 0x40 /* sonic_mel writes `features` only, not the encoder's time-major copy (front-end
                                         bandwidth sweep, BASELINE.json configs[4]); a following sonic_encode is refused   */
+#define SONIC_FLAG_SHORT_WINDOW 0x80  /* OPT-IN streaming encoder for interim calls (audio_manager.py:106-114 hands
+                                        the last 1.28 s to transcribe, which the reference pads to 30 s): when every segment of the
+                                        call has the same frame count F, the encoder runs over T = ceil(F/2) rounded up to 8
+                                        positions instead of 1500.  NOT the reference's numbers — the reference attends over the
+                                        padded positions too; parity is against the same HF classes fed the truncated features
+                                        input_features[:, :, :2T].  Calls with mixed lengths use the full window.                  */
 #define SONIC_FLAG_REFERENCE_PRESTEP (SONIC_FLAG_PEAK_NORM | SONIC_FLAG_PCM16)
 
 typedef struct {

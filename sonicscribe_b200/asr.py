@@ -25,7 +25,7 @@ import numpy as np
 import torch
 
 from .batcher import DynamicBatcher, Request
-from .engine import FLAG_PCM_S16, FLAG_REFERENCE_PRESTEP, Engine, num_audio_tokens
+from .engine import FLAG_PCM_S16, FLAG_REFERENCE_PRESTEP, FLAG_SHORT_WINDOW, Engine, num_audio_tokens
 from .prompt import PromptBuilder
 from .weights import ModelDims, dims_from_state_dict, load_checkpoint_dir, synthetic_state_dict
 
@@ -58,7 +58,7 @@ def _run_batch(ref: "weakref.ReferenceType[ASRModel]", reqs: List[Request]):
     eng = getattr(self, "model", None) if self is not None else None
     if eng is None or eng.h is None:
         raise RuntimeError("ASR model has been released")
-    flags = FLAG_REFERENCE_PRESTEP | (FLAG_PCM_S16 if reqs[0].s16 else 0)
+    flags = FLAG_REFERENCE_PRESTEP | (FLAG_PCM_S16 if reqs[0].s16 else 0) | (FLAG_SHORT_WINDOW if reqs[0].short else 0)
     g = max(r.max_new for r in reqs)
     t0 = time.perf_counter()
     out = eng.transcribe_ids([r.wav for r in reqs], [r.prompt for r in reqs], g, flags)
@@ -119,6 +119,7 @@ class ASRModel:
         self._prompts = PromptBuilder(self.processor, max_prompt=max_prompt)
         self._max_batch = max_batch
         self._max_new = max_new_tokens
+        self._short_window_max_new = int(os.environ.get("SONIC_SHORT_WINDOW_MAX_NEW", "0"))     # 0: the reference's full 30 s window always
         ref = weakref.ref(self)
         self._batcher = DynamicBatcher(lambda reqs: _run_batch(ref, reqs), max_batch, batch_window_ms / 1000.0)
 
@@ -174,34 +175,37 @@ class ASRModel:
             return self.processor.batch_decode([ids], skip_special_tokens=True)[0].strip()     # asr.py:425-429
         return " ".join(f"<{t}>" for t in ids if t not in EOS_IDS).strip()
 
-    def _submit(self, wavs: Sequence[np.ndarray], s16: bool, max_new_tokens: int, hotwords) -> List[Request]:
+    def _submit(self, wavs: Sequence[np.ndarray], s16: bool, max_new_tokens: int, hotwords, short_window: Optional[bool] = None) -> List[Request]:
         self._engine()
         if max_new_tokens < 1 or max_new_tokens > self._max_new:
             raise ValueError(f"max_new_tokens={max_new_tokens} outside 1..{self._max_new} (the engine's decode buffers)")
-        reqs = [Request(w, s16, self._prompts.build(num_audio_tokens(w.shape[0]), hotwords), max_new_tokens) for w in wavs]
+        # opt-in streaming encoder (SONIC_FLAG_SHORT_WINDOW): explicit per call, or every call whose token budget is at most
+        # SONIC_SHORT_WINDOW_MAX_NEW (the reference's interim calls ask for 15 tokens, config.py:40); default off
+        short = (max_new_tokens <= self._short_window_max_new) if short_window is None else bool(short_window)
+        reqs = [Request(w, s16, self._prompts.build(num_audio_tokens(w.shape[0]), hotwords), max_new_tokens, short) for w in wavs]
         self._batcher.submit_many(reqs)
         self._batcher.wait(reqs)
         return reqs
 
     # -- public API ---------------------------------------------------------------------------------------------------
     def transcribe_ids(self, audios: Sequence, sampling_rate: int = 16000, max_new_tokens: int = 128,
-                       hotwords: Optional[List[str]] = None) -> List[List[int]]:
+                       hotwords: Optional[List[str]] = None, short_window: Optional[bool] = None) -> List[List[int]]:
         """Generated token ids of several independent segments (results in input order)."""
         wavs = [self._to_mono_16k(a, sampling_rate) for a in audios]
-        return [r.ids for r in self._submit(wavs, False, max_new_tokens, hotwords)]
+        return [r.ids for r in self._submit(wavs, False, max_new_tokens, hotwords, short_window)]
 
     def transcribe_batch(self, audios: Sequence, sampling_rate: int = 16000, max_new_tokens: int = 128,
                          hotwords: Optional[List[str]] = None) -> List[str]:
         return [self._decode(ids) for ids in self.transcribe_ids(audios, sampling_rate, max_new_tokens, hotwords)]
 
     def transcribe_pcm16(self, pcm: Union[bytes, bytearray, memoryview, np.ndarray], max_new_tokens: int = 128,
-                         hotwords: Optional[List[str]] = None) -> str:
+                         hotwords: Optional[List[str]] = None, short_window: Optional[bool] = None) -> str:
         """int16 LE 16 kHz mono samples (the WebSocket wire format, frontend pcm-processor.js:59-75) -> text.  Equivalent to
         ``transcribe(torch.from_numpy(int16).float() / 32768.0)`` (transcription_manager.py:45-62) with the widening done on
         the device: 2 bytes per sample cross PCIe and no float copy is made on the host."""
         a = np.frombuffer(pcm, dtype=np.int16) if not isinstance(pcm, np.ndarray) else np.ascontiguousarray(pcm, dtype=np.int16).reshape(-1)
         self._check_length(a.shape[0])
-        return self._decode(self._submit([a], True, max_new_tokens, hotwords)[0].ids)
+        return self._decode(self._submit([a], True, max_new_tokens, hotwords, short_window)[0].ids)
 
     def transcribe(self, audio_tensor: torch.Tensor, sampling_rate: int = 16000, max_new_tokens: int = 128,
                    hotwords: Optional[List[str]] = None, return_debug_info: bool = False) -> Union[str, Dict[str, Any]]:

@@ -13,7 +13,7 @@ Policy
 * while a batch runs, new requests accumulate and form the next batch ("batch whatever is queued");
 * when recent concurrency was higher than what is queued, the worker waits up to ``window_s`` (default 3 ms) for the
   stragglers — N looping callers converge to batches of N instead of alternating halves;
-* requests are grouped by (sample dtype, max_new_tokens bucket): the batch decodes max(max_new_tokens) steps and every
+* requests are grouped by (sample dtype, max_new_tokens bucket, encoder window): the batch decodes max(max_new_tokens) steps and every
   request keeps the prefix it asked for — greedy decoding is causal, so that prefix is identical to a solo run.
 """
 from __future__ import annotations
@@ -34,10 +34,11 @@ def bucket_of(max_new_tokens: int) -> int:
 
 
 class Request:
-    __slots__ = ("wav", "s16", "prompt", "max_new", "done", "ids", "error", "info")
+    __slots__ = ("wav", "s16", "prompt", "max_new", "short", "done", "ids", "error", "info")
 
-    def __init__(self, wav, s16: bool, prompt: Sequence[int], max_new: int):
+    def __init__(self, wav, s16: bool, prompt: Sequence[int], max_new: int, short: bool = False):
         self.wav, self.s16, self.prompt, self.max_new = wav, bool(s16), prompt, int(max_new)
+        self.short = bool(short)          # opt-in short encoder window (interim calls); never mixed with full-window requests
         self.done = threading.Event()
         self.ids: Optional[List[int]] = None
         self.error: Optional[BaseException] = None
@@ -86,13 +87,13 @@ class DynamicBatcher:
         return max((c for _, c in self._recent), default=0)
 
     def _take_group(self) -> List[Request]:
-        """Pop the head request and every queued request of the same (dtype, bucket), in arrival order."""
+        """Pop the head request and every queued request of the same (dtype, bucket, encoder window), in arrival order."""
         head = self._q[0]
-        key = (head.s16, bucket_of(head.max_new))
+        key = (head.s16, bucket_of(head.max_new), head.short)
         group, rest = [], collections.deque()
         while self._q:
             r = self._q.popleft()
-            if len(group) < self.max_batch and (r.s16, bucket_of(r.max_new)) == key:
+            if len(group) < self.max_batch and (r.s16, bucket_of(r.max_new), r.short) == key:
                 group.append(r)
             else:
                 rest.append(r)

@@ -167,6 +167,7 @@ struct sonic_ctx {
   void* mel_tm = nullptr;
   std::vector<int> last_lens;           // lengths of the segments currently held in mel_tm
   int last_batch = 0;
+  int enc_T = 0;                        // encoder positions per segment for the features in mel_tm: kEncT, or fewer (SONIC_FLAG_SHORT_WINDOW)
 
   // encoder buffers
   void *h1 = nullptr, *ex = nullptr, *eu = nullptr, *eqkv = nullptr, *eattn = nullptr, *emlp = nullptr, *a1 = nullptr, *audio = nullptr;
@@ -383,17 +384,25 @@ struct Engine {
     T* mel_tm = reinterpret_cast<T*>(h->mel_tm);
     T *h1 = reinterpret_cast<T*>(h->h1), *x = reinterpret_cast<T*>(h->ex), *u = reinterpret_cast<T*>(h->eu);
     T *qkv = reinterpret_cast<T*>(h->eqkv), *attn = reinterpret_cast<T*>(h->eattn), *mlp = reinterpret_cast<T*>(h->emlp);
-    const int rows = B * kEncT;
+    // encT positions per segment: 1500, or the short window of SONIC_FLAG_SHORT_WINDOW (the encoder then sees the first 2 encT
+    // frames only: the row after them is zeroed in the time-major features and in the conv1 output, as the convolutions' own
+    // zero padding of a truncated input would be)
+    const int encT = h->enc_T > 0 ? h->enc_T : kEncT, encF = 2 * encT;
+    const int rows = B * encT;
     if (probe(h, "mel_tm", mel_tm, (size_t)B * (kFrames + 2) * kMels)) return -1;
+    if (encT < kEncT) {
+      CK(cudaMemset2DAsync(mel_tm + (size_t)(1 + encF) * kMels, (size_t)(kFrames + 2) * kMels * sizeof(T), 0, kMels * sizeof(T), B, h->stream));
+      CK(cudaMemset2DAsync(h1 + (size_t)(1 + encF) * kEncH, (size_t)(kFrames + 2) * kEncH * sizeof(T), 0, kEncH * sizeof(T), B, h->stream));
+    }
     {  // conv1 + GELU (modeling_glmasr.py:317)
-      GemmArgs g = lin(mel_tm, kMels, h->conv1_w, 3 * kMels, h1, kEncH, h->conv1_b, kFrames, kEncH, ACT_GELU);
+      GemmArgs g = lin(mel_tm, kMels, h->conv1_w, 3 * kMels, h1, kEncH, h->conv1_b, encF, kEncH, ACT_GELU);
       g.batch = B; g.a_bstride = (long long)(kFrames + 2) * kMels; g.c_bstride = (long long)(kFrames + 2) * kEncH; g.c_row0 = 1;
       g.conv_cin = kMels; g.conv_stride = 1; g.conv_rows_pad = kFrames + 2;
       if (gemm(h, g, false, PC_ENC_GEMM)) return -1;
     }
     {  // conv2 (stride 2) + GELU (modeling_glmasr.py:318)
-      GemmArgs g = lin(h1, 2 * kEncH, h->conv2_w, 3 * kEncH, x, kEncH, h->conv2_b, kEncT, kEncH, ACT_GELU);
-      g.batch = B; g.a_bstride = (long long)(kFrames + 2) * kEncH; g.c_bstride = (long long)kEncT * kEncH;
+      GemmArgs g = lin(h1, 2 * kEncH, h->conv2_w, 3 * kEncH, x, kEncH, h->conv2_b, encT, kEncH, ACT_GELU);
+      g.batch = B; g.a_bstride = (long long)(kFrames + 2) * kEncH; g.c_bstride = (long long)encT * kEncH;
       g.conv_cin = kEncH; g.conv_stride = 2; g.conv_rows_pad = kFrames + 2;
       if (gemm(h, g, false, PC_ENC_GEMM)) return -1;
     }
@@ -405,26 +414,26 @@ struct Engine {
       {
         GemmArgs g = lin(u, kEncH, w.wqkv, kEncH, qkv, 3 * kEncH, w.bqkv, rows, 3 * kEncH, ACT_NONE, nullptr, 0, w.s_qkv);
         const bool fused_rope = std::is_same<T, bf16>::value && !h->force_simt;     // tcgen05 epilogue rotates q and k
-        if (fused_rope) { g.rope_cos = h->rope_enc_cos; g.rope_sin = h->rope_enc_sin; g.rope_T = kEncT; g.rope_ncols = 2 * kEncH; }
+        if (fused_rope) { g.rope_cos = h->rope_enc_cos; g.rope_sin = h->rope_enc_sin; g.rope_T = encT; g.rope_ncols = 2 * kEncH; }
         if (gemm(h, g, false, PC_ENC_GEMM)) return -1;
         if (!fused_rope) {
           TAG(PC_ENC_OTHER);
-          CKL(launch_rope_enc<T>(qkv, h->rope_enc_cos, h->rope_enc_sin, rows, kEncT, kEncHeads, kEncHd, kEncRot, h->stream), 1);
+          CKL(launch_rope_enc<T>(qkv, h->rope_enc_cos, h->rope_enc_sin, rows, encT, kEncHeads, kEncHd, kEncRot, h->stream), 1);
         }
       }
       {
         AttnArgs a;
         memset(&a, 0, sizeof(a));
         a.q = qkv; a.q_row_stride = 3 * kEncH;
-        a.k = qkv + kEncH; a.k_tok_stride = 3 * kEncH; a.k_head_stride = kEncHd; a.k_seg_stride = (long long)kEncT * 3 * kEncH;
-        a.v = qkv + 2 * kEncH; a.v_tok_stride = 3 * kEncH; a.v_head_stride = kEncHd; a.v_seg_stride = (long long)kEncT * 3 * kEncH;
+        a.k = qkv + kEncH; a.k_tok_stride = 3 * kEncH; a.k_head_stride = kEncHd; a.k_seg_stride = (long long)encT * 3 * kEncH;
+        a.v = qkv + 2 * kEncH; a.v_tok_stride = 3 * kEncH; a.v_head_stride = kEncHd; a.v_seg_stride = (long long)encT * 3 * kEncH;
         a.o = attn; a.o_row_stride = kEncH;
-        a.q_len_fixed = kEncT; a.kv_len_fixed = kEncT; a.causal = 0; a.decode = 0;
-        a.heads = kEncHeads; a.kv_heads = kEncHeads; a.hd = kEncHd; a.batch = B; a.max_q = kEncT; a.scale = 0.125f;
+        a.q_len_fixed = encT; a.kv_len_fixed = encT; a.causal = 0; a.decode = 0;
+        a.heads = kEncHeads; a.kv_heads = kEncHeads; a.hd = kEncHd; a.batch = B; a.max_q = encT; a.scale = 0.125f;
         TAG(PC_ENC_ATTN);
         if (std::is_same<T, bf16>::value && !h->force_simt) {
           CKL(launch_attention_tc(reinterpret_cast<const bf16*>(qkv), 3 * kEncH, 0, kEncH, 2 * kEncH, reinterpret_cast<bf16*>(attn), kEncH, B,
-                                  kEncT, kEncHeads, 0.125f, h->stream), 1);
+                                  encT, kEncHeads, 0.125f, h->stream), 1);
         } else {
           CKL(launch_attention_simt<T>(a, h->stream), 1);
         }
@@ -440,7 +449,7 @@ struct Engine {
     CKL(launch_layernorm<T>(x, u, h->enc_norm_g, h->enc_norm_b, rows, kEncH, kLnEps, h->stream), 1);
     if (probe(h, "enc_out", u, (size_t)rows * kEncH)) return -1;
     // adapter: [B*375, 5120] -> 4096 (GELU) -> 2048 (modeling_glmasr.py:412-415, 333-349)
-    const int mrows = B * kMerged;
+    const int mrows = B * (encT / 4);                      // dense: segment b's merged rows start at b * encT / 4
     if (gemm(h, lin(u, kEncInter, h->proj1_w, kEncInter, h->a1, 2 * kDecH, h->proj1_b, mrows, 2 * kDecH, ACT_GELU, nullptr, 0, h->s_proj1), false, PC_ENC_GEMM)) return -1;
     if (gemm(h, lin(h->a1, 2 * kDecH, h->proj2_w, 2 * kDecH, h->audio, kDecH, h->proj2_b, mrows, kDecH, ACT_NONE, nullptr, 0, h->s_proj2), false, PC_ENC_GEMM)) return -1;
     if (probe(h, "audio_embeds", h->audio, (size_t)mrows * kDecH)) return -1;
@@ -848,6 +857,14 @@ int do_mel(sonic_ctx* h, const void* pcm_any, const int64_t* offsets, const int3
   }
   if ((flags & SONIC_FLAG_FEATURES_ONLY) && !features) return fail(h, "sonic_mel: SONIC_FLAG_FEATURES_ONLY without a features pointer");
   h->last_batch = (flags & SONIC_FLAG_FEATURES_ONLY) ? 0 : batch;      // features only: nothing for sonic_encode to consume
+  h->enc_T = kEncT;
+  if (flags & SONIC_FLAG_SHORT_WINDOW) {                               // opt-in: every segment has the same frame count
+    const int f0 = n_valid_frames(lengths[0]);
+    bool same = true;
+    for (int b = 1; b < batch; ++b) same = same && n_valid_frames(lengths[b]) == f0;
+    const int te = ((f0 + 1) / 2 + 7) / 8 * 8;
+    if (same && te < kEncT) h->enc_T = te;
+  }
   CK(cudaMemcpyAsync(h->offs_dev, h_offs, batch * 8, cudaMemcpyHostToDevice, h->stream));
   CK(cudaMemcpyAsync(h->lens_dev, h_lens, batch * 4, cudaMemcpyHostToDevice, h->stream));
   float* feat_dev = nullptr;
@@ -869,15 +886,19 @@ int do_encode(sonic_ctx* h, int batch, float* audio_embeds, int32_t* n_audio) {
   if (rc) return rc;
   if (n_audio) for (int b = 0; b < batch; ++b) n_audio[b] = n_audio_tokens(h->last_lens[b]);
   if (audio_embeds) {
-    const size_t n = (size_t)batch * kMerged * kDecH;
-    if (h->is_f32) {
-      CK(cudaMemcpyAsync(audio_embeds, h->audio, n * 4, cudaMemcpyDeviceToHost, h->stream));
-    } else {
+    // the caller's buffer is [batch, 375, 2048]; with a short window only the first enc_T / 4 rows of a segment exist
+    const int merged = (h->enc_T > 0 ? h->enc_T : kEncT) / 4;
+    const size_t n = (size_t)batch * merged * kDecH;
+    const float* src = reinterpret_cast<const float*>(h->audio);
+    if (!h->is_f32) {
       float* tmp = reinterpret_cast<float*>(h->emlp);   // free scratch at this point
       convert_flat_kernel<bf16, float><<<1024, 256, 0, h->stream>>>(reinterpret_cast<const bf16*>(h->audio), tmp, (long long)n);
       CK(cudaGetLastError());
-      CK(cudaMemcpyAsync(audio_embeds, tmp, n * 4, cudaMemcpyDeviceToHost, h->stream));
+      src = tmp;
     }
+    if (merged < kMerged) memset(audio_embeds, 0, (size_t)batch * kMerged * kDecH * 4);
+    CK(cudaMemcpy2DAsync(audio_embeds, (size_t)kMerged * kDecH * 4, src, (size_t)merged * kDecH * 4, (size_t)merged * kDecH * 4, batch,
+                         cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
   }
   return 0;
@@ -889,6 +910,7 @@ int do_generate(sonic_ctx* h, const int32_t* ids, const int32_t* id_offsets, int
   if (batch <= 0 || batch > h->cfg.max_batch) return fail(h, "sonic_generate: batch out of range");
   if (max_new <= 0 || max_new > h->cfg.max_new) return fail(h, "sonic_generate: max_new_tokens out of range");
   const int total = id_offsets[batch] - id_offsets[0];
+  const int enc_merged = (h->enc_T > 0 ? h->enc_T : kEncT) / 4;      // merged audio rows per segment in h->audio (dense)
   int max_q = 0;
   // host metadata: ids, audio_src, row_seg, row_pos | tok_off | last_rows | ctx_len
   int* p = h->h_pinned + 4 * h->cfg.max_batch;                             // generate metadata region
@@ -905,7 +927,7 @@ int do_generate(sonic_ctx* h, const int32_t* ids, const int32_t* id_offsets, int
       const int id = ids[id_offsets[b] + i];
       if (id < 0 || id >= kVocab) return fail(h, "sonic_generate: token id out of range");
       m_ids[r0 + i] = id;
-      m_src[r0 + i] = (id == kAudioTok) ? (b * kMerged + na++) : -1;
+      m_src[r0 + i] = (id == kAudioTok) ? (b * enc_merged + na++) : -1;
       m_seg[r0 + i] = b;
       m_pos[r0 + i] = i;
     }

@@ -18,6 +18,7 @@ _lib = None
 MODE_BF16, MODE_FP32, MODE_INT8 = 0, 1, 2
 MODES = {"bf16": MODE_BF16, "native": MODE_BF16, "fp32": MODE_FP32, "int8": MODE_INT8}
 FLAG_PEAK_NORM, FLAG_PCM16, FLAG_PCM_S16, FLAG_PCM_DEVICE, FLAG_OUT_DEVICE, FLAG_FEATURES_ONLY = 0x01, 0x02, 0x04, 0x10, 0x20, 0x40
+FLAG_SHORT_WINDOW = 0x80      # opt-in streaming encoder for interim calls (include/sonic_b200.h)
 ERR_UNKNOWN_TENSOR = -2
 FLAG_REFERENCE_PRESTEP = FLAG_PEAK_NORM | FLAG_PCM16
 

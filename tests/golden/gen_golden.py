@@ -116,13 +116,54 @@ def gen_model(tag: str, dims: ModelDims, cases, seed=0):
     print(f"wrote model_{tag}.npz")
 
 
+def short_window_T(n_samples: int) -> int:
+    """Encoder positions of the opt-in short window (include/sonic_b200.h SONIC_FLAG_SHORT_WINDOW)."""
+    f = mo.n_valid_frames(n_samples)
+    return min(1500, ((f + 1) // 2 + 7) // 8 * 8)
+
+
+def gen_short_window(seed=0):
+    """The opt-in streaming-encoder mode has its own reference: the SAME HF classes fed input_features[:, :, :2T]."""
+    dims = ModelDims(enc_layers=2, dec_layers=2)
+    sd = synthetic_state_dict(dims, seed=seed)
+    model = build_hf(dims, sd)
+    out = {}
+    for ci, (kind, n, aseed, G) in enumerate([("noise", 20480, 3, 15), ("speech", 20480, 7, 15), ("speech", 48000, 9, 12)]):
+        xp = mo.prestep(mo.synth_audio(kind, n, aseed))
+        feat, mask = hf_features(xp)
+        T = short_window_T(n)
+        feat, mask = feat[:, :2 * T].contiguous(), mask[:2 * T].contiguous()
+        n_audio = mo.n_audio_tokens(n)
+        ids = synthetic_prompt_ids(n_audio)
+        with torch.no_grad():
+            enc = model.audio_tower(feat[None]).last_hidden_state[0]
+            ae = model.get_audio_features(feat[None], mask[None], return_dict=True).pooler_output
+            kw = dict(input_ids=torch.tensor([ids]), input_features=feat[None], input_features_mask=mask[None],
+                      attention_mask=torch.ones(1, len(ids), dtype=torch.long))
+            gen = model.generate(**kw, max_new_tokens=G, do_sample=False, output_scores=True, return_dict_in_generate=True)
+        new = gen.sequences[0, len(ids):].numpy()
+        margins = [float((lambda t2: t2[0] - t2[1])(torch.topk(s[0].float(), 2).values)) for s in gen.scores]
+        p = f"c{ci}_"
+        out[p + "case"] = np.array([n, aseed, G, n_audio, T])
+        out[p + "kind"] = np.array(kind)
+        out[p + "enc_out_sub"] = enc[::4].numpy().copy()
+        out[p + "audio_embeds"] = ae.numpy().copy()
+        out[p + "new_ids"] = new
+        out[p + "margins"] = np.array(margins, dtype=np.float32)
+        print("short", kind, n, "T", T, "enc", tuple(enc.shape), "ae", tuple(ae.shape), "ids", new[:10], "min margin", min(margins))
+    np.savez_compressed(os.path.join(OUT, "short_window_tiny.npz"), **out)
+    print("wrote short_window_tiny.npz")
+
+
 if __name__ == "__main__":
     torch.set_num_threads(os.cpu_count() or 1)
-    what = sys.argv[1:] or ["mel", "tiny", "full"]
+    what = sys.argv[1:] or ["mel", "tiny", "short", "full"]
     if "mel" in what:
         gen_mel()
     if "tiny" in what:
         gen_model("tiny", ModelDims(enc_layers=2, dec_layers=2),
                   [("speech", 320000, 1, 32), ("noise", 20480, 3, 15), ("speech", 163840, 11, 24)])
+    if "short" in what:
+        gen_short_window()
     if "full" in what:
         gen_model("full", ModelDims(), [("speech", 320000, 1, 128), ("noise", 20480, 3, 15)])

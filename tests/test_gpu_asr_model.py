@@ -152,6 +152,23 @@ def test_pcm16_entry_point_equals_float_path(asr):
     assert asr.transcribe_pcm16(s16, max_new_tokens=15) == via_float
 
 
+def test_short_window_interim_call(asr_fp32):
+    """Opt-in streaming encoder through the drop-in class: explicit per call, and by token budget (SONIC_SHORT_WINDOW_MAX_NEW,
+    which serves the reference's unchanged interim call transcribe(..., max_new_tokens=15))."""
+    x = (mo.synth_audio("speech", 20480, 21) * 32767).astype(np.int16)
+    full = asr_fp32.transcribe_pcm16(x, max_new_tokens=15)
+    short = asr_fp32.transcribe_pcm16(x, max_new_tokens=15, short_window=True)
+    assert isinstance(short, str) and short
+    old = asr_fp32._short_window_max_new
+    try:
+        asr_fp32._short_window_max_new = 16
+        assert asr_fp32.transcribe_pcm16(x, max_new_tokens=15) == short           # by budget
+        assert asr_fp32.transcribe_pcm16(x, max_new_tokens=15, short_window=False) == full
+        assert asr_fp32.transcribe_pcm16(x, max_new_tokens=32) == asr_fp32.transcribe_pcm16(x, max_new_tokens=32, short_window=False)   # larger budgets keep the full window
+    finally:
+        asr_fp32._short_window_max_new = old
+
+
 def test_hotwords_and_argument_errors(asr):
     x = _segments(1)[0]
     a = asr.transcribe(x, max_new_tokens=8, hotwords=["Kubernetes", "B200"])

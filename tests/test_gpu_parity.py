@@ -99,6 +99,53 @@ def test_mel_features_only_flag(eng_bf16):
 
 
 # ---------------------------------------------------------------------------------------------------------------------
+# opt-in streaming encoder (SONIC_FLAG_SHORT_WINDOW): parity against the oracle fed the truncated
+# features — which tests/test_oracle_golden.py pins to the HF classes on the same truncated features
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kind,n,seed,G", [("noise", 20480, 3, 15), ("speech", 48000, 9, 12)])
+def test_short_window_encoder_vs_oracle(tiny_sd, eng_fp32, eng_bf16, kind, n, seed, G):
+    from sonicscribe_b200.engine import FLAG_REFERENCE_PRESTEP, FLAG_SHORT_WINDOW
+    from tests.golden.gen_golden import short_window_T
+    cfg = ora.OracleConfig(enc_layers=2, dec_layers=2)
+    flags = FLAG_REFERENCE_PRESTEP | FLAG_SHORT_WINDOW
+    x = mo.synth_audio(kind, n, seed)
+    T = short_window_T(n)
+    n_audio = num_audio_tokens(n)
+    ids = synthetic_prompt_ids(n_audio)
+    mel, _ = mo.log_mel(mo.prestep(x))
+    probes = {}
+    ref_ids, margins, _ = ora.generate_greedy(tiny_sd, cfg, torch.from_numpy(mel[:, :2 * T].copy()), n_audio, ids, G, probes=probes)
+    ref_ae = probes["audio_embeds"].numpy()
+    full_ids = eng_fp32.transcribe_ids([x], [ids], G)[0]           # the reference's 30 s window, for the state check below
+    for eng in (eng_fp32, eng_bf16):
+        eng.mel([x], flags=flags, want_features=False)
+        emb, na = eng.encode()
+        assert na[0] == n_audio
+        got_ae = emb[0, :n_audio]
+        if eng.mode == "fp32":
+            assert np.abs(got_ae - ref_ae).max() < 2e-3
+        else:
+            assert rel_l2(got_ae, ref_ae) < 3e-2                   # the stated bf16 tolerance
+        assert np.all(emb[0, T // 4:] == 0)                        # rows past the short window do not exist
+        got = eng.transcribe_ids([x], [ids], G, flags=flags)[0]
+        if eng.mode == "fp32":
+            assert got == ref_ids
+        else:
+            k = next((i for i, m in enumerate(margins) if m < 0.25), len(margins))
+            assert got[:k] == ref_ids[:k]
+    # a full-window call after a short one is unaffected (the zeroed padding rows are rewritten)
+    assert eng_fp32.transcribe_ids([x], [ids], G)[0] == full_ids
+    # two segments of the same length share the short window; their ids equal the solo runs (fp32: batch-invariant)
+    x2 = mo.synth_audio("speech", n, seed + 1)
+    solo2 = eng_fp32.transcribe_ids([x2], [ids], G, flags=flags)[0]
+    assert eng_fp32.transcribe_ids([x, x2], [ids, ids], G, flags=flags) == [ref_ids, solo2]
+    # mixed lengths: the flag is ignored and the call uses the full window
+    x3 = mo.synth_audio("noise", n + 16000, seed + 2)
+    ids3 = synthetic_prompt_ids(num_audio_tokens(n + 16000))
+    assert eng_fp32.transcribe_ids([x, x3], [ids, ids3], G, flags=flags) == eng_fp32.transcribe_ids([x, x3], [ids, ids3], G)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
 # tcgen05 GEMM against a float64 product of the bf16-rounded operands
 # ---------------------------------------------------------------------------------------------------------------------
 GEMM_SHAPES = [(128, 128, 64), (256, 384, 128), (300, 256, 1280), (1500, 1280, 1280), (77, 3840, 1280), (1, 128, 64),

@@ -98,6 +98,27 @@ def test_model_oracle_vs_hf_golden_full_short(golden_dir):
     _check_model(golden_dir, "full", ModelDims(), [1])
 
 
+def test_short_window_oracle_vs_hf_golden(golden_dir):
+    """The opt-in streaming-encoder mode (SONIC_FLAG_SHORT_WINDOW) has its own reference: the HF classes fed the truncated
+    features input_features[:, :, :2T].  The oracle, given the same truncated features, must reproduce them."""
+    from tests.golden.gen_golden import short_window_T
+    g = np.load(os.path.join(golden_dir, "short_window_tiny.npz"))
+    dims = ModelDims(enc_layers=2, dec_layers=2)
+    sd = synthetic_state_dict(dims, seed=0)
+    cfg = ora.OracleConfig(enc_layers=2, dec_layers=2)
+    for ci in range(3):
+        n, aseed, G, n_audio, T = [int(v) for v in g[f"c{ci}_case"]]
+        assert T == short_window_T(n) and T % 8 == 0 and T // 4 >= n_audio
+        mel, _ = mo.log_mel(mo.prestep(mo.synth_audio(str(g[f"c{ci}_kind"]), n, aseed)))
+        probes = {}
+        new, margins, _ = ora.generate_greedy(sd, cfg, torch.from_numpy(mel[:, :2 * T].copy()), n_audio, synthetic_prompt_ids(n_audio), G,
+                                              probes=probes)
+        assert probes["enc_out"].shape[0] == T
+        assert np.abs(probes["enc_out"][::4].numpy() - g[f"c{ci}_enc_out_sub"]).max() < 2e-3
+        assert np.abs(probes["audio_embeds"].numpy() - g[f"c{ci}_audio_embeds"]).max() < 2e-3
+        assert new == g[f"c{ci}_new_ids"].tolist()
+
+
 def test_streamed_synthetic_checkpoint_equals_dict():
     """bench.py streams the synthetic checkpoint tensor by tensor; same names, order and values as the dict form."""
     import torch
