@@ -183,6 +183,9 @@ mel_frames_kernel(const float* __restrict__ pcm, const long long* __restrict__ o
   const int cls1 = tab->cls_end[0], cls2 = tab->cls_end[1];
   for (int i = tid; i < 16; i += kMelThreads) s_P[kTileFrames * kPStride + i] = 0.f;
 
+  // the next group's peak kernel (launched with programmatic stream serialization; it reads nothing this kernel writes) may
+  // take the SMs this grid's CTAs leave at its tail instead of waiting for the whole grid
+  pdl_launch_dependents();
   const bool norm_flag = (flags & SONIC_MEL_PEAK_NORM) != 0, pcm16 = (flags & SONIC_MEL_PCM16) != 0;
   const int total = batch * tiles_per_seg;
   // work item = (segment, tile of 32 frames); tiles that hold no transformed frame are skipped (CTA-uniform)
@@ -530,12 +533,13 @@ cudaError_t launch_mel(const float* pcm, const long long* offs, const int* lens,
   // groups of <= 64 segments (82 MB of fp32 PCM): the frames kernel of a group re-reads from L2 what its peak pass just read
   // (measured at 1024 segments: 620 GB/s in groups of 64, 684 GB/s as one launch that reads the PCM twice from HBM; SONIC_MEL_GROUP)
   static const int kGroup = [] { const char* v = getenv("SONIC_MEL_GROUP"); const int g = v ? atoi(v) : 64; return g > 0 ? g : 64; }();
+  static const bool mel_pdl = [] { const char* v = getenv("SONIC_NO_PDL"); return !(v && v[0] == '1'); }();
   for (int g0 = 0; g0 < batch; g0 += kGroup) {
     const int gb = min(kGroup, batch - g0);
     if (flags & SONIC_MEL_PEAK_NORM) {
       int gx = max(1, min(cdiv(max_len, 256 * 8), 64));
-      mel_peak_kernel<<<dim3(gx, gb), 256, 0, st>>>(pcm, offs + g0, lens + g0, peak_bits + g0, flags);
-      SONIC_LAUNCH_CHECK();
+      // groups after the first: programmatic dependent launch behind the previous group's frames kernel (no data dependency)
+      SONIC_CUDA_TRY(launch_ex(mel_peak_kernel, dim3(gx, gb), dim3(256), 0, st, g0 > 0 && mel_pdl, pcm, offs + g0, lens + g0, peak_bits + g0, flags));
     }
     const long long total = (long long)tiles * gb;
     const int grid = (int)(total < 2LL * sms ? total : 2LL * sms);      // two resident CTAs per SM, persistent
