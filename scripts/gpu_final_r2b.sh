@@ -15,7 +15,8 @@ timeout 400 python bench.py --mode int8 --no-cpu-baseline --no-api-threads --ste
 timeout 300 python bench.py --workload realtime > $O/bench_realtime.json 2>/dev/null; echo "realtime rc=$?"
 SONIC_SHORT_WINDOW_MAX_NEW=15 timeout 300 python bench.py --workload realtime > $O/bench_realtime_short_window.json 2>/dev/null; echo "realtime short rc=$?"
 timeout 300 python bench.py --workload file1h --steps 2 --warmup 1 > $O/bench_file1h_1gpu.json 2>/dev/null; echo "file1h rc=$?"
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 20000 --csv --log-file $O/launches.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-api-threads > $O/ncu_bench.log 2>&1; echo "ncu list rc=$?"
+# -c 4400: set-up + the warm-up / timed 256-segment steps (595 launches each); the single-segment latency probes that follow are not needed
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 4400 --csv --log-file $O/launches.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-api-threads > $O/ncu_bench.log 2>&1; echo "ncu list rc=$?"
 SONIC_REF_BUDGET_S=60 timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > $O/bench_reference.json 2> $O/bench_reference.err; echo "reference rc=$?"
 python - <<'PY'
 import json, glob
