@@ -110,3 +110,24 @@ def test_closed_batcher_raises():
     b.close()
     with pytest.raises(RuntimeError, match="released"):
         b.submit_many([_req(5)])
+
+
+def test_short_window_requests_never_share_a_batch_with_full_window_requests():
+    """The opt-in short encoder window (SONIC_FLAG_SHORT_WINDOW) is a property of the whole device call, so the batcher keys its
+    groups on it: interim calls that asked for it are batched together, everything else keeps the reference's full window."""
+    seen = []
+
+    def run(reqs):
+        seen.append(sorted({r.short for r in reqs}))
+        time.sleep(0.02)
+        return [[r.wav.shape[0]] * r.max_new for r in reqs], {}
+
+    b = DynamicBatcher(run, max_batch=16, window_s=0.02)
+    reqs = [Request(np.zeros(100 + i, np.float32), False, [1], 4, short=(i % 2 == 0)) for i in range(12)]
+    th = [threading.Thread(target=lambda r=r: (b.submit_many([r]), b.wait([r]))) for r in reqs]
+    [t.start() for t in th]; [t.join() for t in th]
+    assert all(len(s) == 1 for s in seen), seen                     # no batch mixed the two kinds
+    assert [True] in seen and [False] in seen
+    assert all(r.ids == [100 + i] * 4 for i, r in enumerate(reqs))
+    assert Request(np.zeros(1, np.float32), False, [1], 4).short is False       # default: the reference's full window
+    b.close()

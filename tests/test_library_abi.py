@@ -45,3 +45,15 @@ def test_no_cpu_fallback():
         ASRModel("synthetic:enc=2,dec=2", device="cpu")
     with pytest.raises(ValueError):
         ASRModel("synthetic", mode="fp16")
+
+
+def test_flag_values_match_the_header():
+    """engine.py mirrors the SONIC_FLAG_* bits of include/sonic_b200.h by value."""
+    txt = open(os.path.join(ROOT, "include", "sonic_b200.h")).read()
+    header = {m.group(1): int(m.group(2), 16) for m in re.finditer(r"#define\s+SONIC_FLAG_(\w+)\s+0x([0-9a-fA-F]+)", txt)}
+    mirror = {"PEAK_NORM": engine.FLAG_PEAK_NORM, "PCM16": engine.FLAG_PCM16, "PCM_S16": engine.FLAG_PCM_S16,
+              "PCM_DEVICE": engine.FLAG_PCM_DEVICE, "OUT_DEVICE": engine.FLAG_OUT_DEVICE, "FEATURES_ONLY": engine.FLAG_FEATURES_ONLY,
+              "SHORT_WINDOW": engine.FLAG_SHORT_WINDOW}
+    assert header == mirror
+    assert len(set(mirror.values())) == len(mirror) and all(v & (v - 1) == 0 for v in mirror.values())     # distinct single bits
+    assert engine.FLAG_REFERENCE_PRESTEP == engine.FLAG_PEAK_NORM | engine.FLAG_PCM16
